@@ -1,0 +1,778 @@
+// az_kernels.cu - kernels and C ABI of libaz_b200.so (see include/az_b200.h).
+//
+// Kernel inventory (one warp per tree unless noted):
+//   k_step    lock-step advance with an external evaluator: consume evaluation (K4 expand + K5 backup),
+//             K1 select, K3 encode the leaf for the policy/value net
+//   k_search  all remaining simulations of a move with an in-kernel evaluator (uniform / hash)
+//   k_play    K6: root policy, edge choice, game record, move on the live board, re-root with
+//             breadth-first compaction into the other pool half, game finish + refill
+//   k_env_*   K2/K3 standalone, one thread per board (compat Board, unit tests)
+// Built for sm_100a only.  There is no CPU implementation behind this ABI.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/az_b200.h"
+#include "az_tree.cuh"
+
+namespace az {
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+#define AZ_CUDA(call)                                                                    \
+    do {                                                                                 \
+        cudaError_t err__ = (call);                                                      \
+        if (err__ != cudaSuccess) return fail(AZ_ERR_CUDA, #call ": %s", cudaGetErrorString(err__)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ header kernels
+__global__ void k_reset(Eng e) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        *e.fin_count = 0;
+        long long started = e.T < e.games_target ? e.T : e.games_target;
+        *e.games_started = (unsigned long long)started;
+    }
+    if (t >= e.T) return;
+    const int nw2 = (e.r.bits > 64 ? 2 : 1) * 2;
+    e.status[t] = t < e.games_target ? AZ_PHASE_SEARCH : AZ_PHASE_IDLE;
+    e.ply[t] = 0;
+    e.game_id[t] = e.game_base + t;
+    for (int i = 0; i < nw2; ++i) e.root_board[(size_t)t * nw2 + i] = 0;
+    e.half[t] = 0;
+    e.n_nodes[t] = 1;
+    e.sims_done[t] = 0;
+    e.pending[t] = 0;
+    e.path_len[t] = 0;
+    for (int i = 0; i < 4; ++i) e.counters[(size_t)t * 4 + i] = 0;
+    NodeA z;
+    z.w = 0.0;
+    z.n = 0;
+    z.link = 0;
+    store_node(e.node_a + (size_t)t * 2 * e.C, z);
+    e.node_p[(size_t)t * 2 * e.C] = 0.0;
+}
+
+// header arrays only k_play / k_set_roots touch
+struct Aux {
+    int32_t* rec_len;
+    int32_t* result;
+};
+
+__global__ void k_reset_aux(Aux a, int T) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    a.rec_len[t] = 0;
+    a.result[t] = 0;
+}
+
+__global__ void k_set_roots(Eng e, Aux aux, const int32_t* ids, const int8_t* cells, const int32_t* plies, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int t = ids[i];
+    if (t < 0 || t >= e.T) return;
+    const int nw = e.r.bits > 64 ? 2 : 1;
+    uint64_t cur[2] = {0, 0}, opp[2] = {0, 0};
+    const int8_t* c = cells + (size_t)i * e.r.cells;
+    for (int y = 0; y < e.r.H; ++y)
+        for (int x = 0; x < e.r.W; ++x) {
+            int v = c[y * e.r.W + x], b = y * e.r.stride + x;
+            if (v > 0) cur[b >> 6] |= 1ull << (b & 63);
+            if (v < 0) opp[b >> 6] |= 1ull << (b & 63);
+        }
+    uint64_t* rb = e.root_board + (size_t)t * 2 * nw;
+    for (int w = 0; w < nw; ++w) {
+        rb[w] = cur[w];
+        rb[nw + w] = opp[w];
+    }
+    e.status[t] = AZ_PHASE_SEARCH;
+    e.ply[t] = plies[i];
+    e.half[t] = 0;
+    e.n_nodes[t] = 1;
+    e.sims_done[t] = 0;
+    e.pending[t] = 0;
+    e.path_len[t] = 0;
+    aux.rec_len[t] = 0;
+    aux.result[t] = 0;
+    NodeA z;
+    z.w = 0.0;
+    z.n = 0;
+    z.link = 0;
+    store_node(e.node_a + (size_t)t * 2 * e.C, z);
+    e.node_p[(size_t)t * 2 * e.C] = 0.0;
+}
+
+__global__ void k_begin_search(Eng e) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= e.T) return;
+    int st = e.status[t], ph = st & AZ_PHASE_MASK;
+    if (ph == AZ_PHASE_SEARCH || ph == AZ_PHASE_READY) {
+        e.status[t] = (st & ~AZ_PHASE_MASK) | AZ_PHASE_SEARCH;
+        if (!e.pending[t]) e.sims_done[t] = 0;
+    }
+}
+
+__global__ void k_fin_clear(Eng e) { *e.fin_count = 0; }
+
+// ------------------------------------------------------------------------------------------ k_step
+template <int NW, int KC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    k_step(Eng e, const void* __restrict__ priors, const void* __restrict__ values, int eval_dtype, void* states,
+           int state_dtype, int32_t* leaf_valid) {
+    __shared__ WarpScratch s_ws[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= e.T) return;
+    WarpScratch& ws = s_ws[warp];
+    const int st = e.status[t];
+    uint32_t flags = 0;
+    int valid = 0;
+    if ((st & AZ_PHASE_MASK) == AZ_PHASE_SEARCH) {
+        const size_t pool = ((size_t)t * 2 + e.half[t]) * e.C;
+        NodeA* A = e.node_a + pool;
+        double* Pr = e.node_p + pool;
+        int sims = e.sims_done[t];
+        long long nsim = 0, neval = 0;
+        if (e.pending[t] && priors != nullptr) {
+            const int depth = e.path_len[t];
+            for (int i = lane; i < depth; i += 32) ws.path[i] = e.path[(size_t)t * kMaxDepth + i];
+            const Pos<NW> leaf = load_pos<NW>(e.leaf_board + (size_t)t * 2 * NW);
+            __syncwarp();
+            double v;
+            uint32_t link;
+            if (eval_dtype == AZ_F64) {
+                const double* p = static_cast<const double*>(priors) + (size_t)t * e.r.A;
+                v = static_cast<const double*>(values)[t];
+                link = expand_leaf<NW>(e, A, Pr, leaf, t, ws, lane, flags, [p](int a) { return p[a]; });
+            } else {
+                const float* p = static_cast<const float*>(priors) + (size_t)t * e.r.A;
+                v = (double)static_cast<const float*>(values)[t];  // value.numpy().item() (mcts.py:136)
+                link = expand_leaf<NW>(e, A, Pr, leaf, t, ws, lane, flags, [p](int a) { return (double)p[a]; });
+            }
+            backup_path(A, ws, depth, -v, link, lane);  // mcts.py:175: value seen by the player who moved in
+            ++sims;
+            ++nsim;
+            ++neval;
+        }
+        int pend = (e.pending[t] && priors == nullptr) ? 1 : 0;
+        int freed = 0;
+        while (!pend && sims < e.sims_target) {
+            Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
+            int depth, term;
+            select_leaf<NW, KC>(e, A, Pr, pos, ws, lane, depth, term, flags);
+            if (term) {  // mcts.py:179: terminal leaf, result 1 (win of the mover) or 0 (draw)
+                backup_path(A, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
+                ++sims;
+                ++nsim;
+                if (++freed >= e.max_free) break;
+                continue;
+            }
+            for (int i = lane; i < depth; i += 32) e.path[(size_t)t * kMaxDepth + i] = ws.path[i];
+            store_pos<NW>(e.leaf_board + (size_t)t * 2 * NW, pos, lane);
+            if (lane == 0) e.path_len[t] = depth;
+            if (state_dtype == AZ_BF16)
+                encode_state_bf16<NW>(e.r, pos, static_cast<__nv_bfloat16*>(states) + (size_t)t * e.r.cells * 4, lane);
+            else
+                encode_state_f32<NW>(e.r, pos, static_cast<float*>(states) + (size_t)t * e.r.cells * 4, lane);
+            pend = 1;
+        }
+        valid = pend;
+        if (lane == 0) {
+            e.sims_done[t] = sims;
+            e.pending[t] = pend;
+            e.counters[(size_t)t * 4 + 0] += nsim;
+            e.counters[(size_t)t * 4 + 1] += neval;
+            int ph = (sims >= e.sims_target && !pend) ? AZ_PHASE_READY : AZ_PHASE_SEARCH;
+            e.status[t] = (st & ~AZ_PHASE_MASK) | ph | (int)flags;
+        }
+    }
+    if (lane == 0) leaf_valid[t] = valid;
+}
+
+// ------------------------------------------------------------------------------------------ k_search
+template <int NW, int KC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
+    __shared__ WarpScratch s_ws[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= e.T) return;
+    WarpScratch& ws = s_ws[warp];
+    const int st = e.status[t];
+    if ((st & AZ_PHASE_MASK) != AZ_PHASE_SEARCH) return;
+    uint32_t flags = 0;
+    const size_t pool = ((size_t)t * 2 + e.half[t]) * e.C;
+    NodeA* A = e.node_a + pool;
+    double* Pr = e.node_p + pool;
+    const Pos<NW> root = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
+    const double uniform_prior = __ddiv_rn(1.0, (double)e.r.A);  // np.full(A, 1 / A)
+    int sims = e.sims_done[t];
+    long long nsim = 0, neval = 0;
+    while (sims < e.sims_target && !(flags & AZ_FLAG_POOL_OVERFLOW)) {
+        Pos<NW> pos = root;
+        int depth, term;
+        select_leaf<NW, KC>(e, A, Pr, pos, ws, lane, depth, term, flags);
+        if (term) {
+            backup_path(A, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
+        } else {
+            double v = 0.0;
+            uint32_t link;
+            if (e.eval_mode == AZ_EVAL_HASH) {
+                const uint64_t h = hash_position<NW>(e.r, pos);
+                v = hash_value(h);
+                link = expand_leaf<NW>(e, A, Pr, pos, t, ws, lane, flags, [h](int a) { return hash_prior(h, a); });
+            } else {
+                link = expand_leaf<NW>(e, A, Pr, pos, t, ws, lane, flags, [uniform_prior](int) { return uniform_prior; });
+            }
+            backup_path(A, ws, depth, -v, link, lane);
+            ++neval;
+        }
+        ++sims;
+        ++nsim;
+    }
+    if (lane == 0) {
+        e.sims_done[t] = sims;
+        e.counters[(size_t)t * 4 + 0] += nsim;
+        e.counters[(size_t)t * 4 + 1] += neval;
+        int ph = sims >= e.sims_target ? AZ_PHASE_READY : AZ_PHASE_SEARCH;
+        e.status[t] = (st & ~AZ_PHASE_MASK) | ph | (int)flags;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ k_play
+// rank (edge index) of a legal action among the moves in board order
+template <int NW>
+__device__ __forceinline__ int edge_of_action(const Rules& r, const BB<NW>& legal, int a) {
+    if (r.gravity) return __popcll(legal.w[0] & ((1ull << a) - 1ull));
+    int x = a / r.H, y = a - x * r.H, bit = y * r.stride + x;
+    if (NW == 2 && bit >= 64) return popc64(legal.w[0]) + __popcll(legal.w[NW - 1] & ((1ull << (bit - 64)) - 1ull));
+    return __popcll(legal.w[0] & ((1ull << bit) - 1ull));
+}
+
+template <int NW>
+__device__ __forceinline__ void finish_game(const Eng& e, const Aux& aux, int t, int st, int lane) {
+    // finished-game ring slot (self_play.py:66-78 hands the game's arrays to the caller)
+    int slot = 0;
+    if (lane == 0) {
+        slot = atomicAdd(e.fin_count, 1);
+        if (slot >= e.F) {
+            atomicSub(e.fin_count, 1);
+            slot = -1;
+        }
+    }
+    slot = __shfl_sync(kFull, slot, 0);
+    if (slot < 0) {
+        if (lane == 0) e.status[t] = (st & ~AZ_PHASE_MASK) | AZ_PHASE_STALLED;
+        return;
+    }
+    const int len = aux.rec_len[t], A = e.r.A;
+    for (int i = lane; i < len * A; i += 32)
+        e.fin_visits[(size_t)slot * e.P * A + i] = e.rec_visits[(size_t)t * e.P * A + i];
+    for (int i = lane; i < len; i += 32) e.fin_action[(size_t)slot * e.P + i] = e.rec_action[(size_t)t * e.P + i];
+    for (int i = lane; i < len * 2 * NW; i += 32)
+        e.fin_board[(size_t)slot * e.P * 2 * NW + i] = e.rec_board[(size_t)t * e.P * 2 * NW + i];
+    unsigned long long g = 0;
+    if (lane == 0) {
+        e.fin_game_id[slot] = e.game_id[t];
+        e.fin_len[slot] = len;
+        e.fin_result[slot] = aux.result[t];
+        e.counters[(size_t)t * 4 + 3] += 1;
+        if (e.auto_restart) g = atomicAdd(e.games_started, 1ull);
+    }
+    g = __shfl_sync(kFull, g, 0);
+    if (e.auto_restart && (long long)g < e.games_target) {  // next game in this slot: Board() + fresh MCTS
+        if (lane < 2 * NW) e.root_board[(size_t)t * 2 * NW + lane] = 0;
+        if (lane == 0) {
+            e.game_id[t] = e.game_base + (long long)g;
+            e.ply[t] = 0;
+            aux.rec_len[t] = 0;
+            e.n_nodes[t] = 1;
+            e.sims_done[t] = 0;
+            e.pending[t] = 0;
+            NodeA z;
+            z.w = 0.0;
+            z.n = 0;
+            z.link = 0;
+            store_node(e.node_a + ((size_t)t * 2 + e.half[t]) * e.C, z);
+            e.status[t] = (st & ~AZ_PHASE_MASK) | AZ_PHASE_SEARCH;
+        }
+    } else if (lane == 0) {
+        e.status[t] = (st & ~AZ_PHASE_MASK) | AZ_PHASE_IDLE;
+    }
+}
+
+template <int NW, int KC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, int greedy_override, int move_mode) {
+    __shared__ WarpScratch s_ws[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= e.T) return;
+    WarpScratch& ws = s_ws[warp];
+    int st = e.status[t];
+    const int phase = st & AZ_PHASE_MASK;
+    if (phase == AZ_PHASE_STALLED) {
+        finish_game<NW>(e, aux, t, st, lane);
+        return;
+    }
+    if (phase != AZ_PHASE_READY) return;
+    const int h = e.half[t];
+    const size_t pool = ((size_t)t * 2 + h) * e.C, pool2 = ((size_t)t * 2 + (h ^ 1)) * e.C;
+    NodeA* As = e.node_a + pool;
+    double* Ps = e.node_p + pool;
+    NodeA* Ad = e.node_a + pool2;
+    double* Pd = e.node_p + pool2;
+    const uint32_t rlink = load_node(As).link;
+    const int base = (int)(rlink & 0xffffffu), k = (int)(rlink >> 24);
+    const int ply = e.ply[t], rec = aux.rec_len[t];
+    if (k == 0 || rec >= e.P) {  // the reference would raise on an edgeless root (np.argmax of [])
+        if (lane == 0) e.status[t] = st | AZ_FLAG_ILLEGAL;
+        return;
+    }
+    // root visit counts (mcts.py:189-197)
+    for (int j = lane; j < k; j += 32) ws.sel[j] = (double)load_node(As + base + j).n;
+    __syncwarp();
+    int am = 0;
+    {
+        double bv = ws.sel[0];
+        for (int j = 1; j < k; ++j)
+            if (ws.sel[j] > bv) {
+                bv = ws.sel[j];
+                am = j;
+            }
+    }
+    const bool greedy = greedy_override >= 0 ? greedy_override != 0 : ply >= e.greedy_idx;  // self_play.py:62
+    int pick = am;  // deterministic=True, and every greedy draw (one-hot policy)
+    if (move_mode != AZ_MOVE_ARGMAX && !greedy) {
+        // np.random.choice(edges, 1, p=pi): cdf = cumsum(pi); cdf /= cdf[-1]; searchsorted(cdf, u, 'right')
+        const double u = move_mode == AZ_MOVE_HOST_UNIFORMS ? e.uniforms[(size_t)t * e.P + rec]
+                                                            : philox_uniform(e.seed, e.game_id[t], ply);
+        double total = 0.0;
+        for (int j = 0; j < k; ++j) total = __dadd_rn(total, ws.sel[j]);  // integers: exact in any order
+        double last = 0.0;
+        for (int j = 0; j < k; ++j) {
+            double pj = total == 0.0 ? __ddiv_rn(1.0, (double)k) : __ddiv_rn(ws.sel[j], total);
+            last = j == 0 ? pj : __dadd_rn(last, pj);
+        }
+        double acc = 0.0;
+        pick = k - 1;
+        for (int j = 0; j < k; ++j) {
+            double pj = total == 0.0 ? __ddiv_rn(1.0, (double)k) : __ddiv_rn(ws.sel[j], total);
+            acc = j == 0 ? pj : __dadd_rn(acc, pj);
+            if (__ddiv_rn(acc, last) > u) {
+                pick = j;
+                break;
+            }
+        }
+    }
+    // record: parent position, visit counts by action, chosen action (self_play.py:63-66)
+    Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
+    const BB<NW> legal = legal_set(e.r, pos);
+    for (int a = lane; a < e.r.A; a += 32) {
+        int v = -1;
+        if (action_legal(e.r, pos, legal, a)) v = (int)ws.sel[edge_of_action<NW>(e.r, legal, a)];
+        e.rec_visits[((size_t)t * e.P + rec) * e.r.A + a] = v;
+    }
+    store_pos<NW>(e.rec_board + ((size_t)t * e.P + rec) * 2 * NW, pos, lane);
+    int bit, action;
+    edge_move(e.r, pos, legal, pick, bit, action);
+    const int term = place(e.r, pos, bit);  // mcts.py:205
+    store_pos<NW>(e.root_board + (size_t)t * 2 * NW, pos, lane);
+    if (lane == 0) {
+        e.rec_action[(size_t)t * e.P + rec] = action | (greedy ? 1 << 16 : 0);
+        aux.rec_len[t] = rec + 1;
+        e.ply[t] = ply + 1;
+        e.counters[(size_t)t * 4 + 2] += 1;
+        e.sims_done[t] = 0;
+    }
+    __syncwarp();
+    if (term) {
+        if (lane == 0) aux.result[t] = term == 1 ? 1 : 0;  // board.py:258-268 with keep_same_player
+        __syncwarp();
+        finish_game<NW>(e, aux, t, st, lane);
+        return;
+    }
+    // re-root to the chosen child, keeping its subtree (mcts.py:207): breadth-first copy into the
+    // other half, 32 queue nodes per wave, children re-based with a warp prefix sum.
+    if (lane == 0) {
+        store_node(Ad, load_node(As + base + pick));
+        Pd[0] = Ps[base + pick];
+    }
+    __syncwarp();
+    int n_dst = 1, head = 0;
+    while (head < n_dst) {
+        const int cnt = min(32, n_dst - head);
+        uint32_t lk = 0;
+        if (lane < cnt) lk = load_node(Ad + head + lane).link;
+        const int kk = (int)(lk >> 24), ob = (int)(lk & 0xffffffu);
+        int incl = kk;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int excl = incl - kk, total = __shfl_sync(kFull, incl, 31);
+        if (kk) {
+            NodeA r2 = load_node(Ad + head + lane);
+            r2.link = (uint32_t)(n_dst + excl) | ((uint32_t)kk << 24);
+            store_node(Ad + head + lane, r2);
+        }
+        ws.off[lane] = excl;
+        ws.ob[lane] = ob;
+        __syncwarp();
+        for (int idx = lane; idx < total; idx += 32) {
+            int lo = 0, hi = 32;  // last lane whose exclusive offset is <= idx
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (ws.off[mid] <= idx) lo = mid; else hi = mid;
+            }
+            const int src = ws.ob[lo] + (idx - ws.off[lo]);
+            store_node(Ad + n_dst + idx, load_node(As + src));
+            Pd[n_dst + idx] = Ps[src];
+        }
+        n_dst += total;
+        head += cnt;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        e.half[t] = h ^ 1;
+        e.n_nodes[t] = n_dst;
+        e.pending[t] = 0;
+        e.status[t] = (st & ~AZ_PHASE_MASK) | AZ_PHASE_SEARCH;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ env kernels
+__device__ __forceinline__ Pos<2> pos_from_cells(const Rules& r, const int8_t* c) {
+    Pos<2> p;
+    p.cur.w[0] = p.cur.w[1] = p.opp.w[0] = p.opp.w[1] = 0;
+    for (int y = 0; y < r.H; ++y)
+        for (int x = 0; x < r.W; ++x) {
+            int v = c[y * r.W + x];
+            if (v > 0) bb_set(p.cur, y * r.stride + x);
+            if (v < 0) bb_set(p.opp, y * r.stride + x);
+        }
+    return p;
+}
+
+__global__ void k_env_play(Rules r, const int8_t* cells_in, const int32_t* actions, int n, int8_t* cells_out,
+                           int32_t* status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int8_t* c = cells_in + (size_t)i * r.cells;
+    int8_t* o = cells_out + (size_t)i * r.cells;
+    Pos<2> p = pos_from_cells(r, c);
+    const BB<2> legal = legal_set(r, p);
+    const int a = actions[i];
+    if (a < 0 || !action_legal(r, p, legal, a)) {  // board.py:221-224,228: AssertionError in the reference
+        for (int j = 0; j < r.cells; ++j) o[j] = c[j];
+        status[i] = -1;
+        return;
+    }
+    int bit, action;
+    edge_move(r, p, legal, edge_of_action<2>(r, legal, a), bit, action);
+    status[i] = place(r, p, bit);
+    for (int j = 0; j < r.cells; ++j) {
+        int code = cell_code(r, p, j);
+        o[j] = code == 1 ? 1 : (code == 2 ? -1 : 0);
+    }
+}
+
+__global__ void k_env_legal(Rules r, const int8_t* cells, int n, uint8_t* legal_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pos<2> p = pos_from_cells(r, cells + (size_t)i * r.cells);
+    const BB<2> legal = legal_set(r, p);
+    for (int a = 0; a < r.A; ++a) legal_out[(size_t)i * r.A + a] = action_legal(r, p, legal, a) ? 1 : 0;
+}
+
+__global__ void k_env_encode(Rules r, const int8_t* cells, int n, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pos<2> p = pos_from_cells(r, cells + (size_t)i * r.cells);
+    for (int j = 0; j < r.cells; ++j) {
+        int code = cell_code(r, p, j);
+        reinterpret_cast<float4*>(out + (size_t)i * r.cells * 4)[j] = make_float4(code == 0, code == 1, code == 2, 1.0f);
+    }
+}
+
+}  // namespace az
+
+// ========================================================================================== C ABI
+using namespace az;
+
+struct az_engine {
+    az_config cfg;
+    az_layout lay;
+    Eng eng;
+    Aux aux;
+    int nw, kc;
+};
+
+static int check_cfg(const az_config* c) {
+    if (!c) return fail(AZ_ERR_ARG, "null config%s");
+    if (c->abi_version != AZ_ABI_VERSION) return fail(AZ_ERR_ARG, "abi_version mismatch%s");
+    if (c->width < 2 || c->height < 2 || c->width > kMaxDim || c->height > kMaxDim)
+        return fail(AZ_ERR_ARG, "board dimensions out of range%s");
+    if (c->height * (c->width + 1) > 128) return fail(AZ_ERR_ARG, "board needs more than 128 bits%s");
+    int m = c->width < c->height ? c->width : c->height;
+    if (c->n_connect < 2 || c->n_connect > m) return fail(AZ_ERR_ARG, "n_connect must be in [2, min(W, H)]%s");
+    return AZ_OK;
+}
+
+static size_t take(size_t& off, size_t bytes) {
+    size_t at = (off + 255) & ~(size_t)255;
+    off = at + bytes;
+    return at;
+}
+
+#define AZ_API extern "C" __attribute__((visibility("default")))
+AZ_API const char* az_last_error(void) { return g_err; }
+AZ_API int az_abi_version(void) { return AZ_ABI_VERSION; }
+AZ_API void az_struct_sizes(size_t* c, size_t* l) {
+    if (c) *c = sizeof(az_config);
+    if (l) *l = sizeof(az_layout);
+}
+
+AZ_API int az_query_layout(const az_config* c, az_layout* L) {
+    if (int rc = check_cfg(c)) return rc;
+    if (!L) return fail(AZ_ERR_ARG, "null layout%s");
+    if (c->n_trees < 1 || c->node_capacity < 2 || c->node_capacity > 0xffffff || c->fin_capacity < 1 ||
+        c->pow_lut_len < 2 || c->sims_per_move < 1 || c->max_free_sims < 1)
+        return fail(AZ_ERR_ARG, "n_trees / node_capacity / fin_capacity / pow_lut_len / sims_per_move out of range%s");
+    memset(L, 0, sizeof(*L));
+    const size_t T = c->n_trees, C = c->node_capacity, F = c->fin_capacity;
+    const size_t A = c->gravity ? c->width : c->width * c->height, P = (size_t)c->width * c->height;
+    const size_t WD = c->height * (c->width + 1) > 64 ? 2 : 1;
+    L->n_actions = (int)A;
+    L->max_plies = (int)P;
+    L->words = (int)WD;
+    L->max_depth = kMaxDepth;
+    size_t off = 0;
+    L->status = take(off, 4 * T);
+    L->ply = take(off, 4 * T);
+    L->game_id = take(off, 8 * T);
+    L->root_board = take(off, 8 * T * 2 * WD);
+    L->half = take(off, 4 * T);
+    L->n_nodes = take(off, 4 * T);
+    L->sims_done = take(off, 4 * T);
+    L->pending = take(off, 4 * T);
+    L->path_len = take(off, 4 * T);
+    L->path = take(off, 4 * T * kMaxDepth);
+    L->leaf_board = take(off, 8 * T * 2 * WD);
+    L->counters = take(off, 8 * T * 4);
+    L->uniforms = take(off, 8 * T * P);
+    L->node_a = take(off, 16 * T * 2 * C);
+    L->node_p = take(off, 8 * T * 2 * C);
+    L->rec_visits = take(off, 4 * T * P * A);
+    L->rec_action = take(off, 4 * T * P);
+    L->rec_board = take(off, 8 * T * P * 2 * WD);
+    L->fin_count = take(off, 16);
+    L->fin_game_id = take(off, 8 * F);
+    L->fin_len = take(off, 4 * F);
+    L->fin_result = take(off, 4 * F);
+    L->fin_visits = take(off, 4 * F * P * A);
+    L->fin_action = take(off, 4 * F * P);
+    L->fin_board = take(off, 8 * F * P * 2 * WD);
+    L->pow_lut = take(off, 8 * (size_t)c->pow_lut_len);
+    L->rec_len = take(off, 4 * T);
+    L->result = take(off, 4 * T);
+    L->total_bytes = (off + 255) & ~(size_t)255;
+    return AZ_OK;
+}
+
+AZ_API int az_engine_create(const az_config* c, void* slab, size_t bytes, const double* host_lut, void* stream,
+                                az_engine** out) {
+    if (!out) return fail(AZ_ERR_ARG, "null out%s");
+    *out = nullptr;
+    az_layout L;
+    if (int rc = az_query_layout(c, &L)) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback%s");
+    }
+    if (!slab || !host_lut) return fail(AZ_ERR_ARG, "null slab / pow table%s");
+    if (bytes < L.total_bytes || (reinterpret_cast<uintptr_t>(slab) & 255)) return fail(AZ_ERR_SLAB, "slab too small or not 256-byte aligned%s");
+    az_engine* e = new (std::nothrow) az_engine();
+    if (!e) return fail(AZ_ERR_ARG, "out of host memory%s");
+    e->cfg = *c;
+    e->lay = L;
+    char* b = static_cast<char*>(slab);
+    Eng& g = e->eng;
+    g.r = make_rules(c->width, c->height, c->n_connect, c->gravity ? 1 : 0);
+    g.T = c->n_trees;
+    g.C = c->node_capacity;
+    g.P = L.max_plies;
+    g.F = c->fin_capacity;
+    g.sims_target = c->sims_per_move;
+    g.greedy_idx = c->index_move_greedy;
+    g.eval_mode = c->eval_mode;
+    g.prior_mode = c->prior_mode;
+    g.move_mode = c->move_mode;
+    g.max_free = c->max_free_sims;
+    g.lut_len = c->pow_lut_len;
+    g.auto_restart = c->auto_restart;
+    g.c_puct = c->c_puct;
+    g.seed = c->seed;
+    g.game_base = c->game_id_base;
+    g.games_target = c->games_target;
+    g.status = reinterpret_cast<int32_t*>(b + L.status);
+    g.ply = reinterpret_cast<int32_t*>(b + L.ply);
+    g.game_id = reinterpret_cast<long long*>(b + L.game_id);
+    g.root_board = reinterpret_cast<uint64_t*>(b + L.root_board);
+    g.half = reinterpret_cast<int32_t*>(b + L.half);
+    g.n_nodes = reinterpret_cast<int32_t*>(b + L.n_nodes);
+    g.sims_done = reinterpret_cast<int32_t*>(b + L.sims_done);
+    g.pending = reinterpret_cast<int32_t*>(b + L.pending);
+    g.path_len = reinterpret_cast<int32_t*>(b + L.path_len);
+    g.path = reinterpret_cast<int32_t*>(b + L.path);
+    g.leaf_board = reinterpret_cast<uint64_t*>(b + L.leaf_board);
+    g.counters = reinterpret_cast<long long*>(b + L.counters);
+    g.uniforms = reinterpret_cast<double*>(b + L.uniforms);
+    g.node_a = reinterpret_cast<NodeA*>(b + L.node_a);
+    g.node_p = reinterpret_cast<double*>(b + L.node_p);
+    g.rec_visits = reinterpret_cast<int32_t*>(b + L.rec_visits);
+    g.rec_action = reinterpret_cast<int32_t*>(b + L.rec_action);
+    g.rec_board = reinterpret_cast<uint64_t*>(b + L.rec_board);
+    g.fin_count = reinterpret_cast<int32_t*>(b + L.fin_count);
+    g.games_started = reinterpret_cast<unsigned long long*>(b + L.fin_count + 8);
+    g.fin_game_id = reinterpret_cast<long long*>(b + L.fin_game_id);
+    g.fin_len = reinterpret_cast<int32_t*>(b + L.fin_len);
+    g.fin_result = reinterpret_cast<int32_t*>(b + L.fin_result);
+    g.fin_visits = reinterpret_cast<int32_t*>(b + L.fin_visits);
+    g.fin_action = reinterpret_cast<int32_t*>(b + L.fin_action);
+    g.fin_board = reinterpret_cast<uint64_t*>(b + L.fin_board);
+    g.pow_lut = reinterpret_cast<const double*>(b + L.pow_lut);
+    e->aux.rec_len = reinterpret_cast<int32_t*>(b + L.rec_len);
+    e->aux.result = reinterpret_cast<int32_t*>(b + L.result);
+    e->nw = L.words;
+    e->kc = L.n_actions <= 32 ? 1 : 4;
+    cudaError_t err = cudaMemcpyAsync(b + L.pow_lut, host_lut, 8 * (size_t)c->pow_lut_len, cudaMemcpyHostToDevice,
+                                      static_cast<cudaStream_t>(stream));
+    if (err == cudaSuccess) err = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));  // host_lut may be freed
+    if (err != cudaSuccess) {
+        delete e;
+        return fail(AZ_ERR_CUDA, "pow table upload: %s", cudaGetErrorString(err));
+    }
+    *out = e;
+    return az_reset_games(e, stream);
+}
+
+AZ_API void az_engine_destroy(az_engine* e) { delete e; }
+
+static inline dim3 tree_grid(const az_engine* e) { return dim3((e->eng.T + kWarpsPerBlock - 1) / kWarpsPerBlock); }
+static inline dim3 flat_grid(int n) { return dim3((n + 127) / 128); }
+
+AZ_API int az_reset_games(az_engine* e, void* stream) {
+    if (!e) return fail(AZ_ERR_ARG, "null engine%s");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    e->eng.sims_target = e->cfg.sims_per_move;
+    k_reset<<<flat_grid(e->eng.T), 128, 0, s>>>(e->eng);
+    k_reset_aux<<<flat_grid(e->eng.T), 128, 0, s>>>(e->aux, e->eng.T);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_set_roots(az_engine* e, const int32_t* ids, const int8_t* cells, const int32_t* plies, int32_t n,
+                            void* stream) {
+    if (!e || !ids || !cells || !plies || n < 0) return fail(AZ_ERR_ARG, "az_set_roots: bad argument%s");
+    if (n == 0) return AZ_OK;
+    k_set_roots<<<flat_grid(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(e->eng, e->aux, ids, cells, plies, n);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_begin_search(az_engine* e, int32_t sims, void* stream) {
+    if (!e || sims < 1) return fail(AZ_ERR_ARG, "az_begin_search: bad argument%s");
+    e->eng.sims_target = sims;
+    k_begin_search<<<flat_grid(e->eng.T), 128, 0, static_cast<cudaStream_t>(stream)>>>(e->eng);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+#define AZ_DISPATCH(kernel, ...)                                                                  \
+    do {                                                                                          \
+        cudaStream_t s__ = static_cast<cudaStream_t>(stream);                                     \
+        dim3 g__ = tree_grid(e), b__(kWarpsPerBlock * 32);                                        \
+        if (e->nw == 1 && e->kc == 1) kernel<1, 1><<<g__, b__, 0, s__>>>(__VA_ARGS__);            \
+        else if (e->nw == 1) kernel<1, 4><<<g__, b__, 0, s__>>>(__VA_ARGS__);                     \
+        else if (e->kc == 1) kernel<2, 1><<<g__, b__, 0, s__>>>(__VA_ARGS__);                     \
+        else kernel<2, 4><<<g__, b__, 0, s__>>>(__VA_ARGS__);                                     \
+        AZ_CUDA(cudaGetLastError());                                                              \
+    } while (0)
+
+AZ_API int az_step(az_engine* e, const void* priors, const void* values, int32_t eval_dtype, void* states,
+                       int32_t state_dtype, int32_t* leaf_valid, void* stream) {
+    if (!e || !states || !leaf_valid) return fail(AZ_ERR_ARG, "az_step: null pointer%s");
+    if ((priors == nullptr) != (values == nullptr)) return fail(AZ_ERR_ARG, "az_step: priors and values go together%s");
+    if ((eval_dtype != AZ_F32 && eval_dtype != AZ_F64) || (state_dtype != AZ_BF16 && state_dtype != AZ_F32))
+        return fail(AZ_ERR_ARG, "az_step: unsupported dtype%s");
+    AZ_DISPATCH(k_step, e->eng, priors, values, eval_dtype, states, state_dtype, leaf_valid);
+    return AZ_OK;
+}
+
+AZ_API int az_search(az_engine* e, void* stream) {
+    if (!e) return fail(AZ_ERR_ARG, "null engine%s");
+    if (e->eng.eval_mode != AZ_EVAL_UNIFORM && e->eng.eval_mode != AZ_EVAL_HASH)
+        return fail(AZ_ERR_ARG, "az_search needs an in-kernel evaluator (eval_mode UNIFORM or HASH)%s");
+    AZ_DISPATCH(k_search, e->eng);
+    return AZ_OK;
+}
+
+AZ_API int az_play(az_engine* e, int32_t greedy_override, int32_t move_mode_override, void* stream) {
+    if (!e) return fail(AZ_ERR_ARG, "null engine%s");
+    int mode = move_mode_override >= 0 ? move_mode_override : e->eng.move_mode;
+    if (mode < AZ_MOVE_ARGMAX || mode > AZ_MOVE_PHILOX) return fail(AZ_ERR_ARG, "az_play: bad move mode%s");
+    AZ_DISPATCH(k_play, e->eng, e->aux, greedy_override, mode);
+    return AZ_OK;
+}
+
+AZ_API int az_fin_clear(az_engine* e, void* stream) {
+    if (!e) return fail(AZ_ERR_ARG, "null engine%s");
+    k_fin_clear<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(e->eng);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+static int env_rules(const az_config* c, Rules* r) {
+    if (int rc = check_cfg(c)) return rc;
+    *r = make_rules(c->width, c->height, c->n_connect, c->gravity ? 1 : 0);
+    return AZ_OK;
+}
+
+AZ_API int az_env_play(const az_config* c, const int8_t* cells_in, const int32_t* actions, int32_t n,
+                           int8_t* cells_out, int32_t* status, void* stream) {
+    Rules r;
+    if (int rc = env_rules(c, &r)) return rc;
+    if (!cells_in || !actions || !cells_out || !status || n < 0) return fail(AZ_ERR_ARG, "az_env_play: bad argument%s");
+    if (n == 0) return AZ_OK;
+    k_env_play<<<flat_grid(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(r, cells_in, actions, n, cells_out, status);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_env_legal(const az_config* c, const int8_t* cells, int32_t n, uint8_t* legal, void* stream) {
+    Rules r;
+    if (int rc = env_rules(c, &r)) return rc;
+    if (!cells || !legal || n < 0) return fail(AZ_ERR_ARG, "az_env_legal: bad argument%s");
+    if (n == 0) return AZ_OK;
+    k_env_legal<<<flat_grid(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(r, cells, n, legal);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_env_encode(const az_config* c, const int8_t* cells, int32_t n, float* states, void* stream) {
+    Rules r;
+    if (int rc = env_rules(c, &r)) return rc;
+    if (!cells || !states || n < 0) return fail(AZ_ERR_ARG, "az_env_encode: bad argument%s");
+    if (n == 0) return AZ_OK;
+    k_env_encode<<<flat_grid(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(r, cells, n, states);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}

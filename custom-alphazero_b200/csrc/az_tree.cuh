@@ -1,0 +1,384 @@
+// az_tree.cuh - warp-per-tree PUCT search over HBM node pools (K1 select, K4 expand, K5 backup,
+// K6 play / re-root).  One warp owns one game tree; all control flow is warp-uniform, lanes
+// parallelise over the children of a node (select, expand), the nodes of a path (backup) and the
+// nodes of a BFS wave (re-root compaction).
+//
+// Reference behaviour restated (paths relative to /root/reference/custom_alphazero/):
+//   mcts/mcts.py:39-55    Q = W/N (0 when N == 0), U = ((c * prior) * (sum N) ** 0.5) / (1 + N)
+//   mcts/mcts.py:64-68    argmax of Q + U, first maximum wins
+//   mcts/mcts.py:111-120  select
+//   mcts/mcts.py:145-161  evaluate_and_expand (all children created at once)
+//   mcts/mcts.py:163-168  backup with alternating sign
+//   mcts/mcts.py:182-222  play: policy from root visits, edge choice, re-root keeping the subtree
+//   mcts/utils.py:4-16    normalize_probabilities (numpy pairwise sum + divide)
+//
+// Bit-exactness: everything that feeds a comparison is IEEE double with explicit round-to-nearest
+// intrinsics (no FMA contraction), in the reference's evaluation order; (sum N) ** 0.5 is read
+// from a host-built table of CPython's `n ** 0.5` because libm pow(n, .5) != sqrt(n) for some n.
+//
+// Node pool (per tree, two halves of C nodes): a node is at once a position and the edge that
+// leads to it.  Children of an expanded node are contiguous, in board move order, so edge j of
+// node v is node first_child(v) + j and its move is the j-th legal move of v's position: neither
+// moves nor boards are stored per node - the position is replayed in registers while descending.
+//   node_a[v] = {double W; int32 N; uint32 link}   16 B, one 128-bit load per lane
+//   node_p[v] = double prior                        8 B
+//   link = first_child | (k << 24); 0 = no edges (unexpanded or terminal)
+#pragma once
+#include <cuda_bf16.h>
+
+#include "az_bitboard.cuh"
+
+namespace az {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxActions = 128;
+constexpr int kMaxDepth = 128;
+constexpr int kWarpsPerBlock = 4;
+
+struct __align__(16) NodeA {
+    double w;
+    int32_t n;
+    uint32_t link;
+};
+
+__device__ __forceinline__ NodeA load_node(const NodeA* p) {
+    int4 v = *reinterpret_cast<const int4*>(p);
+    NodeA r;
+    r.w = __hiloint2double(v.y, v.x);
+    r.n = v.z;
+    r.link = (uint32_t)v.w;
+    return r;
+}
+
+__device__ __forceinline__ void store_node(NodeA* p, const NodeA& r) {
+    int4 v;
+    v.x = __double2loint(r.w);
+    v.y = __double2hiint(r.w);
+    v.z = r.n;
+    v.w = (int)r.link;
+    *reinterpret_cast<int4*>(p) = v;
+}
+
+// Device view of the engine: rules, knobs and typed pointers into the slab (az_layout).
+struct Eng {
+    Rules r;
+    int T, C, P, F;  // trees, node capacity per half, max plies, finished-ring entries
+    int sims_target, greedy_idx, eval_mode, prior_mode, move_mode, max_free, lut_len, auto_restart;
+    double c_puct;
+    uint64_t seed;
+    long long game_base, games_target;
+    int32_t* status;
+    int32_t* ply;
+    long long* game_id;
+    uint64_t* root_board;
+    int32_t* half;
+    int32_t* n_nodes;
+    int32_t* sims_done;
+    int32_t* pending;
+    int32_t* path_len;
+    int32_t* path;
+    uint64_t* leaf_board;
+    long long* counters;
+    double* uniforms;
+    NodeA* node_a;
+    double* node_p;
+    int32_t* rec_visits;
+    int32_t* rec_action;
+    uint64_t* rec_board;
+    int32_t* fin_count;
+    unsigned long long* games_started;
+    long long* fin_game_id;
+    int32_t* fin_len;
+    int32_t* fin_result;
+    int32_t* fin_visits;
+    int32_t* fin_action;
+    uint64_t* fin_board;
+    const double* pow_lut;
+};
+
+// per-warp scratch in shared memory
+struct WarpScratch {
+    double sel[kMaxActions];  // legal priors in action-list order / visit counts
+    int32_t path[kMaxDepth];
+    int32_t off[32];
+    int32_t ob[32];
+};
+
+template <int NW>
+__device__ __forceinline__ Pos<NW> load_pos(const uint64_t* p) {
+    Pos<NW> r;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        r.cur.w[i] = p[i];
+        r.opp.w[i] = p[NW + i];
+    }
+    return r;
+}
+
+template <int NW>
+__device__ __forceinline__ void store_pos(uint64_t* p, const Pos<NW>& v, int lane) {
+    if (lane < 2 * NW) p[lane] = lane < NW ? v.cur.w[lane % NW] : v.opp.w[lane % NW];
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 select (mcts.py:111-120).  pos: root position in, leaf position out.
+// Returns the leaf node; depth/ws.path receive the path; term = 0 none, 1 mover won, 2 draw.
+// ------------------------------------------------------------------------------------------
+template <int NW, int KC>
+__device__ __forceinline__ int select_leaf(const Eng& e, const NodeA* A, const double* Pr, Pos<NW>& pos,
+                                           WarpScratch& ws, int lane, int& depth, int& term, uint32_t& flags) {
+    int node = 0;
+    uint32_t link = load_node(A).link;
+    depth = 0;
+    term = 0;
+    while (link) {
+        const int base = (int)(link & 0xffffffu), k = (int)(link >> 24);
+        NodeA rec[KC];
+        double pr[KC];
+        int ln = 0;
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            int j = lane + 32 * c;
+            if (j < k) {
+                rec[c] = load_node(A + base + j);
+                pr[c] = Pr[base + j];
+                ln += rec[c].n;
+            } else {
+                rec[c].n = 0;
+                rec[c].w = 0.0;
+                rec[c].link = 0;
+                pr[c] = 0.0;
+            }
+        }
+        const int total = __reduce_add_sync(kFull, ln);  // mcts.py:50: sum over the node's edges
+        double s;
+        if (total < e.lut_len) {
+            s = __ldg(e.pow_lut + total);
+        } else {
+            s = sqrt((double)total);
+            flags |= AZ_FLAG_LUT_OVERFLOW;
+        }
+        double best = -INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            int j = lane + 32 * c;
+            if (j < k) {
+                double q = rec[c].n ? __ddiv_rn(rec[c].w, (double)rec[c].n) : 0.0;  // mcts.py:39-43
+                double u = __dmul_rn(e.c_puct, pr[c]);                               // mcts.py:47-48
+                u = __dmul_rn(u, s);                                                 // :49-50
+                u = __ddiv_rn(u, (double)(1 + rec[c].n));                            // :51
+                double v = __dadd_rn(q, u);                                          // :55
+                if (v > best || bi == 0x7fffffff) {
+                    best = v;
+                    bi = j;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {  // first maximum wins (np.argmax, mcts.py:65-67)
+            double ov = __shfl_xor_sync(kFull, best, o);
+            int oi = __shfl_xor_sync(kFull, bi, o);
+            if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > best || (ov == best && oi < bi))) {
+                best = ov;
+                bi = oi;
+            }
+        }
+        uint32_t clink = 0;
+#pragma unroll
+        for (int c = 0; c < KC; ++c)
+            if ((bi >> 5) == c) clink = rec[c].link;
+        clink = __shfl_sync(kFull, clink, bi & 31);
+        node = base + bi;
+        if (lane == 0) ws.path[depth] = node;
+        ++depth;
+        // replay the move of edge bi on the register position (board.py:233-250)
+        BB<NW> legal = legal_set(e.r, pos);
+        int bit, action;
+        edge_move(e.r, pos, legal, bi, bit, action);
+        term = place(e.r, pos, bit);
+        if (term) break;
+        link = clink;
+    }
+    __syncwarp();
+    return node;
+}
+
+// numpy add.reduce over a contiguous 1-D array (pairwise sum): left fold for n < 8, otherwise
+// eight strided accumulators combined as a balanced tree, then the tail (n <= 128 here).
+__device__ __forceinline__ double np_sum_f64(const double* a, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+__device__ __forceinline__ float np_sum_f32(const double* a, int n) {
+    if (n < 8) {
+        float res = 0.0f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, (float)a[i]);
+        return res;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = (float)a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], (float)a[i + j]);
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, (float)a[i]);
+    return res;
+}
+
+// mcts/utils.py:4-16 on ws.sel[0..k): result written back into ws.sel.
+__device__ __forceinline__ void normalise_sel(WarpScratch& ws, int k, int prior_mode, int lane) {
+    __syncwarp();
+    if (prior_mode == AZ_PRIOR_F32) {
+        float s = np_sum_f32(ws.sel, k);
+        __syncwarp();
+        for (int j = lane; j < k; j += 32)
+            ws.sel[j] = s == 0.0f ? __ddiv_rn(1.0, (double)k) : (double)__fdiv_rn((float)ws.sel[j], s);
+    } else {
+        double s = np_sum_f64(ws.sel, k);
+        __syncwarp();
+        for (int j = lane; j < k; j += 32) ws.sel[j] = s == 0.0 ? __ddiv_rn(1.0, (double)k) : __ddiv_rn(ws.sel[j], s);
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 expand (mcts.py:145-161).  prior_of(a) yields the evaluator's prior for action a (double).
+// Gathers the legal priors in action-list order, normalises them, appends k children in board
+// order (Q1: the j-th normalised prior goes to the j-th move in board order).  Returns the new
+// link (0 when the pool is exhausted).
+// ------------------------------------------------------------------------------------------
+template <int NW, typename PriorFn>
+__device__ __forceinline__ uint32_t expand_leaf(const Eng& e, NodeA* A, double* Pr, const Pos<NW>& pos, int t,
+                                                WarpScratch& ws, int lane, uint32_t& flags, PriorFn prior_of) {
+    BB<NW> legal = legal_set(e.r, pos);
+    int k = 0;
+    for (int a0 = 0; a0 < e.r.A; a0 += 32) {
+        int a = a0 + lane;
+        bool ok = action_legal(e.r, pos, legal, a);
+        unsigned m = __ballot_sync(kFull, ok);
+        if (ok) ws.sel[k + __popc(m & ((1u << lane) - 1u))] = prior_of(a);
+        k += __popc(m);
+    }
+    normalise_sel(ws, k, e.prior_mode, lane);
+    const int base = e.n_nodes[t];
+    if (base + k > e.C || base + k > 0xffffff) {
+        flags |= AZ_FLAG_POOL_OVERFLOW;
+        return 0;
+    }
+    NodeA fresh;
+    fresh.w = 0.0;
+    fresh.n = 0;
+    fresh.link = 0;
+    for (int j = lane; j < k; j += 32) {
+        store_node(A + base + j, fresh);
+        Pr[base + j] = ws.sel[j];
+    }
+    if (lane == 0) e.n_nodes[t] = base + k;
+    return (uint32_t)base | ((uint32_t)k << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// K5 backup (mcts.py:163-168): path nodes are distinct, so each lane owns one read-modify-write;
+// no atomics.  v0 is the value for the player who moved into the leaf; sign alternates upward.
+// new_link != 0 also publishes the leaf's fresh children in the same 16-byte store.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void backup_path(NodeA* A, const WarpScratch& ws, int depth, double v0, uint32_t new_link,
+                                            int lane) {
+    for (int i = lane; i < depth; i += 32) {
+        NodeA* p = A + ws.path[depth - 1 - i];
+        NodeA rec = load_node(p);
+        rec.n += 1;
+        rec.w = __dadd_rn(rec.w, (i & 1) ? -v0 : v0);
+        if (i == 0 && new_link) rec.link = new_link;
+        store_node(p, rec);
+    }
+    if (depth == 0 && new_link && lane == 0) {  // first simulation on an edgeless root: nothing to back up
+        NodeA rec = load_node(A);
+        rec.link = new_link;
+        store_node(A, rec);
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// in-kernel evaluators (oracle/evaluators.py)
+// ------------------------------------------------------------------------------------------
+template <int NW>
+__device__ __forceinline__ uint64_t hash_position(const Rules& r, const Pos<NW>& p) {
+    uint64_t h = 0xCBF29CE484222325ull;
+    for (int c = 0; c < r.cells; ++c) h = (h ^ (uint64_t)(cell_code(r, p, c) + 1)) * 0x100000001B3ull;
+    return h;
+}
+
+__device__ __forceinline__ double hash_prior(uint64_t h, int a) {
+    uint64_t m = (h ^ ((uint64_t)a * 0x9E3779B97F4A7C15ull)) * 0xFF51AFD7ED558CCDull;
+    return (double)(((m >> 40) % 1000ull) + 1ull);
+}
+
+__device__ __forceinline__ double hash_value(uint64_t h) {
+    return __ddiv_rn((double)((h >> 20) % 2001ull) - 1000.0, 1000.0);
+}
+
+// Philox4x32-10, counter (game id lo, game id hi, ply, 0), key = seed; 53-bit uniform in [0, 1)
+// built like numpy's random_sample: (a >> 5) * 2^26 + (b >> 6), / 2^53.
+__device__ __forceinline__ double philox_uniform(uint64_t seed, long long game, int ply) {
+    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)((uint64_t)game >> 32), c2 = (uint32_t)ply, c3 = 0;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+        c0 = n0;
+        c1 = n1;
+        c2 = n2;
+        c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return ((double)(c0 >> 5) * 67108864.0 + (double)(c1 >> 6)) / 9007199254740992.0;
+}
+
+// K3: Board.full_state (board.py:83-98) of `pos` into out[H][W][4]; lanes stride over cells.
+template <int NW>
+__device__ __forceinline__ void encode_state_bf16(const Rules& r, const Pos<NW>& pos, __nv_bfloat16* out, int lane) {
+    for (int c = lane; c < r.cells; c += 32) {
+        int code = cell_code(r, pos, c);
+        // bf16 1.0 = 0x3F80; planes: empty, side to move, opponent, turn (+1 under keep_same_player)
+        uint2 v;
+        v.x = (code == 0 ? 0x3F80u : 0u) | (code == 1 ? 0x3F800000u : 0u);
+        v.y = (code == 2 ? 0x3F80u : 0u) | 0x3F800000u;
+        reinterpret_cast<uint2*>(out)[c] = v;
+    }
+}
+
+template <int NW>
+__device__ __forceinline__ void encode_state_f32(const Rules& r, const Pos<NW>& pos, float* out, int lane) {
+    for (int c = lane; c < r.cells; c += 32) {
+        int code = cell_code(r, pos, c);
+        reinterpret_cast<float4*>(out)[c] = make_float4(code == 0, code == 1, code == 2, 1.0f);
+    }
+}
+
+}  // namespace az

@@ -1,0 +1,210 @@
+/* az_b200.h - C ABI of the B200-native self-play search engine (libaz_b200.so).
+ *
+ * This is the drop-in boundary for the reference's self-play hot path.  The reference
+ * (neuronest/custom-alphazero) is pure Python and has no FFI of its own; each entry point below
+ * names the reference interface it replaces (paths relative to custom_alphazero/ in the
+ * reference).  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, a config struct; no torch / C++ types
+ *   - every pointer marked "dev" is DEVICE memory owned by the caller (the Python host allocates
+ *     it through torch); the library allocates nothing on the device
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it, never
+ *     synchronises and is CUDA-graph capturable
+ *   - return value: 0 on success, otherwise an AZ_ERR_* code (host-side argument errors).
+ *     Device-side conditions (node pool exhausted, sqrt table exceeded, illegal action) are
+ *     sticky per-tree bits in the `status` array that the host reads once per move
+ *   - one engine per GPU per process; games are sharded across ranks by game id
+ */
+#ifndef AZ_B200_H
+#define AZ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZ_ABI_VERSION 1
+#define AZ_MAX_ACTIONS 128 /* W*H <= 121, bitboard needs H*(W+1) <= 128 */
+#define AZ_MAX_DEPTH 128
+
+enum {
+    AZ_OK = 0,
+    AZ_ERR_ARG = 1,      /* bad configuration / null pointer */
+    AZ_ERR_SLAB = 2,     /* slab too small or misaligned */
+    AZ_ERR_CUDA = 3,     /* a CUDA runtime call failed (message via az_last_error) */
+    AZ_ERR_NO_DEVICE = 4 /* no CUDA device: there is no CPU fallback */
+};
+
+/* evaluator that turns a leaf position into (priors, value) */
+enum {
+    AZ_EVAL_EXTERNAL = 0, /* the policy/value net (or any host evaluator) between two az_step calls */
+    AZ_EVAL_UNIFORM = 1,  /* in-kernel: np.full(A, 1/A), value 0 (SURVEY 8c fixed evaluator) */
+    AZ_EVAL_HASH = 2      /* in-kernel: oracle/evaluators.py hash evaluator */
+};
+/* arithmetic of the prior normalisation (mcts/utils.py:4-16) */
+enum {
+    AZ_PRIOR_F64 = 0, /* float64 evaluator output (serving/factory.py:55) */
+    AZ_PRIOR_F32 = 1  /* float32 net output normalised in float32, then widened (mcts.py:131-137) */
+};
+/* how MCTS.play picks the edge (mcts.py:198-201) */
+enum {
+    AZ_MOVE_ARGMAX = 0,       /* play(deterministic=True) */
+    AZ_MOVE_HOST_UNIFORMS = 1, /* np.random.choice with the draw supplied by the host: uniforms[tree][ply] */
+    AZ_MOVE_PHILOX = 2        /* same sampling rule, draw = Philox4x32-10(seed, game_id, ply) on device */
+};
+/* dtypes of evaluator tensors */
+enum { AZ_F32 = 0, AZ_F64 = 1, AZ_BF16 = 2 };
+
+/* per-tree status word (dev int32): phase in the low byte, sticky error bits above */
+enum {
+    AZ_PHASE_IDLE = 0,    /* no game assigned */
+    AZ_PHASE_SEARCH = 1,  /* simulations still to run for the current move */
+    AZ_PHASE_READY = 2,   /* sims_per_move reached: waiting for az_play */
+    AZ_PHASE_STALLED = 3, /* game finished but the finished-game ring is full */
+    AZ_PHASE_MASK = 0xff,
+    AZ_FLAG_POOL_OVERFLOW = 1 << 8, /* node pool exhausted: results of this tree are invalid */
+    AZ_FLAG_LUT_OVERFLOW = 1 << 9,  /* sum of visits exceeded the pow-half table */
+    AZ_FLAG_ILLEGAL = 1 << 10       /* illegal action / inconsistent root */
+};
+
+/* Replaces the class-attribute configuration the hot path reads (config.py:19-56):
+ * ConfigConnectN.{board_width, board_height, n, gravity}, ConfigSelfPlay.mcts_iterations,
+ * ConfigMCTS.{exploration_constant, index_move_greedy}. */
+typedef struct az_config {
+    int32_t abi_version;       /* AZ_ABI_VERSION */
+    int32_t width, height;     /* board; H*(W+1) <= 128 */
+    int32_t n_connect;         /* stones in a row to win */
+    int32_t gravity;           /* 1: Connect-4 style columns (A = W); 0: free placement (A = W*H) */
+    int32_t n_trees;           /* concurrent games (one warp each) on this GPU */
+    int32_t node_capacity;     /* nodes per tree per pool half (two halves: re-root compaction ping-pongs) */
+    int32_t sims_per_move;     /* ConfigSelfPlay.mcts_iterations */
+    int32_t index_move_greedy; /* ConfigMCTS.index_move_greedy (self_play.py:62) */
+    int32_t eval_mode;         /* AZ_EVAL_* */
+    int32_t prior_mode;        /* AZ_PRIOR_* */
+    int32_t move_mode;         /* AZ_MOVE_* */
+    int32_t max_free_sims;     /* simulations ending in a terminal leaf that one az_step may run per tree
+                                  before handing the batch slot back (they need no evaluation) */
+    int32_t fin_capacity;      /* finished-game ring entries */
+    int32_t pow_lut_len;       /* entries of the host-built table n -> n ** 0.5 (Q3: libm pow, not sqrt) */
+    int32_t auto_restart;      /* 1: a finished game is replaced by the next game id while any remain */
+    double c_puct;             /* ConfigMCTS.exploration_constant */
+    uint64_t seed;             /* Philox key for AZ_MOVE_PHILOX */
+    int64_t game_id_base;      /* first global game id of this rank */
+    int64_t games_target;      /* games this rank may start in total (auto_restart) */
+} az_config;
+
+/* Byte offsets of every array inside the caller-provided slab, so the host can make typed
+ * views (torch) of records, finished games and node pools without further calls.
+ * Shapes use T = n_trees, C = node_capacity, A = n_actions, P = max_plies = W*H, WD = words. */
+typedef struct az_layout {
+    size_t total_bytes;
+    int32_t n_actions, max_plies, words, max_depth;
+    /* per-tree header */
+    size_t status;      /* int32  [T] */
+    size_t ply;         /* int32  [T]      fullmove_number of the live game board (board.py:40) */
+    size_t game_id;     /* int64  [T] */
+    size_t root_board;  /* uint64 [T][2][WD]  (side-to-move stones, opponent stones) */
+    size_t half;        /* int32  [T]      which pool half holds the live tree */
+    size_t n_nodes;     /* int32  [T]      nodes used in the live half */
+    size_t sims_done;   /* int32  [T] */
+    size_t pending;     /* int32  [T]      1 = a leaf awaits its evaluation */
+    size_t path_len;    /* int32  [T] */
+    size_t path;        /* int32  [T][max_depth]  node indices root-child ... leaf */
+    size_t leaf_board;  /* uint64 [T][2][WD] */
+    size_t counters;    /* int64  [T][4]   cumulative simulations, evaluations, moves, games finished */
+    size_t uniforms;    /* double [T][P]   AZ_MOVE_HOST_UNIFORMS draws */
+    /* node pools: record A = {double W; int32 N; uint32 link}, link = first_child | k << 24, 0 = no edges */
+    size_t node_a;      /* 16 B   [T][2][C] */
+    size_t node_p;      /* double [T][2][C]  prior of the edge into the node */
+    /* per-tree record of the game in progress (what play_game accumulates, self_play.py:58-66) */
+    size_t rec_visits;  /* int32  [T][P][A]  root visit counts by action, -1 = illegal */
+    size_t rec_action;  /* int32  [T][P]     action | greedy << 16 */
+    size_t rec_board;   /* uint64 [T][P][2][WD]  parent position of each ply */
+    size_t rec_len;     /* int32  [T]      plies recorded so far for the game in progress */
+    size_t result;      /* int32  [T]      result of the game once it is over (see fin_result) */
+    /* finished-game ring */
+    size_t fin_count;   /* int32  [1] (+ games_started int64 at fin_count + 8) */
+    size_t fin_game_id; /* int64  [F] */
+    size_t fin_len;     /* int32  [F] */
+    size_t fin_result;  /* int32  [F]   1 = the player who moved last won, 0 = draw (board.py:258-268) */
+    size_t fin_visits;  /* int32  [F][P][A] */
+    size_t fin_action;  /* int32  [F][P]     action | greedy << 16 */
+    size_t fin_board;   /* uint64 [F][P][2][WD] */
+    size_t pow_lut;     /* double [pow_lut_len] */
+} az_layout;
+
+typedef struct az_engine az_engine;
+
+const char *az_last_error(void);
+int az_abi_version(void);
+/* sizeof(az_config), sizeof(az_layout) as compiled: lets a foreign-language binding verify its mirror */
+void az_struct_sizes(size_t *config_bytes, size_t *layout_bytes);
+
+/* Layout / size of the slab for a configuration (host only, no device needed). */
+int az_query_layout(const az_config *cfg, az_layout *out);
+
+/* Binds a configuration to a zero-initialised device slab and uploads the pow-half table.
+ * Replaces MCTS.__init__ / initialize_root (mcts/mcts.py:89-109) for n_trees trees at once. */
+int az_engine_create(const az_config *cfg, void *dev_slab, size_t slab_bytes, const double *host_pow_lut,
+                     void *stream, az_engine **out);
+void az_engine_destroy(az_engine *e);
+
+/* Starts a fresh game from the empty board in every tree (Board(), board.py:13-42); game ids are
+ * game_id_base + tree.  Also clears the finished-game ring and the counters. */
+int az_reset_games(az_engine *e, void *stream);
+
+/* Roots given trees at arbitrary positions: what MCTS(board=...) does with a caller-supplied Board
+ * (mcts/mcts.py:98,108-109).  cells: dev int8 [n][H][W] in the reference's convention (+1 = side to
+ * move, row 0 = top); plies: dev int32 [n]; tree_ids: dev int32 [n]. */
+int az_set_roots(az_engine *e, const int32_t *dev_tree_ids, const int8_t *dev_cells, const int32_t *dev_plies,
+                 int32_t n, void *stream);
+
+/* Overrides the per-move simulation budget for subsequent az_step / az_search calls
+ * (MCTS.search(iterations_number), mcts/mcts.py:170) and re-arms trees in AZ_PHASE_READY. */
+int az_begin_search(az_engine *e, int32_t sims, void *stream);
+
+/* One lock-step advance of every tree with an EXTERNAL evaluator (mcts/mcts.py:170-180):
+ *   1. a tree whose leaf was evaluated since the last call expands it with priors/values
+ *      (evaluate_and_expand, :145-161) and backs the value up its stored path (backup, :163-168);
+ *   2. it then selects the next leaf by PUCT (select, :111-120; UCTEdge terms :39-55); simulations
+ *      that end in a terminal leaf are finished on the spot (:179), up to max_free_sims of them;
+ *   3. a non-terminal leaf is encoded as the NN input (Board.full_state, connect_n/board.py:83-98)
+ *      into states_out[tree] and leaf_valid_out[tree] = 1.
+ * priors: dev [T][A], values: dev [T] (dtype AZ_F32 or AZ_F64); may be NULL on the first call.
+ * states_out: dev [T][H][W][4] (AZ_BF16 or AZ_F32); leaf_valid_out: dev int32 [T]. */
+int az_step(az_engine *e, const void *dev_priors, const void *dev_values, int32_t eval_dtype, void *dev_states_out,
+            int32_t state_dtype, int32_t *dev_leaf_valid_out, void *stream);
+
+/* Runs the remaining simulations of the current move for every tree inside ONE kernel using the
+ * in-kernel evaluator (eval_mode UNIFORM or HASH): MCTS.search(n) with the fixed evaluator. */
+int az_search(az_engine *e, void *stream);
+
+/* MCTS.play (mcts/mcts.py:182-222) for every tree in AZ_PHASE_READY: root policy from visit counts,
+ * edge choice, record (parent position, visit counts, action), move applied to the live board
+ * (Board.play(..., keep_same_player=True), connect_n/board.py:233-250), re-root to the chosen child
+ * keeping its subtree (compacted into the other pool half).  greedy_override: -1 = the self-play rule
+ * ply >= index_move_greedy, 0 / 1 = force; move_mode_override: -1 = cfg.move_mode.
+ * Finished games are moved to the ring and, with auto_restart, replaced (play_game, self_play.py:59-78). */
+int az_play(az_engine *e, int32_t greedy_override, int32_t move_mode_override, void *stream);
+
+/* Empties the finished-game ring after the host copied it; re-arms stalled trees. */
+int az_fin_clear(az_engine *e, void *stream);
+
+/* Standalone environment kernels (K2/K3), batched over n boards in the reference's cell convention.
+ * Replaces Board.play(move, keep_same_player=True) (board.py:233-250) incl. push (:210-231) and
+ * update_game_over (:178-208); Board.legal_moves_mask (:154-155); Board.full_state (:83-98).
+ *   cells_in/out: dev int8 [n][H][W]; actions: dev int32 [n] (index into get_all_possible_moves, :130-146)
+ *   status_out: dev int32 [n]: 0 ongoing, 1 mover won, 2 draw, -1 illegal action (board unchanged)
+ *   legal_out: dev uint8 [n][A]; states_out: dev float32 [n][H][W][4] */
+int az_env_play(const az_config *cfg, const int8_t *dev_cells_in, const int32_t *dev_actions, int32_t n,
+                int8_t *dev_cells_out, int32_t *dev_status_out, void *stream);
+int az_env_legal(const az_config *cfg, const int8_t *dev_cells, int32_t n, uint8_t *dev_legal_out, void *stream);
+int az_env_encode(const az_config *cfg, const int8_t *dev_cells, int32_t n, float *dev_states_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZ_B200_H */

@@ -99,7 +99,7 @@ class TreeEngine:
         self.sims_per_move = int(sims_per_move)
         T, F, WD, C = self.n_trees, cfg.fin_capacity, self.layout.words, cfg.node_capacity
         self._shapes = {
-            "root_board": (T, 2, WD), "path": (T, native.AZ_MAX_DEPTH), "leaf_board": (T, 2, WD), "counters": (T, 4),
+            "root_board": (T, 2, WD), "path": (T, native.AZ_MAX_DEPTH), "leaf_board": (T, 2, WD), "counters": (T, 8),
             "uniforms": (T, P), "node_p": (T, 2, C), "rec_visits": (T, P, A), "rec_action": (T, P),
             "rec_board": (T, P, 2, WD), "fin_visits": (F, P, A), "fin_action": (F, P), "fin_board": (F, P, 2, WD),
             "fin_game_id": (F,), "fin_len": (F,), "fin_result": (F,), "fin_count": (4,), "pow_lut": (cfg.pow_lut_len,),
@@ -107,8 +107,11 @@ class TreeEngine:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            lib().az_engine_destroy(h)
+        if h and lib is not None:  # module globals may already be gone at interpreter shutdown
+            try:
+                lib().az_engine_destroy(h)
+            except Exception:
+                pass
             self._h = None
 
     # ------------------------------------------------------------------ typed views into the slab
@@ -187,7 +190,8 @@ class TreeEngine:
 
     def totals(self):
         c = self.view("counters").sum(dim=0).tolist()
-        return {"sims": c[0], "evals": c[1], "moves": c[2], "games": c[3]}
+        return {"sims": c[0], "evals": c[1], "moves": c[2], "games": c[3], "depth_sum": c[4], "children": c[5],
+                "reroot_nodes": c[6]}
 
     def drain_finished(self):
         """Copies the finished-game ring to the host and empties it."""

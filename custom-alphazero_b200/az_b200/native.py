@@ -82,6 +82,7 @@ SYMBOLS = {
     "az_env_play": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _P, _I, _P, _P, _P]),
     "az_env_legal": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _I, _P, _P]),
     "az_env_encode": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _I, _P, _P]),
+    "az_decode_samples": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
 }
 
 _lib = None

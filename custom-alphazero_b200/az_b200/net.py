@@ -1,0 +1,187 @@
+"""Policy/value network of the reference, restated for PyTorch (the only dense contraction on the
+self-play path; it runs bf16 on the tensor cores through cuDNN/cuBLAS under the step's CUDA graph).
+
+Architecture follows /root/reference/custom_alphazero/model/tensorflow/model.py:21-188 and
+base_layers.py:20-125 (the TensorFlow/Keras model; the PyTorch copy in the reference is dead code):
+  input  x [B, H, W, 4] float (Board.full_state, NHWC)
+  stem   Conv3x3(4 -> F) + BN + ReLU                                     (model.py:36-46)
+  tower  depth x { Conv3x3+BN+ReLU -> Conv3x3+BN ; shortcut Conv1x1+BN of the block INPUT ;
+                   add ; ReLU }                                          (base_layers.py:85-125)
+  policy Conv1x1(F -> 2)+BN+ReLU -> Flatten (NHWC order) -> Dense(A) softmax     (model.py:68-103)
+  value  Conv1x1(F -> 1)+BN+ReLU -> Flatten -> Dense(256) ReLU -> Dense(1) tanh  (model.py:106-149)
+Keras defaults: Conv2D/Dense use_bias=True, glorot-uniform kernels, zero biases; BatchNormalization
+eps 1e-3, momentum 0.99.  F = 128, depth = 4 (config.py:63,71): 1 267 037 trainable parameters at 6x7.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+BN_EPS = 1e-3
+BN_MOMENTUM = 0.01  # Keras momentum 0.99
+
+
+def flops_per_eval(height, width, n_actions, filters=128, depth=4):
+    """2 * MAC over the layers above: 105 037 976 at 6x7 / A=7."""
+    px = height * width
+    macs = px * 9 * 4 * filters
+    macs += depth * (2 * px * 9 * filters * filters + px * filters * filters)
+    macs += px * filters * 2 + 2 * px * n_actions
+    macs += px * filters * 1 + px * 256 + 256
+    return 2 * macs
+
+
+class ConvBN(nn.Module):
+    def __init__(self, cin, cout, k, relu):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, padding=k // 2, bias=True)
+        self.bn = nn.BatchNorm2d(cout, eps=BN_EPS, momentum=BN_MOMENTUM)
+        self.relu = relu
+        nn.init.xavier_uniform_(self.conv.weight)
+        nn.init.zeros_(self.conv.bias)
+
+    def forward(self, x):
+        y = self.bn(self.conv(x))
+        return F.relu(y) if self.relu else y
+
+    def folded(self):
+        """(weight, bias) of the equivalent conv with the BN inference transform folded in."""
+        s = self.bn.weight / torch.sqrt(self.bn.running_var + self.bn.eps)
+        w = self.conv.weight * s[:, None, None, None]
+        b = (self.conv.bias - self.bn.running_mean) * s + self.bn.bias
+        return w, b
+
+
+class ResBlock(nn.Module):
+    def __init__(self, filters):
+        super().__init__()
+        self.c1 = ConvBN(filters, filters, 3, relu=True)
+        self.c2 = ConvBN(filters, filters, 3, relu=False)
+        self.proj = ConvBN(filters, filters, 1, relu=False)
+
+    def forward(self, x):
+        return F.relu(self.proj(x) + self.c2(self.c1(x)))
+
+
+class PolicyValueNet(nn.Module):
+    """Trainable fp32 module (the checker for the bf16 inference path and the thing a trainer updates)."""
+
+    def __init__(self, height=6, width=7, n_actions=7, filters=128, depth=4):
+        super().__init__()
+        self.height, self.width, self.n_actions, self.filters, self.depth = height, width, n_actions, filters, depth
+        self.stem = ConvBN(4, filters, 3, relu=True)
+        self.blocks = nn.ModuleList([ResBlock(filters) for _ in range(depth)])
+        self.policy_conv = ConvBN(filters, 2, 1, relu=True)
+        self.policy_fc = nn.Linear(2 * height * width, n_actions)
+        self.value_conv = ConvBN(filters, 1, 1, relu=True)
+        self.value_fc1 = nn.Linear(height * width, 256)
+        self.value_fc2 = nn.Linear(256, 1)
+        for fc in (self.policy_fc, self.value_fc1, self.value_fc2):
+            nn.init.xavier_uniform_(fc.weight)
+            nn.init.zeros_(fc.bias)
+
+    def trunk(self, x_nhwc):
+        x = x_nhwc.permute(0, 3, 1, 2)  # logical NCHW over NHWC memory
+        x = self.stem(x)
+        for b in self.blocks:
+            x = b(x)
+        return x
+
+    def heads(self, x):
+        B = x.shape[0]
+        p = self.policy_conv(x).permute(0, 2, 3, 1).reshape(B, -1)  # Keras Flatten on NHWC
+        v = self.value_conv(x).permute(0, 2, 3, 1).reshape(B, -1)
+        logits = self.policy_fc(p)
+        value = torch.tanh(self.value_fc2(F.relu(self.value_fc1(v))))
+        return logits, value
+
+    def forward(self, x_nhwc):
+        """-> (policy [B, A] softmax, value [B, 1] tanh), like PolicyValueModel.call (model.py:182-188)."""
+        logits, value = self.heads(self.trunk(x_nhwc))
+        return torch.softmax(logits, dim=-1), value
+
+    def n_parameters(self):
+        return sum(p.numel() for p in self.parameters())
+
+
+class InferenceNet(nn.Module):
+    """Inference-only copy: BN folded into the convolutions, channels-last, one dtype (bf16 on the
+    GPU path, fp32 for the CPU checker).  Outputs float32 (policy [B, A], value [B])."""
+
+    def __init__(self, net: PolicyValueNet, dtype=torch.bfloat16, device="cuda"):
+        super().__init__()
+        net = net.eval()
+        self.height, self.width, self.n_actions = net.height, net.width, net.n_actions
+        self.dtype = dtype
+        cl = torch.channels_last
+
+        def conv_params(cb):
+            w, b = cb.folded()
+            return (nn.Parameter(w.detach().to(device=device, dtype=dtype).contiguous(memory_format=cl), requires_grad=False),
+                    nn.Parameter(b.detach().to(device=device, dtype=dtype), requires_grad=False))
+
+        self.stem_w, self.stem_b = conv_params(net.stem)
+        self.block_params = nn.ParameterList()
+        for blk in net.blocks:
+            w1, b1 = conv_params(blk.c1)
+            w2, b2 = conv_params(blk.c2)
+            wp, bp = conv_params(blk.proj)
+            # the two biases that meet at the add are summed once here
+            b2p = nn.Parameter((b2.float() + bp.float()).to(dtype), requires_grad=False)
+            self.block_params.extend([w1, b1, w2, wp, b2p])
+        self.depth = len(net.blocks)
+        # both 1x1 head convolutions as one conv with 3 output channels (2 policy + 1 value)
+        pw, pb = net.policy_conv.folded()
+        vw, vb = net.value_conv.folded()
+        self.head_w = nn.Parameter(torch.cat([pw, vw], 0).detach().to(device=device, dtype=dtype).contiguous(memory_format=cl), requires_grad=False)
+        self.head_b = nn.Parameter(torch.cat([pb, vb], 0).detach().to(device=device, dtype=dtype), requires_grad=False)
+        f32 = lambda t: nn.Parameter(t.detach().to(device=device, dtype=torch.float32).contiguous(), requires_grad=False)  # noqa: E731
+        self.pfc_w, self.pfc_b = f32(net.policy_fc.weight), f32(net.policy_fc.bias)
+        self.v1_w, self.v1_b = f32(net.value_fc1.weight), f32(net.value_fc1.bias)
+        self.v2_w, self.v2_b = f32(net.value_fc2.weight), f32(net.value_fc2.bias)
+
+    @torch.no_grad()
+    def forward(self, x_nhwc):
+        B = x_nhwc.shape[0]
+        x = x_nhwc.to(self.dtype).permute(0, 3, 1, 2)
+        x = F.relu_(F.conv2d(x, self.stem_w, self.stem_b, padding=1))
+        for i in range(self.depth):
+            w1, b1, w2, wp, b2p = self.block_params[5 * i: 5 * i + 5]
+            h = F.relu_(F.conv2d(x, w1, b1, padding=1))
+            y = F.conv2d(h, w2, b2p, padding=1)
+            y += F.conv2d(x, wp)
+            x = F.relu_(y)
+        hd = F.relu_(F.conv2d(x, self.head_w, self.head_b)).permute(0, 2, 3, 1).float()  # [B, H, W, 3]
+        p = hd[..., :2].reshape(B, -1)
+        v = hd[..., 2].reshape(B, -1)
+        policy = torch.softmax(F.linear(p, self.pfc_w, self.pfc_b), dim=-1)
+        value = torch.tanh(F.linear(F.relu_(F.linear(v, self.v1_w, self.v1_b)), self.v2_w, self.v2_b))
+        return policy, value.reshape(B)
+
+    def load_from(self, net: PolicyValueNet):
+        """Refreshes the folded weights in place (after a training step / weight broadcast): the CUDA
+        graph that captured forward() keeps replaying with the new values."""
+        fresh = InferenceNet(net, dtype=self.dtype, device=self.stem_w.device)
+        with torch.no_grad():
+            for dst, src in zip(self.parameters(), fresh.parameters()):
+                dst.copy_(src)
+
+    def flat_weights(self):
+        return torch.cat([p.detach().reshape(-1).float() for p in self.parameters()])
+
+
+def randomise_bn(net: PolicyValueNet, seed=0):
+    """Gives the BN layers non-trivial statistics so that folding is actually exercised in tests."""
+    g = torch.Generator().manual_seed(seed)
+    for m in net.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5, generator=g)
+            m.bias.data.uniform_(-0.2, 0.2, generator=g)
+            m.running_mean.data.uniform_(-0.2, 0.2, generator=g)
+            m.running_var.data.uniform_(0.5, 1.5, generator=g)
+    return net
+
+
+def glorot_limit(fan_in, fan_out):
+    return math.sqrt(6.0 / (fan_in + fan_out))

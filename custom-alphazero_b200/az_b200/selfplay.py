@@ -1,0 +1,167 @@
+"""SelfPlayRunner - the batched self-play loop on one GPU: tree kernels + bf16 net under CUDA graphs.
+
+One lock-step iteration ("advance") of all trees is
+    az_step  (consume last evaluation: expand + backup; select next leaf; encode it)
+ -> InferenceNet forward on the [T, H, W, 4] bf16 leaf batch   (the only dense contraction)
+ -> az_play  (trees whose move budget is spent: record, move, re-root, finish / refill)
+`unroll` such iterations are captured into one CUDA graph and replayed; nothing synchronises with the
+host inside.  Replaces the per-process loop of the reference's play_game (self_play.py:37-82) and the
+joblib fan-out of play (self_play.py:85-119): games are independent, so they become the batch.
+"""
+import ctypes
+import time
+
+import numpy as np
+import torch
+
+from . import native
+from .engine import Rules, TreeEngine, _ptr, _stream
+from .env import _cfg
+from .native import check, lib
+from .net import InferenceNet, PolicyValueNet, flops_per_eval
+
+
+def decode_samples(rules: Rules, fin_dev, exclude_null_games=False):
+    """Finished-game records (device tensors, ring layout) -> (states f32 [S,H,W,4], policies f64 [S,A],
+    values int64 [S]) on the host, via the az_decode_samples kernel.  Games are emitted in game-id order."""
+    n = fin_dev["len"].numel()
+    A = rules.n_actions
+    if n == 0:
+        return (np.zeros((0, rules.height, rules.width, 4), np.float32), np.zeros((0, A)), np.zeros(0, np.int64))
+    order = torch.argsort(fin_dev["game_id"])
+    lens = fin_dev["len"][order].contiguous()
+    results = fin_dev["result"][order].contiguous()
+    boards = fin_dev["board"][order].contiguous()
+    visits = fin_dev["visits"][order].contiguous()
+    actions = fin_dev["action"][order].contiguous()
+    if exclude_null_games:  # self_play.py:155-162 drops every sample of a drawn game (reward 0)
+        lens = torch.where(results == 0, torch.zeros_like(lens), lens)
+    offsets = (torch.cumsum(lens, 0) - lens).to(torch.int32)
+    S = int(lens.sum())
+    dev = lens.device
+    states = torch.empty((S, rules.height, rules.width, 4), dtype=torch.float32, device=dev)
+    policies = torch.empty((S, A), dtype=torch.float64, device=dev)
+    values = torch.empty(S, dtype=torch.int32, device=dev)
+    cfg = _cfg(rules)
+    check(lib().az_decode_samples(ctypes.byref(cfg), _ptr(boards), _ptr(visits), _ptr(actions), _ptr(lens),
+                                  _ptr(results), _ptr(offsets), n, _ptr(states), _ptr(policies), _ptr(values),
+                                  _stream()))
+    return states.cpu().numpy(), policies.cpu().numpy(), values.cpu().numpy().astype(np.int64)
+
+
+class SelfPlayRunner:
+    def __init__(self, rules=Rules(), n_trees=4096, sims_per_move=800, net=None, *, games_target=None,
+                 game_id_base=0, seed=0, move_mode="philox", auto_restart=True, dtype=torch.bfloat16, unroll=8,
+                 use_graph=True, max_free_sims=8, node_capacity=None, fin_capacity=None, device=None,
+                 index_move_greedy=8):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.rules = rules
+        T, A = int(n_trees), rules.n_actions
+        if net is None:
+            net = PolicyValueNet(rules.height, rules.width, A)
+        self.fp32_net = net
+        self.net = net if isinstance(net, InferenceNet) else InferenceNet(net, dtype=dtype, device=self.device)
+        self.engine = TreeEngine(rules, T, sims_per_move, eval_mode="external", prior_mode="f32", move_mode=move_mode,
+                                 games_target=games_target, game_id_base=game_id_base, seed=seed,
+                                 auto_restart=auto_restart, max_free_sims=max_free_sims, node_capacity=node_capacity,
+                                 fin_capacity=fin_capacity, device=self.device, index_move_greedy=index_move_greedy)
+        self.states = torch.zeros((T, rules.height, rules.width, 4), dtype=dtype, device=self.device)
+        self.valid = torch.zeros(T, dtype=torch.int32, device=self.device)
+        self.priors = torch.zeros((T, A), dtype=torch.float32, device=self.device)
+        self.values = torch.zeros(T, dtype=torch.float32, device=self.device)
+        self.unroll = int(unroll)
+        self.use_graph = use_graph
+        self.graph = None
+        self.advances = 0
+        self.flops_per_eval = flops_per_eval(rules.height, rules.width, A)
+        # kernels of libaz_b200 launched per advance: az_step + az_play
+        self.launches_per_advance = 2
+
+    # one lock-step iteration; everything is enqueued on the current stream
+    def _advance(self):
+        self.engine.step(self.priors, self.values, self.states, self.valid)
+        p, v = self.net(self.states)
+        self.priors.copy_(p)
+        self.values.copy_(v)
+        self.engine.play()
+
+    def capture(self):
+        if self.graph is not None or not self.use_graph:
+            return
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm up cuDNN heuristics / workspaces outside capture
+            for _ in range(3):
+                p, v = self.net(self.states)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(self.unroll):
+                self._advance()
+        self.graph = g
+
+    def run(self, advances):
+        """Enqueues `advances` lock-step iterations (rounded up to a multiple of `unroll` under graphs)."""
+        if self.use_graph:
+            self.capture()
+            n = (advances + self.unroll - 1) // self.unroll
+            for _ in range(n):
+                self.graph.replay()
+            self.advances += n * self.unroll
+            return n * self.unroll
+        for _ in range(advances):
+            self._advance()
+        self.advances += advances
+        return advances
+
+    def reset(self):
+        self.engine.reset()
+        self.valid.zero_()
+
+    def active_trees(self):
+        return int((self.engine.phases() != native.AZ_PHASE_IDLE).sum())
+
+    def run_until_done(self, poll_every=64, max_advances=None):
+        """Runs until every tree is idle (all games_target games finished); returns advances executed."""
+        done = 0
+        while True:
+            done += self.run(poll_every)
+            if self.active_trees() == 0:
+                break
+            if max_advances is not None and done >= max_advances:
+                break
+        self.engine.check_status()
+        return done
+
+    def finished_device(self):
+        e = self.engine
+        n = int(e.view("fin_count")[0])
+        return {"game_id": e.view("fin_game_id")[:n], "len": e.view("fin_len")[:n], "result": e.view("fin_result")[:n],
+                "visits": e.view("fin_visits")[:n], "action": e.view("fin_action")[:n], "board": e.view("fin_board")[:n]}
+
+    def collect(self, exclude_null_games=False):
+        """Decodes and drains the finished-game ring: (states, policies, values) host arrays."""
+        out = decode_samples(self.rules, self.finished_device(), exclude_null_games)
+        self.engine.fin_clear()
+        return out
+
+    def load_weights(self, net: PolicyValueNet):
+        self.fp32_net = net
+        self.net.load_from(net)
+
+
+def smoke_net_step():
+    """Tiny end-to-end: 64 trees x 16 simulations per move through the bf16 net, a few full games."""
+    rules = Rules(7, 6, 4, True)
+    torch.manual_seed(0)
+    r = SelfPlayRunner(rules, n_trees=64, sims_per_move=16, games_target=96, unroll=4)
+    t0 = time.time()
+    r.run_until_done(poll_every=64, max_advances=200000)
+    torch.cuda.synchronize()
+    tot = r.engine.totals()
+    states, policies, values = r.collect()
+    assert tot["games"] == 96 and states.shape[0] == policies.shape[0] == values.shape[0] == tot["moves"]
+    assert np.isfinite(policies).all() and np.allclose(policies.sum(-1), 1.0)
+    assert set(np.unique(values)).issubset({-1, 0, 1})
+    print("net smoke ok: %d games, %d samples, %d sims in %.2fs" % (tot["games"], len(values), tot["sims"], time.time() - t0))

@@ -51,7 +51,7 @@ __global__ void k_reset(Eng e) {
     e.sims_done[t] = 0;
     e.pending[t] = 0;
     e.path_len[t] = 0;
-    for (int i = 0; i < 4; ++i) e.counters[(size_t)t * 4 + i] = 0;
+    for (int i = 0; i < 8; ++i) e.counters[(size_t)t * 8 + i] = 0;
     NodeA z;
     z.w = 0.0;
     z.n = 0;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         NodeA* A = e.node_a + pool;
         double* Pr = e.node_p + pool;
         int sims = e.sims_done[t];
-        long long nsim = 0, neval = 0;
+        long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
         if (e.pending[t] && priors != nullptr) {
             const int depth = e.path_len[t];
             for (int i = lane; i < depth; i += 32) ws.path[i] = e.path[(size_t)t * kMaxDepth + i];
@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
             ++sims;
             ++nsim;
             ++neval;
+            nchild += link >> 24;
         }
         int pend = (e.pending[t] && priors == nullptr) ? 1 : 0;
         int freed = 0;
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
             Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
             int depth, term;
             select_leaf<NW, KC>(e, A, Pr, pos, ws, lane, depth, term, flags);
+            ndepth += depth;
             if (term) {  // mcts.py:179: terminal leaf, result 1 (win of the mover) or 0 (draw)
                 backup_path(A, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
                 ++sims;
@@ -187,8 +189,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         if (lane == 0) {
             e.sims_done[t] = sims;
             e.pending[t] = pend;
-            e.counters[(size_t)t * 4 + 0] += nsim;
-            e.counters[(size_t)t * 4 + 1] += neval;
+            e.counters[(size_t)t * 8 + 0] += nsim;
+            e.counters[(size_t)t * 8 + 1] += neval;
+            e.counters[(size_t)t * 8 + 4] += ndepth;
+            e.counters[(size_t)t * 8 + 5] += nchild;
             int ph = (sims >= e.sims_target && !pend) ? AZ_PHASE_READY : AZ_PHASE_SEARCH;
             e.status[t] = (st & ~AZ_PHASE_MASK) | ph | (int)flags;
         }
@@ -213,11 +217,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
     const Pos<NW> root = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
     const double uniform_prior = __ddiv_rn(1.0, (double)e.r.A);  // np.full(A, 1 / A)
     int sims = e.sims_done[t];
-    long long nsim = 0, neval = 0;
+    long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
     while (sims < e.sims_target && !(flags & AZ_FLAG_POOL_OVERFLOW)) {
         Pos<NW> pos = root;
         int depth, term;
         select_leaf<NW, KC>(e, A, Pr, pos, ws, lane, depth, term, flags);
+        ndepth += depth;
         if (term) {
             backup_path(A, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
         } else {
@@ -232,14 +237,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
             }
             backup_path(A, ws, depth, -v, link, lane);
             ++neval;
+            nchild += link >> 24;
         }
         ++sims;
         ++nsim;
     }
     if (lane == 0) {
         e.sims_done[t] = sims;
-        e.counters[(size_t)t * 4 + 0] += nsim;
-        e.counters[(size_t)t * 4 + 1] += neval;
+        e.counters[(size_t)t * 8 + 0] += nsim;
+        e.counters[(size_t)t * 8 + 1] += neval;
+        e.counters[(size_t)t * 8 + 4] += ndepth;
+        e.counters[(size_t)t * 8 + 5] += nchild;
         int ph = sims >= e.sims_target ? AZ_PHASE_READY : AZ_PHASE_SEARCH;
         e.status[t] = (st & ~AZ_PHASE_MASK) | ph | (int)flags;
     }
@@ -282,7 +290,7 @@ __device__ __forceinline__ void finish_game(const Eng& e, const Aux& aux, int t,
         e.fin_game_id[slot] = e.game_id[t];
         e.fin_len[slot] = len;
         e.fin_result[slot] = aux.result[t];
-        e.counters[(size_t)t * 4 + 3] += 1;
+        e.counters[(size_t)t * 8 + 3] += 1;
         if (e.auto_restart) g = atomicAdd(e.games_started, 1ull);
     }
     g = __shfl_sync(kFull, g, 0);
@@ -387,7 +395,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
         e.rec_action[(size_t)t * e.P + rec] = action | (greedy ? 1 << 16 : 0);
         aux.rec_len[t] = rec + 1;
         e.ply[t] = ply + 1;
-        e.counters[(size_t)t * 4 + 2] += 1;
+        e.counters[(size_t)t * 8 + 2] += 1;
         e.sims_done[t] = 0;
     }
     __syncwarp();
@@ -440,6 +448,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
         __syncwarp();
     }
     if (lane == 0) {
+        e.counters[(size_t)t * 8 + 6] += n_dst;
         e.half[t] = h ^ 1;
         e.n_nodes[t] = n_dst;
         e.pending[t] = 0;
@@ -498,6 +507,59 @@ __global__ void k_env_encode(Rules r, const int8_t* cells, int n, float* out) {
     for (int j = 0; j < r.cells; ++j) {
         int code = cell_code(r, p, j);
         reinterpret_cast<float4*>(out + (size_t)i * r.cells * 4)[j] = make_float4(code == 0, code == 1, code == 2, 1.0f);
+    }
+}
+
+// one block per finished game, one warp per ply (round-robin): states, policy targets, rewards
+template <int NW>
+__global__ void __launch_bounds__(128) k_decode(Rules r, int P, const uint64_t* boards, const int32_t* visits,
+                                                 const int32_t* actions, const int32_t* lens, const int32_t* results,
+                                                 const int32_t* offsets, float* states, double* policies,
+                                                 int32_t* values) {
+    const int g = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int len = lens[g], res = results[g], off = offsets[g];
+    for (int i = warp; i < len; i += 4) {
+        const size_t s = (size_t)off + i;
+        const Pos<NW> pos = load_pos<NW>(boards + ((size_t)g * P + i) * 2 * NW);
+        encode_state_f32<NW>(r, pos, states + s * r.cells * 4, lane);
+        const int32_t* v = visits + ((size_t)g * P + i) * r.A;
+        const bool greedy = (actions[(size_t)g * P + i] >> 16) & 1;
+        // sum, number of legal actions and first maximum in EDGE (board move) order
+        int sum = 0, k = 0, bestn = -1, bestkey = 0x7fffffff;
+        for (int a = lane; a < r.A; a += 32) {
+            int n = v[a];
+            if (n < 0) continue;
+            sum += n;
+            ++k;
+            int key = r.gravity ? a : (a % r.H) * r.W + a / r.H;  // row-major rank of the cell
+            if (n > bestn || (n == bestn && key < bestkey)) {
+                bestn = n;
+                bestkey = key;
+            }
+        }
+        sum = __reduce_add_sync(kFull, sum);
+        k = __reduce_add_sync(kFull, k);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            int on = __shfl_xor_sync(kFull, bestn, o), ok = __shfl_xor_sync(kFull, bestkey, o);
+            if (on > bestn || (on == bestn && ok < bestkey)) {
+                bestn = on;
+                bestkey = ok;
+            }
+        }
+        for (int a = lane; a < r.A; a += 32) {
+            int n = v[a];
+            double p = 0.0;
+            if (n >= 0) {
+                int key = r.gravity ? a : (a % r.H) * r.W + a / r.H;
+                if (greedy)
+                    p = key == bestkey ? 1.0 : 0.0;
+                else
+                    p = sum == 0 ? __ddiv_rn(1.0, (double)k) : __ddiv_rn((double)n, (double)sum);
+            }
+            policies[s * r.A + a] = p;
+        }
+        if (lane == 0) values[s] = ((len - 1 - i) & 1) ? -res : res;
     }
 }
 
@@ -565,7 +627,7 @@ AZ_API int az_query_layout(const az_config* c, az_layout* L) {
     L->path_len = take(off, 4 * T);
     L->path = take(off, 4 * T * kMaxDepth);
     L->leaf_board = take(off, 8 * T * 2 * WD);
-    L->counters = take(off, 8 * T * 4);
+    L->counters = take(off, 8 * T * 8);
     L->uniforms = take(off, 8 * T * P);
     L->node_a = take(off, 16 * T * 2 * C);
     L->node_p = take(off, 8 * T * 2 * C);
@@ -773,6 +835,23 @@ AZ_API int az_env_encode(const az_config* c, const int8_t* cells, int32_t n, flo
     if (!cells || !states || n < 0) return fail(AZ_ERR_ARG, "az_env_encode: bad argument%s");
     if (n == 0) return AZ_OK;
     k_env_encode<<<flat_grid(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(r, cells, n, states);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_decode_samples(const az_config* c, const uint64_t* boards, const int32_t* visits, const int32_t* actions,
+                             const int32_t* lens, const int32_t* results, const int32_t* offsets, int32_t n_games,
+                             float* states, double* policies, int32_t* values, void* stream) {
+    Rules r;
+    if (int rc = env_rules(c, &r)) return rc;
+    if (!boards || !visits || !actions || !lens || !results || !offsets || !states || !policies || !values || n_games < 0)
+        return fail(AZ_ERR_ARG, "az_decode_samples: bad argument%s");
+    if (n_games == 0) return AZ_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (r.bits > 64)
+        k_decode<2><<<n_games, 128, 0, s>>>(r, r.cells, boards, visits, actions, lens, results, offsets, states, policies, values);
+    else
+        k_decode<1><<<n_games, 128, 0, s>>>(r, r.cells, boards, visits, actions, lens, results, offsets, states, policies, values);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }

@@ -114,7 +114,8 @@ typedef struct az_layout {
     size_t path_len;    /* int32  [T] */
     size_t path;        /* int32  [T][max_depth]  node indices root-child ... leaf */
     size_t leaf_board;  /* uint64 [T][2][WD] */
-    size_t counters;    /* int64  [T][4]   cumulative simulations, evaluations, moves, games finished */
+    size_t counters;    /* int64  [T][8]   cumulative: simulations, evaluations, moves, games finished, sum of
+                                           selection depths, children created, nodes copied by re-root, spare */
     size_t uniforms;    /* double [T][P]   AZ_MOVE_HOST_UNIFORMS draws */
     /* node pools: record A = {double W; int32 N; uint32 link}, link = first_child | k << 24, 0 = no edges */
     size_t node_a;      /* 16 B   [T][2][C] */
@@ -203,6 +204,19 @@ int az_env_play(const az_config *cfg, const int8_t *dev_cells_in, const int32_t 
                 int8_t *dev_cells_out, int32_t *dev_status_out, void *stream);
 int az_env_legal(const az_config *cfg, const int8_t *dev_cells, int32_t n, uint8_t *dev_legal_out, void *stream);
 int az_env_encode(const az_config *cfg, const int8_t *dev_cells, int32_t n, float *dev_states_out, void *stream);
+
+/* Turns finished-game records (finished-ring layout) into the training arrays play_game returns
+ * (self_play.py:66-78), one sample per ply:
+ *   states_out   float32 [S][H][W][4]  parent position of the ply (Board.full_state, board.py:83-98)
+ *   policies_out float64 [S][A]        N / sum N, or one-hot at the first maximum in edge order when the
+ *                                      ply was played greedily; 0 for illegal actions (mcts.py:189-197, 210-214)
+ *   values_out   int32   [S]           result * (+1 for the last ply, alternating backwards) (self_play.py:71-78)
+ * boards: dev uint64 [G][P][2][WD]; visits: dev int32 [G][P][A]; actions: dev int32 [G][P]; lens, results:
+ * dev int32 [G]; offsets: dev int32 [G] = index of the first sample of game g (exclusive prefix sum of lens). */
+int az_decode_samples(const az_config *cfg, const uint64_t *dev_boards, const int32_t *dev_visits,
+                      const int32_t *dev_actions, const int32_t *dev_lens, const int32_t *dev_results,
+                      const int32_t *dev_offsets, int32_t n_games, float *dev_states_out, double *dev_policies_out,
+                      int32_t *dev_values_out, void *stream);
 
 #ifdef __cplusplus
 }

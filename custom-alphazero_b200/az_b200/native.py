@@ -63,6 +63,11 @@ class AzLayout(ctypes.Structure):
     )
 
 
+class AzHeadWeights(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("conv_w", "conv_b", "policy_w", "policy_b", "value1_w", "value1_b",
+                                                "value2_w", "value2_b")]
+
+
 # every symbol include/az_b200.h declares: (restype, argtypes)
 _P, _I, _S = ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t
 SYMBOLS = {
@@ -82,6 +87,8 @@ SYMBOLS = {
     "az_env_play": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _P, _I, _P, _P, _P]),
     "az_env_legal": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _I, _P, _P]),
     "az_env_encode": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _I, _P, _P]),
+    "az_net_stem": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "az_net_heads": (ctypes.c_int, [_P, ctypes.POINTER(AzHeadWeights), _I, _I, _I, _I, _P, _P, _P]),
     "az_decode_samples": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
 }
 

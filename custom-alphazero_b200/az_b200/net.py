@@ -131,18 +131,40 @@ class InferenceNet(nn.Module):
             b2p = nn.Parameter((b2.float() + bp.float()).to(dtype), requires_grad=False)
             self.block_params.extend([w1, b1, w2, wp, b2p])
         self.depth = len(net.blocks)
-        # both 1x1 head convolutions as one conv with 3 output channels (2 policy + 1 value)
+        f32 = lambda t: nn.Parameter(t.detach().to(device=device, dtype=torch.float32).contiguous(), requires_grad=False)  # noqa: E731
+        # float32 copies for the hand-written stem / heads kernels (az_net_stem, az_net_heads)
+        sw, sb = net.stem.folded()
+        self.stem_w32, self.stem_b32 = f32(sw), f32(sb)
+        # both 1x1 head convolutions as one [3, C] matrix (2 policy planes + 1 value plane)
         pw, pb = net.policy_conv.folded()
         vw, vb = net.value_conv.folded()
-        self.head_w = nn.Parameter(torch.cat([pw, vw], 0).detach().to(device=device, dtype=dtype).contiguous(memory_format=cl), requires_grad=False)
-        self.head_b = nn.Parameter(torch.cat([pb, vb], 0).detach().to(device=device, dtype=dtype), requires_grad=False)
-        f32 = lambda t: nn.Parameter(t.detach().to(device=device, dtype=torch.float32).contiguous(), requires_grad=False)  # noqa: E731
+        self.head_w32 = f32(torch.cat([pw, vw], 0).reshape(3, -1))
+        self.head_b32 = f32(torch.cat([pb, vb], 0))
         self.pfc_w, self.pfc_b = f32(net.policy_fc.weight), f32(net.policy_fc.bias)
         self.v1_w, self.v1_b = f32(net.value_fc1.weight), f32(net.value_fc1.bias)
         self.v2_w, self.v2_b = f32(net.value_fc2.weight), f32(net.value_fc2.bias)
+        self.filters = net.filters
+        dev = torch.device(device)
+        # fast path: custom stem/heads kernels + cuDNN fused-epilogue tower (GPU, bf16, 128 filters)
+        self.fast = dev.type == "cuda" and dtype == torch.bfloat16 and net.filters == 128 and net.value_fc1.out_features == 256
+        self._head_struct = None
+
+    def _heads_arg(self):
+        from . import native
+
+        if self._head_struct is None:
+            self._head_struct = native.AzHeadWeights(
+                conv_w=self.head_w32.data_ptr(), conv_b=self.head_b32.data_ptr(), policy_w=self.pfc_w.data_ptr(),
+                policy_b=self.pfc_b.data_ptr(), value1_w=self.v1_w.data_ptr(), value1_b=self.v1_b.data_ptr(),
+                value2_w=self.v2_w.data_ptr(), value2_b=self.v2_b.data_ptr())
+        return self._head_struct
 
     @torch.no_grad()
-    def forward(self, x_nhwc):
+    def forward(self, x_nhwc, priors_out=None, values_out=None):
+        """x [B, H, W, 4] -> (policy [B, A] float32 softmax, value [B] float32 tanh).  On the GPU fast path
+        the results are written into priors_out / values_out when given (no extra copy kernels)."""
+        if self.fast and x_nhwc.is_cuda:
+            return self._forward_fast(x_nhwc, priors_out, values_out)
         B = x_nhwc.shape[0]
         x = x_nhwc.to(self.dtype).permute(0, 3, 1, 2)
         x = F.relu_(F.conv2d(x, self.stem_w, self.stem_b, padding=1))
@@ -152,12 +174,46 @@ class InferenceNet(nn.Module):
             y = F.conv2d(h, w2, b2p, padding=1)
             y += F.conv2d(x, wp)
             x = F.relu_(y)
-        hd = F.relu_(F.conv2d(x, self.head_w, self.head_b)).permute(0, 2, 3, 1).float()  # [B, H, W, 3]
+        xf = x.permute(0, 2, 3, 1).float()  # [B, H, W, C]
+        hd = F.relu_(F.linear(xf, self.head_w32, self.head_b32))  # 1x1 convs: [B, H, W, 3]
         p = hd[..., :2].reshape(B, -1)
         v = hd[..., 2].reshape(B, -1)
         policy = torch.softmax(F.linear(p, self.pfc_w, self.pfc_b), dim=-1)
-        value = torch.tanh(F.linear(F.relu_(F.linear(v, self.v1_w, self.v1_b)), self.v2_w, self.v2_b))
-        return policy, value.reshape(B)
+        value = torch.tanh(F.linear(F.relu_(F.linear(v, self.v1_w, self.v1_b)), self.v2_w, self.v2_b)).reshape(B)
+        if priors_out is not None:
+            priors_out.copy_(policy)
+            values_out.copy_(value)
+            return priors_out, values_out
+        return policy, value
+
+    def _forward_fast(self, x_nhwc, priors_out, values_out):
+        import ctypes
+
+        from .engine import _ptr, _stream
+        from .native import check, lib
+
+        B, H, W = x_nhwc.shape[0], self.height, self.width
+        x_nhwc = x_nhwc.to(torch.bfloat16).contiguous()
+        h0 = torch.empty((B, H, W, self.filters), dtype=torch.bfloat16, device=x_nhwc.device)
+        check(lib().az_net_stem(_ptr(x_nhwc), _ptr(self.stem_w32), _ptr(self.stem_b32), B, H, W, self.filters,
+                                _ptr(h0), _stream()))
+        x = h0.permute(0, 3, 1, 2)  # logical NCHW over NHWC memory (channels_last)
+        one = (1, 1)
+        for i in range(self.depth):
+            w1, b1, w2, wp, b2p = self.block_params[5 * i: 5 * i + 5]
+            h = torch.cudnn_convolution_relu(x, w1, b1, one, one, one, 1)           # conv + bias + ReLU
+            p = F.conv2d(x, wp)                                                      # projection shortcut
+            x = torch.cudnn_convolution_add_relu(h, w2, p, 1.0, b2p, one, one, one, 1)  # conv + shortcut + bias + ReLU
+        xm = x.permute(0, 2, 3, 1)
+        if not xm.is_contiguous():
+            xm = xm.contiguous()
+        if priors_out is None:
+            priors_out = torch.empty((B, self.n_actions), dtype=torch.float32, device=x.device)
+            values_out = torch.empty(B, dtype=torch.float32, device=x.device)
+        hw = self._heads_arg()
+        check(lib().az_net_heads(_ptr(xm), ctypes.byref(hw), B, H * W, self.filters, self.n_actions, _ptr(priors_out),
+                                 _ptr(values_out), _stream()))
+        return priors_out, values_out
 
     def load_from(self, net: PolicyValueNet):
         """Refreshes the folded weights in place (after a training step / weight broadcast): the CUDA

@@ -80,9 +80,7 @@ class SelfPlayRunner:
     # one lock-step iteration; everything is enqueued on the current stream
     def _advance(self):
         self.engine.step(self.priors, self.values, self.states, self.valid)
-        p, v = self.net(self.states)
-        self.priors.copy_(p)
-        self.values.copy_(v)
+        self.net(self.states, self.priors, self.values)
         self.engine.play()
 
     def capture(self):
@@ -92,7 +90,7 @@ class SelfPlayRunner:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm up cuDNN heuristics / workspaces outside capture
             for _ in range(3):
-                p, v = self.net(self.states)
+                self.net(self.states, self.priors, self.values)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()

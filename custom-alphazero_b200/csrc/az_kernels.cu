@@ -26,6 +26,8 @@ static int fail(int code, const char* fmt, const char* detail = "") {
     return code;
 }
 
+int fail_net(int code, const char* msg) { return fail(code, "%s", msg); }
+
 #define AZ_CUDA(call)                                                                    \
     do {                                                                                 \
         cudaError_t err__ = (call);                                                      \

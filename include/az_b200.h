@@ -218,6 +218,30 @@ int az_decode_samples(const az_config *cfg, const uint64_t *dev_boards, const in
                       const int32_t *dev_offsets, int32_t n_games, float *dev_states_out, double *dev_policies_out,
                       int32_t *dev_values_out, void *stream);
 
+/* ---- the two memory-bound ends of the policy/value net (the tower runs through cuDNN) ----
+ * Weights are float32 with the BatchNormalization inference transform folded in. */
+typedef struct az_head_weights {
+    const float *conv_w;   /* dev [3][C]: rows 0-1 policy 1x1 conv, row 2 value 1x1 conv */
+    const float *conv_b;   /* dev [3] */
+    const float *policy_w; /* dev [A][2*H*W]   Dense(A) on the NHWC-flattened policy planes */
+    const float *policy_b; /* dev [A] */
+    const float *value1_w; /* dev [256][H*W] */
+    const float *value1_b; /* dev [256] */
+    const float *value2_w; /* dev [256] */
+    const float *value2_b; /* dev [1] */
+} az_head_weights;
+
+/* Stem of ResidualTower (model/tensorflow/model.py:36-46): Conv3x3(4 -> C) + BN + ReLU.
+ * states: dev bf16 [n][H][W][4] (what az_step writes); w: dev float [C][4][3][3]; b: dev float [C];
+ * out: dev bf16 [n][H][W][C].  C must be 128 (config.py:71). */
+int az_net_stem(const void *dev_states, const float *dev_w, const float *dev_b, int32_t n, int32_t height,
+                int32_t width, int32_t channels, void *dev_out, void *stream);
+
+/* PolicyHead + ValueHead (model/tensorflow/model.py:68-149) on the tower output x: dev bf16 [n][H*W][C].
+ * priors_out: dev float [n][A] (softmax), values_out: dev float [n] (tanh) - the buffers az_step reads. */
+int az_net_heads(const void *dev_x, const az_head_weights *weights, int32_t n, int32_t cells, int32_t channels,
+                 int32_t n_actions, float *dev_priors_out, float *dev_values_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,92 @@
+"""GPU tests of the policy/value net path: hand-written stem / heads kernels and the bf16 tower
+against the fp32 PyTorch module (floating point: tolerances stated per test)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _mods():
+    from az_b200 import engine, native, net
+
+    return engine, native, net
+
+
+def _random_states(n, H, W, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    code = torch.randint(0, 3, (n, H, W), generator=g)
+    x = torch.zeros(n, H, W, 4)
+    x.scatter_(3, code[..., None], 1.0)
+    x[..., 3] = 1.0
+    return x
+
+
+@pytest.mark.parametrize("H,W", [(6, 7), (9, 9), (3, 3)])
+def test_stem_kernel_matches_fp32_conv(H, W):
+    engine, native, net = _mods()
+    torch.manual_seed(1)
+    n = 257
+    x = _random_states(n, H, W)
+    w = torch.randn(128, 4, 3, 3) * 0.3
+    b = torch.randn(128) * 0.1
+    want = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w, b, padding=1)).permute(0, 2, 3, 1)
+    xd = x.to("cuda", torch.bfloat16).contiguous()
+    out = torch.empty((n, H, W, 128), dtype=torch.bfloat16, device="cuda")
+    wd, bd = w.cuda().contiguous(), b.cuda()
+    native.check(native.lib().az_net_stem(engine._ptr(xd), engine._ptr(wd), engine._ptr(bd), n, H, W, 128,
+                                          engine._ptr(out), engine._stream()))
+    got = out.float().cpu()
+    # fp32 accumulation of exact 0/1 inputs; only the bf16 rounding of the output differs: <= 2^-8 relative
+    assert torch.allclose(got, want, rtol=2 ** -8, atol=1e-6)
+
+
+@pytest.mark.parametrize("H,W,A", [(6, 7, 7), (9, 9, 9), (9, 9, 81), (3, 3, 9)])
+def test_heads_kernel_matches_fp32(H, W, A):
+    engine, native, net = _mods()
+    torch.manual_seed(2)
+    n, cells = 301, H * W
+    x = (torch.randn(n, cells, 128).relu() * 0.7).to(torch.bfloat16)
+    cw, cb = torch.randn(3, 128) * 0.1, torch.randn(3) * 0.1
+    pw, pb = torch.randn(A, 2 * cells) * 0.2, torch.randn(A) * 0.1
+    v1w, v1b = torch.randn(256, cells) * 0.2, torch.randn(256) * 0.1
+    v2w, v2b = torch.randn(256) * 0.1, torch.randn(1) * 0.1
+    xf = x.float()
+    h = torch.relu(xf @ cw.T + cb)  # [n, cells, 3]
+    want_p = torch.softmax(h[..., :2].reshape(n, -1) @ pw.T + pb, -1)
+    want_v = torch.tanh(torch.relu(h[..., 2] @ v1w.T + v1b) @ v2w + v2b)
+    dev = [t.cuda().contiguous() for t in (cw, cb, pw, pb, v1w, v1b, v2w, v2b)]
+    hw = native.AzHeadWeights(*[t.data_ptr() for t in dev])
+    priors = torch.empty((n, A), device="cuda")
+    values = torch.empty(n, device="cuda")
+    xd = x.cuda().contiguous()
+    native.check(native.lib().az_net_heads(engine._ptr(xd), ctypes.byref(hw), n, cells, 128, A, engine._ptr(priors),
+                                           engine._ptr(values), engine._stream()))
+    # same bf16 inputs, fp32 arithmetic on both sides: only summation order differs
+    assert (priors.cpu() - want_p).abs().max() < 2e-5
+    assert (values.cpu() - want_v).abs().max() < 2e-5
+    assert torch.allclose(priors.sum(-1).cpu(), torch.ones(n), atol=1e-5)
+
+
+@pytest.mark.parametrize("H,W,A", [(6, 7, 7), (9, 9, 9)])
+def test_bf16_inference_net_close_to_fp32_module(H, W, A):
+    engine, native, net = _mods()
+    torch.manual_seed(0)
+    ref = net.randomise_bn(net.PolicyValueNet(H, W, A)).eval()
+    x = _random_states(512, H, W, seed=3)
+    with torch.no_grad():
+        want_p, want_v = ref(x)
+    inf = net.InferenceNet(ref, dtype=torch.bfloat16, device="cuda")
+    assert inf.fast
+    p, v = inf(x.cuda().to(torch.bfloat16))
+    dp = (p.cpu() - want_p).abs().max().item()
+    dv = (v.cpu() - want_v.reshape(-1)).abs().max().item()
+    # bf16 weights and activations through 9 sequential 3x3 convolutions vs fp32: tolerance 2e-2 on the
+    # softmax outputs and 5e-2 on tanh values (measured ~5e-3 / ~1e-2; see DESIGN.md "Numerics")
+    assert dp < 2e-2 and dv < 5e-2, (dp, dv)
+    # the slow (library-only) GPU path computes the same function
+    inf.fast = False
+    p2, v2 = inf(x.cuda().to(torch.bfloat16))
+    assert (p2 - p).abs().max().item() < 2e-2 and (v2 - v).abs().max().item() < 5e-2

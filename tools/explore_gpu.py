@@ -62,3 +62,12 @@ for ev in ("uniform", "hash"):
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 4
     print(f"fixed {ev}: search(800)+play for {T} trees: {ms:.2f} ms -> {T*800/ms*1e3/1e6:.1f} M sims/s")
+
+# net accuracy bf16 fast vs fp32
+torch.manual_seed(0)
+ref = N.randomise_bn(N.PolicyValueNet()).eval()
+xs = torch.zeros(2048, 6, 7, 4); code = torch.randint(0, 3, (2048, 6, 7)); xs.scatter_(3, code[..., None], 1.0); xs[..., 3] = 1
+with torch.no_grad(): wp, wv = ref(xs)
+inf = N.InferenceNet(ref, dtype=torch.bfloat16, device="cuda")
+p, v = inf(xs.cuda().to(torch.bfloat16))
+print("bf16 fast vs fp32: max dp %.5f mean dp %.6f max dv %.5f" % ((p.cpu()-wp).abs().max(), (p.cpu()-wp).abs().mean(), (v.cpu()-wv.reshape(-1)).abs().max()))

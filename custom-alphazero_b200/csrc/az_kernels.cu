@@ -149,14 +149,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
             __syncwarp();
             double v;
             uint32_t link;
+            // the dtype of the evaluator output decides the arithmetic of normalize_probabilities, as in
+            // the reference: float64 from infer_sample (factory.py:55), float32 from the model (mcts.py:131-137)
             if (eval_dtype == AZ_F64) {
                 const double* p = static_cast<const double*>(priors) + (size_t)t * e.r.A;
                 v = static_cast<const double*>(values)[t];
-                link = expand_leaf<NW>(e, A, Pr, leaf, t, ws, lane, flags, [p](int a) { return p[a]; });
+                link = expand_leaf<NW>(e, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F64, [p](int a) { return p[a]; });
             } else {
                 const float* p = static_cast<const float*>(priors) + (size_t)t * e.r.A;
                 v = (double)static_cast<const float*>(values)[t];  // value.numpy().item() (mcts.py:136)
-                link = expand_leaf<NW>(e, A, Pr, leaf, t, ws, lane, flags, [p](int a) { return (double)p[a]; });
+                link = expand_leaf<NW>(e, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F32, [p](int a) { return (double)p[a]; });
             }
             backup_path(A, ws, depth, -v, link, lane);  // mcts.py:175: value seen by the player who moved in
             ++sims;
@@ -233,9 +235,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
             if (e.eval_mode == AZ_EVAL_HASH) {
                 const uint64_t h = hash_position<NW>(e.r, pos);
                 v = hash_value(h);
-                link = expand_leaf<NW>(e, A, Pr, pos, t, ws, lane, flags, [h](int a) { return hash_prior(h, a); });
+                link = expand_leaf<NW>(e, A, Pr, pos, t, ws, lane, flags, e.prior_mode, [h](int a) { return hash_prior(h, a); });
             } else {
-                link = expand_leaf<NW>(e, A, Pr, pos, t, ws, lane, flags, [uniform_prior](int) { return uniform_prior; });
+                link = expand_leaf<NW>(e, A, Pr, pos, t, ws, lane, flags, e.prior_mode, [uniform_prior](int) { return uniform_prior; });
             }
             backup_path(A, ws, depth, -v, link, lane);
             ++neval;

@@ -270,7 +270,8 @@ __device__ __forceinline__ void normalise_sel(WarpScratch& ws, int k, int prior_
 // ------------------------------------------------------------------------------------------
 template <int NW, typename PriorFn>
 __device__ __forceinline__ uint32_t expand_leaf(const Eng& e, NodeA* A, double* Pr, const Pos<NW>& pos, int t,
-                                                WarpScratch& ws, int lane, uint32_t& flags, PriorFn prior_of) {
+                                                WarpScratch& ws, int lane, uint32_t& flags, int prior_mode,
+                                                PriorFn prior_of) {
     BB<NW> legal = legal_set(e.r, pos);
     int k = 0;
     for (int a0 = 0; a0 < e.r.A; a0 += 32) {
@@ -280,7 +281,7 @@ __device__ __forceinline__ uint32_t expand_leaf(const Eng& e, NodeA* A, double* 
         if (ok) ws.sel[k + __popc(m & ((1u << lane) - 1u))] = prior_of(a);
         k += __popc(m);
     }
-    normalise_sel(ws, k, e.prior_mode, lane);
+    normalise_sel(ws, k, prior_mode, lane);
     const int base = e.n_nodes[t];
     if (base + k > e.C || base + k > 0xffffff) {
         flags |= AZ_FLAG_POOL_OVERFLOW;

@@ -1,0 +1,68 @@
+"""File-system glue the self-play entry point needs (reference utils.py:24-133): which weights to play
+with.  Checkpoints of the B200 build are torch state dicts (`model.pt`) next to the reference's
+meta.json / MODEL_SAVED_SUCCESSFULLY sentinel; TensorFlow checkpoints cannot be read here."""
+import json
+import os
+from typing import Optional
+
+import torch
+
+from az_b200.net import PolicyValueNet
+from custom_alphazero import paths
+from custom_alphazero.config import ConfigConnectN, ConfigModel, ConfigPath
+from custom_alphazero.connect_n.board import Board
+
+
+def init_model(path: Optional[str] = None) -> PolicyValueNet:
+    A = len(Board.get_all_possible_moves())
+    net = PolicyValueNet(ConfigConnectN.board_height, ConfigConnectN.board_width, A, ConfigModel.filters, ConfigModel.depth)
+    if path is not None:
+        net.load_state_dict(torch.load(os.path.join(path, ConfigPath.model_prefix + ".pt"), map_location="cpu"))
+    return net.eval()
+
+
+def _finished_iterations(run_id: str):
+    root = paths.get_evaluation_path(run_id)
+    if not os.path.isdir(root):
+        return []
+    done = [d for d in os.listdir(root) if os.path.exists(os.path.join(root, d, ConfigPath.model_success))]
+    return sorted(done, key=lambda d: int(d.split("_")[-1]) if d.split("_")[-1].isdigit() else -1)
+
+
+def best_saved_model_path(run_id: str) -> Optional[str]:
+    """Newest finished evaluation iteration, or None (Q8: an empty evaluation directory is 'no model yet')."""
+    done = _finished_iterations(run_id)
+    return os.path.join(paths.get_evaluation_path(run_id), done[-1]) if done else None
+
+
+def best_saved_model(run_id: str) -> PolicyValueNet:
+    path = best_saved_model_path(run_id)
+    if path is None:
+        torch.manual_seed(0)
+    return init_model(path)
+
+
+def best_saved_model_hash(run_id: str):
+    path = best_saved_model_path(run_id)
+    if path is None:
+        return None
+    with open(os.path.join(path, ConfigPath.model_meta)) as fp:
+        return json.load(fp).get("hash")
+
+
+def reset_plays_inferences_dict() -> dict:
+    return {}
+
+
+class HostModel:
+    """Adapter with the reference's model call convention (mcts.py:131-137): called on
+    np.ndarray [1, H, W, 4], returns two tensors with .numpy() - evaluated by the bf16 GPU net."""
+
+    def __init__(self, net: PolicyValueNet):
+        from az_b200.net import InferenceNet
+
+        self.inference = InferenceNet(net, device="cuda")
+
+    def __call__(self, x):
+        p, v = self.inference(torch.as_tensor(x, device="cuda"))
+        return p.cpu(), v.cpu()

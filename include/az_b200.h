@@ -83,7 +83,7 @@ typedef struct az_config {
     int32_t sims_per_move;     /* ConfigSelfPlay.mcts_iterations */
     int32_t index_move_greedy; /* ConfigMCTS.index_move_greedy (self_play.py:62) */
     int32_t eval_mode;         /* AZ_EVAL_* */
-    int32_t prior_mode;        /* AZ_PRIOR_* */
+    int32_t prior_mode;        /* AZ_PRIOR_* for the in-kernel evaluators (az_search); az_step follows eval_dtype */
     int32_t move_mode;         /* AZ_MOVE_* */
     int32_t max_free_sims;     /* simulations ending in a terminal leaf that one az_step may run per tree
                                   before handing the batch slot back (they need no evaluation) */
@@ -174,7 +174,9 @@ int az_begin_search(az_engine *e, int32_t sims, void *stream);
  *      that end in a terminal leaf are finished on the spot (:179), up to max_free_sims of them;
  *   3. a non-terminal leaf is encoded as the NN input (Board.full_state, connect_n/board.py:83-98)
  *      into states_out[tree] and leaf_valid_out[tree] = 1.
- * priors: dev [T][A], values: dev [T] (dtype AZ_F32 or AZ_F64); may be NULL on the first call.
+ * priors: dev [T][A], values: dev [T] (dtype AZ_F32 or AZ_F64); may be NULL on the first call.  As in the
+ * reference the dtype decides the arithmetic of normalize_probabilities: AZ_F32 = float32 sum and divide, then
+ * widened (the model= path, mcts.py:131-137); AZ_F64 = float64 (the infer_sample path, factory.py:55).
  * states_out: dev [T][H][W][4] (AZ_BF16 or AZ_F32); leaf_valid_out: dev int32 [T]. */
 int az_step(az_engine *e, const void *dev_priors, const void *dev_values, int32_t eval_dtype, void *dev_states_out,
             int32_t state_dtype, int32_t *dev_leaf_valid_out, void *stream);

@@ -1,0 +1,162 @@
+"""GPU tests of the drop-in package (custom_alphazero.*): the reference's own call patterns, checked
+against the golden vectors produced by the unmodified reference."""
+import numpy as np
+import pytest
+
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture()
+def c4():
+    from custom_alphazero.config import ConfigConnectN
+
+    saved = (ConfigConnectN.board_width, ConfigConnectN.board_height, ConfigConnectN.n, ConfigConnectN.gravity)
+    yield ConfigConnectN
+    ConfigConnectN.board_width, ConfigConnectN.board_height, ConfigConnectN.n, ConfigConnectN.gravity = saved
+
+
+def _configure(cfg, case):
+    cfg.board_width, cfg.board_height, cfg.n, cfg.gravity = case["W"], case["H"], case["n"], case["gravity"]
+
+
+def test_board_terminal_and_state_semantics(c4):
+    """SURVEY 8c 'terminal / sign semantics' row, through the compat Board."""
+    from custom_alphazero.connect_n.board import Board
+    from custom_alphazero.connect_n.move import Move
+
+    b = Board()
+    for x in (0, 1, 0, 1, 0, 1):
+        b.play(Move(True, x), keep_same_player=True)
+    assert repr(b).split("\n")[3:] == ["XO.....", "XO.....", "XO....."]
+    assert b.turn == 1 and b.fullmove_number == 6 and not b.is_game_over()
+    fs = b.full_state
+    assert fs.dtype == np.float32 and fs.shape == (6, 7, 4)
+    assert fs.sum(axis=(0, 1)).tolist() == [36.0, 3.0, 3.0, 42.0]
+    assert fs[5, 0].tolist() == [0, 1, 0, 1] and fs[5, 1].tolist() == [0, 0, 1, 1] and fs[0, 0].tolist() == [1, 0, 0, 1]
+    child = b.play(Move(True, 0), on_copy=True, keep_same_player=True)
+    assert child.is_game_over() and child.is_null is False and child.get_result(keep_same_player=True) == 1
+    assert not b.is_game_over() and [str(m) for m in b.moves] == ["0", "1", "2", "3", "4", "5", "6"]
+    assert child.play(Move(True, 3), on_copy=True) is child  # Q7
+    mask = b.legal_moves_mask(Board.get_all_possible_moves())
+    assert mask.dtype == bool and mask.all()
+    with pytest.raises(AssertionError):
+        full = Board(np.tile(np.array([[1], [-1], [1], [-1], [1], [-1]], dtype=np.int8), (1, 7)))
+        full.push(Move(True, 2))
+
+
+def test_board_without_keep_same_player_alternates_colours(c4):
+    from custom_alphazero.connect_n.board import Board
+    from custom_alphazero.connect_n.move import Move
+
+    b = Board()
+    b.play(Move(True, 3))
+    b.play(Move(True, 3))
+    assert b.array[5, 3] == 1 and b.array[4, 3] == -1 and b.turn == 1 and b.fullmove_number == 2
+    assert b.full_state[:, :, 3].min() == 1.0
+    b.play(Move(True, 0))
+    assert b.turn == -1 and b.full_state[:, :, 3].max() == -1.0
+
+
+@pytest.mark.parametrize("name", ["game_6x7_250_uniform", "game_6x7_250_hash_seed7", "game_5x5ng_n3_60_hash"])
+def test_compat_mcts_reproduces_reference_game(name, c4):
+    """Drives custom_alphazero.mcts.mcts.MCTS exactly like the golden generator drove the reference
+    (infer_sample patched, model=None, play(greedy, return_details=True, deterministic=...))."""
+    from oracle import evaluators
+
+    case = load_golden(name)
+    _configure(c4, case)
+    import custom_alphazero.mcts.mcts as m
+    from custom_alphazero.connect_n.board import Board
+
+    all_moves = Board.get_all_possible_moves()
+    A = len(all_moves)
+    f = evaluators.make(case["evaluator"], A)
+    saved = m.infer_sample
+    m.infer_sample = lambda state, concurrency: f(state)
+    try:
+        if case.get("seed") is not None:
+            np.random.seed(case["seed"])
+        mcts = m.MCTS(Board(), all_moves, False, {}, model=None)
+        t = 0
+        while not mcts.board.is_game_over():
+            mcts.search(case["sims"])
+            want = case["plies"][t]
+            edges = mcts.current_root.edges
+            assert [e.visit_count for e in edges] == want["N"], f"ply {t}"
+            assert [e.total_action_value for e in edges] == want["W"], f"ply {t}"
+            assert [e.prior for e in edges] == want["P"], f"ply {t}"
+            assert [all_moves.index(e.action) for e in edges] == want["actions"]
+            greedy = mcts.board.fullmove_number >= 8
+            parent_state, child_state, policy, move = mcts.play(greedy, return_details=True,
+                                                                deterministic=case.get("seed") is None)
+            assert all_moves.index(move) == want["move"] and str(move) == want["move_str"]
+            assert policy.dtype == np.float64 and policy.tolist() == want["policy"]
+            assert parent_state.dtype == np.float32 and parent_state.shape == (case["H"], case["W"], 4)
+            assert child_state.shape == parent_state.shape
+            t += 1
+        assert t == case["n_plies"] and mcts.board.get_result(keep_same_player=True) == case["result"]
+        assert repr(mcts.board) == case["final_repr"]
+    finally:
+        m.infer_sample = saved
+
+
+def test_compat_mcts_model_hook_and_cache(c4):
+    """model= hook (mcts.py:131-137): called on [1, H, W, 4], outputs with .numpy(); float32 priors are
+    normalised in float32; the plays_inferences cache is keyed by the position text."""
+    import custom_alphazero.mcts.mcts as m
+    from custom_alphazero.connect_n.board import Board
+    from oracle import c_oracle
+
+    calls = []
+
+    class Out:
+        def __init__(self, a):
+            self.a = a
+
+        def numpy(self):
+            return self.a
+
+    table = np.asarray([0.3, 0.05, 0.2, 0.1, 0.15, 0.12, 0.08], dtype=np.float32)
+
+    def model(x):
+        assert x.shape == (1, 6, 7, 4) and x.dtype == np.float32
+        calls.append(1)
+        shift = int(x[0, :, :, 1].sum()) % 7
+        return Out(np.roll(table, shift)[None]), Out(np.asarray([[0.25 * ((shift % 3) - 1)]], dtype=np.float32))
+
+    cache = {}
+    mcts = m.MCTS(Board(), Board.get_all_possible_moves(), False, cache, model=model)
+    mcts.search(300)
+    got = [e.visit_count for e in mcts.current_root.edges]
+
+    def cb(state):
+        shift = int(state[:, :, 1].sum()) % 7
+        return np.roll(table, shift).astype(np.float64), float(np.float32(0.25 * ((shift % 3) - 1)))
+
+    want = c_oracle.search_once(c_oracle.make_rules(7, 6, 4, True), [], 300, "callback", c_oracle.PRIOR_F32, cb)
+    assert got == want["N"]
+    assert [e.prior for e in mcts.current_root.edges] == want["P"]
+    assert len(cache) == len(calls) and len(calls) <= 300
+    assert all(set(k) <= set("XO.\n") for k in cache)
+
+
+def test_self_play_play_returns_reference_shaped_arrays(c4):
+    from custom_alphazero import self_play
+    from custom_alphazero.config import ConfigB200, ConfigSelfPlay
+
+    saved = (ConfigB200.games_per_iteration, ConfigB200.concurrent_games, ConfigSelfPlay.mcts_iterations)
+    ConfigB200.games_per_iteration, ConfigB200.concurrent_games, ConfigSelfPlay.mcts_iterations = 96, 64, 24
+    try:
+        states, policies, rewards, trees = self_play.play("test-run")
+    finally:
+        ConfigB200.games_per_iteration, ConfigB200.concurrent_games, ConfigSelfPlay.mcts_iterations = saved
+    S = len(rewards)
+    assert states.shape == (S, 6, 7, 4) and states.dtype == np.float32
+    assert policies.shape == (S, 7) and policies.dtype == np.float64
+    assert np.allclose(policies.sum(-1), 1.0) and set(np.unique(rewards)) <= {-1, 0, 1}
+    assert (states[..., 3] == 1).all() and (states[..., :3].sum(-1) == 1).all()
+    # first sample of every game is the empty board; there are 96 games
+    assert int((states[..., 0].sum(axis=(1, 2)) == 42).sum()) == 96

@@ -19,56 +19,116 @@
 namespace az {
 
 int fail_net(int code, const char* msg);
+constexpr int kMaxDimNet = 11;
+
+// Both kernels put their small GEMM on the legacy tensor path (mma.sync m16n8k16 bf16 -> fp32): the stem is
+// 0.4 % and the head convolutions 0.03 % of the net's FLOPs, both are bound by the 44 MB they write / read per
+// 4096 positions, and a scalar-FMA version costs 10x the instructions (it measured 69 us against ~10 us of traffic).
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
+}
 
 // ------------------------------------------------------------------------------------------ stem
-// One block = C threads (thread = output channel), grid-stride over boards.  The board is staged in
-// shared memory with a zero border so the 3x3 window never branches; each tap is one 128-bit
-// broadcast load (the 4 input planes) and 4 FMAs; the 36 weights of the channel live in registers.
-template <int C>
-__global__ void __launch_bounds__(C) k_stem(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
-                                            const float* __restrict__ bias, int n, int H, int W,
-                                            __nv_bfloat16* __restrict__ out) {
-    extern __shared__ float4 s_in[];  // [(H+2)][(W+2)]
-    const int co = threadIdx.x, PW = W + 2, cells = H * W;
-    float wr[36];
+// Implicit GEMM per position: D[pixel][cout] = A[pixel][kk] * B[kk][cout], kk = tap*4 + plane (36, padded to 48).
+// A is read straight from a zero-bordered copy of the position's planes in shared memory (one 32-bit word =
+// two planes of one neighbour cell = one A-fragment register); B (the channel's weights) lives in registers.
+// Block = 4 warps, warp w owns output channels [32w, 32w+32); warps are independent (own staging buffer).
+constexpr int kStemWarps = 4;
+constexpr int kMaxPadCells = (kMaxDimNet + 2) * (kMaxDimNet + 2);
+
+__global__ void __launch_bounds__(kStemWarps * 32) k_stem(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, int n, int H, int W,
+                                                          __nv_bfloat16* __restrict__ out) {
+    __shared__ uint2 s_in[kStemWarps][kMaxPadCells];
+    __shared__ int s_base[kMaxDimNet * kMaxDimNet + 16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    const int PW = W + 2, cells = H * W, C = 128;
+    for (int p = threadIdx.x; p < cells + 16; p += blockDim.x) {
+        int q = p < cells ? p : cells - 1;  // rows past the board repeat the last pixel (discarded)
+        s_base[p] = (q / W) * PW + q % W;
+    }
+    for (int i = lane; i < (H + 2) * PW; i += 32) s_in[warp][i] = make_uint2(0u, 0u);
+    // B fragments: 3 k-steps x 4 n-tiles
+    uint32_t bf[3][4][2];
+    float bv[4][2];
 #pragma unroll
-    for (int i = 0; i < 36; ++i) wr[i] = w[co * 36 + i];  // OIHW: [co][ci][ky][kx]
-    const float b = bias[co];
-    for (int i = threadIdx.x; i < (H + 2) * PW; i += C) s_in[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = blockIdx.x; t < n; t += gridDim.x) {
-        __syncthreads();
-        for (int p = threadIdx.x; p < cells; p += C) {
-            const uint2 v = reinterpret_cast<const uint2*>(in)[(size_t)t * cells + p];
-            const int y = p / W, x = p - y * W;
-            float4 f;
-            f.x = __uint_as_float(v.x << 16);
-            f.y = __uint_as_float(v.x & 0xffff0000u);
-            f.z = __uint_as_float(v.y << 16);
-            f.w = __uint_as_float(v.y & 0xffff0000u);
-            s_in[(y + 1) * PW + x + 1] = f;
-        }
-        __syncthreads();
-        __nv_bfloat16* o = out + (size_t)t * cells * C + co;
-        for (int y = 0; y < H; ++y)
-            for (int x = 0; x < W; ++x) {
-                float acc = b;
+    for (int nt = 0; nt < 4; ++nt) {
+        const int co = warp * 32 + nt * 8 + g;
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+        for (int ks = 0; ks < 3; ++ks)
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const float4 f = s_in[(y + ky) * PW + x + kx];
-                        acc = fmaf(f.x, wr[0 * 9 + ky * 3 + kx], acc);
-                        acc = fmaf(f.y, wr[1 * 9 + ky * 3 + kx], acc);
-                        acc = fmaf(f.z, wr[2 * 9 + ky * 3 + kx], acc);
-                        acc = fmaf(f.w, wr[3 * 9 + ky * 3 + kx], acc);
-                    }
-                o[(size_t)(y * W + x) * C] = __float2bfloat16_rn(fmaxf(acc, 0.f));
+            for (int h = 0; h < 2; ++h) {
+                const int kk = ks * 16 + t4 * 2 + h * 8;  // pair (kk, kk+1) = planes (ci, ci+1) of one tap
+                const int tap = kk >> 2, ci = kk & 3;
+                float lo = 0.f, hi = 0.f;
+                if (tap < 9) {
+                    lo = w[co * 36 + ci * 9 + tap];
+                    hi = w[co * 36 + (ci + 1) * 9 + tap];
+                }
+                bf[ks][nt][h] = pack_bf16(lo, hi);
             }
+        bv[nt][0] = bias[warp * 32 + nt * 8 + t4 * 2];
+        bv[nt][1] = bias[warp * 32 + nt * 8 + t4 * 2 + 1];
+    }
+    // per-lane tap offsets into the padded board for the two k-halves of each k-step
+    int toff[3][2], wsel[3][2];
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int kk = ks * 16 + t4 * 2 + h * 8;
+            int tap = kk >> 2;
+            if (tap > 8) tap = 0;  // padding columns: weights are zero, any finite input will do
+            toff[ks][h] = (tap / 3) * PW + tap % 3;
+            wsel[ks][h] = (kk & 3) >> 1;
+        }
+    __syncthreads();
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_in[warp]);
+    const int mtiles = (cells + 15) >> 4;
+    for (int t = blockIdx.x; t < n; t += gridDim.x) {
+        __syncwarp();
+        for (int p = lane; p < cells; p += 32)
+            s_in[warp][s_base[p] + PW + 1] = reinterpret_cast<const uint2*>(in)[(size_t)t * cells + p];
+        __syncwarp();
+        __nv_bfloat16* o = out + (size_t)t * cells * C + warp * 32 + t4 * 2;
+        for (int mt = 0; mt < mtiles; ++mt) {
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+            const int c0 = s_base[r0], c1 = s_base[r1];
+            float acc[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+                uint32_t a[4];
+                a[0] = sw[(c0 + toff[ks][0]) * 2 + wsel[ks][0]];
+                a[1] = sw[(c1 + toff[ks][0]) * 2 + wsel[ks][0]];
+                a[2] = sw[(c0 + toff[ks][1]) * 2 + wsel[ks][1]];
+                a[3] = sw[(c1 + toff[ks][1]) * 2 + wsel[ks][1]];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) mma_16816(acc[nt], a, bf[ks][nt]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                if (r0 < cells)
+                    *reinterpret_cast<uint32_t*>(o + (size_t)r0 * C + nt * 8) =
+                        pack_bf16(fmaxf(acc[nt][0] + bv[nt][0], 0.f), fmaxf(acc[nt][1] + bv[nt][1], 0.f));
+                if (r1 < cells)
+                    *reinterpret_cast<uint32_t*>(o + (size_t)r1 * C + nt * 8) =
+                        pack_bf16(fmaxf(acc[nt][2] + bv[nt][0], 0.f), fmaxf(acc[nt][3] + bv[nt][1], 0.f));
+            }
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------ heads
-constexpr int kHeadWarps = 8;
+constexpr int kHeadWarps = 16;
 constexpr int kHidden = 256;
 
 struct HeadParams {
@@ -76,56 +136,59 @@ struct HeadParams {
     int n, cells, A;
 };
 
-// One warp per board, grid-stride; all head weights staged once per block in shared memory.
-// Shared layout (floats): conv_w [3][C] | policy_w [A][2*cells | 1 pad] | value1_w [256][cells | 1 pad] |
-//                         per-warp h [kHeadWarps][3*cells]
+// One warp per position, grid-stride; dense weights staged once per block in shared memory.
+// 1x1 convolutions: D[pixel][3] = X[pixel][128] * Wc[128][3] with mma.sync, the A fragments loaded straight
+// from global memory (every byte of the position is requested exactly once, 96 independent loads per lane).
+// Shared layout (floats): policy_w [A][2*cells | 1 pad] | value1_w [256][cells | 1 pad] | per-warp h [3*cells]
 template <int C>
 __global__ void __launch_bounds__(kHeadWarps * 32) k_heads(const __nv_bfloat16* __restrict__ x, HeadParams hp,
                                                            float* __restrict__ priors, float* __restrict__ values) {
+    static_assert(C == 128, "8 k-steps of 16 channels");
     extern __shared__ float s_f[];
     const int cells = hp.cells, A = hp.A;
     const int ps = 2 * cells + 1, vs = cells | 1;  // odd row strides: conflict-free across lanes
-    float* s_cw = s_f;
-    float* s_pw = s_cw + 3 * C;
+    float* s_pw = s_f;
     float* s_vw = s_pw + A * ps;
     float* s_h = s_vw + kHidden * vs;
-    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_cw[i] = hp.conv_w[i];
     for (int i = threadIdx.x; i < A * 2 * cells; i += blockDim.x) s_pw[(i / (2 * cells)) * ps + i % (2 * cells)] = hp.policy_w[i];
     for (int i = threadIdx.x; i < kHidden * cells; i += blockDim.x) s_vw[(i / cells) * vs + i % cells] = hp.value1_w[i];
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* h = s_h + warp * 3 * cells;  // [cells][2] policy planes then [cells] value plane
-    float cw[3][C / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    float* h = s_h + warp * 3 * cells;  // [cells][2] policy planes (Keras Flatten of [H][W][2]) then [cells] value plane
+    // B fragments of the 1x1 convolutions: column n = g (only n < 3 is non-zero)
+    uint32_t bf[C / 16][2];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+    for (int ks = 0; ks < C / 16; ++ks)
 #pragma unroll
-        for (int j = 0; j < C / 32; ++j) cw[c][j] = s_cw[c * C + lane * (C / 32) + j];
+        for (int hh = 0; hh < 2; ++hh) {
+            const int k = ks * 16 + t4 * 2 + hh * 8;
+            bf[ks][hh] = g < 3 ? pack_bf16(hp.conv_w[g * C + k], hp.conv_w[g * C + k + 1]) : 0u;
+        }
     const float cb0 = hp.conv_b[0], cb1 = hp.conv_b[1], cb2 = hp.conv_b[2];
-    static_assert(C == 128, "one 8-byte load per lane covers C = 128 channels");
+    __syncthreads();
+    const int mtiles = (cells + 15) >> 4;
     for (int t = blockIdx.x * kHeadWarps + warp; t < hp.n; t += gridDim.x * kHeadWarps) {
-        const uint2* row = reinterpret_cast<const uint2*>(x + (size_t)t * cells * C) + lane;
-        for (int p0 = 0; p0 < cells; p0 += 4) {  // 4 pixels in flight per lane
-            uint2 v[4];
+        const uint32_t* xb = reinterpret_cast<const uint32_t*>(x + (size_t)t * cells * C);
+        for (int mt = 0; mt < mtiles; ++mt) {
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+            const int q0 = r0 < cells ? r0 : cells - 1, q1 = r1 < cells ? r1 : cells - 1;
+            uint32_t a[C / 16][4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = p0 + u < cells ? row[(size_t)(p0 + u) * (C / 4)] : make_uint2(0u, 0u);
+            for (int ks = 0; ks < C / 16; ++ks) {
+                a[ks][0] = xb[q0 * (C / 2) + ks * 8 + t4];
+                a[ks][1] = xb[q1 * (C / 2) + ks * 8 + t4];
+                a[ks][2] = xb[q0 * (C / 2) + ks * 8 + t4 + 4];
+                a[ks][3] = xb[q1 * (C / 2) + ks * 8 + t4 + 4];
+            }
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float f0 = __uint_as_float(v[u].x << 16), f1 = __uint_as_float(v[u].x & 0xffff0000u);
-                const float f2 = __uint_as_float(v[u].y << 16), f3 = __uint_as_float(v[u].y & 0xffff0000u);
-                float a0 = f0 * cw[0][0] + f1 * cw[0][1] + f2 * cw[0][2] + f3 * cw[0][3];
-                float a1 = f0 * cw[1][0] + f1 * cw[1][1] + f2 * cw[1][2] + f3 * cw[1][3];
-                float a2 = f0 * cw[2][0] + f1 * cw[2][1] + f2 * cw[2][2] + f3 * cw[2][3];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-                    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-                }
-                if (lane == 0 && p0 + u < cells) {
-                    h[(p0 + u) * 2 + 0] = fmaxf(a0 + cb0, 0.f);  // Keras Flatten of [H][W][2]
-                    h[(p0 + u) * 2 + 1] = fmaxf(a1 + cb1, 0.f);
-                    h[2 * cells + p0 + u] = fmaxf(a2 + cb2, 0.f);
-                }
+            for (int ks = 0; ks < C / 16; ++ks) mma_16816(acc, a[ks], bf[ks]);
+            // acc[0], acc[1]: row r0, columns 2*t4, 2*t4+1; acc[2], acc[3]: row r1
+            if (t4 == 0) {
+                if (r0 < cells) { h[r0 * 2] = fmaxf(acc[0] + cb0, 0.f); h[r0 * 2 + 1] = fmaxf(acc[1] + cb1, 0.f); }
+                if (r1 < cells) { h[r1 * 2] = fmaxf(acc[2] + cb0, 0.f); h[r1 * 2 + 1] = fmaxf(acc[3] + cb1, 0.f); }
+            } else if (t4 == 1) {
+                if (r0 < cells) h[2 * cells + r0] = fmaxf(acc[0] + cb2, 0.f);
+                if (r1 < cells) h[2 * cells + r1] = fmaxf(acc[2] + cb2, 0.f);
             }
         }
         __syncwarp();
@@ -156,17 +219,19 @@ __global__ void __launch_bounds__(kHeadWarps * 32) k_heads(const __nv_bfloat16* 
 #pragma unroll
         for (int m = 0; m < 4; ++m)
             if (lane + 32 * m < A) priors[(size_t)t * A + lane + 32 * m] = ex[m] / sum;
-        // value: Dense(256) ReLU -> Dense(1) tanh
-        float part = 0.f;
-        const float* hv = h + 2 * cells;
+        // value: Dense(256) ReLU -> Dense(1) tanh; lane owns hidden units lane, lane+32, ...
+        float hacc[kHidden / 32];
 #pragma unroll
-        for (int m = 0; m < kHidden / 32; ++m) {
-            const int j = lane + 32 * m;
-            float acc = hp.value1_b[j];
-            const float* wrow = s_vw + j * vs;
-            for (int p = 0; p < cells; ++p) acc = fmaf(hv[p], wrow[p], acc);
-            part = fmaf(fmaxf(acc, 0.f), hp.value2_w[j], part);
+        for (int m = 0; m < kHidden / 32; ++m) hacc[m] = hp.value1_b[lane + 32 * m];
+        const float* hv = h + 2 * cells;
+        for (int p = 0; p < cells; ++p) {
+            const float hvp = hv[p];
+#pragma unroll
+            for (int m = 0; m < kHidden / 32; ++m) hacc[m] = fmaf(hvp, s_vw[(lane + 32 * m) * vs + p], hacc[m]);
         }
+        float part = 0.f;
+#pragma unroll
+        for (int m = 0; m < kHidden / 32; ++m) part = fmaf(fmaxf(hacc[m], 0.f), hp.value2_w[lane + 32 * m], part);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) values[t] = tanhf(part + hp.value2_b[0]);
@@ -187,9 +252,9 @@ AZ_API int az_net_stem(const void* states, const float* w, const float* b, int32
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = n < sms * 8 ? n : sms * 8;
-    const size_t smem = sizeof(float4) * (size_t)(H + 2) * (W + 2);
-    k_stem<128><<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+    if (H > kMaxDimNet || W > kMaxDimNet) return fail_net(AZ_ERR_ARG, "az_net_stem: board larger than 11x11");
+    const int grid = n < sms * 5 ? n : sms * 5;
+    k_stem<<<grid, kStemWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(states), w, b, n, H, W, static_cast<__nv_bfloat16*>(out));
     if (cudaGetLastError() != cudaSuccess) return fail_net(AZ_ERR_CUDA, "az_net_stem: launch failed");
     return AZ_OK;
@@ -203,7 +268,7 @@ AZ_API int az_net_heads(const void* x, const az_head_weights* hw, int32_t n, int
     if (n == 0) return AZ_OK;
     HeadParams hp{hw->conv_w, hw->conv_b, hw->policy_w, hw->policy_b, hw->value1_w, hw->value1_b, hw->value2_w, hw->value2_b,
                   n, cells, A};
-    const size_t smem = sizeof(float) * (3 * 128 + (size_t)A * (2 * cells + 1) + (size_t)kHidden * (cells | 1) +
+    const size_t smem = sizeof(float) * ((size_t)A * (2 * cells + 1) + (size_t)kHidden * (cells | 1) +
                                          (size_t)kHeadWarps * 3 * cells);
     static size_t configured = 0;
     if (smem > configured) {
@@ -215,7 +280,8 @@ AZ_API int az_net_heads(const void* x, const az_head_weights* hw, int32_t n, int
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = (n + kHeadWarps - 1) / kHeadWarps;
-    if (grid > sms * 2) grid = sms * 2;
+    const int per_sm = smem > 100 * 1024 ? 1 : 2;
+    if (grid > sms * per_sm) grid = sms * per_sm;
     k_heads<128><<<grid, kHeadWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), hp, priors, values);
     if (cudaGetLastError() != cudaSuccess) return fail_net(AZ_ERR_CUDA, "az_net_heads: launch failed");

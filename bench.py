@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--advances", type=int, default=800, help="lock-step advances per step")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bounded CPU baseline sample (0 = skip)")
     ap.add_argument("--unroll", type=int, default=8)
+    ap.add_argument("--groups", type=int, default=2, help="tree slices advanced on parallel graph branches")
+    ap.add_argument("--max-free", type=int, default=8)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -185,7 +187,7 @@ def main():
     fp32 = PolicyValueNet(rules.height, rules.width, rules.n_actions)
     runner = selfplay.SelfPlayRunner(rules, n_trees=T, sims_per_move=S, net=fp32, games_target=1 << 40,
                                      game_id_base=rank << 40, seed=1234, move_mode="philox", auto_restart=True,
-                                     unroll=args.unroll, fin_capacity=4 * T)
+                                     unroll=args.unroll, fin_capacity=4 * T, groups=args.groups, max_free_sims=args.max_free)
     flat_dev = runner.net.flat_weights()  # what the trainer rank would broadcast after a training step
     n_w = flat_dev.numel()
 
@@ -201,9 +203,9 @@ def main():
 
     for _ in range(args.warmup):
         step_device()
-    runner.engine.fin_clear()
+    runner.fin_clear()
     barrier()
-    c0 = runner.engine.totals()
+    c0 = runner.totals()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -213,11 +215,11 @@ def main():
     for k in range(args.steps):
         step_device()
         if (k + 1) % 2 == 0:
-            runner.engine.fin_clear()  # ring bookkeeping only; samples are consumed in the e2e leg
+            runner.fin_clear()  # ring bookkeeping only; samples are consumed in the e2e leg
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    c1 = runner.engine.totals()
+    c1 = runner.totals()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     delta = torch.tensor([c1[k] - c0[k] for k in ("sims", "evals", "moves", "games", "depth_sum", "children")],
                          dtype=torch.float64, device=dev)
@@ -226,14 +228,14 @@ def main():
         dist.all_reduce(delta, op=dist.ReduceOp.SUM)
     ms = float(ms)
     sims, evals, moves, games, depth_sum, children = [float(x) for x in delta]
-    runner.engine.check_status()
+    runner.check_status()
 
     # ---- e2e: public API with host buffers (weights up from pinned memory, decoded samples down)
     flat_host = flat_dev.cpu().pin_memory()
     params = list(runner.net.parameters())
-    runner.engine.fin_clear()
+    runner.fin_clear()
     barrier()
-    e0 = runner.engine.totals()
+    e0 = runner.totals()
     h2d = d2h = 0
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
@@ -255,10 +257,10 @@ def main():
         if rank == 0 or world == 1:
             st, po, va = selfplay.decode_samples(rules, fin)
             d2h += st.nbytes + po.nbytes + va.nbytes // 2
-        runner.engine.fin_clear()
+        runner.fin_clear()
     t1.record()
     barrier()
-    e1 = runner.engine.totals()
+    e1 = runner.totals()
     e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     e2e_sims = torch.tensor([e1["sims"] - e0["sims"]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -269,7 +271,8 @@ def main():
     # ---- roofline of the dominant kernels: the net forward (tensor bound), timed alone with CUDA events
     roof = roof_tree = None
     if rank == 0:
-        x = runner.states
+        x = runner.states  # the batch one net call really sees: T / groups positions
+        Tg = x.shape[0]
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             runner.net(x)
@@ -283,11 +286,11 @@ def main():
         b.record()
         torch.cuda.synchronize()
         net_ms = a.elapsed_time(b) / n_rep
-        ach = T * runner.flops_per_eval / (net_ms * 1e-3) / 1e12
+        ach = Tg * runner.flops_per_eval / (net_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_sustained"], "traffic": None,
-                "kernel": "policy/value net forward (cuDNN/cuBLAS bf16, 13 tower convs + heads), one launch group per advance",
-                "flops_per_launch": T * runner.flops_per_eval, "ms_per_launch": net_ms, "peak_source": peaks["source"] + ", sustained"}
+                "kernel": "policy/value net forward: az_net_stem + 12 cuDNN tcgen05 implicit-GEMM convs (fused bias/ReLU/residual) + az_net_heads, timed alone",
+                "flops_per_launch": Tg * runner.flops_per_eval, "positions_per_launch": Tg, "ms_per_launch": net_ms, "peak_source": peaks["source"] + ", sustained"}
         # az_step alone (HBM bound): algorithmic bytes per simulation with the measured mean depth / fan-out
         d_bar = depth_sum / max(sims, 1.0)
         k_bar = children / max(evals, 1.0)
@@ -306,11 +309,11 @@ def main():
         b.record()
         torch.cuda.synchronize()
         step_ms = a.elapsed_time(b) / n_rep
-        ach_gbs = T * bytes_per_sim / (step_ms * 1e-3) / 1e9
+        ach_gbs = Tg * bytes_per_sim / (step_ms * 1e-3) / 1e9
         roof_tree = {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": ach_gbs / peaks["hbm_gbs"], "traffic": None, "kernel": "az::k_step<1,1>",
                      "bytes_per_sim": bytes_per_sim, "mean_depth": d_bar, "mean_children": k_bar,
-                     "ms_per_launch": step_ms, "peak_source": peaks["source"]}
+                     "trees_per_launch": Tg, "ms_per_launch": step_ms, "peak_source": peaks["source"]}
 
     if rank == 0:
         per_adv = args.steps * ADV
@@ -319,7 +322,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "C2: 4096 concurrent 6x7 Connect-4 self-play games per GPU x 800 simulations/move, bf16 net leaf evaluation",
-                       "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "board": "6x7", "n_connect": 4,
+                       "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "board": "6x7", "n_connect": 4,
                        "net": "4-block 128-filter projection-residual tower, 1267037 params, random init",
                        "l2": "working set per advance (node pools ~GBs + 177 MB activations per conv) exceeds the 126 MB L2; no flush needed"},
             "leaf_evals_per_sec": evals / ms * 1e3, "selfplay_moves_per_sec": moves / ms * 1e3,

@@ -33,7 +33,7 @@ class Rules:
 
 _VIEW_DTYPES = {
     "status": torch.int32, "ply": torch.int32, "game_id": torch.int64, "root_board": torch.int64,
-    "half": torch.int32, "n_nodes": torch.int32, "sims_done": torch.int32, "pending": torch.int32,
+    "half": torch.int32, "root_node": torch.int32, "n_nodes": torch.int32, "sims_done": torch.int32, "pending": torch.int32,
     "path_len": torch.int32, "path": torch.int32, "leaf_board": torch.int64, "counters": torch.int64,
     "uniforms": torch.float64, "node_p": torch.float64, "rec_visits": torch.int32, "rec_action": torch.int32,
     "rec_board": torch.int64, "rec_len": torch.int32, "result": torch.int32, "fin_count": torch.int32,
@@ -67,8 +67,14 @@ class TreeEngine:
         self.n_trees = int(n_trees)
         A, P = rules.n_actions, rules.max_plies
         if node_capacity is None:
-            # nodes under the new root <= expansions retained + sims_per_move, k <= A children each
-            node_capacity = min(0xFFFFFF, (4 * sims_per_move + 8) * A + 1)
+            # Enough for every expansion of a whole game (re-root then never has to compact), unless that
+            # does not fit in half of the free HBM: then at least 4 searches' worth and the kept subtree is
+            # compacted into the other pool half whenever the live half runs short.
+            worst = P * sims_per_move * A + A + 2
+            floor = (4 * sims_per_move + 8) * A + 1
+            free_bytes, _ = torch.cuda.mem_get_info(self.device)
+            budget = (free_bytes // 2) // (self.n_trees * 2 * 24)
+            node_capacity = min(0xFFFFFF, worst, max(floor, budget))
         if games_target is None:
             games_target = n_trees
         if fin_capacity is None:
@@ -222,7 +228,8 @@ class TreeEngine:
         """Root edges of one tree: (N, W, P) lists in board move order."""
         w, n, link = self.node_view()
         half = int(self.view("half")[tree])
-        lk = int(link[tree, half, 0]) & 0xFFFFFFFF
+        root = int(self.view("root_node")[tree])
+        lk = int(link[tree, half, root]) & 0xFFFFFFFF
         base, k = lk & 0xFFFFFF, lk >> 24
         p = self.view("node_p")
         sl = slice(base, base + k)

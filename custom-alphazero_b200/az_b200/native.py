@@ -49,7 +49,7 @@ class AzConfig(ctypes.Structure):
 
 
 LAYOUT_ARRAYS = [
-    "status", "ply", "game_id", "root_board", "half", "n_nodes", "sims_done", "pending", "path_len", "path",
+    "status", "ply", "game_id", "root_board", "half", "root_node", "n_nodes", "sims_done", "pending", "path_len", "path",
     "leaf_board", "counters", "uniforms", "node_a", "node_p", "rec_visits", "rec_action", "rec_board", "rec_len",
     "result", "fin_count", "fin_game_id", "fin_len", "fin_result", "fin_visits", "fin_action", "fin_board", "pow_lut",
 ]

@@ -49,11 +49,27 @@ def decode_samples(rules: Rules, fin_dev, exclude_null_games=False):
     return states.cpu().numpy(), policies.cpu().numpy(), values.cpu().numpy().astype(np.int64)
 
 
+class _Group:
+    """One slice of the trees with its own engine and evaluator buffers."""
+
+    def __init__(self, engine, rules, dtype, device):
+        T, A = engine.n_trees, rules.n_actions
+        self.engine = engine
+        self.states = torch.zeros((T, rules.height, rules.width, 4), dtype=dtype, device=device)
+        self.valid = torch.zeros(T, dtype=torch.int32, device=device)
+        self.priors = torch.zeros((T, A), dtype=torch.float32, device=device)
+        self.values = torch.zeros(T, dtype=torch.float32, device=device)
+
+
 class SelfPlayRunner:
+    """`groups` > 1 splits the trees into independent slices whose advances are captured on parallel
+    branches of the CUDA graph: while the tensor cores run the net of one slice, the latency-bound tree
+    kernels (and the memory-bound stem / heads) of another slice run underneath."""
+
     def __init__(self, rules=Rules(), n_trees=4096, sims_per_move=800, net=None, *, games_target=None,
                  game_id_base=0, seed=0, move_mode="philox", auto_restart=True, dtype=torch.bfloat16, unroll=8,
                  use_graph=True, max_free_sims=8, node_capacity=None, fin_capacity=None, device=None,
-                 index_move_greedy=8):
+                 index_move_greedy=8, groups=1):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.rules = rules
         T, A = int(n_trees), rules.n_actions
@@ -61,27 +77,72 @@ class SelfPlayRunner:
             net = PolicyValueNet(rules.height, rules.width, A)
         self.fp32_net = net
         self.net = net if isinstance(net, InferenceNet) else InferenceNet(net, dtype=dtype, device=self.device)
-        self.engine = TreeEngine(rules, T, sims_per_move, eval_mode="external", prior_mode="f32", move_mode=move_mode,
-                                 games_target=games_target, game_id_base=game_id_base, seed=seed,
-                                 auto_restart=auto_restart, max_free_sims=max_free_sims, node_capacity=node_capacity,
-                                 fin_capacity=fin_capacity, device=self.device, index_move_greedy=index_move_greedy)
-        self.states = torch.zeros((T, rules.height, rules.width, 4), dtype=dtype, device=self.device)
-        self.valid = torch.zeros(T, dtype=torch.int32, device=self.device)
-        self.priors = torch.zeros((T, A), dtype=torch.float32, device=self.device)
-        self.values = torch.zeros(T, dtype=torch.float32, device=self.device)
+        groups = max(1, min(int(groups), T))
+        if games_target is None:
+            games_target = T
+        self.groups = []
+        t0 = g0 = 0
+        for i in range(groups):
+            ti = T // groups + (1 if i < T % groups else 0)
+            gi = games_target // groups + (1 if i < games_target % groups else 0)
+            eng = TreeEngine(rules, ti, sims_per_move, eval_mode="external", prior_mode="f32", move_mode=move_mode,
+                             games_target=gi, game_id_base=game_id_base + g0, seed=seed, auto_restart=auto_restart,
+                             max_free_sims=max_free_sims, node_capacity=node_capacity,
+                             fin_capacity=None if fin_capacity is None else max(1, -(-fin_capacity // groups)),
+                             device=self.device, index_move_greedy=index_move_greedy)
+            self.groups.append(_Group(eng, rules, dtype, self.device))
+            t0 += ti
+            g0 += gi
+        self.n_trees = T
         self.unroll = int(unroll)
         self.use_graph = use_graph
         self.graph = None
         self.advances = 0
         self.flops_per_eval = flops_per_eval(rules.height, rules.width, A)
-        # kernels of libaz_b200 launched per advance: az_step + az_play
-        self.launches_per_advance = 2
+        # kernels of libaz_b200 launched per advance and group: az_step, az_net_stem, az_net_heads, az_play
+        self.launches_per_advance = 4 * groups
+        self._side = [torch.cuda.Stream(device=self.device) for _ in range(groups - 1)]
 
-    # one lock-step iteration; everything is enqueued on the current stream
-    def _advance(self):
-        self.engine.step(self.priors, self.values, self.states, self.valid)
-        self.net(self.states, self.priors, self.values)
-        self.engine.play()
+    # single-group conveniences (tests, compat code)
+    @property
+    def engine(self):
+        return self.groups[0].engine
+
+    @property
+    def states(self):
+        return self.groups[0].states
+
+    @property
+    def valid(self):
+        return self.groups[0].valid
+
+    @property
+    def priors(self):
+        return self.groups[0].priors
+
+    @property
+    def values(self):
+        return self.groups[0].values
+
+    # one lock-step iteration of one group; everything is enqueued on the current stream
+    def _advance(self, g):
+        g.engine.step(g.priors, g.values, g.states, g.valid)
+        self.net(g.states, g.priors, g.values)
+        g.engine.play()
+
+    def _advance_all(self, n):
+        """n advances of every group: group 0 on the current stream, the others on forked side streams."""
+        cur = torch.cuda.current_stream()
+        for s in self._side:
+            s.wait_stream(cur)
+        for g, s in zip(self.groups[1:], self._side):
+            with torch.cuda.stream(s):
+                for _ in range(n):
+                    self._advance(g)
+        for _ in range(n):
+            self._advance(self.groups[0])
+        for s in self._side:
+            cur.wait_stream(s)
 
     def capture(self):
         if self.graph is not None or not self.use_graph:
@@ -90,14 +151,14 @@ class SelfPlayRunner:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm up cuDNN heuristics / workspaces outside capture
             for _ in range(3):
-                self.net(self.states, self.priors, self.values)
+                for g in self.groups:
+                    self.net(g.states, g.priors, g.values)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for _ in range(self.unroll):
-                self._advance()
-        self.graph = g
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._advance_all(self.unroll)
+        self.graph = graph
 
     def run(self, advances):
         """Enqueues `advances` lock-step iterations (rounded up to a multiple of `unroll` under graphs)."""
@@ -108,17 +169,17 @@ class SelfPlayRunner:
                 self.graph.replay()
             self.advances += n * self.unroll
             return n * self.unroll
-        for _ in range(advances):
-            self._advance()
+        self._advance_all(advances)
         self.advances += advances
         return advances
 
     def reset(self):
-        self.engine.reset()
-        self.valid.zero_()
+        for g in self.groups:
+            g.engine.reset()
+            g.valid.zero_()
 
     def active_trees(self):
-        return int((self.engine.phases() != native.AZ_PHASE_IDLE).sum())
+        return sum(int((g.engine.phases() != native.AZ_PHASE_IDLE).sum()) for g in self.groups)
 
     def run_until_done(self, poll_every=64, max_advances=None):
         """Runs until every tree is idle (all games_target games finished); returns advances executed."""
@@ -129,19 +190,40 @@ class SelfPlayRunner:
                 break
             if max_advances is not None and done >= max_advances:
                 break
-        self.engine.check_status()
+        self.check_status()
         return done
 
+    def check_status(self):
+        for g in self.groups:
+            g.engine.check_status()
+
+    def totals(self):
+        out = {}
+        for g in self.groups:
+            for k, v in g.engine.totals().items():
+                out[k] = out.get(k, 0) + v
+        return out
+
+    def fin_clear(self):
+        for g in self.groups:
+            g.engine.fin_clear()
+
     def finished_device(self):
-        e = self.engine
-        n = int(e.view("fin_count")[0])
-        return {"game_id": e.view("fin_game_id")[:n], "len": e.view("fin_len")[:n], "result": e.view("fin_result")[:n],
-                "visits": e.view("fin_visits")[:n], "action": e.view("fin_action")[:n], "board": e.view("fin_board")[:n]}
+        parts = []
+        for g in self.groups:
+            e = g.engine
+            n = int(e.view("fin_count")[0])
+            parts.append({"game_id": e.view("fin_game_id")[:n], "len": e.view("fin_len")[:n],
+                          "result": e.view("fin_result")[:n], "visits": e.view("fin_visits")[:n],
+                          "action": e.view("fin_action")[:n], "board": e.view("fin_board")[:n]})
+        if len(parts) == 1:
+            return parts[0]
+        return {k: torch.cat([p[k] for p in parts], dim=0) for k in parts[0]}
 
     def collect(self, exclude_null_games=False):
-        """Decodes and drains the finished-game ring: (states, policies, values) host arrays."""
+        """Decodes and drains the finished-game rings: (states, policies, values) host arrays."""
         out = decode_samples(self.rules, self.finished_device(), exclude_null_games)
-        self.engine.fin_clear()
+        self.fin_clear()
         return out
 
     def load_weights(self, net: PolicyValueNet):
@@ -153,11 +235,11 @@ def smoke_net_step():
     """Tiny end-to-end: 64 trees x 16 simulations per move through the bf16 net, a few full games."""
     rules = Rules(7, 6, 4, True)
     torch.manual_seed(0)
-    r = SelfPlayRunner(rules, n_trees=64, sims_per_move=16, games_target=96, unroll=4)
+    r = SelfPlayRunner(rules, n_trees=64, sims_per_move=16, games_target=96, unroll=4, groups=2)
     t0 = time.time()
     r.run_until_done(poll_every=64, max_advances=200000)
     torch.cuda.synchronize()
-    tot = r.engine.totals()
+    tot = r.totals()
     states, policies, values = r.collect()
     assert tot["games"] == 96 and states.shape[0] == policies.shape[0] == values.shape[0] == tot["moves"]
     assert np.isfinite(policies).all() and np.allclose(policies.sum(-1), 1.0)

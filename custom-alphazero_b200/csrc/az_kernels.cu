@@ -49,6 +49,7 @@ __global__ void k_reset(Eng e) {
     e.game_id[t] = e.game_base + t;
     for (int i = 0; i < nw2; ++i) e.root_board[(size_t)t * nw2 + i] = 0;
     e.half[t] = 0;
+    e.root_node[t] = 0;
     e.n_nodes[t] = 1;
     e.sims_done[t] = 0;
     e.pending[t] = 0;
@@ -97,6 +98,7 @@ __global__ void k_set_roots(Eng e, Aux aux, const int32_t* ids, const int8_t* ce
     e.status[t] = AZ_PHASE_SEARCH;
     e.ply[t] = plies[i];
     e.half[t] = 0;
+    e.root_node[t] = 0;
     e.n_nodes[t] = 1;
     e.sims_done[t] = 0;
     e.pending[t] = 0;
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         NodeA* A = e.node_a + pool;
         double* Pr = e.node_p + pool;
         int sims = e.sims_done[t];
+        const int root = e.root_node[t];
         long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
         if (e.pending[t] && priors != nullptr) {
             const int depth = e.path_len[t];
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
                 v = (double)static_cast<const float*>(values)[t];  // value.numpy().item() (mcts.py:136)
                 link = expand_leaf<NW>(e, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F32, [p](int a) { return (double)p[a]; });
             }
-            backup_path(A, ws, depth, -v, link, lane);  // mcts.py:175: value seen by the player who moved in
+            backup_path(A, root, ws, depth, -v, link, lane);  // mcts.py:175: value seen by the player who moved in
             ++sims;
             ++nsim;
             ++neval;
@@ -171,10 +174,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         while (!pend && sims < e.sims_target) {
             Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
             int depth, term;
-            select_leaf<NW, KC>(e, A, Pr, pos, ws, lane, depth, term, flags);
+            select_leaf<NW, KC>(e, A, Pr, root, pos, ws, lane, depth, term, flags);
             ndepth += depth;
             if (term) {  // mcts.py:179: terminal leaf, result 1 (win of the mover) or 0 (draw)
-                backup_path(A, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
+                backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
                 ++sims;
                 ++nsim;
                 if (++freed >= e.max_free) break;
@@ -218,17 +221,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
     const size_t pool = ((size_t)t * 2 + e.half[t]) * e.C;
     NodeA* A = e.node_a + pool;
     double* Pr = e.node_p + pool;
-    const Pos<NW> root = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
+    const Pos<NW> root_pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
+    const int root = e.root_node[t];
     const double uniform_prior = __ddiv_rn(1.0, (double)e.r.A);  // np.full(A, 1 / A)
     int sims = e.sims_done[t];
     long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
     while (sims < e.sims_target && !(flags & AZ_FLAG_POOL_OVERFLOW)) {
-        Pos<NW> pos = root;
+        Pos<NW> pos = root_pos;
         int depth, term;
-        select_leaf<NW, KC>(e, A, Pr, pos, ws, lane, depth, term, flags);
+        select_leaf<NW, KC>(e, A, Pr, root, pos, ws, lane, depth, term, flags);
         ndepth += depth;
         if (term) {
-            backup_path(A, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
+            backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
         } else {
             double v = 0.0;
             uint32_t link;
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
             } else {
                 link = expand_leaf<NW>(e, A, Pr, pos, t, ws, lane, flags, e.prior_mode, [uniform_prior](int) { return uniform_prior; });
             }
-            backup_path(A, ws, depth, -v, link, lane);
+            backup_path(A, root, ws, depth, -v, link, lane);
             ++neval;
             nchild += link >> 24;
         }
@@ -305,6 +309,7 @@ __device__ __forceinline__ void finish_game(const Eng& e, const Aux& aux, int t,
             e.ply[t] = 0;
             aux.rec_len[t] = 0;
             e.n_nodes[t] = 1;
+            e.root_node[t] = 0;
             e.sims_done[t] = 0;
             e.pending[t] = 0;
             NodeA z;
@@ -339,7 +344,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
     double* Ps = e.node_p + pool;
     NodeA* Ad = e.node_a + pool2;
     double* Pd = e.node_p + pool2;
-    const uint32_t rlink = load_node(As).link;
+    const int root = e.root_node[t];
+    const uint32_t rlink = load_node(As + root).link;
     const int base = (int)(rlink & 0xffffffu), k = (int)(rlink >> 24);
     const int ply = e.ply[t], rec = aux.rec_len[t];
     if (k == 0 || rec >= e.P) {  // the reference would raise on an edgeless root (np.argmax of [])
@@ -409,8 +415,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
         finish_game<NW>(e, aux, t, st, lane);
         return;
     }
-    // re-root to the chosen child, keeping its subtree (mcts.py:207): breadth-first copy into the
-    // other half, 32 queue nodes per wave, children re-based with a warp prefix sum.
+    // re-root to the chosen child, keeping its subtree (mcts.py:207).  In place while this half still
+    // has room for a whole search (sims_target expansions of at most A children each) ...
+    const int used = e.n_nodes[t];
+    if ((long long)used + (long long)(e.sims_target + 1) * e.r.A <= (long long)e.C) {
+        if (lane == 0) {
+            e.root_node[t] = base + pick;
+            e.pending[t] = 0;
+            e.status[t] = (st & ~AZ_PHASE_MASK) | AZ_PHASE_SEARCH;
+        }
+        return;
+    }
+    // ... otherwise the kept subtree is copied breadth-first into the other half: 32 queue nodes per
+    // wave, children re-based with a warp prefix sum, dead siblings left behind.
     if (lane == 0) {
         store_node(Ad, load_node(As + base + pick));
         Pd[0] = Ps[base + pick];
@@ -454,6 +471,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
     if (lane == 0) {
         e.counters[(size_t)t * 8 + 6] += n_dst;
         e.half[t] = h ^ 1;
+        e.root_node[t] = 0;
         e.n_nodes[t] = n_dst;
         e.pending[t] = 0;
         e.status[t] = (st & ~AZ_PHASE_MASK) | AZ_PHASE_SEARCH;
@@ -625,6 +643,7 @@ AZ_API int az_query_layout(const az_config* c, az_layout* L) {
     L->game_id = take(off, 8 * T);
     L->root_board = take(off, 8 * T * 2 * WD);
     L->half = take(off, 4 * T);
+    L->root_node = take(off, 4 * T);
     L->n_nodes = take(off, 4 * T);
     L->sims_done = take(off, 4 * T);
     L->pending = take(off, 4 * T);
@@ -693,6 +712,7 @@ AZ_API int az_engine_create(const az_config* c, void* slab, size_t bytes, const 
     g.game_id = reinterpret_cast<long long*>(b + L.game_id);
     g.root_board = reinterpret_cast<uint64_t*>(b + L.root_board);
     g.half = reinterpret_cast<int32_t*>(b + L.half);
+    g.root_node = reinterpret_cast<int32_t*>(b + L.root_node);
     g.n_nodes = reinterpret_cast<int32_t*>(b + L.n_nodes);
     g.sims_done = reinterpret_cast<int32_t*>(b + L.sims_done);
     g.pending = reinterpret_cast<int32_t*>(b + L.pending);

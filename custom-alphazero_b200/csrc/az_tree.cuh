@@ -72,6 +72,7 @@ struct Eng {
     long long* game_id;
     uint64_t* root_board;
     int32_t* half;
+    int32_t* root_node;
     int32_t* n_nodes;
     int32_t* sims_done;
     int32_t* pending;
@@ -125,10 +126,10 @@ __device__ __forceinline__ void store_pos(uint64_t* p, const Pos<NW>& v, int lan
 // Returns the leaf node; depth/ws.path receive the path; term = 0 none, 1 mover won, 2 draw.
 // ------------------------------------------------------------------------------------------
 template <int NW, int KC>
-__device__ __forceinline__ int select_leaf(const Eng& e, const NodeA* A, const double* Pr, Pos<NW>& pos,
+__device__ __forceinline__ int select_leaf(const Eng& e, const NodeA* A, const double* Pr, int root, Pos<NW>& pos,
                                            WarpScratch& ws, int lane, int& depth, int& term, uint32_t& flags) {
-    int node = 0;
-    uint32_t link = load_node(A).link;
+    int node = root;
+    uint32_t link = load_node(A + root).link;
     depth = 0;
     term = 0;
     while (link) {
@@ -304,8 +305,8 @@ __device__ __forceinline__ uint32_t expand_leaf(const Eng& e, NodeA* A, double* 
 // no atomics.  v0 is the value for the player who moved into the leaf; sign alternates upward.
 // new_link != 0 also publishes the leaf's fresh children in the same 16-byte store.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void backup_path(NodeA* A, const WarpScratch& ws, int depth, double v0, uint32_t new_link,
-                                            int lane) {
+__device__ __forceinline__ void backup_path(NodeA* A, int root, const WarpScratch& ws, int depth, double v0,
+                                            uint32_t new_link, int lane) {
     for (int i = lane; i < depth; i += 32) {
         NodeA* p = A + ws.path[depth - 1 - i];
         NodeA rec = load_node(p);
@@ -315,9 +316,9 @@ __device__ __forceinline__ void backup_path(NodeA* A, const WarpScratch& ws, int
         store_node(p, rec);
     }
     if (depth == 0 && new_link && lane == 0) {  // first simulation on an edgeless root: nothing to back up
-        NodeA rec = load_node(A);
+        NodeA rec = load_node(A + root);
         rec.link = new_link;
-        store_node(A, rec);
+        store_node(A + root, rec);
     }
     __syncwarp();
 }

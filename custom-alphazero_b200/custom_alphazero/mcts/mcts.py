@@ -128,10 +128,12 @@ class MCTS:
         half = int(e.view("half")[0])
         used = int(e.view("n_nodes")[0])
         return {"W": w[0, half, :used].cpu().numpy(), "N": n[0, half, :used].cpu().numpy(),
-                "link": link[0, half, :used].cpu().numpy(), "P": e.view("node_p")[0, half, :used].cpu().numpy()}
+                "link": link[0, half, :used].cpu().numpy(), "P": e.view("node_p")[0, half, :used].cpu().numpy(),
+                "root": int(e.view("root_node")[0])}
 
     def _root_view(self) -> UCTNode:
-        return UCTNode(deepcopy(self.board), None, self._export(), 0)
+        ex = self._export()
+        return UCTNode(deepcopy(self.board), None, ex, ex["root"])
 
     def initialize_root(self) -> UCTNode:
         """mcts.py:108-109: an edgeless root at the caller's position (az_set_roots)."""

@@ -108,6 +108,9 @@ typedef struct az_layout {
     size_t game_id;     /* int64  [T] */
     size_t root_board;  /* uint64 [T][2][WD]  (side-to-move stones, opponent stones) */
     size_t half;        /* int32  [T]      which pool half holds the live tree */
+    size_t root_node;   /* int32  [T]      index of the current root in the live half (re-root is in place
+                                           while the half has room for the next search, else the kept subtree
+                                           is compacted into the other half and the root is node 0) */
     size_t n_nodes;     /* int32  [T]      nodes used in the live half */
     size_t sims_done;   /* int32  [T] */
     size_t pending;     /* int32  [T]      1 = a leaf awaits its evaluation */

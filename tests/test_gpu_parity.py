@@ -208,6 +208,21 @@ def test_external_evaluator_path_bit_exact(name):
 
 
 # ------------------------------------------------------------------ many different games vs the C oracle
+@pytest.mark.parametrize("capacity", [7000, 12000])
+def test_on_demand_compaction_keeps_results(capacity):
+    """A pool half too small for in-place re-rooting forces the breadth-first compaction path on most
+    moves; the golden 800-simulation game must still be reproduced exactly."""
+    engine, _ = _engine_mod()
+    case = load_golden("game_6x7_800_hash")
+    rules = rules_of(case)
+    eng = engine.TreeEngine(rules, n_trees=3, sims_per_move=800, eval_mode="hash", prior_mode="f64",
+                            node_capacity=capacity)
+    fin = _play_games(eng, rules.max_plies)
+    for g in range(3):
+        _check_against_golden(case, fin, g)
+    assert eng.totals()["reroot_nodes"] > 0  # compaction really ran
+
+
 def test_batch_of_different_games_matches_c_oracle():
     from oracle import c_oracle
 

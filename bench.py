@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--advances", type=int, default=800, help="lock-step advances per step")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bounded CPU baseline sample (0 = skip)")
     ap.add_argument("--unroll", type=int, default=8)
-    ap.add_argument("--groups", type=int, default=2, help="tree slices advanced on parallel graph branches")
+    ap.add_argument("--groups", type=int, default=1, help="tree slices advanced on parallel graph branches")
     ap.add_argument("--max-free", type=int, default=8)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -240,7 +240,9 @@ def main():
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
+    dbg = []
     for _ in range(args.steps):
+        dbg.append(time.perf_counter())
         flat_dev.copy_(flat_host, non_blocking=True)
         h2d += n_w * 4
         if world > 1:
@@ -258,6 +260,7 @@ def main():
             st, po, va = selfplay.decode_samples(rules, fin)
             d2h += st.nbytes + po.nbytes + va.nbytes // 2
         runner.fin_clear()
+        dbg.append(time.perf_counter())
     t1.record()
     barrier()
     e1 = runner.totals()
@@ -267,6 +270,9 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_sims, op=dist.ReduceOp.SUM)
     e2e_value = float(e2e_sims) / float(e2e_ms) * 1e3
+    if rank == 0 and os.environ.get("AZ_BENCH_DEBUG"):
+        print("e2e host wall per step (ms):", [round((dbg[i + 1] - dbg[i]) * 1e3, 1) for i in range(0, len(dbg), 2)],
+              "device ms:", float(e2e_ms), file=sys.stderr)
 
     # ---- roofline of the dominant kernels: the net forward (tensor bound), timed alone with CUDA events
     roof = roof_tree = None

@@ -148,6 +148,14 @@ class InferenceNet(nn.Module):
         # fast path: custom stem/heads kernels + cuDNN fused-epilogue tower (GPU, bf16, 128 filters)
         self.fast = dev.type == "cuda" and dtype == torch.bfloat16 and net.filters == 128 and net.value_fc1.out_features == 256
         self._head_struct = None
+        self.overlap_shortcut = False
+        self._side = {}
+
+    def _side_stream(self, device):
+        key = (device, torch.cuda.current_stream().cuda_stream)
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=device)
+        return self._side[key]
 
     def _heads_arg(self):
         from . import native
@@ -199,10 +207,21 @@ class InferenceNet(nn.Module):
                                 _ptr(h0), _stream()))
         x = h0.permute(0, 3, 1, 2)  # logical NCHW over NHWC memory (channels_last)
         one = (1, 1)
+        cur = torch.cuda.current_stream()
+        side = self._side_stream(x.device) if self.overlap_shortcut else None
         for i in range(self.depth):
             w1, b1, w2, wp, b2p = self.block_params[5 * i: 5 * i + 5]
-            h = torch.cudnn_convolution_relu(x, w1, b1, one, one, one, 1)           # conv + bias + ReLU
-            p = F.conv2d(x, wp)                                                      # projection shortcut
+            if side is not None:
+                # the bandwidth-bound 1x1 shortcut runs beside the compute-bound 3x3 on a forked stream
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    p = F.conv2d(x, wp)
+                p.record_stream(cur)
+                h = torch.cudnn_convolution_relu(x, w1, b1, one, one, one, 1)
+                cur.wait_stream(side)
+            else:
+                h = torch.cudnn_convolution_relu(x, w1, b1, one, one, one, 1)       # conv + bias + ReLU
+                p = F.conv2d(x, wp)                                                  # projection shortcut
             x = torch.cudnn_convolution_add_relu(h, w2, p, 1.0, b2p, one, one, one, 1)  # conv + shortcut + bias + ReLU
         xm = x.permute(0, 2, 3, 1)
         if not xm.is_contiguous():

@@ -208,7 +208,7 @@ def test_external_evaluator_path_bit_exact(name):
 
 
 # ------------------------------------------------------------------ many different games vs the C oracle
-@pytest.mark.parametrize("capacity", [7000, 12000])
+@pytest.mark.parametrize("capacity", [30000, 45000])
 def test_on_demand_compaction_keeps_results(capacity):
     """A pool half too small for in-place re-rooting forces the breadth-first compaction path on most
     moves; the golden 800-simulation game must still be reproduced exactly."""

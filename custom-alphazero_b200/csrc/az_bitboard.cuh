@@ -30,6 +30,32 @@ struct Rules {
     uint64_t boardmask[2];         // all real cells
 };
 
+// Compile-time rules for the headline configuration: the same member names as Rules (static members
+// are reachable through an instance), so every rule function below is written once, `template <class R>`;
+// with FixedRules all divisions by W / stride and all loop bounds fold to constants.
+template <int W_, int H_, int N_, int G_>
+struct FixedRules {
+    static constexpr int W = W_, H = H_, n = N_, gravity = G_;
+    static constexpr int A = G_ ? W_ : W_ * H_;
+    static constexpr int cells = W_ * H_, stride = W_ + 1, bits = H_ * (W_ + 1);
+    static_assert(H_ * (W_ + 1) <= 64, "FixedRules is the one-word fast path");
+    __host__ __device__ static constexpr uint64_t col0() {
+        uint64_t m = 0;
+        for (int y = 0; y < H_; ++y) m |= 1ull << (y * (W_ + 1));
+        return m;
+    }
+    __host__ __device__ static constexpr uint64_t board() {
+        uint64_t m = 0;
+        for (int x = 0; x < W_; ++x) m |= col0() << x;
+        return m;
+    }
+};
+
+template <class R>
+struct is_fixed_rules { static constexpr bool value = false; };
+template <int W_, int H_, int N_, int G_>
+struct is_fixed_rules<FixedRules<W_, H_, N_, G_>> { static constexpr bool value = true; };
+
 template <int NW>
 struct BB {
     uint64_t w[NW];
@@ -85,15 +111,19 @@ __device__ __forceinline__ int nth_set(const BB<NW>& b, int j) {
 // Legal moves in BOARD order (board.py:113-124).
 //   gravity: bit x of the result = column x has an empty top cell (ascending x)
 //   free:    every empty cell, ascending bit index == row-major (y, x)
-template <int NW>
-__device__ __forceinline__ BB<NW> legal_set(const Rules& r, const Pos<NW>& p) {
+template <int NW, class R>
+__device__ __forceinline__ BB<NW> legal_set(const R& r, const Pos<NW>& p) {
     BB<NW> occ = bb_or(p.cur, p.opp), l;
     if (r.gravity) {
         l.w[0] = ~occ.w[0] & ((1ull << r.W) - 1ull);
         if (NW == 2) l.w[NW - 1] = 0;
     } else {
+        if constexpr (is_fixed_rules<R>::value) {
+            l.w[0] = ~occ.w[0] & R::board();
+        } else {
 #pragma unroll
-        for (int i = 0; i < NW; ++i) l.w[i] = ~occ.w[i] & r.boardmask[i];
+            for (int i = 0; i < NW; ++i) l.w[i] = ~occ.w[i] & r.boardmask[i];
+        }
     }
     return l;
 }
@@ -106,13 +136,20 @@ __device__ __forceinline__ int bb_count(const BB<NW>& b) {
 }
 
 // j-th legal move in board order -> (cell bit, action index)
-template <int NW>
-__device__ __forceinline__ void edge_move(const Rules& r, const Pos<NW>& p, const BB<NW>& legal, int j, int& bit,
+template <int NW, class R>
+__device__ __forceinline__ void edge_move(const R& r, const Pos<NW>& p, const BB<NW>& legal, int j, int& bit,
                                           int& action) {
     if (r.gravity) {
-        int x = (int)__fns((uint32_t)legal.w[0], 0, j + 1);
-        int filled = popc64((p.cur.w[0] | p.opp.w[0]) & r.colmask[x][0]);
-        if (NW == 2) filled += popc64((p.cur.w[NW - 1] | p.opp.w[NW - 1]) & r.colmask[x][1]);
+        uint32_t m = (uint32_t)legal.w[0];  // j-th set bit of at most 11: peel j lowest bits
+        for (int i = 0; i < j; ++i) m &= m - 1;
+        int x = __ffs((int)m) - 1;
+        int filled;
+        if constexpr (is_fixed_rules<R>::value) {
+            filled = popc64((p.cur.w[0] | p.opp.w[0]) & (R::col0() << x));
+        } else {
+            filled = popc64((p.cur.w[0] | p.opp.w[0]) & r.colmask[x][0]);
+            if (NW == 2) filled += popc64((p.cur.w[NW - 1] | p.opp.w[NW - 1]) & r.colmask[x][1]);
+        }
         bit = (r.H - 1 - filled) * r.stride + x;  // board.py:212-226: lowest empty row
         action = x;
     } else {
@@ -123,8 +160,8 @@ __device__ __forceinline__ void edge_move(const Rules& r, const Pos<NW>& p, cons
 }
 
 // legality of action a in ACTION-LIST order (board.py:154-155)
-template <int NW>
-__device__ __forceinline__ bool action_legal(const Rules& r, const Pos<NW>& p, const BB<NW>& legal, int a) {
+template <int NW, class R>
+__device__ __forceinline__ bool action_legal(const R& r, const Pos<NW>& p, const BB<NW>& legal, int a) {
     if (a >= r.A) return false;
     if (r.gravity) return (legal.w[0] >> a) & 1ull;
     int x = a / r.H, y = a - x * r.H;
@@ -132,8 +169,8 @@ __device__ __forceinline__ bool action_legal(const Rules& r, const Pos<NW>& p, c
 }
 
 // Number of the mover's stones in line through `bit` along bit-delta d (board.py:186-203).
-template <int NW>
-__device__ __forceinline__ int run_through(const Rules& r, const BB<NW>& m, int bit, int d) {
+template <int NW, class R>
+__device__ __forceinline__ int run_through(const R& r, const BB<NW>& m, int bit, int d) {
     int run = 1;
     for (int i = bit + d; i < r.bits && run < r.n && bb_test(m, i); i += d) ++run;
     for (int i = bit - d; i >= 0 && run < r.n && bb_test(m, i); i -= d) ++run;
@@ -142,17 +179,34 @@ __device__ __forceinline__ int run_through(const Rules& r, const BB<NW>& m, int 
 
 // Board.play(move, keep_same_player=True) for the stone at `bit` (board.py:233-250):
 // returns 0 = game goes on, 1 = the mover connected n (is_null False), 2 = draw (is_null True).
-template <int NW>
-__device__ __forceinline__ int place(const Rules& r, Pos<NW>& p, int bit) {
+template <int NW, class R>
+__device__ __forceinline__ int place(const R& r, Pos<NW>& p, int bit) {
     BB<NW> mover = p.cur;
     bb_set(mover, bit);
     p.cur = p.opp;  // mirror: the opponent becomes the side to move (+1)
     p.opp = mover;
     const int s = r.stride;
     // config.py:47 directions (dx,dy): (0,1) vertical, (1,1), (1,0) horizontal, (1,-1)
-    if (run_through(r, mover, bit, s) >= r.n || run_through(r, mover, bit, s + 1) >= r.n ||
-        run_through(r, mover, bit, 1) >= r.n || run_through(r, mover, bit, s - 1) >= r.n)
+    if (NW == 1) {
+        // one-word boards: starts of n-runs by shift-and (the sentinel column stops wrap-around), kept
+        // only where the run passes through the new stone - same answer as the scan of board.py:186-203
+        const uint64_t m = mover.w[0];
+        const int d4[4] = {s, s + 1, 1, s - 1};
+        bool win = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int d = d4[k];
+            uint64_t run = m, through = 0;
+            for (int i = 1; i < r.n; ++i) run &= m >> (i * d);
+            for (int i = 0; i < r.n; ++i)
+                if (bit - i * d >= 0) through |= 1ull << (bit - i * d);
+            win = win || (run & through) != 0;
+        }
+        if (win) return 1;
+    } else if (run_through(r, mover, bit, s) >= r.n || run_through(r, mover, bit, s + 1) >= r.n ||
+               run_through(r, mover, bit, 1) >= r.n || run_through(r, mover, bit, s - 1) >= r.n) {
         return 1;
+    }
     BB<NW> l = legal_set(r, p);  // board.py:206-208: no move left -> draw
     bool any = l.w[0] != 0;
     if (NW == 2) any = any || l.w[NW - 1] != 0;
@@ -160,8 +214,8 @@ __device__ __forceinline__ int place(const Rules& r, Pos<NW>& p, int bit) {
 }
 
 // cell index (row-major, 0..W*H-1) -> plane code: 0 empty, 1 side to move, 2 opponent
-template <int NW>
-__device__ __forceinline__ int cell_code(const Rules& r, const Pos<NW>& p, int cell) {
+template <int NW, class R>
+__device__ __forceinline__ int cell_code(const R& r, const Pos<NW>& p, int cell) {
     int y = cell / r.W, x = cell - y * r.W, b = y * r.stride + x;
     return bb_test(p.cur, b) ? 1 : (bb_test(p.opp, b) ? 2 : 0);
 }

@@ -125,8 +125,19 @@ __global__ void k_begin_search(Eng e) {
 
 __global__ void k_fin_clear(Eng e) { *e.fin_count = 0; }
 
+// Rules as seen by a kernel instance: the runtime struct, or the compile-time headline configuration.
+using C4Rules = FixedRules<7, 6, 4, 1>;
+template <class R>
+struct RulesView {
+    __device__ static __forceinline__ const Rules& get(const Eng& e) { return e.r; }
+};
+template <int W_, int H_, int N_, int G_>
+struct RulesView<FixedRules<W_, H_, N_, G_>> {
+    __device__ static __forceinline__ FixedRules<W_, H_, N_, G_> get(const Eng&) { return {}; }
+};
+
 // ------------------------------------------------------------------------------------------ k_step
-template <int NW, int KC>
+template <int NW, int KC, class R>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     k_step(Eng e, const void* __restrict__ priors, const void* __restrict__ values, int eval_dtype, void* states,
            int state_dtype, int32_t* leaf_valid) {
@@ -135,6 +146,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     const int t = blockIdx.x * kWarpsPerBlock + warp;
     if (t >= e.T) return;
     WarpScratch& ws = s_ws[warp];
+    const auto r = RulesView<R>::get(e);
     const int st = e.status[t];
     uint32_t flags = 0;
     int valid = 0;
@@ -155,13 +167,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
             // the dtype of the evaluator output decides the arithmetic of normalize_probabilities, as in
             // the reference: float64 from infer_sample (factory.py:55), float32 from the model (mcts.py:131-137)
             if (eval_dtype == AZ_F64) {
-                const double* p = static_cast<const double*>(priors) + (size_t)t * e.r.A;
+                const double* p = static_cast<const double*>(priors) + (size_t)t * r.A;
                 v = static_cast<const double*>(values)[t];
-                link = expand_leaf<NW>(e, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F64, [p](int a) { return p[a]; });
+                link = expand_leaf<NW>(e, r, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F64, [p](int a) { return p[a]; });
             } else {
-                const float* p = static_cast<const float*>(priors) + (size_t)t * e.r.A;
+                const float* p = static_cast<const float*>(priors) + (size_t)t * r.A;
                 v = (double)static_cast<const float*>(values)[t];  // value.numpy().item() (mcts.py:136)
-                link = expand_leaf<NW>(e, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F32, [p](int a) { return (double)p[a]; });
+                link = expand_leaf<NW>(e, r, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F32, [p](int a) { return (double)p[a]; });
             }
             backup_path(A, root, ws, depth, -v, link, lane);  // mcts.py:175: value seen by the player who moved in
             ++sims;
@@ -174,7 +186,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         while (!pend && sims < e.sims_target) {
             Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
             int depth, term;
-            select_leaf<NW, KC>(e, A, Pr, root, pos, ws, lane, depth, term, flags);
+            select_leaf<NW, KC>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags);
             ndepth += depth;
             if (term) {  // mcts.py:179: terminal leaf, result 1 (win of the mover) or 0 (draw)
                 backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
@@ -187,9 +199,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
             store_pos<NW>(e.leaf_board + (size_t)t * 2 * NW, pos, lane);
             if (lane == 0) e.path_len[t] = depth;
             if (state_dtype == AZ_BF16)
-                encode_state_bf16<NW>(e.r, pos, static_cast<__nv_bfloat16*>(states) + (size_t)t * e.r.cells * 4, lane);
+                encode_state_bf16<NW>(r, pos, static_cast<__nv_bfloat16*>(states) + (size_t)t * r.cells * 4, lane);
             else
-                encode_state_f32<NW>(e.r, pos, static_cast<float*>(states) + (size_t)t * e.r.cells * 4, lane);
+                encode_state_f32<NW>(r, pos, static_cast<float*>(states) + (size_t)t * r.cells * 4, lane);
             pend = 1;
         }
         valid = pend;
@@ -208,13 +220,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 }
 
 // ------------------------------------------------------------------------------------------ k_search
-template <int NW, int KC>
+template <int NW, int KC, class R>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
     __shared__ WarpScratch s_ws[kWarpsPerBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * kWarpsPerBlock + warp;
     if (t >= e.T) return;
     WarpScratch& ws = s_ws[warp];
+    const auto r = RulesView<R>::get(e);
     const int st = e.status[t];
     if ((st & AZ_PHASE_MASK) != AZ_PHASE_SEARCH) return;
     uint32_t flags = 0;
@@ -223,13 +236,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
     double* Pr = e.node_p + pool;
     const Pos<NW> root_pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
     const int root = e.root_node[t];
-    const double uniform_prior = __ddiv_rn(1.0, (double)e.r.A);  // np.full(A, 1 / A)
+    const double uniform_prior = __ddiv_rn(1.0, (double)r.A);  // np.full(A, 1 / A)
     int sims = e.sims_done[t];
     long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
     while (sims < e.sims_target && !(flags & AZ_FLAG_POOL_OVERFLOW)) {
         Pos<NW> pos = root_pos;
         int depth, term;
-        select_leaf<NW, KC>(e, A, Pr, root, pos, ws, lane, depth, term, flags);
+        select_leaf<NW, KC>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags);
         ndepth += depth;
         if (term) {
             backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
@@ -237,11 +250,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
             double v = 0.0;
             uint32_t link;
             if (e.eval_mode == AZ_EVAL_HASH) {
-                const uint64_t h = hash_position<NW>(e.r, pos);
+                const uint64_t h = hash_position<NW>(r, pos);
                 v = hash_value(h);
-                link = expand_leaf<NW>(e, A, Pr, pos, t, ws, lane, flags, e.prior_mode, [h](int a) { return hash_prior(h, a); });
+                link = expand_leaf<NW>(e, r, A, Pr, pos, t, ws, lane, flags, e.prior_mode, [h](int a) { return hash_prior(h, a); });
             } else {
-                link = expand_leaf<NW>(e, A, Pr, pos, t, ws, lane, flags, e.prior_mode, [uniform_prior](int) { return uniform_prior; });
+                link = expand_leaf<NW>(e, r, A, Pr, pos, t, ws, lane, flags, e.prior_mode, [uniform_prior](int) { return uniform_prior; });
             }
             backup_path(A, root, ws, depth, -v, link, lane);
             ++neval;
@@ -263,8 +276,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
 
 // ------------------------------------------------------------------------------------------ k_play
 // rank (edge index) of a legal action among the moves in board order
-template <int NW>
-__device__ __forceinline__ int edge_of_action(const Rules& r, const BB<NW>& legal, int a) {
+template <int NW, class R>
+__device__ __forceinline__ int edge_of_action(const R& r, const BB<NW>& legal, int a) {
     if (r.gravity) return __popcll(legal.w[0] & ((1ull << a) - 1ull));
     int x = a / r.H, y = a - x * r.H, bit = y * r.stride + x;
     if (NW == 2 && bit >= 64) return popc64(legal.w[0]) + __popcll(legal.w[NW - 1] & ((1ull << (bit - 64)) - 1ull));
@@ -324,13 +337,14 @@ __device__ __forceinline__ void finish_game(const Eng& e, const Aux& aux, int t,
     }
 }
 
-template <int NW, int KC>
+template <int NW, int KC, class R>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, int greedy_override, int move_mode) {
     __shared__ WarpScratch s_ws[kWarpsPerBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * kWarpsPerBlock + warp;
     if (t >= e.T) return;
     WarpScratch& ws = s_ws[warp];
+    const auto r = RulesView<R>::get(e);
     int st = e.status[t];
     const int phase = st & AZ_PHASE_MASK;
     if (phase == AZ_PHASE_STALLED) {
@@ -390,16 +404,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
     }
     // record: parent position, visit counts by action, chosen action (self_play.py:63-66)
     Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
-    const BB<NW> legal = legal_set(e.r, pos);
-    for (int a = lane; a < e.r.A; a += 32) {
+    const BB<NW> legal = legal_set(r, pos);
+    for (int a = lane; a < r.A; a += 32) {
         int v = -1;
-        if (action_legal(e.r, pos, legal, a)) v = (int)ws.sel[edge_of_action<NW>(e.r, legal, a)];
-        e.rec_visits[((size_t)t * e.P + rec) * e.r.A + a] = v;
+        if (action_legal(r, pos, legal, a)) v = (int)ws.sel[edge_of_action<NW>(r, legal, a)];
+        e.rec_visits[((size_t)t * e.P + rec) * r.A + a] = v;
     }
     store_pos<NW>(e.rec_board + ((size_t)t * e.P + rec) * 2 * NW, pos, lane);
     int bit, action;
-    edge_move(e.r, pos, legal, pick, bit, action);
-    const int term = place(e.r, pos, bit);  // mcts.py:205
+    edge_move(r, pos, legal, pick, bit, action);
+    const int term = place(r, pos, bit);  // mcts.py:205
     store_pos<NW>(e.root_board + (size_t)t * 2 * NW, pos, lane);
     if (lane == 0) {
         e.rec_action[(size_t)t * e.P + rec] = action | (greedy ? 1 << 16 : 0);
@@ -418,7 +432,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
     // re-root to the chosen child, keeping its subtree (mcts.py:207).  In place while this half still
     // has room for a whole search (sims_target expansions of at most A children each) ...
     const int used = e.n_nodes[t];
-    if ((long long)used + (long long)(e.sims_target + 1) * e.r.A <= (long long)e.C) {
+    if ((long long)used + (long long)(e.sims_target + 1) * r.A <= (long long)e.C) {
         if (lane == 0) {
             e.root_node[t] = base + pick;
             e.pending[t] = 0;
@@ -596,6 +610,7 @@ struct az_engine {
     Eng eng;
     Aux aux;
     int nw, kc;
+    bool c4;  // headline configuration: 6x7, connect 4, gravity -> compile-time rules
 };
 
 static int check_cfg(const az_config* c) {
@@ -739,6 +754,7 @@ AZ_API int az_engine_create(const az_config* c, void* slab, size_t bytes, const 
     e->aux.result = reinterpret_cast<int32_t*>(b + L.result);
     e->nw = L.words;
     e->kc = L.n_actions <= 32 ? 1 : 4;
+    e->c4 = c->width == 7 && c->height == 6 && c->n_connect == 4 && c->gravity != 0;
     cudaError_t err = cudaMemcpyAsync(b + L.pow_lut, host_lut, 8 * (size_t)c->pow_lut_len, cudaMemcpyHostToDevice,
                                       static_cast<cudaStream_t>(stream));
     if (err == cudaSuccess) err = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));  // host_lut may be freed
@@ -782,15 +798,16 @@ AZ_API int az_begin_search(az_engine* e, int32_t sims, void* stream) {
     return AZ_OK;
 }
 
-#define AZ_DISPATCH(kernel, ...)                                                                  \
-    do {                                                                                          \
-        cudaStream_t s__ = static_cast<cudaStream_t>(stream);                                     \
-        dim3 g__ = tree_grid(e), b__(kWarpsPerBlock * 32);                                        \
-        if (e->nw == 1 && e->kc == 1) kernel<1, 1><<<g__, b__, 0, s__>>>(__VA_ARGS__);            \
-        else if (e->nw == 1) kernel<1, 4><<<g__, b__, 0, s__>>>(__VA_ARGS__);                     \
-        else if (e->kc == 1) kernel<2, 1><<<g__, b__, 0, s__>>>(__VA_ARGS__);                     \
-        else kernel<2, 4><<<g__, b__, 0, s__>>>(__VA_ARGS__);                                     \
-        AZ_CUDA(cudaGetLastError());                                                              \
+#define AZ_DISPATCH(kernel, ...)                                                                          \
+    do {                                                                                                  \
+        cudaStream_t s__ = static_cast<cudaStream_t>(stream);                                             \
+        dim3 g__ = tree_grid(e), b__(kWarpsPerBlock * 32);                                                \
+        if (e->c4) kernel<1, 1, C4Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);                              \
+        else if (e->nw == 1 && e->kc == 1) kernel<1, 1, Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);        \
+        else if (e->nw == 1) kernel<1, 4, Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);                      \
+        else if (e->kc == 1) kernel<2, 1, Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);                      \
+        else kernel<2, 4, Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);                                      \
+        AZ_CUDA(cudaGetLastError());                                                                      \
     } while (0)
 
 AZ_API int az_step(az_engine* e, const void* priors, const void* values, int32_t eval_dtype, void* states,

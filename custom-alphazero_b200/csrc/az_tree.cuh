@@ -50,6 +50,8 @@ __device__ __forceinline__ NodeA load_node(const NodeA* p) {
     return r;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void store_node(NodeA* p, const NodeA& r) {
     int4 v;
     v.x = __double2loint(r.w);
@@ -125,8 +127,8 @@ __device__ __forceinline__ void store_pos(uint64_t* p, const Pos<NW>& v, int lan
 // K1 select (mcts.py:111-120).  pos: root position in, leaf position out.
 // Returns the leaf node; depth/ws.path receive the path; term = 0 none, 1 mover won, 2 draw.
 // ------------------------------------------------------------------------------------------
-template <int NW, int KC>
-__device__ __forceinline__ int select_leaf(const Eng& e, const NodeA* A, const double* Pr, int root, Pos<NW>& pos,
+template <int NW, int KC, class R>
+__device__ __forceinline__ int select_leaf(const Eng& e, const R& r, const NodeA* A, const double* Pr, int root, Pos<NW>& pos,
                                            WarpScratch& ws, int lane, int& depth, int& term, uint32_t& flags) {
     int node = root;
     uint32_t link = load_node(A + root).link;
@@ -149,6 +151,21 @@ __device__ __forceinline__ int select_leaf(const Eng& e, const NodeA* A, const d
                 rec[c].w = 0.0;
                 rec[c].link = 0;
                 pr[c] = 0.0;
+            }
+        }
+        // one level ahead: ask L2 for the child blocks of every child while this level is being scored,
+        // so the next level's dependent loads find their lines on chip instead of paying an HBM round trip
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            const uint32_t cl = rec[c].link;
+            if (cl) {
+                const int cb = (int)(cl & 0xffffffu), ck = (int)(cl >> 24);
+                const char* pa = reinterpret_cast<const char*>(A + cb);
+                const char* pp = reinterpret_cast<const char*>(Pr + cb);
+                for (int o = 0; o < ck * 16; o += 32) prefetch_l2(pa + o);
+                prefetch_l2(pa + ck * 16 - 1);
+                for (int o = 0; o < ck * 8; o += 32) prefetch_l2(pp + o);
+                prefetch_l2(pp + ck * 8 - 1);
             }
         }
         const int total = __reduce_add_sync(kFull, ln);  // mcts.py:50: sum over the node's edges
@@ -194,10 +211,10 @@ __device__ __forceinline__ int select_leaf(const Eng& e, const NodeA* A, const d
         if (lane == 0) ws.path[depth] = node;
         ++depth;
         // replay the move of edge bi on the register position (board.py:233-250)
-        BB<NW> legal = legal_set(e.r, pos);
+        BB<NW> legal = legal_set(r, pos);
         int bit, action;
-        edge_move(e.r, pos, legal, bi, bit, action);
-        term = place(e.r, pos, bit);
+        edge_move(r, pos, legal, bi, bit, action);
+        term = place(r, pos, bit);
         if (term) break;
         link = clink;
     }
@@ -269,15 +286,15 @@ __device__ __forceinline__ void normalise_sel(WarpScratch& ws, int k, int prior_
 // order (Q1: the j-th normalised prior goes to the j-th move in board order).  Returns the new
 // link (0 when the pool is exhausted).
 // ------------------------------------------------------------------------------------------
-template <int NW, typename PriorFn>
-__device__ __forceinline__ uint32_t expand_leaf(const Eng& e, NodeA* A, double* Pr, const Pos<NW>& pos, int t,
+template <int NW, class R, typename PriorFn>
+__device__ __forceinline__ uint32_t expand_leaf(const Eng& e, const R& r, NodeA* A, double* Pr, const Pos<NW>& pos, int t,
                                                 WarpScratch& ws, int lane, uint32_t& flags, int prior_mode,
                                                 PriorFn prior_of) {
-    BB<NW> legal = legal_set(e.r, pos);
+    BB<NW> legal = legal_set(r, pos);
     int k = 0;
-    for (int a0 = 0; a0 < e.r.A; a0 += 32) {
+    for (int a0 = 0; a0 < r.A; a0 += 32) {
         int a = a0 + lane;
-        bool ok = action_legal(e.r, pos, legal, a);
+        bool ok = action_legal(r, pos, legal, a);
         unsigned m = __ballot_sync(kFull, ok);
         if (ok) ws.sel[k + __popc(m & ((1u << lane) - 1u))] = prior_of(a);
         k += __popc(m);
@@ -326,8 +343,8 @@ __device__ __forceinline__ void backup_path(NodeA* A, int root, const WarpScratc
 // ------------------------------------------------------------------------------------------
 // in-kernel evaluators (oracle/evaluators.py)
 // ------------------------------------------------------------------------------------------
-template <int NW>
-__device__ __forceinline__ uint64_t hash_position(const Rules& r, const Pos<NW>& p) {
+template <int NW, class R>
+__device__ __forceinline__ uint64_t hash_position(const R& r, const Pos<NW>& p) {
     uint64_t h = 0xCBF29CE484222325ull;
     for (int c = 0; c < r.cells; ++c) h = (h ^ (uint64_t)(cell_code(r, p, c) + 1)) * 0x100000001B3ull;
     return h;
@@ -363,8 +380,8 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, long long game, 
 }
 
 // K3: Board.full_state (board.py:83-98) of `pos` into out[H][W][4]; lanes stride over cells.
-template <int NW>
-__device__ __forceinline__ void encode_state_bf16(const Rules& r, const Pos<NW>& pos, __nv_bfloat16* out, int lane) {
+template <int NW, class R>
+__device__ __forceinline__ void encode_state_bf16(const R& r, const Pos<NW>& pos, __nv_bfloat16* out, int lane) {
     for (int c = lane; c < r.cells; c += 32) {
         int code = cell_code(r, pos, c);
         // bf16 1.0 = 0x3F80; planes: empty, side to move, opponent, turn (+1 under keep_same_player)
@@ -375,8 +392,8 @@ __device__ __forceinline__ void encode_state_bf16(const Rules& r, const Pos<NW>&
     }
 }
 
-template <int NW>
-__device__ __forceinline__ void encode_state_f32(const Rules& r, const Pos<NW>& pos, float* out, int lane) {
+template <int NW, class R>
+__device__ __forceinline__ void encode_state_f32(const R& r, const Pos<NW>& pos, float* out, int lane) {
     for (int c = lane; c < r.cells; c += 32) {
         int code = cell_code(r, pos, c);
         reinterpret_cast<float4*>(out)[c] = make_float4(code == 0, code == 1, code == 2, 1.0f);

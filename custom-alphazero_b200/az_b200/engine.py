@@ -70,8 +70,9 @@ class TreeEngine:
             # Enough for every expansion of a whole game (re-root then never has to compact), unless that
             # does not fit in half of the free HBM: then at least 4 searches' worth and the kept subtree is
             # compacted into the other pool half whenever the live half runs short.
-            worst = P * sims_per_move * A + A + 2
-            floor = (4 * sims_per_move + 8) * A + 1
+            A8 = (A + 7) & ~7  # child blocks are 8-node aligned
+            worst = (P * sims_per_move + 2) * A8 + 16
+            floor = (4 * sims_per_move + 8) * A8 + 16
             free_bytes, _ = torch.cuda.mem_get_info(self.device)
             budget = (free_bytes // 2) // (self.n_trees * 2 * 24)
             node_capacity = min(0xFFFFFF, worst, max(floor, budget))

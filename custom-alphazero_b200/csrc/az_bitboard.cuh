@@ -140,9 +140,11 @@ template <int NW, class R>
 __device__ __forceinline__ void edge_move(const R& r, const Pos<NW>& p, const BB<NW>& legal, int j, int& bit,
                                           int& action) {
     if (r.gravity) {
-        uint32_t m = (uint32_t)legal.w[0];  // j-th set bit of at most 11: peel j lowest bits
-        for (int i = 0; i < j; ++i) m &= m - 1;
-        int x = __ffs((int)m) - 1;
+        // j-th set bit of at most 11: lane x votes when column x is legal and has rank j
+        const uint32_t lm = (uint32_t)legal.w[0];
+        const int ln = (int)(threadIdx.x & 31);
+        const unsigned vote = __ballot_sync(0xffffffffu, ((lm >> ln) & 1u) && __popc(lm & ((1u << ln) - 1u)) == j);
+        int x = __ffs((int)vote) - 1;
         int filled;
         if constexpr (is_fixed_rules<R>::value) {
             filled = popc64((p.cur.w[0] | p.opp.w[0]) & (R::col0() << x));
@@ -190,16 +192,17 @@ __device__ __forceinline__ int place(const R& r, Pos<NW>& p, int bit) {
     if (NW == 1) {
         // one-word boards: starts of n-runs by shift-and (the sentinel column stops wrap-around), kept
         // only where the run passes through the new stone - same answer as the scan of board.py:186-203
-        const uint64_t m = mover.w[0];
+        const uint64_t m = mover.w[0], stone = 1ull << bit;
         const int d4[4] = {s, s + 1, 1, s - 1};
         bool win = false;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int d = d4[k];
-            uint64_t run = m, through = 0;
-            for (int i = 1; i < r.n; ++i) run &= m >> (i * d);
-            for (int i = 0; i < r.n; ++i)
-                if (bit - i * d >= 0) through |= 1ull << (bit - i * d);
+            uint64_t run = m, through = stone;  // through: possible run starts bit, bit-d, ... (negative ones fall off)
+            for (int i = 1; i < r.n; ++i) {
+                run &= m >> (i * d);
+                through |= stone >> (i * d);
+            }
             win = win || (run & through) != 0;
         }
         if (win) return 1;

@@ -125,6 +125,11 @@ __global__ void k_begin_search(Eng e) {
 
 __global__ void k_fin_clear(Eng e) { *e.fin_count = 0; }
 
+// per-tree statistics: a reduction the warp never waits for (no read-modify-write round trip)
+__device__ __forceinline__ void bump(long long* p, long long v) {
+    if (v) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+
 // Rules as seen by a kernel instance: the runtime struct, or the compile-time headline configuration.
 using C4Rules = FixedRules<7, 6, 4, 1>;
 template <class R>
@@ -208,10 +213,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         if (lane == 0) {
             e.sims_done[t] = sims;
             e.pending[t] = pend;
-            e.counters[(size_t)t * 8 + 0] += nsim;
-            e.counters[(size_t)t * 8 + 1] += neval;
-            e.counters[(size_t)t * 8 + 4] += ndepth;
-            e.counters[(size_t)t * 8 + 5] += nchild;
+            bump(e.counters + (size_t)t * 8 + 0, nsim);
+            bump(e.counters + (size_t)t * 8 + 1, neval);
+            bump(e.counters + (size_t)t * 8 + 4, ndepth);
+            bump(e.counters + (size_t)t * 8 + 5, nchild);
             int ph = (sims >= e.sims_target && !pend) ? AZ_PHASE_READY : AZ_PHASE_SEARCH;
             e.status[t] = (st & ~AZ_PHASE_MASK) | ph | (int)flags;
         }
@@ -432,7 +437,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
     // re-root to the chosen child, keeping its subtree (mcts.py:207).  In place while this half still
     // has room for a whole search (sims_target expansions of at most A children each) ...
     const int used = e.n_nodes[t];
-    if ((long long)used + (long long)(e.sims_target + 1) * r.A <= (long long)e.C) {
+    if ((long long)used + (long long)(e.sims_target + 1) * ((r.A + 7) & ~7) + 8 <= (long long)e.C) {
         if (lane == 0) {
             e.root_node[t] = base + pick;
             e.pending[t] = 0;
@@ -442,24 +447,37 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
     }
     // ... otherwise the kept subtree is copied breadth-first into the other half: 32 queue nodes per
     // wave, children re-based with a warp prefix sum, dead siblings left behind.
-    if (lane == 0) {
-        store_node(Ad, load_node(As + base + pick));
-        Pd[0] = Ps[base + pick];
+    {
+        NodeA z;
+        z.w = 0.0;
+        z.n = 0;
+        z.link = 0;
+        if (lane == 0) {
+            store_node(Ad, load_node(As + base + pick));
+            Pd[0] = Ps[base + pick];
+        } else if (lane < 8) {  // the root's block is padded to 8 slots so that every child block stays aligned
+            store_node(Ad + lane, z);
+        }
     }
     __syncwarp();
-    int n_dst = 1, head = 0;
+    int n_dst = 8, head = 0;
     while (head < n_dst) {
         const int cnt = min(32, n_dst - head);
         uint32_t lk = 0;
         if (lane < cnt) lk = load_node(Ad + head + lane).link;
         const int kk = (int)(lk >> 24), ob = (int)(lk & 0xffffffu);
-        int incl = kk;
+        const int kp = (kk + 7) & ~7;  // child blocks are 8-node aligned in the new half too
+        int incl = kp;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int v = __shfl_up_sync(kFull, incl, o);
             if (lane >= o) incl += v;
         }
-        const int excl = incl - kk, total = __shfl_sync(kFull, incl, 31);
+        const int excl = incl - kp, total = __shfl_sync(kFull, incl, 31);
+        if (n_dst + total > e.C) {  // cannot happen when both halves have the same capacity; never write past it
+            if (lane == 0) e.status[t] = st | AZ_FLAG_POOL_OVERFLOW;
+            return;
+        }
         if (kk) {
             NodeA r2 = load_node(Ad + head + lane);
             r2.link = (uint32_t)(n_dst + excl) | ((uint32_t)kk << 24);
@@ -467,6 +485,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
         }
         ws.off[lane] = excl;
         ws.ob[lane] = ob;
+        ws.path[lane] = kk;
         __syncwarp();
         for (int idx = lane; idx < total; idx += 32) {
             int lo = 0, hi = 32;  // last lane whose exclusive offset is <= idx
@@ -474,9 +493,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
                 int mid = (lo + hi) >> 1;
                 if (ws.off[mid] <= idx) lo = mid; else hi = mid;
             }
-            const int src = ws.ob[lo] + (idx - ws.off[lo]);
-            store_node(Ad + n_dst + idx, load_node(As + src));
-            Pd[n_dst + idx] = Ps[src];
+            const int j = idx - ws.off[lo];
+            if (j < ws.path[lo]) {
+                const int src = ws.ob[lo] + j;
+                store_node(Ad + n_dst + idx, load_node(As + src));
+                Pd[n_dst + idx] = Ps[src];
+            } else {  // alignment padding: an edgeless dummy the queue skips over
+                NodeA z;
+                z.w = 0.0;
+                z.n = 0;
+                z.link = 0;
+                store_node(Ad + n_dst + idx, z);
+            }
         }
         n_dst += total;
         head += cnt;

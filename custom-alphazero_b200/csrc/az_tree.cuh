@@ -158,14 +158,12 @@ __device__ __forceinline__ int select_leaf(const Eng& e, const R& r, const NodeA
 #pragma unroll
         for (int c = 0; c < KC; ++c) {
             const uint32_t cl = rec[c].link;
-            if (cl) {
+            if (cl) {  // child blocks start on 8-node boundaries: 128 B of records, 64 B of priors per 8 children
                 const int cb = (int)(cl & 0xffffffu), ck = (int)(cl >> 24);
-                const char* pa = reinterpret_cast<const char*>(A + cb);
-                const char* pp = reinterpret_cast<const char*>(Pr + cb);
-                for (int o = 0; o < ck * 16; o += 32) prefetch_l2(pa + o);
-                prefetch_l2(pa + ck * 16 - 1);
-                for (int o = 0; o < ck * 8; o += 32) prefetch_l2(pp + o);
-                prefetch_l2(pp + ck * 8 - 1);
+                for (int o = 0; o < ck; o += 8) {
+                    prefetch_l2(A + cb + o);
+                    prefetch_l2(Pr + cb + o);
+                }
             }
         }
         const int total = __reduce_add_sync(kFull, ln);  // mcts.py:50: sum over the node's edges
@@ -193,14 +191,20 @@ __device__ __forceinline__ int select_leaf(const Eng& e, const R& r, const NodeA
                 }
             }
         }
+        // first maximum wins (np.argmax, mcts.py:65-67): butterfly max of the score, then the lowest
+        // edge index among the lanes that hold it
+        double mx = best;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {  // first maximum wins (np.argmax, mcts.py:65-67)
-            double ov = __shfl_xor_sync(kFull, best, o);
-            int oi = __shfl_xor_sync(kFull, bi, o);
-            if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > best || (ov == best && oi < bi))) {
-                best = ov;
-                bi = oi;
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            if (KC == 1 && r.A <= 8 && o >= 8) continue;  // at most 8 candidates sit in lanes 0..7
+            const double ov = __shfl_xor_sync(kFull, mx, o);
+            mx = ov > mx ? ov : mx;
+        }
+        if (KC == 1 && r.A <= 8) mx = __shfl_sync(kFull, mx, 0);
+        if (KC == 1) {
+            bi = __ffs((int)__ballot_sync(kFull, bi != 0x7fffffff && best == mx)) - 1;
+        } else {
+            bi = __reduce_min_sync(kFull, (bi != 0x7fffffff && best == mx) ? bi : 0x7fffffff);
         }
         uint32_t clink = 0;
 #pragma unroll
@@ -300,7 +304,7 @@ __device__ __forceinline__ uint32_t expand_leaf(const Eng& e, const R& r, NodeA*
         k += __popc(m);
     }
     normalise_sel(ws, k, prior_mode, lane);
-    const int base = e.n_nodes[t];
+    const int base = (e.n_nodes[t] + 7) & ~7;  // 8-node alignment: a block of <= 8 children is one 128 B line
     if (base + k > e.C || base + k > 0xffffff) {
         flags |= AZ_FLAG_POOL_OVERFLOW;
         return 0;

@@ -135,16 +135,24 @@ __device__ __forceinline__ int bb_count(const BB<NW>& b) {
     return c;
 }
 
-// j-th legal move in board order -> (cell bit, action index)
-template <int NW, class R>
+// j-th legal move in board order -> (cell bit, action index).  kWarpUniform: all 32 lanes of the warp
+// call with the same position and j (tree kernels), which lets a ballot find the j-th legal column;
+// the per-thread environment kernels pass false.
+template <bool kWarpUniform = true, int NW, class R>
 __device__ __forceinline__ void edge_move(const R& r, const Pos<NW>& p, const BB<NW>& legal, int j, int& bit,
                                           int& action) {
     if (r.gravity) {
-        // j-th set bit of at most 11: lane x votes when column x is legal and has rank j
         const uint32_t lm = (uint32_t)legal.w[0];
-        const int ln = (int)(threadIdx.x & 31);
-        const unsigned vote = __ballot_sync(0xffffffffu, ((lm >> ln) & 1u) && __popc(lm & ((1u << ln) - 1u)) == j);
-        int x = __ffs((int)vote) - 1;
+        int x;
+        if (kWarpUniform) {  // lane x votes when column x is legal and has rank j
+            const int ln = (int)(threadIdx.x & 31);
+            const unsigned vote = __ballot_sync(0xffffffffu, ((lm >> ln) & 1u) && __popc(lm & ((1u << ln) - 1u)) == j);
+            x = __ffs((int)vote) - 1;
+        } else {  // j-th set bit of at most 11: peel j lowest bits
+            uint32_t m = lm;
+            for (int i = 0; i < j; ++i) m &= m - 1;
+            x = __ffs((int)m) - 1;
+        }
         int filled;
         if constexpr (is_fixed_rules<R>::value) {
             filled = popc64((p.cur.w[0] | p.opp.w[0]) & (R::col0() << x));

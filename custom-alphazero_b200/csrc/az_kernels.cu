@@ -548,7 +548,7 @@ __global__ void k_env_play(Rules r, const int8_t* cells_in, const int32_t* actio
         return;
     }
     int bit, action;
-    edge_move(r, p, legal, edge_of_action<2>(r, legal, a), bit, action);
+    edge_move<false>(r, p, legal, edge_of_action<2>(r, legal, a), bit, action);
     status[i] = place(r, p, bit);
     for (int j = 0; j < r.cells; ++j) {
         int code = cell_code(r, p, j);

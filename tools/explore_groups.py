@@ -8,7 +8,7 @@ rules = engine.Rules(7, 6, 4, True)
 torch.manual_seed(0)
 fp32 = N.PolicyValueNet()
 torch.backends.cudnn.benchmark = True
-for groups, mf in [(1, 8), (1, 2), (1, 1), (2, 8), (2, 2), (3, 8), (4, 8), (4, 2)]:
+for groups, mf in [(1, 8), (1, 4), (1, 2), (2, 8), (2, 4), (2, 16)]:
     r = selfplay.SelfPlayRunner(rules, n_trees=4096, sims_per_move=800, net=fp32, games_target=1 << 40, unroll=8,
                                 groups=groups, max_free_sims=mf, fin_capacity=16384)
     r.run(800 * 12); torch.cuda.synchronize()   # 12 moves in: trees desynchronised, terminal hits appear

@@ -342,7 +342,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(args.steps, 1),
                     "d2h_bytes_per_step": d2h // max(args.steps, 1),
                     "what": "per step: weights from pinned host memory -> device (+ NCCL broadcast), 800 advances, finished games decoded to (states f32, policies f64, values) and copied to the host"},
-            "gpu_launches": int((runner.launches_per_advance * per_adv + args.steps // 2) * world),
+            "gpu_launches": int((runner.launches_per_advance * per_adv + per_adv // args.unroll + args.steps // 2) * world),
             "roofline": roof, "roofline_tree": roof_tree, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(out))

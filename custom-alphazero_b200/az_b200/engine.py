@@ -59,7 +59,7 @@ class TreeEngine:
     def __init__(self, rules=Rules(), n_trees=1, sims_per_move=250, *, eval_mode="external", prior_mode="f32",
                  move_mode="argmax", node_capacity=None, games_target=None, game_id_base=0, seed=0,
                  auto_restart=False, fin_capacity=None, max_free_sims=8, index_move_greedy=8, c_puct=1.5,
-                 pow_lut_len=None, device=None):
+                 pow_lut_len=None, device=None, inline_play=False):
         if not torch.cuda.is_available():
             raise NativeError("no CUDA device: the self-play engine has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -90,7 +90,7 @@ class TreeEngine:
             prior_mode={"f64": 0, "f32": 1}[prior_mode],
             move_mode={"argmax": 0, "host_uniforms": 1, "philox": 2}[move_mode],
             max_free_sims=int(max_free_sims), fin_capacity=int(fin_capacity), pow_lut_len=int(pow_lut_len),
-            auto_restart=int(auto_restart), c_puct=float(c_puct), seed=int(seed), game_id_base=int(game_id_base),
+            auto_restart=int(auto_restart), inline_play=int(inline_play), c_puct=float(c_puct), seed=int(seed), game_id_base=int(game_id_base),
             games_target=int(games_target),
         )
         self.cfg = cfg
@@ -104,6 +104,9 @@ class TreeEngine:
                                          lut.ctypes.data_as(ctypes.c_void_p), _stream(), ctypes.byref(handle)))
         self._h = handle
         self.sims_per_move = int(sims_per_move)
+        A8 = (A + 7) & ~7
+        # with room for every expansion of a whole game the re-root never needs the compaction path
+        self.never_compacts = cfg.node_capacity >= (P * sims_per_move + 2) * A8 + 16
         T, F, WD, C = self.n_trees, cfg.fin_capacity, self.layout.words, cfg.node_capacity
         self._shapes = {
             "root_board": (T, 2, WD), "path": (T, native.AZ_MAX_DEPTH), "leaf_board": (T, 2, WD), "counters": (T, 8),

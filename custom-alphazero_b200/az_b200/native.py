@@ -41,6 +41,7 @@ class AzConfig(ctypes.Structure):
         ("fin_capacity", ctypes.c_int32),
         ("pow_lut_len", ctypes.c_int32),
         ("auto_restart", ctypes.c_int32),
+        ("inline_play", ctypes.c_int32),
         ("c_puct", ctypes.c_double),
         ("seed", ctypes.c_uint64),
         ("game_id_base", ctypes.c_int64),

@@ -142,6 +142,10 @@ class InferenceNet(nn.Module):
         self.head_b32 = f32(torch.cat([pb, vb], 0))
         self.pfc_w, self.pfc_b = f32(net.policy_fc.weight), f32(net.policy_fc.bias)
         self.v1_w, self.v1_b = f32(net.value_fc1.weight), f32(net.value_fc1.bias)
+        # az_net_heads wants the dense rows padded to an odd stride (bank-conflict-free shared memory image)
+        cells = net.height * net.width
+        self.pfc_w_pad = f32(F.pad(net.policy_fc.weight.detach(), (0, 1)))
+        self.v1_w_pad = f32(F.pad(net.value_fc1.weight.detach(), (0, (cells | 1) - cells)))
         self.v2_w, self.v2_b = f32(net.value_fc2.weight), f32(net.value_fc2.bias)
         self.filters = net.filters
         dev = torch.device(device)
@@ -162,8 +166,8 @@ class InferenceNet(nn.Module):
 
         if self._head_struct is None:
             self._head_struct = native.AzHeadWeights(
-                conv_w=self.head_w32.data_ptr(), conv_b=self.head_b32.data_ptr(), policy_w=self.pfc_w.data_ptr(),
-                policy_b=self.pfc_b.data_ptr(), value1_w=self.v1_w.data_ptr(), value1_b=self.v1_b.data_ptr(),
+                conv_w=self.head_w32.data_ptr(), conv_b=self.head_b32.data_ptr(), policy_w=self.pfc_w_pad.data_ptr(),
+                policy_b=self.pfc_b.data_ptr(), value1_w=self.v1_w_pad.data_ptr(), value1_b=self.v1_b.data_ptr(),
                 value2_w=self.v2_w.data_ptr(), value2_b=self.v2_b.data_ptr())
         return self._head_struct
 

@@ -89,7 +89,7 @@ class SelfPlayRunner:
                              games_target=gi, game_id_base=game_id_base + g0, seed=seed, auto_restart=auto_restart,
                              max_free_sims=max_free_sims, node_capacity=node_capacity,
                              fin_capacity=None if fin_capacity is None else max(1, -(-fin_capacity // groups)),
-                             device=self.device, index_move_greedy=index_move_greedy)
+                             device=self.device, index_move_greedy=index_move_greedy, inline_play=True)
             self.groups.append(_Group(eng, rules, dtype, self.device))
             t0 += ti
             g0 += gi
@@ -99,8 +99,8 @@ class SelfPlayRunner:
         self.graph = None
         self.advances = 0
         self.flops_per_eval = flops_per_eval(rules.height, rules.width, A)
-        # kernels of libaz_b200 launched per advance and group: az_step, az_net_stem, az_net_heads, az_play
-        self.launches_per_advance = 4 * groups
+        # kernels of libaz_b200 launched per advance and group: az_step, az_net_stem, az_net_heads (+ az_play sweeps)
+        self.launches_per_advance = 3 * groups
         self._side = [torch.cuda.Stream(device=self.device) for _ in range(groups - 1)]
 
     # single-group conveniences (tests, compat code)
@@ -125,10 +125,14 @@ class SelfPlayRunner:
         return self.groups[0].values
 
     # one lock-step iteration of one group; everything is enqueued on the current stream
-    def _advance(self, g):
+    def _advance(self, g, sweep=True):
+        """az_step plays moves itself (inline_play) whenever the re-root fits in place; az_play is only needed
+        for the compaction path and for games stalled on a full ring: every advance if the pool can run
+        short, else once per captured graph as a safety net (`sweep`)."""
         g.engine.step(g.priors, g.values, g.states, g.valid)
         self.net(g.states, g.priors, g.values)
-        g.engine.play()
+        if sweep or not g.engine.never_compacts:
+            g.engine.play()
 
     def _advance_all(self, n):
         """n advances of every group: group 0 on the current stream, the others on forked side streams."""
@@ -137,10 +141,10 @@ class SelfPlayRunner:
             s.wait_stream(cur)
         for g, s in zip(self.groups[1:], self._side):
             with torch.cuda.stream(s):
-                for _ in range(n):
-                    self._advance(g)
-        for _ in range(n):
-            self._advance(self.groups[0])
+                for i in range(n):
+                    self._advance(g, sweep=i == n - 1)
+        for i in range(n):
+            self._advance(self.groups[0], sweep=i == n - 1)
         for s in self._side:
             cur.wait_stream(s)
 

@@ -141,144 +141,6 @@ struct RulesView<FixedRules<W_, H_, N_, G_>> {
     __device__ static __forceinline__ FixedRules<W_, H_, N_, G_> get(const Eng&) { return {}; }
 };
 
-// ------------------------------------------------------------------------------------------ k_step
-template <int NW, int KC, class R>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-    k_step(Eng e, const void* __restrict__ priors, const void* __restrict__ values, int eval_dtype, void* states,
-           int state_dtype, int32_t* leaf_valid) {
-    __shared__ WarpScratch s_ws[kWarpsPerBlock];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * kWarpsPerBlock + warp;
-    if (t >= e.T) return;
-    WarpScratch& ws = s_ws[warp];
-    const auto r = RulesView<R>::get(e);
-    const int st = e.status[t];
-    uint32_t flags = 0;
-    int valid = 0;
-    if ((st & AZ_PHASE_MASK) == AZ_PHASE_SEARCH) {
-        const size_t pool = ((size_t)t * 2 + e.half[t]) * e.C;
-        NodeA* A = e.node_a + pool;
-        double* Pr = e.node_p + pool;
-        int sims = e.sims_done[t];
-        const int root = e.root_node[t];
-        long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
-        if (e.pending[t] && priors != nullptr) {
-            const int depth = e.path_len[t];
-            for (int i = lane; i < depth; i += 32) ws.path[i] = e.path[(size_t)t * kMaxDepth + i];
-            const Pos<NW> leaf = load_pos<NW>(e.leaf_board + (size_t)t * 2 * NW);
-            __syncwarp();
-            double v;
-            uint32_t link;
-            // the dtype of the evaluator output decides the arithmetic of normalize_probabilities, as in
-            // the reference: float64 from infer_sample (factory.py:55), float32 from the model (mcts.py:131-137)
-            if (eval_dtype == AZ_F64) {
-                const double* p = static_cast<const double*>(priors) + (size_t)t * r.A;
-                v = static_cast<const double*>(values)[t];
-                link = expand_leaf<NW>(e, r, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F64, [p](int a) { return p[a]; });
-            } else {
-                const float* p = static_cast<const float*>(priors) + (size_t)t * r.A;
-                v = (double)static_cast<const float*>(values)[t];  // value.numpy().item() (mcts.py:136)
-                link = expand_leaf<NW>(e, r, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F32, [p](int a) { return (double)p[a]; });
-            }
-            backup_path(A, root, ws, depth, -v, link, lane);  // mcts.py:175: value seen by the player who moved in
-            ++sims;
-            ++nsim;
-            ++neval;
-            nchild += link >> 24;
-        }
-        int pend = (e.pending[t] && priors == nullptr) ? 1 : 0;
-        int freed = 0;
-        while (!pend && sims < e.sims_target) {
-            Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
-            int depth, term;
-            select_leaf<NW, KC>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags);
-            ndepth += depth;
-            if (term) {  // mcts.py:179: terminal leaf, result 1 (win of the mover) or 0 (draw)
-                backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
-                ++sims;
-                ++nsim;
-                if (++freed >= e.max_free) break;
-                continue;
-            }
-            for (int i = lane; i < depth; i += 32) e.path[(size_t)t * kMaxDepth + i] = ws.path[i];
-            store_pos<NW>(e.leaf_board + (size_t)t * 2 * NW, pos, lane);
-            if (lane == 0) e.path_len[t] = depth;
-            if (state_dtype == AZ_BF16)
-                encode_state_bf16<NW>(r, pos, static_cast<__nv_bfloat16*>(states) + (size_t)t * r.cells * 4, lane);
-            else
-                encode_state_f32<NW>(r, pos, static_cast<float*>(states) + (size_t)t * r.cells * 4, lane);
-            pend = 1;
-        }
-        valid = pend;
-        if (lane == 0) {
-            e.sims_done[t] = sims;
-            e.pending[t] = pend;
-            bump(e.counters + (size_t)t * 8 + 0, nsim);
-            bump(e.counters + (size_t)t * 8 + 1, neval);
-            bump(e.counters + (size_t)t * 8 + 4, ndepth);
-            bump(e.counters + (size_t)t * 8 + 5, nchild);
-            int ph = (sims >= e.sims_target && !pend) ? AZ_PHASE_READY : AZ_PHASE_SEARCH;
-            e.status[t] = (st & ~AZ_PHASE_MASK) | ph | (int)flags;
-        }
-    }
-    if (lane == 0) leaf_valid[t] = valid;
-}
-
-// ------------------------------------------------------------------------------------------ k_search
-template <int NW, int KC, class R>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
-    __shared__ WarpScratch s_ws[kWarpsPerBlock];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * kWarpsPerBlock + warp;
-    if (t >= e.T) return;
-    WarpScratch& ws = s_ws[warp];
-    const auto r = RulesView<R>::get(e);
-    const int st = e.status[t];
-    if ((st & AZ_PHASE_MASK) != AZ_PHASE_SEARCH) return;
-    uint32_t flags = 0;
-    const size_t pool = ((size_t)t * 2 + e.half[t]) * e.C;
-    NodeA* A = e.node_a + pool;
-    double* Pr = e.node_p + pool;
-    const Pos<NW> root_pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
-    const int root = e.root_node[t];
-    const double uniform_prior = __ddiv_rn(1.0, (double)r.A);  // np.full(A, 1 / A)
-    int sims = e.sims_done[t];
-    long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
-    while (sims < e.sims_target && !(flags & AZ_FLAG_POOL_OVERFLOW)) {
-        Pos<NW> pos = root_pos;
-        int depth, term;
-        select_leaf<NW, KC>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags);
-        ndepth += depth;
-        if (term) {
-            backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
-        } else {
-            double v = 0.0;
-            uint32_t link;
-            if (e.eval_mode == AZ_EVAL_HASH) {
-                const uint64_t h = hash_position<NW>(r, pos);
-                v = hash_value(h);
-                link = expand_leaf<NW>(e, r, A, Pr, pos, t, ws, lane, flags, e.prior_mode, [h](int a) { return hash_prior(h, a); });
-            } else {
-                link = expand_leaf<NW>(e, r, A, Pr, pos, t, ws, lane, flags, e.prior_mode, [uniform_prior](int) { return uniform_prior; });
-            }
-            backup_path(A, root, ws, depth, -v, link, lane);
-            ++neval;
-            nchild += link >> 24;
-        }
-        ++sims;
-        ++nsim;
-    }
-    if (lane == 0) {
-        e.sims_done[t] = sims;
-        e.counters[(size_t)t * 8 + 0] += nsim;
-        e.counters[(size_t)t * 8 + 1] += neval;
-        e.counters[(size_t)t * 8 + 4] += ndepth;
-        e.counters[(size_t)t * 8 + 5] += nchild;
-        int ph = sims >= e.sims_target ? AZ_PHASE_READY : AZ_PHASE_SEARCH;
-        e.status[t] = (st & ~AZ_PHASE_MASK) | ph | (int)flags;
-    }
-}
-
 // ------------------------------------------------------------------------------------------ k_play
 // rank (edge index) of a legal action among the moves in board order
 template <int NW, class R>
@@ -342,21 +204,12 @@ __device__ __forceinline__ void finish_game(const Eng& e, const Aux& aux, int t,
     }
 }
 
+// K6 for one tree in AZ_PHASE_READY (MCTS.play, mcts.py:182-222): root policy from the visit counts, edge
+// choice, game record, move on the live board, re-root.  Called by az_play for every READY tree and, with
+// inline_play, by az_step itself the moment a tree's budget is spent (then only when the re-root fits in place).
 template <int NW, int KC, class R>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, int greedy_override, int move_mode) {
-    __shared__ WarpScratch s_ws[kWarpsPerBlock];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * kWarpsPerBlock + warp;
-    if (t >= e.T) return;
-    WarpScratch& ws = s_ws[warp];
-    const auto r = RulesView<R>::get(e);
-    int st = e.status[t];
-    const int phase = st & AZ_PHASE_MASK;
-    if (phase == AZ_PHASE_STALLED) {
-        finish_game<NW>(e, aux, t, st, lane);
-        return;
-    }
-    if (phase != AZ_PHASE_READY) return;
+__device__ __forceinline__ bool play_tree(const Eng& e, const Aux& aux, const R& r, int t, int st, WarpScratch& ws,
+                                          int lane, int greedy_override, int move_mode, bool allow_compact) {
     const int h = e.half[t];
     const size_t pool = ((size_t)t * 2 + h) * e.C, pool2 = ((size_t)t * 2 + (h ^ 1)) * e.C;
     NodeA* As = e.node_a + pool;
@@ -367,9 +220,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
     const uint32_t rlink = load_node(As + root).link;
     const int base = (int)(rlink & 0xffffffu), k = (int)(rlink >> 24);
     const int ply = e.ply[t], rec = aux.rec_len[t];
+    const int used = e.n_nodes[t];
+    const bool fits = (long long)used + (long long)(e.sims_target + 1) * ((r.A + 7) & ~7) + 8 <= (long long)e.C;
+    if (!fits && !allow_compact) return false;  // leave the tree READY for az_play
     if (k == 0 || rec >= e.P) {  // the reference would raise on an edgeless root (np.argmax of [])
         if (lane == 0) e.status[t] = st | AZ_FLAG_ILLEGAL;
-        return;
+        return true;
     }
     // root visit counts (mcts.py:189-197)
     for (int j = lane; j < k; j += 32) ws.sel[j] = (double)load_node(As + base + j).n;
@@ -432,18 +288,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
         if (lane == 0) aux.result[t] = term == 1 ? 1 : 0;  // board.py:258-268 with keep_same_player
         __syncwarp();
         finish_game<NW>(e, aux, t, st, lane);
-        return;
+        return true;
     }
     // re-root to the chosen child, keeping its subtree (mcts.py:207).  In place while this half still
     // has room for a whole search (sims_target expansions of at most A children each) ...
-    const int used = e.n_nodes[t];
-    if ((long long)used + (long long)(e.sims_target + 1) * ((r.A + 7) & ~7) + 8 <= (long long)e.C) {
+    if (fits) {
         if (lane == 0) {
             e.root_node[t] = base + pick;
             e.pending[t] = 0;
             e.status[t] = (st & ~AZ_PHASE_MASK) | AZ_PHASE_SEARCH;
         }
-        return;
+        return true;
     }
     // ... otherwise the kept subtree is copied breadth-first into the other half: 32 queue nodes per
     // wave, children re-based with a warp prefix sum, dead siblings left behind.
@@ -476,7 +331,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
         const int excl = incl - kp, total = __shfl_sync(kFull, incl, 31);
         if (n_dst + total > e.C) {  // cannot happen when both halves have the same capacity; never write past it
             if (lane == 0) e.status[t] = st | AZ_FLAG_POOL_OVERFLOW;
-            return;
+            return true;
         }
         if (kk) {
             NodeA r2 = load_node(Ad + head + lane);
@@ -517,6 +372,188 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
         e.n_nodes[t] = n_dst;
         e.pending[t] = 0;
         e.status[t] = (st & ~AZ_PHASE_MASK) | AZ_PHASE_SEARCH;
+    }
+    return true;
+}
+
+template <int NW, int KC, class R>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, int greedy_override, int move_mode) {
+    __shared__ WarpScratch s_ws[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= e.T) return;
+    const auto r = RulesView<R>::get(e);
+    const int st = e.status[t];
+    const int phase = st & AZ_PHASE_MASK;
+    if (phase == AZ_PHASE_STALLED) {
+        finish_game<NW>(e, aux, t, st, lane);
+        return;
+    }
+    if (phase != AZ_PHASE_READY) return;
+    play_tree<NW, KC>(e, aux, r, t, st, s_ws[warp], lane, greedy_override, move_mode, true);
+}
+
+// ------------------------------------------------------------------------------------------ k_step
+template <int NW, int KC, class R>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    k_step(Eng e, Aux aux, const void* __restrict__ priors, const void* __restrict__ values, int eval_dtype, void* states,
+           int state_dtype, int32_t* leaf_valid) {
+    __shared__ WarpScratch s_ws[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= e.T) return;
+    WarpScratch& ws = s_ws[warp];
+    const auto r = RulesView<R>::get(e);
+    int st = e.status[t];
+    uint32_t flags = 0;
+    int valid = 0;
+    if ((st & AZ_PHASE_MASK) == AZ_PHASE_SEARCH) {
+        const size_t pool = ((size_t)t * 2 + e.half[t]) * e.C;
+        NodeA* A = e.node_a + pool;
+        double* Pr = e.node_p + pool;
+        int sims = e.sims_done[t];
+        int root = e.root_node[t];
+        long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
+        if (e.pending[t] && priors != nullptr) {
+            const int depth = e.path_len[t];
+            for (int i = lane; i < depth; i += 32) ws.path[i] = e.path[(size_t)t * kMaxDepth + i];
+            const Pos<NW> leaf = load_pos<NW>(e.leaf_board + (size_t)t * 2 * NW);
+            __syncwarp();
+            double v;
+            uint32_t link;
+            // the dtype of the evaluator output decides the arithmetic of normalize_probabilities, as in
+            // the reference: float64 from infer_sample (factory.py:55), float32 from the model (mcts.py:131-137)
+            if (eval_dtype == AZ_F64) {
+                const double* p = static_cast<const double*>(priors) + (size_t)t * r.A;
+                v = static_cast<const double*>(values)[t];
+                link = expand_leaf<NW>(e, r, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F64, [p](int a) { return p[a]; });
+            } else {
+                const float* p = static_cast<const float*>(priors) + (size_t)t * r.A;
+                v = (double)static_cast<const float*>(values)[t];  // value.numpy().item() (mcts.py:136)
+                link = expand_leaf<NW>(e, r, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F32, [p](int a) { return (double)p[a]; });
+            }
+            backup_path(A, root, ws, depth, -v, link, lane);  // mcts.py:175: value seen by the player who moved in
+            ++sims;
+            ++nsim;
+            ++neval;
+            nchild += link >> 24;
+        }
+        int pend = (e.pending[t] && priors == nullptr) ? 1 : 0;
+        int freed = 0;
+        for (;;) {
+            if (!pend && sims >= e.sims_target && e.inline_play) {
+                // budget spent: play the move right here (K6) and carry on with the first simulation of the
+                // next search, unless the re-root needs the compaction path (left to az_play)
+                if (lane == 0) {
+                    e.sims_done[t] = sims;
+                    e.pending[t] = 0;
+                }
+                __syncwarp();
+                if (!play_tree<NW, KC>(e, aux, r, t, (st & ~AZ_PHASE_MASK) | AZ_PHASE_READY | (int)flags, ws, lane, -1,
+                                       e.move_mode, false))
+                    break;
+                __syncwarp();
+                st = e.status[t];
+                if ((st & AZ_PHASE_MASK) != AZ_PHASE_SEARCH) {  // game over and no further game for this tree
+                    sims = -1;
+                    break;
+                }
+                root = e.root_node[t];
+                sims = 0;
+                if (++freed >= e.max_free) break;
+            }
+            if (pend || sims >= e.sims_target) break;
+            Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
+            int depth, term;
+            select_leaf<NW, KC>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags);
+            ndepth += depth;
+            if (term) {  // mcts.py:179: terminal leaf, result 1 (win of the mover) or 0 (draw)
+                backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
+                ++sims;
+                ++nsim;
+                if (++freed >= e.max_free) break;
+                continue;
+            }
+            for (int i = lane; i < depth; i += 32) e.path[(size_t)t * kMaxDepth + i] = ws.path[i];
+            store_pos<NW>(e.leaf_board + (size_t)t * 2 * NW, pos, lane);
+            if (lane == 0) e.path_len[t] = depth;
+            if (state_dtype == AZ_BF16)
+                encode_state_bf16<NW>(r, pos, static_cast<__nv_bfloat16*>(states) + (size_t)t * r.cells * 4, lane);
+            else
+                encode_state_f32<NW>(r, pos, static_cast<float*>(states) + (size_t)t * r.cells * 4, lane);
+            pend = 1;
+        }
+        valid = pend;
+        if (lane == 0) {
+            bump(e.counters + (size_t)t * 8 + 0, nsim);
+            bump(e.counters + (size_t)t * 8 + 1, neval);
+            bump(e.counters + (size_t)t * 8 + 4, ndepth);
+            bump(e.counters + (size_t)t * 8 + 5, nchild);
+            if (sims >= 0) {
+                e.sims_done[t] = sims;
+                e.pending[t] = pend;
+                int ph = (sims >= e.sims_target && !pend) ? AZ_PHASE_READY : AZ_PHASE_SEARCH;
+                e.status[t] = (st & ~AZ_PHASE_MASK) | ph | (int)flags;
+            } else if (flags) {
+                e.status[t] = st | (int)flags;
+            }
+        }
+    }
+    if (lane == 0) leaf_valid[t] = valid;
+}
+
+// ------------------------------------------------------------------------------------------ k_search
+template <int NW, int KC, class R>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
+    __shared__ WarpScratch s_ws[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= e.T) return;
+    WarpScratch& ws = s_ws[warp];
+    const auto r = RulesView<R>::get(e);
+    const int st = e.status[t];
+    if ((st & AZ_PHASE_MASK) != AZ_PHASE_SEARCH) return;
+    uint32_t flags = 0;
+    const size_t pool = ((size_t)t * 2 + e.half[t]) * e.C;
+    NodeA* A = e.node_a + pool;
+    double* Pr = e.node_p + pool;
+    const Pos<NW> root_pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
+    const int root = e.root_node[t];
+    const double uniform_prior = __ddiv_rn(1.0, (double)r.A);  // np.full(A, 1 / A)
+    int sims = e.sims_done[t];
+    long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
+    while (sims < e.sims_target && !(flags & AZ_FLAG_POOL_OVERFLOW)) {
+        Pos<NW> pos = root_pos;
+        int depth, term;
+        select_leaf<NW, KC>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags);
+        ndepth += depth;
+        if (term) {
+            backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
+        } else {
+            double v = 0.0;
+            uint32_t link;
+            if (e.eval_mode == AZ_EVAL_HASH) {
+                const uint64_t h = hash_position<NW>(r, pos);
+                v = hash_value(h);
+                link = expand_leaf<NW>(e, r, A, Pr, pos, t, ws, lane, flags, e.prior_mode, [h](int a) { return hash_prior(h, a); });
+            } else {
+                link = expand_leaf<NW>(e, r, A, Pr, pos, t, ws, lane, flags, e.prior_mode, [uniform_prior](int) { return uniform_prior; });
+            }
+            backup_path(A, root, ws, depth, -v, link, lane);
+            ++neval;
+            nchild += link >> 24;
+        }
+        ++sims;
+        ++nsim;
+    }
+    if (lane == 0) {
+        e.sims_done[t] = sims;
+        e.counters[(size_t)t * 8 + 0] += nsim;
+        e.counters[(size_t)t * 8 + 1] += neval;
+        e.counters[(size_t)t * 8 + 4] += ndepth;
+        e.counters[(size_t)t * 8 + 5] += nchild;
+        int ph = sims >= e.sims_target ? AZ_PHASE_READY : AZ_PHASE_SEARCH;
+        e.status[t] = (st & ~AZ_PHASE_MASK) | ph | (int)flags;
     }
 }
 
@@ -746,6 +783,7 @@ AZ_API int az_engine_create(const az_config* c, void* slab, size_t bytes, const 
     g.max_free = c->max_free_sims;
     g.lut_len = c->pow_lut_len;
     g.auto_restart = c->auto_restart;
+    g.inline_play = c->inline_play;
     g.c_puct = c->c_puct;
     g.seed = c->seed;
     g.game_base = c->game_id_base;
@@ -844,7 +882,7 @@ AZ_API int az_step(az_engine* e, const void* priors, const void* values, int32_t
     if ((priors == nullptr) != (values == nullptr)) return fail(AZ_ERR_ARG, "az_step: priors and values go together%s");
     if ((eval_dtype != AZ_F32 && eval_dtype != AZ_F64) || (state_dtype != AZ_BF16 && state_dtype != AZ_F32))
         return fail(AZ_ERR_ARG, "az_step: unsupported dtype%s");
-    AZ_DISPATCH(k_step, e->eng, priors, values, eval_dtype, states, state_dtype, leaf_valid);
+    AZ_DISPATCH(k_step, e->eng, e->aux, priors, values, eval_dtype, states, state_dtype, leaf_valid);
     return AZ_OK;
 }
 

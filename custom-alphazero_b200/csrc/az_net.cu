@@ -148,10 +148,18 @@ __global__ void __launch_bounds__(kHeadWarps * 32) k_heads(const __nv_bfloat16* 
     const int cells = hp.cells, A = hp.A;
     const int ps = 2 * cells + 1, vs = cells | 1;  // odd row strides: conflict-free across lanes
     float* s_pw = s_f;
-    float* s_vw = s_pw + A * ps;
+    float* s_vw = s_pw + ((A * ps + 3) & ~3);
     float* s_h = s_vw + kHidden * vs;
-    for (int i = threadIdx.x; i < A * 2 * cells; i += blockDim.x) s_pw[(i / (2 * cells)) * ps + i % (2 * cells)] = hp.policy_w[i];
-    for (int i = threadIdx.x; i < kHidden * cells; i += blockDim.x) s_vw[(i / cells) * vs + i % cells] = hp.value1_w[i];
+    // the dense weights arrive already in the padded (odd row stride) layout: two straight 128-bit copies
+    {
+        const int np4 = (A * ps) >> 2, nv4 = (kHidden * vs) >> 2;
+        const float4* gp = reinterpret_cast<const float4*>(hp.policy_w);
+        const float4* gv = reinterpret_cast<const float4*>(hp.value1_w);
+        for (int i = threadIdx.x; i < np4; i += blockDim.x) reinterpret_cast<float4*>(s_pw)[i] = gp[i];
+        for (int i = (np4 << 2) + threadIdx.x; i < A * ps; i += blockDim.x) s_pw[i] = hp.policy_w[i];
+        for (int i = threadIdx.x; i < nv4; i += blockDim.x) reinterpret_cast<float4*>(s_vw)[i] = gv[i];
+        for (int i = (nv4 << 2) + threadIdx.x; i < kHidden * vs; i += blockDim.x) s_vw[i] = hp.value1_w[i];
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
     float* h = s_h + warp * 3 * cells;  // [cells][2] policy planes (Keras Flatten of [H][W][2]) then [cells] value plane
     // B fragments of the 1x1 convolutions: column n = g (only n < 3 is non-zero)
@@ -268,7 +276,7 @@ AZ_API int az_net_heads(const void* x, const az_head_weights* hw, int32_t n, int
     if (n == 0) return AZ_OK;
     HeadParams hp{hw->conv_w, hw->conv_b, hw->policy_w, hw->policy_b, hw->value1_w, hw->value1_b, hw->value2_w, hw->value2_b,
                   n, cells, A};
-    const size_t smem = sizeof(float) * ((size_t)A * (2 * cells + 1) + (size_t)kHidden * (cells | 1) +
+    const size_t smem = sizeof(float) * ((((size_t)A * (2 * cells + 1) + 3) & ~(size_t)3) + (size_t)kHidden * (cells | 1) +
                                          (size_t)kHeadWarps * 3 * cells);
     static size_t configured = 0;
     if (smem > configured) {

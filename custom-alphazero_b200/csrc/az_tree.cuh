@@ -65,7 +65,7 @@ __device__ __forceinline__ void store_node(NodeA* p, const NodeA& r) {
 struct Eng {
     Rules r;
     int T, C, P, F;  // trees, node capacity per half, max plies, finished-ring entries
-    int sims_target, greedy_idx, eval_mode, prior_mode, move_mode, max_free, lut_len, auto_restart;
+    int sims_target, greedy_idx, eval_mode, prior_mode, move_mode, max_free, lut_len, auto_restart, inline_play;
     double c_puct;
     uint64_t seed;
     long long game_base, games_target;

@@ -90,6 +90,9 @@ typedef struct az_config {
     int32_t fin_capacity;      /* finished-game ring entries */
     int32_t pow_lut_len;       /* entries of the host-built table n -> n ** 0.5 (Q3: libm pow, not sqrt) */
     int32_t auto_restart;      /* 1: a finished game is replaced by the next game id while any remain */
+    int32_t inline_play;       /* 1: az_step itself plays the move (the az_play step with the self-play rules) the
+                                  moment a tree's budget is spent, whenever the re-root fits in place; az_play
+                                  then only serves trees that need the compaction path */
     double c_puct;             /* ConfigMCTS.exploration_constant */
     uint64_t seed;             /* Philox key for AZ_MOVE_PHILOX */
     int64_t game_id_base;      /* first global game id of this rank */
@@ -228,9 +231,10 @@ int az_decode_samples(const az_config *cfg, const uint64_t *dev_boards, const in
 typedef struct az_head_weights {
     const float *conv_w;   /* dev [3][C]: rows 0-1 policy 1x1 conv, row 2 value 1x1 conv */
     const float *conv_b;   /* dev [3] */
-    const float *policy_w; /* dev [A][2*H*W]   Dense(A) on the NHWC-flattened policy planes */
+    const float *policy_w; /* dev [A][2*H*W + 1]: Dense(A) on the NHWC-flattened policy planes, rows padded to an odd
+                              stride (the kernel copies it verbatim into conflict-free shared memory); 16 B aligned */
     const float *policy_b; /* dev [A] */
-    const float *value1_w; /* dev [256][H*W] */
+    const float *value1_w; /* dev [256][(H*W) | 1]: rows padded to an odd stride; 16 B aligned */
     const float *value1_b; /* dev [256] */
     const float *value2_w; /* dev [256] */
     const float *value2_b; /* dev [1] */

@@ -59,7 +59,9 @@ def test_heads_kernel_matches_fp32(H, W, A):
     h = torch.relu(xf @ cw.to(torch.bfloat16).float().T + cb)  # [n, cells, 3]; conv weights are bf16 operands
     want_p = torch.softmax(h[..., :2].reshape(n, -1) @ pw.T + pb, -1)
     want_v = torch.tanh(torch.relu(h[..., 2] @ v1w.T + v1b) @ v2w + v2b)
-    dev = [t.cuda().contiguous() for t in (cw, cb, pw, pb, v1w, v1b, v2w, v2b)]
+    pw_pad = torch.nn.functional.pad(pw, (0, 1))  # rows padded to the odd stride az_net_heads expects
+    v1w_pad = torch.nn.functional.pad(v1w, (0, (cells | 1) - cells))
+    dev = [t.cuda().contiguous() for t in (cw, cb, pw_pad, pb, v1w_pad, v1b, v2w, v2b)]
     hw = native.AzHeadWeights(*[t.data_ptr() for t in dev])
     priors = torch.empty((n, A), device="cuda")
     values = torch.empty(n, device="cuda")

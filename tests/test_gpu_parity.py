@@ -264,3 +264,65 @@ def test_full_size_batch_reproduces_golden_in_every_tree():
     _check_against_golden(case, fin, T - 1)
     tot = eng.totals()
     assert tot["sims"] == T * 800 * case["n_plies"] and tot["games"] == T and tot["moves"] == T * case["n_plies"]
+
+
+def _philox_uniform(seed, game, ply):
+    """Philox4x32-10 exactly as csrc/az_tree.cuh:philox_uniform (counter = game id lo/hi, ply, 0)."""
+    M0, M1, W0, W1, mask = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    c = [game & mask, (game >> 32) & mask, ply & mask, 0]
+    k0, k1 = seed & mask, (seed >> 32) & mask
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & mask, p1 & mask, ((p0 >> 32) ^ c[3] ^ k1) & mask, p0 & mask]
+        k0, k1 = (k0 + W0) & mask, (k1 + W1) & mask
+    return ((c[0] >> 5) * 67108864.0 + (c[1] >> 6)) / 9007199254740992.0
+
+
+@pytest.mark.parametrize("inline_play", [False, True])
+def test_async_refill_philox_games_match_c_oracle(inline_play):
+    """The production configuration of the tree engine: more games than trees (refill), device Philox
+    move sampling, moves played inside az_step (inline_play) or by az_play, external evaluator through
+    az_step (hash evaluator computed on the host in float64).  Every finished game, whichever tree slot
+    played it, must equal the C oracle's game for the same uniforms."""
+    from oracle import c_oracle, evaluators
+
+    engine, _ = _engine_mod()
+    rules = engine.Rules(7, 6, 4, True)
+    T, G, sims, seed, base = 6, 14, 48, 99, 1000
+    eng = engine.TreeEngine(rules, n_trees=T, sims_per_move=sims, eval_mode="external", move_mode="philox", seed=seed,
+                            games_target=G, game_id_base=base, auto_restart=True, fin_capacity=G, max_free_sims=3,
+                            inline_play=inline_play)
+    A = rules.n_actions
+    states = torch.zeros((T, 6, 7, 4), dtype=torch.float32, device="cuda")
+    valid = torch.zeros(T, dtype=torch.int32, device="cuda")
+    priors = torch.zeros((T, A), dtype=torch.float64, device="cuda")
+    values = torch.zeros(T, dtype=torch.float64, device="cuda")
+    f = evaluators.hash_evaluator(A)
+    for it in range(400000):
+        eng.step(priors, values, states, valid)
+        v = valid.cpu().numpy()
+        st = states.cpu().numpy()
+        p = np.zeros((T, A))
+        val = np.zeros(T)
+        for t in range(T):
+            if v[t]:
+                p[t], val[t] = f(st[t])
+        priors.copy_(torch.from_numpy(p))
+        values.copy_(torch.from_numpy(val))
+        if not inline_play or it % 16 == 0:
+            eng.play()
+        if it % 64 == 0 and int((eng.phases() != 0).sum()) == 0:
+            break
+    eng.check_status()
+    fin = eng.drain_finished()
+    assert sorted(fin["game_id"].tolist()) == list(range(base, base + G))
+    crules = c_oracle.make_rules(7, 6, 4, True)
+    for i, g in enumerate(fin["game_id"]):
+        u = [_philox_uniform(seed, int(g), ply) for ply in range(rules.max_plies)]
+        want = c_oracle.play_game(crules, sims, "hash", uniforms=u)
+        n = len(want["moves"])
+        assert fin["len"][i] == n and fin["result"][i] == want["result"], int(g)
+        np.testing.assert_array_equal(fin["action"][i][:n] & 0xFFFF, want["moves"])
+        np.testing.assert_array_equal(fin["visits"][i][:n], want["visits"])
+    tot = eng.totals()
+    assert tot["games"] == G and tot["moves"] == int(fin["len"].sum()) and tot["sims"] == tot["moves"] * sims

@@ -94,3 +94,29 @@ def test_bf16_inference_net_close_to_fp32_module(H, W, A):
     inf.fast = False
     p2, v2 = inf(x.cuda().to(torch.bfloat16))
     assert (p2 - p).abs().max().item() < 2e-2 and (v2 - v).abs().max().item() < 5e-2
+
+
+@pytest.mark.parametrize("W,H,n,gravity", [(9, 9, 5, True), (9, 9, 5, False), (5, 4, 3, True)])
+def test_selfplay_runner_other_boards(W, H, n, gravity):
+    """BASELINE config C4 (9x9 connect-5, with and without gravity) through the whole path: generic-rules
+    tree kernels (two-word bitboards, up to 81 children), hand-written stem / heads at that size, bf16 tower."""
+    from az_b200 import selfplay
+
+    engine, native, net = _mods()
+    rules = engine.Rules(W, H, n, gravity)
+    torch.manual_seed(0)
+    r = selfplay.SelfPlayRunner(rules, n_trees=48, sims_per_move=20, games_target=64, unroll=4, seed=5)
+    r.run_until_done(poll_every=64, max_advances=400000)
+    tot = r.totals()
+    states, policies, values = r.collect()
+    assert tot["games"] == 64 and len(values) == tot["moves"] and tot["sims"] == tot["moves"] * 20
+    assert states.shape[1:] == (H, W, 4) and policies.shape[1] == rules.n_actions
+    assert np.allclose(policies.sum(-1), 1.0) and (policies >= 0).all()
+    assert (states[..., :3].sum(-1) == 1).all() and (states[..., 3] == 1).all()
+    # a policy target never puts mass on an occupied cell / full column
+    if gravity:
+        legal = states[:, 0, :, 0] == 1                       # top cell of the column empty
+        assert (policies[~legal] == 0).all()
+    else:
+        legal = np.transpose(states[..., 0], (0, 2, 1)).reshape(len(values), -1) == 1   # action = x * H + y
+        assert (policies[~legal] == 0).all()

@@ -56,8 +56,8 @@ class ReplayWindow:
         self.policies = np.concatenate([self.policies, policies.astype(np.float64)])[-self.capacity:]
         self.values = np.concatenate([self.values, np.asarray(values, dtype=np.float64)])[-self.capacity:]
 
-    def ready(self, minimum=MIN_TRAINING_SIZE):
-        return len(self) >= minimum
+    def ready(self, minimum=None):
+        return len(self) >= (MIN_TRAINING_SIZE if minimum is None else minimum)
 
     def sample(self, batch_size=BATCH_SIZE, rng=np.random):
         idx = rng.choice(len(self), batch_size, replace=False)  # train.py:58-62

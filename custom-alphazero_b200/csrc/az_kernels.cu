@@ -394,6 +394,95 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
 }
 
 // ------------------------------------------------------------------------------------------ k_step
+// One advance of one tree (warp-uniform): consume the evaluation of the pending leaf (K4 + K5), then
+// simulate until a leaf needs the evaluator: terminal leaves are finished on the spot, a spent budget is
+// turned into a move right here when inline_play allows (K6).  Returns 1 with the leaf position in
+// `leaf` when an evaluation is wanted, else 0.
+template <int NW, int KC, class R, class PriorFn>
+__device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& r, int t, WarpScratch& ws, int lane,
+                                         bool have_eval, int prior_mode, double value, PriorFn prior_of, Pos<NW>& leaf) {
+    int st = e.status[t];
+    if ((st & AZ_PHASE_MASK) != AZ_PHASE_SEARCH) return 0;
+    uint32_t flags = 0;
+    const size_t pool = ((size_t)t * 2 + e.half[t]) * e.C;
+    NodeA* A = e.node_a + pool;
+    double* Pr = e.node_p + pool;
+    int sims = e.sims_done[t];
+    int root = e.root_node[t];
+    long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
+    const int was_pending = e.pending[t];
+    if (was_pending && have_eval) {
+        const int depth = e.path_len[t];
+        for (int i = lane; i < depth; i += 32) ws.path[i] = e.path[(size_t)t * kMaxDepth + i];
+        const Pos<NW> at = load_pos<NW>(e.leaf_board + (size_t)t * 2 * NW);
+        __syncwarp();
+        const uint32_t link = expand_leaf<NW>(e, r, A, Pr, at, t, ws, lane, flags, prior_mode, prior_of);
+        backup_path(A, root, ws, depth, -value, link, lane);  // mcts.py:175: value seen by the player who moved in
+        ++sims;
+        ++nsim;
+        ++neval;
+        nchild += link >> 24;
+    }
+    int pend = (was_pending && !have_eval) ? 1 : 0;
+    if (pend) leaf = load_pos<NW>(e.leaf_board + (size_t)t * 2 * NW);  // still waiting: hand the same leaf out again
+    int freed = 0;
+    for (;;) {
+        if (!pend && sims >= e.sims_target && e.inline_play) {
+            // budget spent: play the move right here (K6) and carry on with the first simulation of the
+            // next search, unless the re-root needs the compaction path (left to az_play)
+            if (lane == 0) {
+                e.sims_done[t] = sims;
+                e.pending[t] = 0;
+            }
+            __syncwarp();
+            if (!play_tree<NW, KC>(e, aux, r, t, (st & ~AZ_PHASE_MASK) | AZ_PHASE_READY | (int)flags, ws, lane, -1,
+                                   e.move_mode, false))
+                break;
+            __syncwarp();
+            st = e.status[t];
+            if ((st & AZ_PHASE_MASK) != AZ_PHASE_SEARCH) {  // game over and no further game for this tree
+                sims = -1;
+                break;
+            }
+            root = e.root_node[t];
+            sims = 0;
+            if (++freed >= e.max_free) break;
+        }
+        if (pend || sims >= e.sims_target) break;
+        Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
+        int depth, term;
+        select_leaf<NW, KC>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags);
+        ndepth += depth;
+        if (term) {  // mcts.py:179: terminal leaf, result 1 (win of the mover) or 0 (draw)
+            backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
+            ++sims;
+            ++nsim;
+            if (++freed >= e.max_free) break;
+            continue;
+        }
+        for (int i = lane; i < depth; i += 32) e.path[(size_t)t * kMaxDepth + i] = ws.path[i];
+        store_pos<NW>(e.leaf_board + (size_t)t * 2 * NW, pos, lane);
+        if (lane == 0) e.path_len[t] = depth;
+        leaf = pos;
+        pend = 1;
+    }
+    if (lane == 0) {
+        bump(e.counters + (size_t)t * 8 + 0, nsim);
+        bump(e.counters + (size_t)t * 8 + 1, neval);
+        bump(e.counters + (size_t)t * 8 + 4, ndepth);
+        bump(e.counters + (size_t)t * 8 + 5, nchild);
+        if (sims >= 0) {
+            e.sims_done[t] = sims;
+            e.pending[t] = pend;
+            int ph = (sims >= e.sims_target && !pend) ? AZ_PHASE_READY : AZ_PHASE_SEARCH;
+            e.status[t] = (st & ~AZ_PHASE_MASK) | ph | (int)flags;
+        } else if (flags) {
+            e.status[t] = st | (int)flags;
+        }
+    }
+    return pend;
+}
+
 template <int NW, int KC, class R>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     k_step(Eng e, Aux aux, const void* __restrict__ priors, const void* __restrict__ values, int eval_dtype, void* states,
@@ -404,102 +493,29 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     if (t >= e.T) return;
     WarpScratch& ws = s_ws[warp];
     const auto r = RulesView<R>::get(e);
-    int st = e.status[t];
-    uint32_t flags = 0;
-    int valid = 0;
-    if ((st & AZ_PHASE_MASK) == AZ_PHASE_SEARCH) {
-        const size_t pool = ((size_t)t * 2 + e.half[t]) * e.C;
-        NodeA* A = e.node_a + pool;
-        double* Pr = e.node_p + pool;
-        int sims = e.sims_done[t];
-        int root = e.root_node[t];
-        long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
-        if (e.pending[t] && priors != nullptr) {
-            const int depth = e.path_len[t];
-            for (int i = lane; i < depth; i += 32) ws.path[i] = e.path[(size_t)t * kMaxDepth + i];
-            const Pos<NW> leaf = load_pos<NW>(e.leaf_board + (size_t)t * 2 * NW);
-            __syncwarp();
-            double v;
-            uint32_t link;
-            // the dtype of the evaluator output decides the arithmetic of normalize_probabilities, as in
-            // the reference: float64 from infer_sample (factory.py:55), float32 from the model (mcts.py:131-137)
-            if (eval_dtype == AZ_F64) {
-                const double* p = static_cast<const double*>(priors) + (size_t)t * r.A;
-                v = static_cast<const double*>(values)[t];
-                link = expand_leaf<NW>(e, r, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F64, [p](int a) { return p[a]; });
-            } else {
-                const float* p = static_cast<const float*>(priors) + (size_t)t * r.A;
-                v = (double)static_cast<const float*>(values)[t];  // value.numpy().item() (mcts.py:136)
-                link = expand_leaf<NW>(e, r, A, Pr, leaf, t, ws, lane, flags, AZ_PRIOR_F32, [p](int a) { return (double)p[a]; });
-            }
-            backup_path(A, root, ws, depth, -v, link, lane);  // mcts.py:175: value seen by the player who moved in
-            ++sims;
-            ++nsim;
-            ++neval;
-            nchild += link >> 24;
-        }
-        int pend = (e.pending[t] && priors == nullptr) ? 1 : 0;
-        int freed = 0;
-        for (;;) {
-            if (!pend && sims >= e.sims_target && e.inline_play) {
-                // budget spent: play the move right here (K6) and carry on with the first simulation of the
-                // next search, unless the re-root needs the compaction path (left to az_play)
-                if (lane == 0) {
-                    e.sims_done[t] = sims;
-                    e.pending[t] = 0;
-                }
-                __syncwarp();
-                if (!play_tree<NW, KC>(e, aux, r, t, (st & ~AZ_PHASE_MASK) | AZ_PHASE_READY | (int)flags, ws, lane, -1,
-                                       e.move_mode, false))
-                    break;
-                __syncwarp();
-                st = e.status[t];
-                if ((st & AZ_PHASE_MASK) != AZ_PHASE_SEARCH) {  // game over and no further game for this tree
-                    sims = -1;
-                    break;
-                }
-                root = e.root_node[t];
-                sims = 0;
-                if (++freed >= e.max_free) break;
-            }
-            if (pend || sims >= e.sims_target) break;
-            Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
-            int depth, term;
-            select_leaf<NW, KC>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags);
-            ndepth += depth;
-            if (term) {  // mcts.py:179: terminal leaf, result 1 (win of the mover) or 0 (draw)
-                backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
-                ++sims;
-                ++nsim;
-                if (++freed >= e.max_free) break;
-                continue;
-            }
-            for (int i = lane; i < depth; i += 32) e.path[(size_t)t * kMaxDepth + i] = ws.path[i];
-            store_pos<NW>(e.leaf_board + (size_t)t * 2 * NW, pos, lane);
-            if (lane == 0) e.path_len[t] = depth;
-            if (state_dtype == AZ_BF16)
-                encode_state_bf16<NW>(r, pos, static_cast<__nv_bfloat16*>(states) + (size_t)t * r.cells * 4, lane);
-            else
-                encode_state_f32<NW>(r, pos, static_cast<float*>(states) + (size_t)t * r.cells * 4, lane);
-            pend = 1;
-        }
-        valid = pend;
-        if (lane == 0) {
-            bump(e.counters + (size_t)t * 8 + 0, nsim);
-            bump(e.counters + (size_t)t * 8 + 1, neval);
-            bump(e.counters + (size_t)t * 8 + 4, ndepth);
-            bump(e.counters + (size_t)t * 8 + 5, nchild);
-            if (sims >= 0) {
-                e.sims_done[t] = sims;
-                e.pending[t] = pend;
-                int ph = (sims >= e.sims_target && !pend) ? AZ_PHASE_READY : AZ_PHASE_SEARCH;
-                e.status[t] = (st & ~AZ_PHASE_MASK) | ph | (int)flags;
-            } else if (flags) {
-                e.status[t] = st | (int)flags;
-            }
-        }
+    Pos<NW> leaf;
+    int pend;
+    // the dtype of the evaluator output decides the arithmetic of normalize_probabilities, as in the
+    // reference: float64 from infer_sample (factory.py:55), float32 from the model (mcts.py:131-137)
+    if (priors == nullptr) {
+        pend = step_tree<NW, KC>(e, aux, r, t, ws, lane, false, AZ_PRIOR_F64, 0.0, [](int) { return 0.0; }, leaf);
+    } else if (eval_dtype == AZ_F64) {
+        const double* p = static_cast<const double*>(priors) + (size_t)t * r.A;
+        pend = step_tree<NW, KC>(e, aux, r, t, ws, lane, true, AZ_PRIOR_F64, static_cast<const double*>(values)[t],
+                                 [p](int a) { return p[a]; }, leaf);
+    } else {
+        const float* p = static_cast<const float*>(priors) + (size_t)t * r.A;
+        // value.numpy().item() (mcts.py:136): the float32 value widened
+        pend = step_tree<NW, KC>(e, aux, r, t, ws, lane, true, AZ_PRIOR_F32, (double)static_cast<const float*>(values)[t],
+                                 [p](int a) { return (double)p[a]; }, leaf);
     }
-    if (lane == 0) leaf_valid[t] = valid;
+    if (pend) {
+        if (state_dtype == AZ_BF16)
+            encode_state_bf16<NW>(r, leaf, static_cast<__nv_bfloat16*>(states) + (size_t)t * r.cells * 4, lane);
+        else
+            encode_state_f32<NW>(r, leaf, static_cast<float*>(states) + (size_t)t * r.cells * 4, lane);
+    }
+    if (lane == 0) leaf_valid[t] = pend;
 }
 
 // ------------------------------------------------------------------------------------------ k_search

@@ -15,25 +15,16 @@
 #include <cstdio>
 
 #include "../../include/az_b200.h"
+#include "az_mma.cuh"
 
 namespace az {
 
 int fail_net(int code, const char* msg);
 constexpr int kMaxDimNet = 11;
 
-// Both kernels put their small GEMM on the legacy tensor path (mma.sync m16n8k16 bf16 -> fp32): the stem is
-// 0.4 % and the head convolutions 0.03 % of the net's FLOPs, both are bound by the 44 MB they write / read per
-// 4096 positions, and a scalar-FMA version costs 10x the instructions (it measured 69 us against ~10 us of traffic).
-__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
-}
+// Both kernels put their small GEMM on the legacy tensor path (mma.sync m16n8k16 bf16 -> fp32, az_mma.cuh): the
+// stem is 0.4 % and the head convolutions 0.03 % of the net's FLOPs, both are bound by the 44 MB they write / read
+// per 4096 positions, and a scalar-FMA version costs 10x the instructions (it measured 69 us against ~10 us of traffic).
 
 // ------------------------------------------------------------------------------------------ stem
 // Implicit GEMM per position: D[pixel][cout] = A[pixel][kk] * B[kk][cout], kk = tap*4 + plane (36, padded to 48).
@@ -129,12 +120,6 @@ __global__ void __launch_bounds__(kStemWarps * 32) k_stem(const __nv_bfloat16* _
 
 // ------------------------------------------------------------------------------------------ heads
 constexpr int kHeadWarps = 16;
-constexpr int kHidden = 256;
-
-struct HeadParams {
-    const float *conv_w, *conv_b, *policy_w, *policy_b, *value1_w, *value1_b, *value2_w, *value2_b;
-    int n, cells, A;
-};
 
 // One warp per position, grid-stride; dense weights staged once per block in shared memory.
 // 1x1 convolutions: D[pixel][3] = X[pixel][128] * Wc[128][3] with mma.sync, the A fragments loaded straight

@@ -209,6 +209,19 @@ class InferenceNet(nn.Module):
         h0 = torch.empty((B, H, W, self.filters), dtype=torch.bfloat16, device=x_nhwc.device)
         check(lib().az_net_stem(_ptr(x_nhwc), _ptr(self.stem_w32), _ptr(self.stem_b32), B, H, W, self.filters,
                                 _ptr(h0), _stream()))
+        xm = self.tower(h0)
+        if priors_out is None:
+            priors_out = torch.empty((B, self.n_actions), dtype=torch.float32, device=xm.device)
+            values_out = torch.empty(B, dtype=torch.float32, device=xm.device)
+        hw = self._heads_arg()
+        check(lib().az_net_heads(_ptr(xm), ctypes.byref(hw), B, H * W, self.filters, self.n_actions, _ptr(priors_out),
+                                 _ptr(values_out), _stream()))
+        return priors_out, values_out
+
+    @torch.no_grad()
+    def tower(self, h0):
+        """The residual tower on the stem output h0 [B, H, W, 128] bf16 (NHWC): 4 x (cuDNN conv+bias+ReLU,
+        cuDNN 1x1 shortcut, cuDNN conv+shortcut+bias+ReLU) -> [B, H, W, 128] bf16, NHWC-contiguous."""
         x = h0.permute(0, 3, 1, 2)  # logical NCHW over NHWC memory (channels_last)
         one = (1, 1)
         cur = torch.cuda.current_stream()
@@ -228,15 +241,7 @@ class InferenceNet(nn.Module):
                 p = F.conv2d(x, wp)                                                  # projection shortcut
             x = torch.cudnn_convolution_add_relu(h, w2, p, 1.0, b2p, one, one, one, 1)  # conv + shortcut + bias + ReLU
         xm = x.permute(0, 2, 3, 1)
-        if not xm.is_contiguous():
-            xm = xm.contiguous()
-        if priors_out is None:
-            priors_out = torch.empty((B, self.n_actions), dtype=torch.float32, device=x.device)
-            values_out = torch.empty(B, dtype=torch.float32, device=x.device)
-        hw = self._heads_arg()
-        check(lib().az_net_heads(_ptr(xm), ctypes.byref(hw), B, H * W, self.filters, self.n_actions, _ptr(priors_out),
-                                 _ptr(values_out), _stream()))
-        return priors_out, values_out
+        return xm if xm.is_contiguous() else xm.contiguous()
 
     def load_from(self, net: PolicyValueNet):
         """Refreshes the folded weights in place (after a training step / weight broadcast): the CUDA

@@ -59,6 +59,10 @@ class _Group:
         self.valid = torch.zeros(T, dtype=torch.int32, device=device)
         self.priors = torch.zeros((T, A), dtype=torch.float32, device=device)
         self.values = torch.zeros(T, dtype=torch.float32, device=device)
+        # fused route: the stem's output (tower input) and the tower's output carried between advances
+        self.stem_out = None
+        self.tower_out = None
+        self.tower_carry = None
 
 
 class SelfPlayRunner:
@@ -69,7 +73,7 @@ class SelfPlayRunner:
     def __init__(self, rules=Rules(), n_trees=4096, sims_per_move=800, net=None, *, games_target=None,
                  game_id_base=0, seed=0, move_mode="philox", auto_restart=True, dtype=torch.bfloat16, unroll=8,
                  use_graph=True, max_free_sims=8, node_capacity=None, fin_capacity=None, device=None,
-                 index_move_greedy=8, groups=1):
+                 index_move_greedy=8, groups=1, fused=True):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.rules = rules
         T, A = int(n_trees), rules.n_actions
@@ -94,13 +98,21 @@ class SelfPlayRunner:
             t0 += ti
             g0 += gi
         self.n_trees = T
+        # fused route: heads + tree step + stem in one launch (az_advance_fused) around the cuDNN tower
+        self.fused = bool(fused) and getattr(self.net, "fast", False)
+        if self.fused:
+            for g in self.groups:
+                shape = (g.engine.n_trees, rules.height, rules.width, self.net.filters)
+                g.stem_out = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
+                g.tower_carry = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
         self.unroll = int(unroll)
         self.use_graph = use_graph
         self.graph = None
         self.advances = 0
         self.flops_per_eval = flops_per_eval(rules.height, rules.width, A)
-        # kernels of libaz_b200 launched per advance and group: az_step, az_net_stem, az_net_heads (+ az_play sweeps)
-        self.launches_per_advance = 3 * groups
+        # kernels of libaz_b200 launched per advance and group: az_advance_fused, or az_step + az_net_stem +
+        # az_net_heads (+ az_play sweeps)
+        self.launches_per_advance = (1 if self.fused else 3) * groups
         self._side = [torch.cuda.Stream(device=self.device) for _ in range(groups - 1)]
 
     # single-group conveniences (tests, compat code)
@@ -129,8 +141,16 @@ class SelfPlayRunner:
         """az_step plays moves itself (inline_play) whenever the re-root fits in place; az_play is only needed
         for the compaction path and for games stalled on a full ring: every advance if the pool can run
         short, else once per captured graph as a safety net (`sweep`)."""
-        g.engine.step(g.priors, g.values, g.states, g.valid)
-        self.net(g.states, g.priors, g.values)
+        if self.fused:
+            # no tree has a pending leaf right after a reset, so a stale carry buffer is never consumed
+            src = g.tower_out if g.tower_out is not None else g.tower_carry
+            hw = self.net._heads_arg()
+            check(lib().az_advance_fused(g.engine._h, _ptr(src), ctypes.byref(hw), _ptr(self.net.stem_w32),
+                                         _ptr(self.net.stem_b32), _ptr(g.stem_out), _ptr(g.valid), _stream()))
+            g.tower_out = self.net.tower(g.stem_out)
+        else:
+            g.engine.step(g.priors, g.values, g.states, g.valid)
+            self.net(g.states, g.priors, g.values)
         if sweep or not g.engine.never_compacts:
             g.engine.play()
 
@@ -139,12 +159,20 @@ class SelfPlayRunner:
         cur = torch.cuda.current_stream()
         for s in self._side:
             s.wait_stream(cur)
+        def chain(g):
+            # the first advance of a batch reads the tower output the previous batch left in tower_carry (a fixed
+            # address, so a captured graph can be replayed back to back); the last one refreshes it
+            g.tower_out = None
+            for i in range(n):
+                self._advance(g, sweep=i == n - 1)
+            if self.fused:
+                g.tower_carry.copy_(g.tower_out)
+                g.tower_out = None
+
         for g, s in zip(self.groups[1:], self._side):
             with torch.cuda.stream(s):
-                for i in range(n):
-                    self._advance(g, sweep=i == n - 1)
-        for i in range(n):
-            self._advance(self.groups[0], sweep=i == n - 1)
+                chain(g)
+        chain(self.groups[0])
         for s in self._side:
             cur.wait_stream(s)
 
@@ -157,6 +185,8 @@ class SelfPlayRunner:
             for _ in range(3):
                 for g in self.groups:
                     self.net(g.states, g.priors, g.values)
+                    if self.fused:
+                        self.net.tower(g.stem_out)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
@@ -181,6 +211,7 @@ class SelfPlayRunner:
         for g in self.groups:
             g.engine.reset()
             g.valid.zero_()
+            g.tower_out = None
 
     def active_trees(self):
         return sum(int((g.engine.phases() != native.AZ_PHASE_IDLE).sum()) for g in self.groups)

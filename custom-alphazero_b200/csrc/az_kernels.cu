@@ -15,6 +15,7 @@
 #include <new>
 
 #include "../../include/az_b200.h"
+#include "az_mma.cuh"
 #include "az_tree.cuh"
 
 namespace az {
@@ -518,6 +519,226 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     if (lane == 0) leaf_valid[t] = pend;
 }
 
+// ------------------------------------------------------------------------------------------ k_advance
+// The three per-tree stages that sit between two tower passes, fused into one launch, one warp per tree:
+//   A  heads   tower output of the tree's pending leaf -> 1x1 convs (mma.sync) -> Dense/softmax priors, Dense/tanh value
+//   B  tree    step_tree: expand + backup with those priors, select the next leaf (moves played in line)
+//   C  stem    the new leaf's planes -> Conv3x3(4 -> 128)+BN+ReLU (mma.sync) -> stem_out[t], the tower's input
+// Priors, value and the leaf's planes never touch global memory, two kernel boundaries disappear, and warps in
+// the latency-bound stage B share their SM with warps issuing the math of A and C.  Same arithmetic as
+// az_net_heads / az_step / az_net_stem (tests compare the two routes bit for bit).
+constexpr int kAdvWarps = 16;
+
+struct StemParams {
+    const float* w;  // [128][4][3][3]
+    const float* b;  // [128]
+};
+
+template <int NW, int KC, class R>
+__global__ void __launch_bounds__(kAdvWarps * 32, 2)
+    k_advance(Eng e, Aux aux, const __nv_bfloat16* __restrict__ x, HeadParams hp, StemParams sp,
+              __nv_bfloat16* __restrict__ stem_out, int32_t* leaf_valid) {
+    constexpr int C = 128;
+    extern __shared__ float s_f[];
+    const auto r = RulesView<R>::get(e);
+    const int cells = r.cells, A = r.A, PW = r.W + 2;
+    const int ps = 2 * cells + 1, vs = cells | 1;
+    float* s_pw = s_f;                                           // policy dense [A][ps]
+    float* s_vw = s_pw + ((A * ps + 3) & ~3);                    // value dense 1 [256][vs]
+    uint32_t* s_sw = reinterpret_cast<uint32_t*>(s_vw + ((kHidden * vs + 3) & ~3));  // stem B fragments [4][3][4][2][32]
+    float* s_sb = reinterpret_cast<float*>(s_sw + 4 * 3 * 4 * 2 * 32);               // stem bias [128]
+    int* s_base = reinterpret_cast<int*>(s_sb + C);                                   // pixel -> padded cell [cells + 16]
+    WarpScratch* s_ws = reinterpret_cast<WarpScratch*>(s_base + ((cells + 16 + 3) & ~3));
+    {
+        const int np4 = (A * ps) >> 2, nv4 = (kHidden * vs) >> 2;
+        const float4* gp = reinterpret_cast<const float4*>(hp.policy_w);
+        const float4* gv = reinterpret_cast<const float4*>(hp.value1_w);
+        for (int i = threadIdx.x; i < np4; i += blockDim.x) reinterpret_cast<float4*>(s_pw)[i] = gp[i];
+        for (int i = (np4 << 2) + threadIdx.x; i < A * ps; i += blockDim.x) s_pw[i] = hp.policy_w[i];
+        for (int i = threadIdx.x; i < nv4; i += blockDim.x) reinterpret_cast<float4*>(s_vw)[i] = gv[i];
+        for (int i = (nv4 << 2) + threadIdx.x; i < kHidden * vs; i += blockDim.x) s_vw[i] = hp.value1_w[i];
+        for (int i = threadIdx.x; i < 4 * 3 * 4 * 2 * 32; i += blockDim.x) {  // pre-packed stem B fragments
+            const int ln = i & 31, h = (i >> 5) & 1, nt = (i >> 6) & 3, ks = (i >> 8) % 3, q = i / 768;
+            const int co = q * 32 + nt * 8 + (ln >> 2), kk = ks * 16 + (ln & 3) * 2 + h * 8, tap = kk >> 2, ci = kk & 3;
+            s_sw[i] = tap < 9 ? pack_bf16(sp.w[co * 36 + ci * 9 + tap], sp.w[co * 36 + (ci + 1) * 9 + tap]) : 0u;
+        }
+        for (int i = threadIdx.x; i < C; i += blockDim.x) s_sb[i] = sp.b[i];
+        for (int p = threadIdx.x; p < cells + 16; p += blockDim.x) {
+            const int q = p < cells ? p : cells - 1;
+            s_base[p] = (q / r.W) * PW + q % r.W;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    const int t = blockIdx.x * kAdvWarps + warp;
+    if (t >= e.T) return;
+    WarpScratch& ws = s_ws[warp];
+    const int mtiles = (cells + 15) >> 4;
+
+    // ---- A: heads for the pending leaf of this tree
+    const bool have_eval = x != nullptr && e.pending[t] && (e.status[t] & AZ_PHASE_MASK) == AZ_PHASE_SEARCH;
+    float pr[4] = {0.f, 0.f, 0.f, 0.f};
+    float value = 0.f;
+    if (have_eval) {
+        float* h = reinterpret_cast<float*>(ws.sel);  // [cells][2] policy planes, then [cells] value plane
+        uint32_t bf[C / 16][2];
+#pragma unroll
+        for (int ks = 0; ks < C / 16; ++ks)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int k = ks * 16 + t4 * 2 + hh * 8;
+                bf[ks][hh] = g < 3 ? pack_bf16(hp.conv_w[g * C + k], hp.conv_w[g * C + k + 1]) : 0u;
+            }
+        const float cb0 = hp.conv_b[0], cb1 = hp.conv_b[1], cb2 = hp.conv_b[2];
+        const uint32_t* xb = reinterpret_cast<const uint32_t*>(x + (size_t)t * cells * C);
+        for (int mt = 0; mt < mtiles; ++mt) {
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+            const int q0 = r0 < cells ? r0 : cells - 1, q1 = r1 < cells ? r1 : cells - 1;
+            uint32_t a[C / 16][4];
+#pragma unroll
+            for (int ks = 0; ks < C / 16; ++ks) {
+                a[ks][0] = xb[q0 * (C / 2) + ks * 8 + t4];
+                a[ks][1] = xb[q1 * (C / 2) + ks * 8 + t4];
+                a[ks][2] = xb[q0 * (C / 2) + ks * 8 + t4 + 4];
+                a[ks][3] = xb[q1 * (C / 2) + ks * 8 + t4 + 4];
+            }
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < C / 16; ++ks) mma_16816(acc, a[ks], bf[ks]);
+            if (t4 == 0) {
+                if (r0 < cells) { h[r0 * 2] = fmaxf(acc[0] + cb0, 0.f); h[r0 * 2 + 1] = fmaxf(acc[1] + cb1, 0.f); }
+                if (r1 < cells) { h[r1 * 2] = fmaxf(acc[2] + cb0, 0.f); h[r1 * 2 + 1] = fmaxf(acc[3] + cb1, 0.f); }
+            } else if (t4 == 1) {
+                if (r0 < cells) h[2 * cells + r0] = fmaxf(acc[0] + cb2, 0.f);
+                if (r1 < cells) h[2 * cells + r1] = fmaxf(acc[2] + cb2, 0.f);
+            }
+        }
+        __syncwarp();
+        float logit[4], mx = -INFINITY;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int a = lane + 32 * m;
+            logit[m] = -INFINITY;
+            if (a < A) {
+                float acc = hp.policy_b[a];
+                const float* wrow = s_pw + a * ps;
+                for (int i = 0; i < 2 * cells; ++i) acc = fmaf(h[i], wrow[i], acc);
+                logit[m] = acc;
+                mx = fmaxf(mx, acc);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            pr[m] = lane + 32 * m < A ? expf(logit[m] - mx) : 0.f;
+            sum += pr[m];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) pr[m] = pr[m] / sum;
+        float hacc[kHidden / 32];
+#pragma unroll
+        for (int m = 0; m < kHidden / 32; ++m) hacc[m] = hp.value1_b[lane + 32 * m];
+        const float* hv = h + 2 * cells;
+        for (int p = 0; p < cells; ++p) {
+            const float hvp = hv[p];
+#pragma unroll
+            for (int m = 0; m < kHidden / 32; ++m) hacc[m] = fmaf(hvp, s_vw[(lane + 32 * m) * vs + p], hacc[m]);
+        }
+        float part = 0.f;
+#pragma unroll
+        for (int m = 0; m < kHidden / 32; ++m) part = fmaf(fmaxf(hacc[m], 0.f), hp.value2_w[lane + 32 * m], part);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+        value = tanhf(part + hp.value2_b[0]);
+        __syncwarp();
+    }
+
+    // ---- B: the tree step with the priors in registers (lane l holds actions l, l+32, ...)
+    Pos<NW> leaf;
+    const float p0 = pr[0], p1 = pr[1], p2 = pr[2], p3 = pr[3];
+    const int pend = step_tree<NW, KC>(e, aux, r, t, ws, lane, have_eval, AZ_PRIOR_F32, (double)value,
+                                       [p0, p1, p2, p3](int a) {
+                                           const int m = a >> 5;
+                                           return (double)(m == 0 ? p0 : (m == 1 ? p1 : (m == 2 ? p2 : p3)));
+                                       },
+                                       leaf);
+    if (lane == 0) leaf_valid[t] = pend;
+    if (!pend) return;
+
+    // ---- C: stem of the new leaf
+    __syncwarp();
+    uint2* board = reinterpret_cast<uint2*>(ws.sel);  // zero-bordered planes [(H+2)][(W+2)] x 4 bf16
+    for (int i = lane; i < (r.H + 2) * PW; i += 32) {
+        const int py = i / PW, px = i - py * PW;
+        uint2 v = make_uint2(0u, 0u);
+        if (py >= 1 && py <= r.H && px >= 1 && px <= r.W) {
+            const int code = cell_code(r, leaf, (py - 1) * r.W + (px - 1));
+            v.x = (code == 0 ? 0x3F80u : 0u) | (code == 1 ? 0x3F800000u : 0u);  // planes: empty, side to move,
+            v.y = (code == 2 ? 0x3F80u : 0u) | 0x3F800000u;                      //         opponent, turn (+1)
+        }
+        board[i] = v;
+    }
+    __syncwarp();
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(board);
+    int toff[3][2], wsel[3][2];
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int kk = ks * 16 + t4 * 2 + hh * 8;
+            int tap = kk >> 2;
+            if (tap > 8) tap = 0;
+            toff[ks][hh] = (tap / 3) * PW + tap % 3;
+            wsel[ks][hh] = (kk & 3) >> 1;
+        }
+    for (int q = 0; q < 4; ++q) {
+        uint32_t bq[3][4][2];
+        float bv[4][2];
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) bq[ks][nt][hh] = s_sw[((((q * 3 + ks) * 4 + nt) * 2 + hh) << 5) + lane];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            bv[nt][0] = s_sb[q * 32 + nt * 8 + t4 * 2];
+            bv[nt][1] = s_sb[q * 32 + nt * 8 + t4 * 2 + 1];
+        }
+        __nv_bfloat16* o = stem_out + (size_t)t * cells * C + q * 32 + t4 * 2;
+        for (int mt = 0; mt < mtiles; ++mt) {
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+            const int c0 = s_base[r0], c1 = s_base[r1];
+            float acc[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+                uint32_t a[4];
+                a[0] = sw[(c0 + toff[ks][0]) * 2 + wsel[ks][0]];
+                a[1] = sw[(c1 + toff[ks][0]) * 2 + wsel[ks][0]];
+                a[2] = sw[(c0 + toff[ks][1]) * 2 + wsel[ks][1]];
+                a[3] = sw[(c1 + toff[ks][1]) * 2 + wsel[ks][1]];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) mma_16816(acc[nt], a, bq[ks][nt]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                if (r0 < cells)
+                    *reinterpret_cast<uint32_t*>(o + (size_t)r0 * C + nt * 8) =
+                        pack_bf16(fmaxf(acc[nt][0] + bv[nt][0], 0.f), fmaxf(acc[nt][1] + bv[nt][1], 0.f));
+                if (r1 < cells)
+                    *reinterpret_cast<uint32_t*>(o + (size_t)r1 * C + nt * 8) =
+                        pack_bf16(fmaxf(acc[nt][2] + bv[nt][0], 0.f), fmaxf(acc[nt][3] + bv[nt][1], 0.f));
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ k_search
 template <int NW, int KC, class R>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
@@ -975,6 +1196,38 @@ AZ_API int az_decode_samples(const az_config* c, const uint64_t* boards, const i
         k_decode<2><<<n_games, 128, 0, s>>>(r, r.cells, boards, visits, actions, lens, results, offsets, states, policies, values);
     else
         k_decode<1><<<n_games, 128, 0, s>>>(r, r.cells, boards, visits, actions, lens, results, offsets, states, policies, values);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_advance_fused(az_engine* e, const void* tower_out, const az_head_weights* hw, const float* stem_w,
+                            const float* stem_b, void* stem_out, int32_t* leaf_valid, void* stream) {
+    if (!e || !hw || !stem_w || !stem_b || !stem_out || !leaf_valid) return fail(AZ_ERR_ARG, "az_advance_fused: null pointer%s");
+    const Rules& r = e->eng.r;
+    const size_t A = r.A, cells = r.cells;
+    const size_t smem = sizeof(float) * (((A * (2 * cells + 1) + 3) & ~(size_t)3) + ((kHidden * (cells | 1) + 3) & ~(size_t)3)) +
+                        sizeof(uint32_t) * 4 * 3 * 4 * 2 * 32 + sizeof(float) * 128 + sizeof(int) * ((cells + 16 + 3) & ~(size_t)3) +
+                        sizeof(WarpScratch) * kAdvWarps;
+    if (smem > 227 * 1024) return fail(AZ_ERR_ARG, "az_advance_fused: head weights do not fit in shared memory for this board%s");
+    HeadParams hp{hw->conv_w, hw->conv_b, hw->policy_w, hw->policy_b, hw->value1_w, hw->value1_b, hw->value2_w, hw->value2_b,
+                  e->eng.T, (int)cells, (int)A};
+    StemParams sp{stem_w, stem_b};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    dim3 grid((e->eng.T + kAdvWarps - 1) / kAdvWarps), block(kAdvWarps * 32);
+    const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(tower_out);
+    __nv_bfloat16* so = static_cast<__nv_bfloat16*>(stem_out);
+#define AZ_ADV(NWv, KCv, Rv)                                                                                         \
+    do {                                                                                                             \
+        auto kfn = k_advance<NWv, KCv, Rv>;                                                                          \
+        AZ_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+        kfn<<<grid, block, smem, s>>>(e->eng, e->aux, x, hp, sp, so, leaf_valid);                                    \
+    } while (0)
+    if (e->c4) AZ_ADV(1, 1, C4Rules);
+    else if (e->nw == 1 && e->kc == 1) AZ_ADV(1, 1, Rules);
+    else if (e->nw == 1) AZ_ADV(1, 4, Rules);
+    else if (e->kc == 1) AZ_ADV(2, 1, Rules);
+    else AZ_ADV(2, 4, Rules);
+#undef AZ_ADV
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }

@@ -251,6 +251,15 @@ int az_net_stem(const void *dev_states, const float *dev_w, const float *dev_b, 
 int az_net_heads(const void *dev_x, const az_head_weights *weights, int32_t n, int32_t cells, int32_t channels,
                  int32_t n_actions, float *dev_priors_out, float *dev_values_out, void *stream);
 
+/* The three per-tree stages between two passes of the tower in ONE launch (one warp per tree):
+ * az_net_heads on the tower output of each tree's pending leaf, az_step with those priors / value (kept in
+ * registers), az_net_stem on the newly selected leaf.  Same results as the three calls in sequence.
+ *   tower_out: dev bf16 [T][H*W][128] = the tower's output for the leaves handed out by the previous call
+ *              (NULL on the first call);  stem_out: dev bf16 [T][H*W][128] = the tower's next input
+ *   leaf_valid_out: dev int32 [T]: 1 = stem_out[tree] holds a fresh leaf. */
+int az_advance_fused(az_engine *e, const void *dev_tower_out, const az_head_weights *weights, const float *dev_stem_w,
+                     const float *dev_stem_b, void *dev_stem_out, int32_t *dev_leaf_valid_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

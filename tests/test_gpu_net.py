@@ -120,3 +120,31 @@ def test_selfplay_runner_other_boards(W, H, n, gravity):
     else:
         legal = np.transpose(states[..., 0], (0, 2, 1)).reshape(len(values), -1) == 1   # action = x * H + y
         assert (policies[~legal] == 0).all()
+
+
+def test_fused_advance_equals_the_three_kernel_route():
+    """az_advance_fused (heads + tree step + stem in one launch) against az_net_heads / az_step / az_net_stem
+    in sequence: same weights, same Philox seeds -> the finished games must be identical, bit for bit."""
+    from az_b200 import selfplay
+
+    engine, native, net = _mods()
+    rules = engine.Rules(7, 6, 4, True)
+    out = []
+    for fused in (False, True):
+        torch.manual_seed(0)
+        fp32 = net.randomise_bn(net.PolicyValueNet())
+        r = selfplay.SelfPlayRunner(rules, n_trees=96, sims_per_move=40, net=fp32, games_target=160, unroll=4, seed=11,
+                                    fused=fused)
+        assert r.fused == fused
+        r.run_until_done(poll_every=64, max_advances=400000)
+        fin = {k: v.cpu().numpy() for k, v in r.finished_device().items()}
+        order = np.argsort(fin["game_id"])
+        out.append(({k: v[order] for k, v in fin.items()}, r.totals()))
+    (a, ta), (b, tb) = out
+    assert ta["games"] == tb["games"] == 160 and ta["sims"] == tb["sims"] and ta["evals"] == tb["evals"]
+    for k in ("game_id", "len", "result"):
+        np.testing.assert_array_equal(a[k], b[k])
+    for g in range(160):
+        n = a["len"][g]
+        np.testing.assert_array_equal(a["visits"][g][:n], b["visits"][g][:n])
+        np.testing.assert_array_equal(a["action"][g][:n], b["action"][g][:n])

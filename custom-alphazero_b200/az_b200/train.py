@@ -100,8 +100,8 @@ class Trainer:
             for p, g, v in zip(net.parameters(), grads, self.velocity):
                 v.mul_(MOMENTUM).add_(g, alpha=-self.lr)  # Keras SGD: v = m*v - lr*g ; w += v
                 p.add_(v)
-        out = {"loss": float(loss), "policy_loss": float(policy_loss), "value_loss": float(value_loss),
-               "l2": float(reg), "lr": self.lr, "steps": self.steps}
+        out = {"loss": float(loss.detach()), "policy_loss": float(policy_loss.detach()),
+               "value_loss": float(value_loss.detach()), "l2": float(reg.detach()), "lr": self.lr, "steps": self.steps}
         n = len(values)
         self.steps += int(np.ceil(n / BATCH_SIZE))  # model/tensorflow/train.py:32
         self.lr = learning_rate_for(self.steps)

@@ -12,6 +12,7 @@ r = selfplay.SelfPlayRunner(rules, n_trees=4096, sims_per_move=800, net=N.Policy
                             groups=1, max_free_sims=mf, fin_capacity=16384)
 r.run(9600); torch.cuda.synchronize()
 g = r.groups[0]
+g.tower_out = None
 for _ in range(12):
     r._advance(g)
 torch.cuda.synchronize()

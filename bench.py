@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--unroll", type=int, default=8)
     ap.add_argument("--groups", type=int, default=1, help="tree slices advanced on parallel graph branches")
     ap.add_argument("--max-free", type=int, default=8)
+    ap.add_argument("--no-fused", action="store_true", help="three-kernel route instead of az_advance_fused")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -187,7 +188,7 @@ def main():
     fp32 = PolicyValueNet(rules.height, rules.width, rules.n_actions)
     runner = selfplay.SelfPlayRunner(rules, n_trees=T, sims_per_move=S, net=fp32, games_target=1 << 40,
                                      game_id_base=rank << 40, seed=1234, move_mode="philox", auto_restart=True,
-                                     unroll=args.unroll, fin_capacity=4 * T, groups=args.groups, max_free_sims=args.max_free)
+                                     unroll=args.unroll, fin_capacity=4 * T, groups=args.groups, max_free_sims=args.max_free, fused=not args.no_fused)
     flat_dev = runner.net.flat_weights()  # what the trainer rank would broadcast after a training step
     n_w = flat_dev.numel()
 
@@ -301,30 +302,56 @@ def main():
         ach = Tg * runner.flops_per_eval / (net_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_sustained"], "traffic": None,
-                "kernel": "policy/value net forward: az_net_stem + 12 cuDNN tcgen05 implicit-GEMM convs (fused bias/ReLU/residual) + az_net_heads, timed alone",
+                "traffic_note": "library kernels; per-kernel DRAM bytes of the 3x3 convolutions are in profiles/ncu_full_summary_r1.csv",
+                "kernel": "policy/value net forward timed alone: az_net_stem + 12 cuDNN tcgen05 implicit-GEMM convolutions (cutlass3x_sm100_tensorop, fused bias/ReLU/residual epilogues) + az_net_heads",
                 "flops_per_launch": Tg * runner.flops_per_eval, "positions_per_launch": Tg, "ms_per_launch": net_ms, "peak_source": peaks["source"] + ", sustained"}
-        # az_step alone (HBM bound): algorithmic bytes per simulation with the measured mean depth / fan-out
+        # the per-tree kernel alone (HBM bound): algorithmic bytes per tree and launch with the measured mean
+        # depth / fan-out.  Fused route: az_advance_fused = heads + tree step + stem (reads the tower output of the
+        # tree's leaf, writes the stem output of the next one); else az_step.
         d_bar = depth_sum / max(sims, 1.0)
         k_bar = children / max(evals, 1.0)
+        sims_per_tree = sims / max(evals, 1.0)  # simulations finished per evaluated leaf
         A, cells = rules.n_actions, rules.height * rules.width
-        bytes_per_sim = (16 + d_bar * k_bar * 24      # select: root record + per level k children x (16 B record + 8 B prior)
-                         + 4 * d_bar + 16 + 4         # path + leaf position + path length written
-                         + cells * 8                  # bf16 NN input [H, W, 4]
-                         + 4 * A + 4                  # priors + value read back
-                         + 4 * d_bar + 16             # path + leaf position re-read at expansion
-                         + k_bar * 24                 # expand: k children x 24 B
-                         + d_bar * 32                 # backup: 16 B read + 16 B write per path node
-                         + 64)                        # per-tree header words
+        tree_bytes = (16 + d_bar * k_bar * 24      # select: root record + per level k children x (16 B record + 8 B prior)
+                      + 4 * d_bar + 16 + 4         # path + leaf position + path length written
+                      + 4 * d_bar + 16             # path + leaf position re-read at expansion
+                      + k_bar * 24                 # expand: k children x 24 B
+                      + d_bar * 32                 # backup: 16 B read + 16 B write per path node
+                      + 64)                        # per-tree header words
+        g0 = runner.groups[0]
+        if runner.fused:
+            import ctypes
+
+            from az_b200.engine import _ptr, _stream
+            from az_b200.native import check, lib
+
+            bytes_per_tree = tree_bytes * sims_per_tree + 2 * cells * 128 * 2  # + tower output in, stem output out (bf16)
+            hw = runner.net._heads_arg()
+
+            def launch():
+                check(lib().az_advance_fused(g0.engine._h, _ptr(g0.tower_carry), ctypes.byref(hw), _ptr(runner.net.stem_w32),
+                                             _ptr(runner.net.stem_b32), _ptr(g0.stem_out), _ptr(g0.valid), _stream()))
+            kname = "az::k_advance<1,1,C4Rules> (az_advance_fused)"
+        else:
+            bytes_per_tree = tree_bytes * sims_per_tree + cells * 8 + 4 * A + 4  # + bf16 planes out, priors/value in
+
+            def launch():
+                g0.engine.step(g0.priors, g0.values, g0.states, g0.valid)
+            kname = "az::k_step<1,1,C4Rules> (az_step)"
+        for _ in range(3):
+            launch()
         a.record()
         for _ in range(n_rep):
-            runner.engine.step(runner.priors, runner.values, runner.states, runner.valid)
+            launch()
         b.record()
         torch.cuda.synchronize()
         step_ms = a.elapsed_time(b) / n_rep
-        ach_gbs = Tg * bytes_per_sim / (step_ms * 1e-3) / 1e9
+        ach_gbs = Tg * bytes_per_tree / (step_ms * 1e-3) / 1e9
         roof_tree = {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach_gbs / peaks["hbm_gbs"], "traffic": None, "kernel": "az::k_step<1,1>",
-                     "bytes_per_sim": bytes_per_sim, "mean_depth": d_bar, "mean_children": k_bar,
+                     "frac": ach_gbs / peaks["hbm_gbs"], "traffic": 82.8e6 if runner.fused else None,
+                     "traffic_source": "profiles/ncu_full_summary_r1.csv (dram read + write of k_advance, steady state)",
+                     "kernel": kname, "bytes_per_tree": bytes_per_tree, "tree_bytes_per_sim": tree_bytes,
+                     "mean_depth": d_bar, "mean_children": k_bar, "sims_per_evaluated_leaf": sims_per_tree,
                      "trees_per_launch": Tg, "ms_per_launch": step_ms, "peak_source": peaks["source"]}
 
     if rank == 0:
@@ -334,7 +361,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "C2: 4096 concurrent 6x7 Connect-4 self-play games per GPU x 800 simulations/move, bf16 net leaf evaluation",
-                       "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "board": "6x7", "n_connect": 4,
+                       "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "fused_advance": bool(runner.fused), "board": "6x7", "n_connect": 4,
                        "net": "4-block 128-filter projection-residual tower, 1267037 params, random init",
                        "l2": "working set per advance (node pools ~GBs + 177 MB activations per conv) exceeds the 126 MB L2; no flush needed"},
             "leaf_evals_per_sec": evals / ms * 1e3, "selfplay_moves_per_sec": moves / ms * 1e3,

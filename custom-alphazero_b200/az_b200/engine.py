@@ -170,6 +170,9 @@ class TreeEngine:
     def search(self):
         check(lib().az_search(self._h, _stream()))
 
+    def extra_sims(self, max_sims):
+        check(lib().az_extra_sims(self._h, int(max_sims), _stream()))
+
     def play(self, greedy=None, move_mode=None):
         g = -1 if greedy is None else int(bool(greedy))
         m = -1 if move_mode is None else {"argmax": 0, "host_uniforms": 1, "philox": 2}[move_mode]

@@ -82,6 +82,7 @@ SYMBOLS = {
     "az_set_roots": (ctypes.c_int, [_P, _P, _P, _P, _I, _P]),
     "az_begin_search": (ctypes.c_int, [_P, _I, _P]),
     "az_step": (ctypes.c_int, [_P, _P, _P, _I, _P, _I, _P, _P]),
+    "az_extra_sims": (ctypes.c_int, [_P, _I, _P]),
     "az_search": (ctypes.c_int, [_P, _P]),
     "az_play": (ctypes.c_int, [_P, _I, _I, _P]),
     "az_fin_clear": (ctypes.c_int, [_P, _P]),

@@ -73,7 +73,7 @@ class SelfPlayRunner:
     def __init__(self, rules=Rules(), n_trees=4096, sims_per_move=800, net=None, *, games_target=None,
                  game_id_base=0, seed=0, move_mode="philox", auto_restart=True, dtype=torch.bfloat16, unroll=8,
                  use_graph=True, max_free_sims=8, node_capacity=None, fin_capacity=None, device=None,
-                 index_move_greedy=8, groups=1, fused=True):
+                 index_move_greedy=8, groups=1, fused=True, extra_sims=0):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.rules = rules
         T, A = int(n_trees), rules.n_actions
@@ -105,6 +105,10 @@ class SelfPlayRunner:
                 shape = (g.engine.n_trees, rules.height, rules.width, self.net.filters)
                 g.stem_out = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
                 g.tower_carry = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
+        # evaluator-free simulations (terminal leaves, in-line moves) continued on a forked stream while the
+        # tower runs: keeps max_free_sims - the tail of the per-tree kernel, which the tower waits for - small
+        self.extra_sims = int(extra_sims)
+        self._extra_streams = [torch.cuda.Stream(device=self.device) for _ in self.groups] if self.extra_sims else []
         self.unroll = int(unroll)
         self.use_graph = use_graph
         self.graph = None
@@ -112,7 +116,7 @@ class SelfPlayRunner:
         self.flops_per_eval = flops_per_eval(rules.height, rules.width, A)
         # kernels of libaz_b200 launched per advance and group: az_advance_fused, or az_step + az_net_stem +
         # az_net_heads (+ az_play sweeps)
-        self.launches_per_advance = (1 if self.fused else 3) * groups
+        self.launches_per_advance = ((1 if self.fused else 3) + (1 if extra_sims and self.fused else 0)) * groups
         self._side = [torch.cuda.Stream(device=self.device) for _ in range(groups - 1)]
 
     # single-group conveniences (tests, compat code)
@@ -147,7 +151,16 @@ class SelfPlayRunner:
             hw = self.net._heads_arg()
             check(lib().az_advance_fused(g.engine._h, _ptr(src), ctypes.byref(hw), _ptr(self.net.stem_w32),
                                          _ptr(self.net.stem_b32), _ptr(g.stem_out), _ptr(g.valid), _stream()))
-            g.tower_out = self.net.tower(g.stem_out)
+            if self.extra_sims:
+                cur = torch.cuda.current_stream()
+                side = self._extra_streams[self.groups.index(g)]
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    g.engine.extra_sims(self.extra_sims)
+                g.tower_out = self.net.tower(g.stem_out)
+                cur.wait_stream(side)
+            else:
+                g.tower_out = self.net.tower(g.stem_out)
         else:
             g.engine.step(g.priors, g.values, g.states, g.valid)
             self.net(g.states, g.priors, g.values)

@@ -401,7 +401,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
 // `leaf` when an evaluation is wanted, else 0.
 template <int NW, int KC, class R, class PriorFn>
 __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& r, int t, WarpScratch& ws, int lane,
-                                         bool have_eval, int prior_mode, double value, PriorFn prior_of, Pos<NW>& leaf) {
+                                         bool have_eval, int prior_mode, double value, PriorFn prior_of, Pos<NW>& leaf,
+                                         int submit = 1) {
     int st = e.status[t];
     if ((st & AZ_PHASE_MASK) != AZ_PHASE_SEARCH) return 0;
     uint32_t flags = 0;
@@ -411,8 +412,10 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
     int sims = e.sims_done[t];
     int root = e.root_node[t];
     long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
+    // pending: 0 = no leaf in flight, 1 = leaf handed to the evaluator, 2 = leaf selected by az_extra_sims but
+    // not handed out yet (it is submitted by the next az_step / az_advance_fused, which finds no answer for it)
     const int was_pending = e.pending[t];
-    if (was_pending && have_eval) {
+    if (was_pending == 1 && have_eval) {
         const int depth = e.path_len[t];
         for (int i = lane; i < depth; i += 32) ws.path[i] = e.path[(size_t)t * kMaxDepth + i];
         const Pos<NW> at = load_pos<NW>(e.leaf_board + (size_t)t * 2 * NW);
@@ -424,8 +427,8 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
         ++neval;
         nchild += link >> 24;
     }
-    int pend = (was_pending && !have_eval) ? 1 : 0;
-    if (pend) leaf = load_pos<NW>(e.leaf_board + (size_t)t * 2 * NW);  // still waiting: hand the same leaf out again
+    int pend = (was_pending == 2 || (was_pending == 1 && !have_eval)) ? 1 : 0;
+    if (pend) leaf = load_pos<NW>(e.leaf_board + (size_t)t * 2 * NW);  // not answered yet: hand the same leaf out (again)
     int freed = 0;
     for (;;) {
         if (!pend && sims >= e.sims_target && e.inline_play) {
@@ -474,7 +477,7 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
         bump(e.counters + (size_t)t * 8 + 5, nchild);
         if (sims >= 0) {
             e.sims_done[t] = sims;
-            e.pending[t] = pend;
+            e.pending[t] = pend ? submit : 0;
             int ph = (sims >= e.sims_target && !pend) ? AZ_PHASE_READY : AZ_PHASE_SEARCH;
             e.status[t] = (st & ~AZ_PHASE_MASK) | ph | (int)flags;
         } else if (flags) {
@@ -576,7 +579,7 @@ __global__ void __launch_bounds__(kAdvWarps * 32, 2)
     const int mtiles = (cells + 15) >> 4;
 
     // ---- A: heads for the pending leaf of this tree
-    const bool have_eval = x != nullptr && e.pending[t] && (e.status[t] & AZ_PHASE_MASK) == AZ_PHASE_SEARCH;
+    const bool have_eval = x != nullptr && e.pending[t] == 1 && (e.status[t] & AZ_PHASE_MASK) == AZ_PHASE_SEARCH;
     float pr[4] = {0.f, 0.f, 0.f, 0.f};
     float value = 0.f;
     if (have_eval) {
@@ -737,6 +740,23 @@ __global__ void __launch_bounds__(kAdvWarps * 32, 2)
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------ k_extra
+// Simulations that need no evaluator, for trees without a leaf in flight (their last simulation hit a terminal
+// leaf or spent the move budget).  Runs beside the tower on a forked stream: such trees keep finishing
+// terminal-leaf simulations and playing moves (up to e.max_free of them) until a leaf does need the net; that
+// leaf is parked (pending = 2) and submitted by the next az_advance_fused / az_step.
+template <int NW, int KC, class R>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_extra(Eng e, Aux aux) {
+    __shared__ WarpScratch s_ws[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= e.T) return;
+    if (e.pending[t] != 0 || (e.status[t] & AZ_PHASE_MASK) != AZ_PHASE_SEARCH) return;
+    const auto r = RulesView<R>::get(e);
+    Pos<NW> leaf;
+    step_tree<NW, KC>(e, aux, r, t, s_ws[warp], lane, false, AZ_PRIOR_F64, 0.0, [](int) { return 0.0; }, leaf, 2);
 }
 
 // ------------------------------------------------------------------------------------------ k_search
@@ -1120,6 +1140,21 @@ AZ_API int az_step(az_engine* e, const void* priors, const void* values, int32_t
     if ((eval_dtype != AZ_F32 && eval_dtype != AZ_F64) || (state_dtype != AZ_BF16 && state_dtype != AZ_F32))
         return fail(AZ_ERR_ARG, "az_step: unsupported dtype%s");
     AZ_DISPATCH(k_step, e->eng, e->aux, priors, values, eval_dtype, states, state_dtype, leaf_valid);
+    return AZ_OK;
+}
+
+AZ_API int az_extra_sims(az_engine* e, int32_t max_sims, void* stream) {
+    if (!e || max_sims < 1) return fail(AZ_ERR_ARG, "az_extra_sims: bad argument%s");
+    Eng g = e->eng;
+    g.max_free = max_sims;
+    cudaStream_t s__ = static_cast<cudaStream_t>(stream);
+    dim3 g__ = tree_grid(e), b__(kWarpsPerBlock * 32);
+    if (e->c4) k_extra<1, 1, C4Rules><<<g__, b__, 0, s__>>>(g, e->aux);
+    else if (e->nw == 1 && e->kc == 1) k_extra<1, 1, Rules><<<g__, b__, 0, s__>>>(g, e->aux);
+    else if (e->nw == 1) k_extra<1, 4, Rules><<<g__, b__, 0, s__>>>(g, e->aux);
+    else if (e->kc == 1) k_extra<2, 1, Rules><<<g__, b__, 0, s__>>>(g, e->aux);
+    else k_extra<2, 4, Rules><<<g__, b__, 0, s__>>>(g, e->aux);
+    AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
 

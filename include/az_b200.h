@@ -116,7 +116,7 @@ typedef struct az_layout {
                                            is compacted into the other half and the root is node 0) */
     size_t n_nodes;     /* int32  [T]      nodes used in the live half */
     size_t sims_done;   /* int32  [T] */
-    size_t pending;     /* int32  [T]      1 = a leaf awaits its evaluation */
+    size_t pending;     /* int32  [T]      1 = a leaf awaits its evaluation, 2 = a leaf is selected but not yet handed out */
     size_t path_len;    /* int32  [T] */
     size_t path;        /* int32  [T][max_depth]  node indices root-child ... leaf */
     size_t leaf_board;  /* uint64 [T][2][WD] */
@@ -186,6 +186,13 @@ int az_begin_search(az_engine *e, int32_t sims, void *stream);
  * states_out: dev [T][H][W][4] (AZ_BF16 or AZ_F32); leaf_valid_out: dev int32 [T]. */
 int az_step(az_engine *e, const void *dev_priors, const void *dev_values, int32_t eval_dtype, void *dev_states_out,
             int32_t state_dtype, int32_t *dev_leaf_valid_out, void *stream);
+
+/* Simulations that need no evaluator, for trees WITHOUT a leaf in flight (their last simulation ended in a
+ * terminal leaf, mcts/mcts.py:179, or spent the move budget): up to max_sims more terminal-leaf simulations /
+ * in-line moves per tree, stopping at the first leaf that does need the evaluator, which is parked and submitted
+ * by the next az_step / az_advance_fused.  Touches no evaluator buffer, so it may run on a forked stream beside the
+ * net; it must complete before the next az_step / az_advance_fused / az_play of the same engine. */
+int az_extra_sims(az_engine *e, int32_t max_sims, void *stream);
 
 /* Runs the remaining simulations of the current move for every tree inside ONE kernel using the
  * in-kernel evaluator (eval_mode UNIFORM or HASH): MCTS.search(n) with the fixed evaluator. */

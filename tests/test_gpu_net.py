@@ -130,21 +130,22 @@ def test_fused_advance_equals_the_three_kernel_route():
     engine, native, net = _mods()
     rules = engine.Rules(7, 6, 4, True)
     out = []
-    for fused in (False, True):
+    for fused, extra, mf in ((False, 0, 8), (True, 0, 8), (True, 12, 1)):
         torch.manual_seed(0)
         fp32 = net.randomise_bn(net.PolicyValueNet())
         r = selfplay.SelfPlayRunner(rules, n_trees=96, sims_per_move=40, net=fp32, games_target=160, unroll=4, seed=11,
-                                    fused=fused)
+                                    fused=fused, extra_sims=extra, max_free_sims=mf)
         assert r.fused == fused
         r.run_until_done(poll_every=64, max_advances=400000)
         fin = {k: v.cpu().numpy() for k, v in r.finished_device().items()}
         order = np.argsort(fin["game_id"])
         out.append(({k: v[order] for k, v in fin.items()}, r.totals()))
-    (a, ta), (b, tb) = out
-    assert ta["games"] == tb["games"] == 160 and ta["sims"] == tb["sims"] and ta["evals"] == tb["evals"]
-    for k in ("game_id", "len", "result"):
-        np.testing.assert_array_equal(a[k], b[k])
-    for g in range(160):
-        n = a["len"][g]
-        np.testing.assert_array_equal(a["visits"][g][:n], b["visits"][g][:n])
-        np.testing.assert_array_equal(a["action"][g][:n], b["action"][g][:n])
+    (a, ta) = out[0]
+    for b, tb in out[1:]:  # the fused launch, and the fused launch with evaluator-free simulations beside the tower
+        assert ta["games"] == tb["games"] == 160 and ta["sims"] == tb["sims"] and ta["evals"] == tb["evals"]
+        for k in ("game_id", "len", "result"):
+            np.testing.assert_array_equal(a[k], b[k])
+        for g in range(160):
+            n = a["len"][g]
+            np.testing.assert_array_equal(a["visits"][g][:n], b["visits"][g][:n])
+            np.testing.assert_array_equal(a["action"][g][:n], b["action"][g][:n])

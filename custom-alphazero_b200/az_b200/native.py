@@ -92,6 +92,7 @@ SYMBOLS = {
     "az_net_stem": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "az_net_heads": (ctypes.c_int, [_P, ctypes.POINTER(AzHeadWeights), _I, _I, _I, _I, _P, _P, _P]),
     "az_advance_fused": (ctypes.c_int, [_P, _P, ctypes.POINTER(AzHeadWeights), _P, _P, _P, _P, _P]),
+    "az_debug_timeline": (ctypes.c_int, [_P, _P, _I]),
     "az_decode_samples": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
 }
 

@@ -540,8 +540,15 @@ struct StemParams {
 template <int NW, int KC, class R>
 __global__ void __launch_bounds__(kAdvWarps * 32, 2)
     k_advance(Eng e, Aux aux, const __nv_bfloat16* __restrict__ x, HeadParams hp, StemParams sp,
-              __nv_bfloat16* __restrict__ stem_out, int32_t* leaf_valid) {
+              __nv_bfloat16* __restrict__ stem_out, int32_t* leaf_valid, unsigned long long* timeline) {
     constexpr int C = 128;
+    // optional timeline slot {first start, last end} in globaltimer ns (az_debug_timeline): measurement aid
+    auto now = []() {
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        return t_;
+    };
+    if (timeline && threadIdx.x == 0) atomicMin(timeline, now());
     extern __shared__ float s_f[];
     const auto r = RulesView<R>::get(e);
     const int cells = r.cells, A = r.A, PW = r.W + 2;
@@ -670,7 +677,10 @@ __global__ void __launch_bounds__(kAdvWarps * 32, 2)
                                        },
                                        leaf);
     if (lane == 0) leaf_valid[t] = pend;
-    if (!pend) return;
+    if (!pend) {
+        if (timeline && lane == 0) atomicMax(timeline + 1, now());
+        return;
+    }
 
     // ---- C: stem of the new leaf
     __syncwarp();
@@ -740,6 +750,7 @@ __global__ void __launch_bounds__(kAdvWarps * 32, 2)
             }
         }
     }
+    if (timeline && lane == 0) atomicMax(timeline + 1, now());
 }
 
 // ------------------------------------------------------------------------------------------ k_extra
@@ -933,6 +944,8 @@ struct az_engine {
     Aux aux;
     int nw, kc;
     bool c4;  // headline configuration: 6x7, connect 4, gravity -> compile-time rules
+    unsigned long long* timeline = nullptr;  // az_debug_timeline
+    int timeline_slots = 0, timeline_next = 0;
 };
 
 static int check_cfg(const az_config* c) {
@@ -1251,11 +1264,16 @@ AZ_API int az_advance_fused(az_engine* e, const void* tower_out, const az_head_w
     dim3 grid((e->eng.T + kAdvWarps - 1) / kAdvWarps), block(kAdvWarps * 32);
     const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(tower_out);
     __nv_bfloat16* so = static_cast<__nv_bfloat16*>(stem_out);
+    unsigned long long* tl = nullptr;
+    if (e->timeline && e->timeline_slots > 0) {
+        tl = e->timeline + 2 * (e->timeline_next % e->timeline_slots);
+        e->timeline_next += 1;
+    }
 #define AZ_ADV(NWv, KCv, Rv)                                                                                         \
     do {                                                                                                             \
         auto kfn = k_advance<NWv, KCv, Rv>;                                                                          \
         AZ_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
-        kfn<<<grid, block, smem, s>>>(e->eng, e->aux, x, hp, sp, so, leaf_valid);                                    \
+        kfn<<<grid, block, smem, s>>>(e->eng, e->aux, x, hp, sp, so, leaf_valid, tl);                                    \
     } while (0)
     if (e->c4) AZ_ADV(1, 1, C4Rules);
     else if (e->nw == 1 && e->kc == 1) AZ_ADV(1, 1, Rules);
@@ -1264,5 +1282,13 @@ AZ_API int az_advance_fused(az_engine* e, const void* tower_out, const az_head_w
     else AZ_ADV(2, 4, Rules);
 #undef AZ_ADV
     AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_debug_timeline(az_engine* e, void* dev_slots, int32_t n_slots) {
+    if (!e || n_slots < 0) return fail(AZ_ERR_ARG, "az_debug_timeline: bad argument%s");
+    e->timeline = static_cast<unsigned long long*>(dev_slots);
+    e->timeline_slots = dev_slots ? n_slots : 0;
+    e->timeline_next = 0;
     return AZ_OK;
 }

@@ -267,6 +267,11 @@ int az_net_heads(const void *dev_x, const az_head_weights *weights, int32_t n, i
 int az_advance_fused(az_engine *e, const void *dev_tower_out, const az_head_weights *weights, const float *dev_stem_w,
                      const float *dev_stem_b, void *dev_stem_out, int32_t *dev_leaf_valid_out, void *stream);
 
+/* Measurement aid: successive az_advance_fused launches record {first block start, last warp end} (globaltimer,
+ * ns) into dev_slots[2 * (launch % n_slots)], which the caller initialises to {UINT64_MAX, 0}.  NULL switches it
+ * off.  The slot is chosen at launch (or graph-capture) time. */
+int az_debug_timeline(az_engine *e, void *dev_slots, int32_t n_slots);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,15 +8,15 @@ rules = engine.Rules(7, 6, 4, True)
 torch.manual_seed(0)
 fp32 = N.PolicyValueNet()
 torch.backends.cudnn.benchmark = True
-for mf, extra in [(8, 0), (1, 16), (2, 16), (1, 32), (2, 8), (4, 16)]:
+for groups, mf, extra in [(1, 8, 0), (2, 8, 0), (2, 4, 0), (3, 8, 0)]:
     r = selfplay.SelfPlayRunner(rules, n_trees=4096, sims_per_move=800, net=fp32, games_target=1 << 40, unroll=8,
-                                groups=1, max_free_sims=mf, fin_capacity=16384, extra_sims=extra)
+                                groups=groups, max_free_sims=mf, fin_capacity=16384, extra_sims=extra)
     r.run(800 * 12); torch.cuda.synchronize()   # 12 moves in: trees desynchronised, terminal hits appear
     t0 = r.totals()
     a, b = torch.cuda.Event(True), torch.cuda.Event(True)
     a.record(); n = r.run(1600); b.record(); torch.cuda.synchronize()
     t1 = r.totals(); ms = a.elapsed_time(b)
-    print(f"max_free={mf} extra={extra}: {ms/n*1e3:.1f} us/advance  sims/s {(t1['sims']-t0['sims'])/ms*1e3/1e6:.3f} M  evals/s {(t1['evals']-t0['evals'])/ms*1e3/1e6:.3f} M", flush=True)
+    print(f"groups={groups} max_free={mf} extra={extra}: {ms/n*1e3:.1f} us/advance  sims/s {(t1['sims']-t0['sims'])/ms*1e3/1e6:.3f} M  evals/s {(t1['evals']-t0['evals'])/ms*1e3/1e6:.3f} M", flush=True)
     r.check_status()
     del r
     torch.cuda.empty_cache()

@@ -1119,8 +1119,9 @@ AZ_API int az_reset_games(az_engine* e, void* stream) {
 
 AZ_API int az_set_roots(az_engine* e, const int32_t* ids, const int8_t* cells, const int32_t* plies, int32_t n,
                             void* stream) {
-    if (!e || !ids || !cells || !plies || n < 0) return fail(AZ_ERR_ARG, "az_set_roots: bad argument%s");
+    if (!e || n < 0) return fail(AZ_ERR_ARG, "az_set_roots: bad argument%s");
     if (n == 0) return AZ_OK;
+    if (!ids || !cells || !plies) return fail(AZ_ERR_ARG, "az_set_roots: null pointer%s");
     k_set_roots<<<flat_grid(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(e->eng, e->aux, ids, cells, plies, n);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
@@ -1204,8 +1205,8 @@ AZ_API int az_env_play(const az_config* c, const int8_t* cells_in, const int32_t
                            int8_t* cells_out, int32_t* status, void* stream) {
     Rules r;
     if (int rc = env_rules(c, &r)) return rc;
+    if (n == 0) return AZ_OK;  // an empty batch has no buffers to point at
     if (!cells_in || !actions || !cells_out || !status || n < 0) return fail(AZ_ERR_ARG, "az_env_play: bad argument%s");
-    if (n == 0) return AZ_OK;
     k_env_play<<<flat_grid(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(r, cells_in, actions, n, cells_out, status);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
@@ -1214,8 +1215,8 @@ AZ_API int az_env_play(const az_config* c, const int8_t* cells_in, const int32_t
 AZ_API int az_env_legal(const az_config* c, const int8_t* cells, int32_t n, uint8_t* legal, void* stream) {
     Rules r;
     if (int rc = env_rules(c, &r)) return rc;
-    if (!cells || !legal || n < 0) return fail(AZ_ERR_ARG, "az_env_legal: bad argument%s");
     if (n == 0) return AZ_OK;
+    if (!cells || !legal || n < 0) return fail(AZ_ERR_ARG, "az_env_legal: bad argument%s");
     k_env_legal<<<flat_grid(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(r, cells, n, legal);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
@@ -1224,8 +1225,8 @@ AZ_API int az_env_legal(const az_config* c, const int8_t* cells, int32_t n, uint
 AZ_API int az_env_encode(const az_config* c, const int8_t* cells, int32_t n, float* states, void* stream) {
     Rules r;
     if (int rc = env_rules(c, &r)) return rc;
-    if (!cells || !states || n < 0) return fail(AZ_ERR_ARG, "az_env_encode: bad argument%s");
     if (n == 0) return AZ_OK;
+    if (!cells || !states || n < 0) return fail(AZ_ERR_ARG, "az_env_encode: bad argument%s");
     k_env_encode<<<flat_grid(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(r, cells, n, states);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
@@ -1236,9 +1237,10 @@ AZ_API int az_decode_samples(const az_config* c, const uint64_t* boards, const i
                              float* states, double* policies, int32_t* values, void* stream) {
     Rules r;
     if (int rc = env_rules(c, &r)) return rc;
-    if (!boards || !visits || !actions || !lens || !results || !offsets || !states || !policies || !values || n_games < 0)
-        return fail(AZ_ERR_ARG, "az_decode_samples: bad argument%s");
     if (n_games == 0) return AZ_OK;
+    if (!boards || !visits || !actions || !lens || !results || !offsets || n_games < 0)
+        return fail(AZ_ERR_ARG, "az_decode_samples: bad argument%s");
+    // states / policies / values may be null only if every game is empty; the kernel then writes nothing
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (r.bits > 64)
         k_decode<2><<<n_games, 128, 0, s>>>(r, r.cells, boards, visits, actions, lens, results, offsets, states, policies, values);

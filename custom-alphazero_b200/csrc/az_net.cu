@@ -239,9 +239,9 @@ using namespace az;
 
 AZ_API int az_net_stem(const void* states, const float* w, const float* b, int32_t n, int32_t H, int32_t W, int32_t C,
                        void* out, void* stream) {
+    if (n == 0) return AZ_OK;
     if (!states || !w || !b || !out || n < 0 || H < 1 || W < 1) return fail_net(AZ_ERR_ARG, "az_net_stem: bad argument");
     if (C != 128) return fail_net(AZ_ERR_ARG, "az_net_stem: built for 128 filters (config.py:71)");
-    if (n == 0) return AZ_OK;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -255,10 +255,10 @@ AZ_API int az_net_stem(const void* states, const float* w, const float* b, int32
 
 AZ_API int az_net_heads(const void* x, const az_head_weights* hw, int32_t n, int32_t cells, int32_t C, int32_t A,
                         float* priors, float* values, void* stream) {
+    if (n == 0) return AZ_OK;
     if (!x || !hw || !priors || !values || n < 0 || cells < 1 || A < 1 || A > AZ_MAX_ACTIONS)
         return fail_net(AZ_ERR_ARG, "az_net_heads: bad argument");
     if (C != 128) return fail_net(AZ_ERR_ARG, "az_net_heads: built for 128 filters (config.py:71)");
-    if (n == 0) return AZ_OK;
     HeadParams hp{hw->conv_w, hw->conv_b, hw->policy_w, hw->policy_b, hw->value1_w, hw->value1_b, hw->value2_w, hw->value2_b,
                   n, cells, A};
     const size_t smem = sizeof(float) * ((((size_t)A * (2 * cells + 1) + 3) & ~(size_t)3) + (size_t)kHidden * (cells | 1) +

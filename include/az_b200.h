@@ -177,7 +177,8 @@ int az_begin_search(az_engine *e, int32_t sims, void *stream);
  *   1. a tree whose leaf was evaluated since the last call expands it with priors/values
  *      (evaluate_and_expand, :145-161) and backs the value up its stored path (backup, :163-168);
  *   2. it then selects the next leaf by PUCT (select, :111-120; UCTEdge terms :39-55); simulations
- *      that end in a terminal leaf are finished on the spot (:179), up to max_free_sims of them;
+ *      that end in a terminal leaf are finished on the spot (:179) and, with cfg.inline_play, a spent move
+ *      budget is turned into a move right here (the az_play step) - up to max_free_sims such events per call;
  *   3. a non-terminal leaf is encoded as the NN input (Board.full_state, connect_n/board.py:83-98)
  *      into states_out[tree] and leaf_valid_out[tree] = 1.
  * priors: dev [T][A], values: dev [T] (dtype AZ_F32 or AZ_F64); may be NULL on the first call.  As in the
@@ -201,12 +202,14 @@ int az_search(az_engine *e, void *stream);
 /* MCTS.play (mcts/mcts.py:182-222) for every tree in AZ_PHASE_READY: root policy from visit counts,
  * edge choice, record (parent position, visit counts, action), move applied to the live board
  * (Board.play(..., keep_same_player=True), connect_n/board.py:233-250), re-root to the chosen child
- * keeping its subtree (compacted into the other pool half).  greedy_override: -1 = the self-play rule
+ * keeping its subtree (in place while the live pool half has room for another search, else compacted
+ * breadth-first into the other half).  greedy_override: -1 = the self-play rule
  * ply >= index_move_greedy, 0 / 1 = force; move_mode_override: -1 = cfg.move_mode.
  * Finished games are moved to the ring and, with auto_restart, replaced (play_game, self_play.py:59-78). */
 int az_play(az_engine *e, int32_t greedy_override, int32_t move_mode_override, void *stream);
 
-/* Empties the finished-game ring after the host copied it; re-arms stalled trees. */
+/* Empties the finished-game ring after the host copied it; trees in AZ_PHASE_STALLED hand their game over at
+ * the next az_play. */
 int az_fin_clear(az_engine *e, void *stream);
 
 /* Standalone environment kernels (K2/K3), batched over n boards in the reference's cell convention.

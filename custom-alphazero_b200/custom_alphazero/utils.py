@@ -1,6 +1,7 @@
 """File-system glue the self-play entry point needs (reference utils.py:24-133): which weights to play
 with.  Checkpoints of the B200 build are torch state dicts (`model.pt`) next to the reference's
 meta.json / MODEL_SAVED_SUCCESSFULLY sentinel; TensorFlow checkpoints cannot be read here."""
+import hashlib
 import json
 import os
 from typing import Optional
@@ -13,11 +14,43 @@ from custom_alphazero.config import ConfigConnectN, ConfigModel, ConfigPath
 from custom_alphazero.connect_n.board import Board
 
 
+def model_hash(net: PolicyValueNet) -> str:
+    """Hash of the weights (the reference sums md5 digests of the printed weights, model.py:168-173; here md5 over
+    the raw parameter and buffer bytes in state-dict order)."""
+    h = hashlib.md5()
+    for name, t in net.state_dict().items():
+        h.update(name.encode())
+        h.update(t.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def save_with_meta(net: PolicyValueNet, path: str, steps: int = 0, learning_rate: float = ConfigModel.maximum_learning_rate):
+    """Checkpoint layout of the reference (model.py:203-212): weights under `model*`, meta.json with steps,
+    learning_rate and hash, and the MODEL_SAVED_SUCCESSFULLY sentinel written last so a half-written checkpoint
+    is never picked up (utils.py:53,113-118)."""
+    os.makedirs(path, exist_ok=True)
+    torch.save(net.state_dict(), os.path.join(path, ConfigPath.model_prefix + ".pt"))
+    meta = {"steps": int(steps), "learning_rate": float(learning_rate), "hash": model_hash(net)}
+    with open(os.path.join(path, ConfigPath.model_meta), "w") as fp:
+        json.dump(meta, fp, sort_keys=True, indent=4)
+    open(os.path.join(path, ConfigPath.model_success), "wb").close()
+
+
+def load_with_meta(net: PolicyValueNet, path: str) -> dict:
+    """model.py:190-201: refuses a checkpoint without the sentinel or whose weights do not match the stored hash."""
+    assert os.path.exists(os.path.join(path, ConfigPath.model_success)), f"No verification file of the model found at {path}!"
+    net.load_state_dict(torch.load(os.path.join(path, ConfigPath.model_prefix + ".pt"), map_location="cpu"))
+    with open(os.path.join(path, ConfigPath.model_meta)) as fp:
+        meta = json.load(fp)
+    assert model_hash(net) == meta.get("hash"), f"Unexpected weights hash recovered during model loading at {path}!"
+    return meta
+
+
 def init_model(path: Optional[str] = None) -> PolicyValueNet:
     A = len(Board.get_all_possible_moves())
     net = PolicyValueNet(ConfigConnectN.board_height, ConfigConnectN.board_width, A, ConfigModel.filters, ConfigModel.depth)
     if path is not None:
-        net.load_state_dict(torch.load(os.path.join(path, ConfigPath.model_prefix + ".pt"), map_location="cpu"))
+        load_with_meta(net, path)
     return net.eval()
 
 

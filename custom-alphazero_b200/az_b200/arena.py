@@ -1,8 +1,9 @@
 """Arena on the GPU: the reference's evaluate_two_models in policy-only mode
 (evaluation/evaluate.py:29-134, the default: ConfigServing.evaluate_with_mcts = False), all games in lock-step.
 
-Per ply and game: the net of the side to move gives probabilities [A]; the legal ones are taken in BOARD move
-order and normalised (mcts/utils.py:4-16); the move is their argmax (deterministic) or one np.random.choice draw;
+Per ply and game: the net of the side to move gives probabilities [A]; the legal ones (action-list order) are
+normalised (mcts/utils.py:4-16); their argmax (deterministic) or one np.random.choice draw gives a rank j, and the
+move is board.moves[j];
 Board.play(move, keep_same_player=True); the other net moves next.  Game g is opened by the candidate when g is
 even (evaluate.py:39).  Score = candidate wins / decisive games, 0.5 if all games were drawn (evaluate.py:124-129).
 Positions live on the device as int8 cells and are advanced by the K2/K3 kernels (az_env_*); torch does the
@@ -55,20 +56,25 @@ def play_arena(net_current, net_previous, rules: Rules, games=EVALUATION_GAMES, 
                 p, _ = net(x.contiguous())
                 probs[sel] = p.float()
         legal = env.env_legal(rules, c)  # K2: mask in action order
-        lp = torch.where(legal, probs, torch.zeros_like(probs))[:, order]  # legal probabilities in board order
-        lm = legal[:, order]
-        s = lp.sum(dim=1, keepdim=True)  # float32 like numpy on the model's float32 output
-        k = lm.sum(dim=1, keepdim=True).float()
-        norm = torch.where(s == 0, lm.float() / k, lp / torch.where(s == 0, torch.ones_like(s), s))
+        # probabilities[legal_moves_mask]: the legal probabilities in ACTION-LIST order, normalised in float32
+        lp = torch.where(legal, probs, torch.zeros_like(probs))
+        s = lp.sum(dim=1, keepdim=True)
+        k = legal.sum(dim=1, keepdim=True).float()
+        norm = torch.where(s == 0, legal.float() / k, lp / torch.where(s == 0, torch.ones_like(s), s))
         if deterministic:
-            score = torch.where(lm, norm, torch.full_like(norm, -1.0))
-            pick = torch.argmax(score, dim=1)  # first maximum among the legal moves in board order
+            score = torch.where(legal, norm, torch.full_like(norm, -1.0))
+            slot = torch.argmax(score, dim=1)  # first maximum among the legal entries
         else:
             u = torch.as_tensor(rng.random_sample(idx.numel()), dtype=torch.float64, device=device)
             cdf = torch.cumsum(norm.double(), dim=1)
             cdf = cdf / cdf[:, -1:]
-            cdf = torch.where(lm, cdf, torch.full_like(cdf, -1.0))  # an illegal slot can never be the first > u
-            pick = (cdf > u[:, None]).float().argmax(dim=1)
+            cdf = torch.where(legal, cdf, torch.full_like(cdf, -1.0))  # an illegal slot can never be the first > u
+            slot = (cdf > u[:, None]).float().argmax(dim=1)
+        # ... and the chosen RANK j among them indexes board.moves, which is in BOARD order (evaluate.py:45-52):
+        # the same pairing by rank as in the search (quirk Q1; identical orders when gravity is on)
+        rank = torch.cumsum(legal.long(), dim=1).gather(1, slot[:, None]) - 1
+        lm = legal[:, order]
+        pick = ((torch.cumsum(lm.long(), dim=1) == rank + 1) & lm).float().argmax(dim=1)
         action = order[pick].to(torch.int32)
         out, status = env.env_play(rules, c, action)  # K2
         assert bool((status >= 0).all())

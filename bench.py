@@ -360,7 +360,7 @@ def main():
             "metric": METRIC, "value": sims / ms * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "C2: 4096 concurrent 6x7 Connect-4 self-play games per GPU x 800 simulations/move, bf16 net leaf evaluation",
+            "config": {"workload": f"C2: {T} concurrent 6x7 Connect-4 self-play games per GPU x {S} simulations/move, bf16 net leaf evaluation",
                        "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "fused_advance": bool(runner.fused), "board": "6x7", "n_connect": 4,
                        "net": "4-block 128-filter projection-residual tower, 1267037 params, random init",
                        "l2": "working set per advance (node pools ~GBs + 177 MB activations per conv) exceeds the 126 MB L2; no flush needed"},

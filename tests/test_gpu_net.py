@@ -149,3 +149,33 @@ def test_fused_advance_equals_the_three_kernel_route():
             n = a["len"][g]
             np.testing.assert_array_equal(a["visits"][g][:n], b["visits"][g][:n])
             np.testing.assert_array_equal(a["action"][g][:n], b["action"][g][:n])
+
+
+def test_games_do_not_depend_on_how_they_are_sharded():
+    """SURVEY 4 test (5): 1 rank playing games [0, G) and 2 ranks playing [0, G/2) and [G/2, G) (az_b200.dist.shard_games)
+    produce the same games id by id - move sampling is keyed by (seed, game id, ply), never by rank or tree slot."""
+    from az_b200 import dist as azdist
+    from az_b200 import selfplay
+
+    engine, native, net = _mods()
+    rules = engine.Rules(7, 6, 4, True)
+    G = 120
+
+    def play(base, count, trees):
+        torch.manual_seed(0)
+        r = selfplay.SelfPlayRunner(rules, n_trees=trees, sims_per_move=32, net=net.PolicyValueNet(), games_target=count,
+                                    game_id_base=base, unroll=4, seed=21)
+        r.run_until_done(poll_every=64, max_advances=400000)
+        fin = {k: v.cpu().numpy() for k, v in r.finished_device().items()}
+        return {int(g): (fin["len"][i], fin["result"][i], fin["action"][i][: fin["len"][i]].tolist(),
+                         fin["visits"][i][: fin["len"][i]].tolist()) for i, g in enumerate(fin["game_id"])}
+
+    whole = play(0, G, 64)
+    parts = {}
+    for rank in range(2):
+        base, count = azdist.shard_games(G, rank, 2)
+        parts.update(play(base, count, 48))
+    assert sorted(whole) == sorted(parts) == list(range(G))
+    for g in range(G):
+        assert whole[g][0] == parts[g][0] and whole[g][1] == parts[g][1], g
+        assert whole[g][2] == parts[g][2] and whole[g][3] == parts[g][3], g

@@ -127,8 +127,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: 6x7 Connect-4 self-play, 800 simulations/move, policy/value net leaf evaluation",
-                   "sims_per_move": args.sims, "board": "6x7", "n_connect": 4},
+        "config": {"workload": f"{RULES[1]}x{RULES[0]} Connect-{RULES[2]} self-play, {args.sims} simulations/move, policy/value net leaf evaluation",
+                   "sims_per_move": args.sims, "board": f"{RULES[1]}x{RULES[0]}", "n_connect": RULES[2], "gravity": RULES[3]},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": sp.workers, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -148,7 +148,13 @@ def main():
     ap.add_argument("--groups", type=int, default=1, help="tree slices advanced on parallel graph branches")
     ap.add_argument("--max-free", type=int, default=8)
     ap.add_argument("--no-fused", action="store_true", help="three-kernel route instead of az_advance_fused")
+    ap.add_argument("--board", default="7x6", help="WxH (headline: 7x6); other boards are extra configurations (C4)")
+    ap.add_argument("--connect", type=int, default=4)
+    ap.add_argument("--no-gravity", action="store_true")
     args = ap.parse_args()
+    global RULES
+    bw, bh = (int(v) for v in args.board.lower().split("x"))
+    RULES = (bw, bh, args.connect, not args.no_gravity)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -331,13 +337,13 @@ def main():
             def launch():
                 check(lib().az_advance_fused(g0.engine._h, _ptr(g0.tower_carry), ctypes.byref(hw), _ptr(runner.net.stem_w32),
                                              _ptr(runner.net.stem_b32), _ptr(g0.stem_out), _ptr(g0.valid), _stream()))
-            kname = "az::k_advance<1,1,C4Rules> (az_advance_fused)"
+            kname = "az::k_advance (az_advance_fused)"
         else:
             bytes_per_tree = tree_bytes * sims_per_tree + cells * 8 + 4 * A + 4  # + bf16 planes out, priors/value in
 
             def launch():
                 g0.engine.step(g0.priors, g0.values, g0.states, g0.valid)
-            kname = "az::k_step<1,1,C4Rules> (az_step)"
+            kname = "az::k_step (az_step)"
         for _ in range(3):
             launch()
         a.record()
@@ -360,9 +366,9 @@ def main():
             "metric": METRIC, "value": sims / ms * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"C2: {T} concurrent 6x7 Connect-4 self-play games per GPU x {S} simulations/move, bf16 net leaf evaluation",
-                       "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "fused_advance": bool(runner.fused), "board": "6x7", "n_connect": 4,
-                       "net": "4-block 128-filter projection-residual tower, 1267037 params, random init",
+            "config": {"workload": f"{'C2' if RULES == (7, 6, 4, True) else 'C4'}: {T} concurrent {rules.height}x{rules.width} Connect-{rules.n} self-play games per GPU x {S} simulations/move, bf16 net leaf evaluation",
+                       "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "fused_advance": bool(runner.fused), "board": f"{rules.height}x{rules.width}", "n_connect": rules.n, "gravity": rules.gravity,
+                       "net": f"4-block 128-filter projection-residual tower, {fp32.n_parameters()} params, random init",
                        "l2": "working set per advance (node pools ~GBs + 177 MB activations per conv) exceeds the 126 MB L2; no flush needed"},
             "leaf_evals_per_sec": evals / ms * 1e3, "selfplay_moves_per_sec": moves / ms * 1e3,
             "games_finished": games,

@@ -24,24 +24,19 @@ def _rules_from_config():
 
 class Board:
     def __init__(self, array: Optional[np.ndarray] = None):
-        assert 2 <= ConfigConnectN.n <= min(ConfigConnectN.board_width, ConfigConnectN.board_height)
-        self.board_width, self.board_height = ConfigConnectN.board_width, ConfigConnectN.board_height
-        self.n, self.gravity = ConfigConnectN.n, ConfigConnectN.gravity
-        self.black, self.empty, self.white = ConfigConnectN.black, ConfigConnectN.empty, ConfigConnectN.white
-        self.pieces = ConfigConnectN.pieces
-        self.pieces_to_int = {s: v for v, s in self.pieces.items()}
-        self.played_moves = []
-        if array is None:
-            self.array = np.zeros((self.board_height, self.board_width), dtype="int8")
-        else:
-            assert isinstance(array, np.ndarray)
-            assert array.shape == (self.board_height, self.board_width)
+        cfg = ConfigConnectN  # read at construction, so the class attributes can be patched per board
+        assert 2 <= cfg.n <= min(cfg.board_width, cfg.board_height)
+        for name in ("board_width", "board_height", "n", "gravity", "black", "empty", "white", "pieces"):
+            setattr(self, name, getattr(cfg, name))
+        self.pieces_to_int = {symbol: value for value, symbol in self.pieces.items()}
+        shape = (self.board_height, self.board_width)
+        if array is not None:
+            assert isinstance(array, np.ndarray) and array.shape == shape
             assert np.unique(array).size <= len(self.pieces)
-            self.array = array.astype("int8")
-        self.turn = ConfigConnectN.white
-        self.fullmove_number = 0
-        self.game_over = False
-        self.is_null = None
+        self.array = np.zeros(shape, dtype="int8") if array is None else array.astype("int8")
+        self.turn, self.fullmove_number = cfg.white, 0
+        self.game_over, self.is_null = False, None
+        self.played_moves = []
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -88,13 +83,18 @@ class Board:
     def mirror(self) -> np.ndarray:
         return (-self.array).astype(self.array.dtype)
 
+    @staticmethod
+    def _one_hot(cells) -> np.ndarray:
+        # planes in the reference's order: empty (0), white (+1), black (-1 indexes the last row of eye(3))
+        return (cells[..., None] == np.asarray([0, 1, -1])).astype(np.float64)
+
     @property
     def array_one_hot(self) -> np.ndarray:
-        return np.eye(len(self.pieces))[self.array]
+        return self._one_hot(self.array)
 
     @property
     def array_one_hot_mirror(self) -> np.ndarray:
-        return np.eye(len(self.pieces))[self.mirror()]
+        return self._one_hot(self.mirror())
 
     def _planes(self, cells, turn):
         # K3 kernel: planes (empty, +1 stones, -1 stones, ones); the 4th plane carries the turn sign
@@ -132,9 +132,8 @@ class Board:
 
     @staticmethod
     def from_one_hot(array_oh: np.ndarray) -> np.ndarray:
-        array = np.argmax(array_oh, axis=-1)
-        array[array > (len(ConfigConnectN.pieces) - 1) / 2] = -1
-        return array
+        plane = np.argmax(array_oh, axis=-1)
+        return np.where(plane == 2, -1, plane)  # third plane = black stones
 
     def legal_moves_mask(self, all_possible_moves: List[Move]) -> np.ndarray:
         legal = _env.env_legal(self._rules, self._relative())[0]
@@ -179,13 +178,14 @@ class Board:
         return board
 
     def play_random(self, on_copy: bool = False, keep_same_player: bool = False) -> "Board":
-        return self.play(self.get_random_move(), on_copy, keep_same_player)
+        return self.play(self.get_random_move(), on_copy=on_copy, keep_same_player=keep_same_player)
 
     def get_result(self, keep_same_player: bool = False):
-        if self.is_null is None or not self.game_over:
+        """None while the game runs, 0 for a draw; otherwise the winner: always +1 under keep_same_player (the
+        player who just moved), else by ply parity (white moves on even plies)."""
+        if not self.game_over or self.is_null is None:
             return None
         if self.is_null:
             return 0
-        if keep_same_player:
-            return ConfigConnectN.white
-        return ConfigConnectN.white if self.odd_moves_number else ConfigConnectN.black
+        white_won = keep_same_player or self.odd_moves_number
+        return ConfigConnectN.white if white_won else ConfigConnectN.black

@@ -30,27 +30,34 @@ else:
     raise NotImplementedError
 
 
+def _alternating_rewards(final_result, n_plies):
+    """self_play.py:69-78 of the reference: the last mover gets the game result (1 win, 0 draw), every other ply
+    going backwards gets its negation; then the (disabled by default) discount by distance to the end."""
+    z = np.repeat(final_result, n_plies)
+    z[-2::-2] = -z[-2::-2]
+    return z * ConfigSelfPlay.discounting_factor ** np.arange(n_plies)[::-1]
+
+
 def play_game(process_id: int, all_possible_moves: List[Move], mcts_iterations: int, run_id: str,
               plays_inferences: Optional[Dict[str, Tuple[np.ndarray, float]]] = None
               ) -> Tuple[np.ndarray, np.ndarray, np.ndarray, MCTS]:
-    np.random.seed(int((process_id + 1) * time.time()) % (2**32 - 1))
-    model = HostModel(best_saved_model(run_id)) if not ConfigGeneral.http_inference else None
-    mcts = MCTS(board=Board(), all_possible_moves=all_possible_moves, concurrency=ConfigGeneral.concurrency,
-                plays_inferences=plays_inferences, model=model, use_solver=ConfigMCTS.use_solver)
-    states_game, policies_game = [], []
-    while not mcts.board.is_game_over():
-        mcts.search(mcts_iterations)
-        greedy = mcts.board.fullmove_number >= ConfigMCTS.index_move_greedy
-        parent_state, _, policy, _ = mcts.play(greedy, return_details=True)
-        states_game.append(parent_state)
-        policies_game.append(policy)
-    states_game, policies_game = np.asarray(states_game), np.asarray(policies_game)
-    reward = mcts.board.get_result(keep_same_player=True)
-    rewards_game = np.repeat(reward, len(states_game))
-    rewards_game[-2::-2] = -rewards_game[-2::-2]
-    rewards_game = rewards_game * ConfigSelfPlay.discounting_factor ** np.arange(len(states_game))[::-1]
-    mcts.model = None
-    return states_game, policies_game, rewards_game, mcts
+    """One game through the drop-in MCTS class; signature and return values of the reference's play_game
+    (self_play.py:37-82): states [T, H, W, 4] float32 (positions BEFORE each move), policies [T, A] float64,
+    rewards [T], and the search object with its model detached."""
+    np.random.seed(int((process_id + 1) * time.time()) % (2**32 - 1))  # every worker samples differently
+    evaluator = None if ConfigGeneral.http_inference else HostModel(best_saved_model(run_id))
+    search = MCTS(board=Board(), all_possible_moves=all_possible_moves, concurrency=ConfigGeneral.concurrency,
+                  plays_inferences=plays_inferences, model=evaluator, use_solver=ConfigMCTS.use_solver)
+    positions, targets = [], []
+    while not search.board.is_game_over():
+        search.search(mcts_iterations)
+        played_greedily = search.board.fullmove_number >= ConfigMCTS.index_move_greedy
+        before, _after, target, _move = search.play(played_greedily, return_details=True)
+        positions.append(before)
+        targets.append(target)
+    rewards = _alternating_rewards(search.board.get_result(keep_same_player=True), len(positions))
+    search.model = None  # the reference drops it so the object can be pickled across processes
+    return np.asarray(positions), np.asarray(targets), rewards, search
 
 
 _live = {}

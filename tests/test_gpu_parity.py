@@ -326,3 +326,28 @@ def test_async_refill_philox_games_match_c_oracle(inline_play):
         np.testing.assert_array_equal(fin["visits"][i][:n], want["visits"])
     tot = eng.totals()
     assert tot["games"] == G and tot["moves"] == int(fin["len"].sum()) and tot["sims"] == tot["moves"] * sims
+
+
+@pytest.mark.parametrize("W,H,n,gravity", [(11, 10, 5, False), (11, 10, 4, True), (2, 2, 2, False), (8, 7, 4, True)])
+def test_extreme_board_sizes_match_c_oracle(W, H, n, gravity):
+    """Largest board the 128-bit layout admits (H*(W+1) = 120 bits, 110 actions), the smallest legal one, and the
+    largest one-word board (7 rows x 9 = 63 bits): full seeded games against the C oracle."""
+    from oracle import c_oracle
+
+    engine, _ = _engine_mod()
+    rules = engine.Rules(W, H, n, gravity)
+    T, sims = 3, 24
+    rng = np.random.RandomState(W * 100 + H)
+    uniforms = rng.random_sample((T, rules.max_plies))
+    eng = engine.TreeEngine(rules, n_trees=T, sims_per_move=sims, eval_mode="hash", prior_mode="f64",
+                            move_mode="host_uniforms")
+    eng.set_uniforms(uniforms)
+    fin = _play_games(eng, rules.max_plies)
+    assert len(fin["len"]) == T
+    crules = c_oracle.make_rules(W, H, n, gravity)
+    for g in range(T):
+        want = c_oracle.play_game(crules, sims, "hash", uniforms=uniforms[g])
+        k = len(want["moves"])
+        assert fin["len"][g] == k and fin["result"][g] == want["result"]
+        np.testing.assert_array_equal(fin["action"][g][:k] & 0xFFFF, want["moves"])
+        np.testing.assert_array_equal(fin["visits"][g][:k], want["visits"])

@@ -142,10 +142,11 @@ class InferenceNet(nn.Module):
         self.head_b32 = f32(torch.cat([pb, vb], 0))
         self.pfc_w, self.pfc_b = f32(net.policy_fc.weight), f32(net.policy_fc.bias)
         self.v1_w, self.v1_b = f32(net.value_fc1.weight), f32(net.value_fc1.bias)
-        # az_net_heads wants the dense rows padded to an odd stride (bank-conflict-free shared memory image)
+        # az_net_heads wants the policy rows padded to an odd stride and the value weights transposed
+        # (bank-conflict-free shared memory images that the kernel copies verbatim)
         cells = net.height * net.width
         self.pfc_w_pad = f32(F.pad(net.policy_fc.weight.detach(), (0, 1)))
-        self.v1_w_pad = f32(F.pad(net.value_fc1.weight.detach(), (0, (cells | 1) - cells)))
+        self.v1_w_pad = f32(net.value_fc1.weight.detach().t())  # transposed [cells][256] for 128-bit smem loads
         self.v2_w, self.v2_b = f32(net.value_fc2.weight), f32(net.value_fc2.bias)
         self.filters = net.filters
         dev = torch.device(device)

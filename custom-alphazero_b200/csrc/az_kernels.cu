@@ -552,21 +552,21 @@ __global__ void __launch_bounds__(kAdvWarps * 32, 2)
     extern __shared__ float s_f[];
     const auto r = RulesView<R>::get(e);
     const int cells = r.cells, A = r.A, PW = r.W + 2;
-    const int ps = 2 * cells + 1, vs = cells | 1;
+    const int ps = 2 * cells + 1;
     float* s_pw = s_f;                                           // policy dense [A][ps]
-    float* s_vw = s_pw + ((A * ps + 3) & ~3);                    // value dense 1 [256][vs]
-    uint32_t* s_sw = reinterpret_cast<uint32_t*>(s_vw + ((kHidden * vs + 3) & ~3));  // stem B fragments [4][3][4][2][32]
+    float* s_vw = s_pw + ((A * ps + 3) & ~3);                    // value dense 1, transposed [cells][256]
+    uint32_t* s_sw = reinterpret_cast<uint32_t*>(s_vw + kHidden * cells);  // stem B fragments [4][3][4][2][32]
     float* s_sb = reinterpret_cast<float*>(s_sw + 4 * 3 * 4 * 2 * 32);               // stem bias [128]
     int* s_base = reinterpret_cast<int*>(s_sb + C);                                   // pixel -> padded cell [cells + 16]
     WarpScratch* s_ws = reinterpret_cast<WarpScratch*>(s_base + ((cells + 16 + 3) & ~3));
     {
-        const int np4 = (A * ps) >> 2, nv4 = (kHidden * vs) >> 2;
+        const int np4 = (A * ps) >> 2, nv4 = (kHidden * cells) >> 2;
         const float4* gp = reinterpret_cast<const float4*>(hp.policy_w);
         const float4* gv = reinterpret_cast<const float4*>(hp.value1_w);
         for (int i = threadIdx.x; i < np4; i += blockDim.x) reinterpret_cast<float4*>(s_pw)[i] = gp[i];
         for (int i = (np4 << 2) + threadIdx.x; i < A * ps; i += blockDim.x) s_pw[i] = hp.policy_w[i];
         for (int i = threadIdx.x; i < nv4; i += blockDim.x) reinterpret_cast<float4*>(s_vw)[i] = gv[i];
-        for (int i = (nv4 << 2) + threadIdx.x; i < kHidden * vs; i += blockDim.x) s_vw[i] = hp.value1_w[i];
+        for (int i = (nv4 << 2) + threadIdx.x; i < kHidden * cells; i += blockDim.x) s_vw[i] = hp.value1_w[i];
         for (int i = threadIdx.x; i < 4 * 3 * 4 * 2 * 32; i += blockDim.x) {  // pre-packed stem B fragments
             const int ln = i & 31, h = (i >> 5) & 1, nt = (i >> 6) & 3, ks = (i >> 8) % 3, q = i / 768;
             const int co = q * 32 + nt * 8 + (ln >> 2), kk = ks * 16 + (ln & 3) * 2 + h * 8, tap = kk >> 2, ci = kk & 3;
@@ -649,18 +649,34 @@ __global__ void __launch_bounds__(kAdvWarps * 32, 2)
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
 #pragma unroll
         for (int m = 0; m < 4; ++m) pr[m] = pr[m] / sum;
-        float hacc[kHidden / 32];
-#pragma unroll
-        for (int m = 0; m < kHidden / 32; ++m) hacc[m] = hp.value1_b[lane + 32 * m];
+        // Dense(256): the weights sit transposed [cell][256] in shared memory; lane l owns hidden units
+        // 4l..4l+3 and 128+4l..128+4l+3, so every cell costs two conflict-free 128-bit loads and 8 FMAs
+        float hacc[8];
+        {
+            const float4 b0 = reinterpret_cast<const float4*>(hp.value1_b)[lane];
+            const float4 b1 = reinterpret_cast<const float4*>(hp.value1_b)[32 + lane];
+            hacc[0] = b0.x; hacc[1] = b0.y; hacc[2] = b0.z; hacc[3] = b0.w;
+            hacc[4] = b1.x; hacc[5] = b1.y; hacc[6] = b1.z; hacc[7] = b1.w;
+        }
         const float* hv = h + 2 * cells;
         for (int p = 0; p < cells; ++p) {
             const float hvp = hv[p];
-#pragma unroll
-            for (int m = 0; m < kHidden / 32; ++m) hacc[m] = fmaf(hvp, s_vw[(lane + 32 * m) * vs + p], hacc[m]);
+            const float4 w0 = reinterpret_cast<const float4*>(s_vw + p * kHidden)[lane];
+            const float4 w1 = reinterpret_cast<const float4*>(s_vw + p * kHidden)[32 + lane];
+            hacc[0] = fmaf(hvp, w0.x, hacc[0]); hacc[1] = fmaf(hvp, w0.y, hacc[1]);
+            hacc[2] = fmaf(hvp, w0.z, hacc[2]); hacc[3] = fmaf(hvp, w0.w, hacc[3]);
+            hacc[4] = fmaf(hvp, w1.x, hacc[4]); hacc[5] = fmaf(hvp, w1.y, hacc[5]);
+            hacc[6] = fmaf(hvp, w1.z, hacc[6]); hacc[7] = fmaf(hvp, w1.w, hacc[7]);
         }
         float part = 0.f;
-#pragma unroll
-        for (int m = 0; m < kHidden / 32; ++m) part = fmaf(fmaxf(hacc[m], 0.f), hp.value2_w[lane + 32 * m], part);
+        {
+            const float4 v0 = reinterpret_cast<const float4*>(hp.value2_w)[lane];
+            const float4 v1 = reinterpret_cast<const float4*>(hp.value2_w)[32 + lane];
+            part = fmaf(fmaxf(hacc[0], 0.f), v0.x, part); part = fmaf(fmaxf(hacc[1], 0.f), v0.y, part);
+            part = fmaf(fmaxf(hacc[2], 0.f), v0.z, part); part = fmaf(fmaxf(hacc[3], 0.f), v0.w, part);
+            part = fmaf(fmaxf(hacc[4], 0.f), v1.x, part); part = fmaf(fmaxf(hacc[5], 0.f), v1.y, part);
+            part = fmaf(fmaxf(hacc[6], 0.f), v1.z, part); part = fmaf(fmaxf(hacc[7], 0.f), v1.w, part);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
         value = tanhf(part + hp.value2_b[0]);
@@ -1255,7 +1271,7 @@ AZ_API int az_advance_fused(az_engine* e, const void* tower_out, const az_head_w
     if (!e || !hw || !stem_w || !stem_b || !stem_out || !leaf_valid) return fail(AZ_ERR_ARG, "az_advance_fused: null pointer%s");
     const Rules& r = e->eng.r;
     const size_t A = r.A, cells = r.cells;
-    const size_t smem = sizeof(float) * (((A * (2 * cells + 1) + 3) & ~(size_t)3) + ((kHidden * (cells | 1) + 3) & ~(size_t)3)) +
+    const size_t smem = sizeof(float) * (((A * (2 * cells + 1) + 3) & ~(size_t)3) + (size_t)kHidden * cells) +
                         sizeof(uint32_t) * 4 * 3 * 4 * 2 * 32 + sizeof(float) * 128 + sizeof(int) * ((cells + 16 + 3) & ~(size_t)3) +
                         sizeof(WarpScratch) * kAdvWarps;
     if (smem > 227 * 1024) return fail(AZ_ERR_ARG, "az_advance_fused: head weights do not fit in shared memory for this board%s");

@@ -14,8 +14,10 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// two floats -> one register of two bf16 (lo in the low half): a single cvt.rn.bf16x2.f32
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
 }
 
 constexpr int kHidden = 256;  // ValueHead hidden_dim (model.py:109)

@@ -124,26 +124,26 @@ constexpr int kHeadWarps = 16;
 // One warp per position, grid-stride; dense weights staged once per block in shared memory.
 // 1x1 convolutions: D[pixel][3] = X[pixel][128] * Wc[128][3] with mma.sync, the A fragments loaded straight
 // from global memory (every byte of the position is requested exactly once, 96 independent loads per lane).
-// Shared layout (floats): policy_w [A][2*cells | 1 pad] | value1_w [256][cells | 1 pad] | per-warp h [3*cells]
+// Shared layout (floats): policy_w [A][2*cells | 1 pad] | value1_w transposed [cells][256] | per-warp h [3*cells]
 template <int C>
 __global__ void __launch_bounds__(kHeadWarps * 32) k_heads(const __nv_bfloat16* __restrict__ x, HeadParams hp,
                                                            float* __restrict__ priors, float* __restrict__ values) {
     static_assert(C == 128, "8 k-steps of 16 channels");
     extern __shared__ float s_f[];
     const int cells = hp.cells, A = hp.A;
-    const int ps = 2 * cells + 1, vs = cells | 1;  // odd row strides: conflict-free across lanes
+    const int ps = 2 * cells + 1;  // odd row stride: conflict-free across lanes
     float* s_pw = s_f;
     float* s_vw = s_pw + ((A * ps + 3) & ~3);
-    float* s_h = s_vw + kHidden * vs;
+    float* s_h = s_vw + kHidden * cells;
     // the dense weights arrive already in the padded (odd row stride) layout: two straight 128-bit copies
     {
-        const int np4 = (A * ps) >> 2, nv4 = (kHidden * vs) >> 2;
+        const int np4 = (A * ps) >> 2, nv4 = (kHidden * cells) >> 2;
         const float4* gp = reinterpret_cast<const float4*>(hp.policy_w);
         const float4* gv = reinterpret_cast<const float4*>(hp.value1_w);
         for (int i = threadIdx.x; i < np4; i += blockDim.x) reinterpret_cast<float4*>(s_pw)[i] = gp[i];
         for (int i = (np4 << 2) + threadIdx.x; i < A * ps; i += blockDim.x) s_pw[i] = hp.policy_w[i];
         for (int i = threadIdx.x; i < nv4; i += blockDim.x) reinterpret_cast<float4*>(s_vw)[i] = gv[i];
-        for (int i = (nv4 << 2) + threadIdx.x; i < kHidden * vs; i += blockDim.x) s_vw[i] = hp.value1_w[i];
+        for (int i = (nv4 << 2) + threadIdx.x; i < kHidden * cells; i += blockDim.x) s_vw[i] = hp.value1_w[i];
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
     float* h = s_h + warp * 3 * cells;  // [cells][2] policy planes (Keras Flatten of [H][W][2]) then [cells] value plane
@@ -213,18 +213,34 @@ __global__ void __launch_bounds__(kHeadWarps * 32) k_heads(const __nv_bfloat16* 
         for (int m = 0; m < 4; ++m)
             if (lane + 32 * m < A) priors[(size_t)t * A + lane + 32 * m] = ex[m] / sum;
         // value: Dense(256) ReLU -> Dense(1) tanh; lane owns hidden units lane, lane+32, ...
-        float hacc[kHidden / 32];
-#pragma unroll
-        for (int m = 0; m < kHidden / 32; ++m) hacc[m] = hp.value1_b[lane + 32 * m];
+        // Dense(256): the weights sit transposed [cell][256] in shared memory; lane l owns hidden units
+        // 4l..4l+3 and 128+4l..128+4l+3, so every cell costs two conflict-free 128-bit loads and 8 FMAs
+        float hacc[8];
+        {
+            const float4 b0 = reinterpret_cast<const float4*>(hp.value1_b)[lane];
+            const float4 b1 = reinterpret_cast<const float4*>(hp.value1_b)[32 + lane];
+            hacc[0] = b0.x; hacc[1] = b0.y; hacc[2] = b0.z; hacc[3] = b0.w;
+            hacc[4] = b1.x; hacc[5] = b1.y; hacc[6] = b1.z; hacc[7] = b1.w;
+        }
         const float* hv = h + 2 * cells;
         for (int p = 0; p < cells; ++p) {
             const float hvp = hv[p];
-#pragma unroll
-            for (int m = 0; m < kHidden / 32; ++m) hacc[m] = fmaf(hvp, s_vw[(lane + 32 * m) * vs + p], hacc[m]);
+            const float4 w0 = reinterpret_cast<const float4*>(s_vw + p * kHidden)[lane];
+            const float4 w1 = reinterpret_cast<const float4*>(s_vw + p * kHidden)[32 + lane];
+            hacc[0] = fmaf(hvp, w0.x, hacc[0]); hacc[1] = fmaf(hvp, w0.y, hacc[1]);
+            hacc[2] = fmaf(hvp, w0.z, hacc[2]); hacc[3] = fmaf(hvp, w0.w, hacc[3]);
+            hacc[4] = fmaf(hvp, w1.x, hacc[4]); hacc[5] = fmaf(hvp, w1.y, hacc[5]);
+            hacc[6] = fmaf(hvp, w1.z, hacc[6]); hacc[7] = fmaf(hvp, w1.w, hacc[7]);
         }
         float part = 0.f;
-#pragma unroll
-        for (int m = 0; m < kHidden / 32; ++m) part = fmaf(fmaxf(hacc[m], 0.f), hp.value2_w[lane + 32 * m], part);
+        {
+            const float4 v0 = reinterpret_cast<const float4*>(hp.value2_w)[lane];
+            const float4 v1 = reinterpret_cast<const float4*>(hp.value2_w)[32 + lane];
+            part = fmaf(fmaxf(hacc[0], 0.f), v0.x, part); part = fmaf(fmaxf(hacc[1], 0.f), v0.y, part);
+            part = fmaf(fmaxf(hacc[2], 0.f), v0.z, part); part = fmaf(fmaxf(hacc[3], 0.f), v0.w, part);
+            part = fmaf(fmaxf(hacc[4], 0.f), v1.x, part); part = fmaf(fmaxf(hacc[5], 0.f), v1.y, part);
+            part = fmaf(fmaxf(hacc[6], 0.f), v1.z, part); part = fmaf(fmaxf(hacc[7], 0.f), v1.w, part);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) values[t] = tanhf(part + hp.value2_b[0]);
@@ -261,7 +277,7 @@ AZ_API int az_net_heads(const void* x, const az_head_weights* hw, int32_t n, int
     if (C != 128) return fail_net(AZ_ERR_ARG, "az_net_heads: built for 128 filters (config.py:71)");
     HeadParams hp{hw->conv_w, hw->conv_b, hw->policy_w, hw->policy_b, hw->value1_w, hw->value1_b, hw->value2_w, hw->value2_b,
                   n, cells, A};
-    const size_t smem = sizeof(float) * ((((size_t)A * (2 * cells + 1) + 3) & ~(size_t)3) + (size_t)kHidden * (cells | 1) +
+    const size_t smem = sizeof(float) * ((((size_t)A * (2 * cells + 1) + 3) & ~(size_t)3) + (size_t)kHidden * cells +
                                          (size_t)kHeadWarps * 3 * cells);
     static size_t configured = 0;
     if (smem > configured) {

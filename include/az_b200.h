@@ -244,9 +244,9 @@ typedef struct az_head_weights {
     const float *policy_w; /* dev [A][2*H*W + 1]: Dense(A) on the NHWC-flattened policy planes, rows padded to an odd
                               stride (the kernel copies it verbatim into conflict-free shared memory); 16 B aligned */
     const float *policy_b; /* dev [A] */
-    const float *value1_w; /* dev [256][(H*W) | 1]: rows padded to an odd stride; 16 B aligned */
-    const float *value1_b; /* dev [256] */
-    const float *value2_w; /* dev [256] */
+    const float *value1_w; /* dev [H*W][256]: Dense(256) weights TRANSPOSED (input cell major); 16 B aligned */
+    const float *value1_b; /* dev [256], 16 B aligned */
+    const float *value2_w; /* dev [256], 16 B aligned */
     const float *value2_b; /* dev [1] */
 } az_head_weights;
 

@@ -60,7 +60,7 @@ def test_heads_kernel_matches_fp32(H, W, A):
     want_p = torch.softmax(h[..., :2].reshape(n, -1) @ pw.T + pb, -1)
     want_v = torch.tanh(torch.relu(h[..., 2] @ v1w.T + v1b) @ v2w + v2b)
     pw_pad = torch.nn.functional.pad(pw, (0, 1))  # rows padded to the odd stride az_net_heads expects
-    v1w_pad = torch.nn.functional.pad(v1w, (0, (cells | 1) - cells))
+    v1w_pad = v1w.t().contiguous()  # Dense(256) weights transposed [cells][256]
     dev = [t.cuda().contiguous() for t in (cw, cb, pw_pad, pb, v1w_pad, v1b, v2w, v2b)]
     hw = native.AzHeadWeights(*[t.data_ptr() for t in dev])
     priors = torch.empty((n, A), device="cuda")

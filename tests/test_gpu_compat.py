@@ -205,3 +205,30 @@ def test_root_policy_targets_bf16_vs_fp32_within_tolerance(c4):
             pis.append(n / n.sum())
         diffs.append(np.abs(pis[0] - pis[1]).max())
     assert len(diffs) >= 4 and max(diffs) <= 2.5e-2 and np.mean(diffs) <= 5e-3, diffs
+
+
+def test_self_play_entry_point_writes_reference_format(tmp_path, monkeypatch, c4):
+    """`python -m custom_alphazero.self_play` (here: its main(), one iteration) without a serving process:
+    stand-alone run id, results/connect_n/{run}/self_play/iteration_0/samples.npz with the reference's keys,
+    drawn games excluded."""
+    import os
+
+    from custom_alphazero import self_play
+    from custom_alphazero.config import ConfigB200, ConfigSelfPlay
+
+    monkeypatch.chdir(tmp_path)
+    saved = (ConfigB200.games_per_iteration, ConfigB200.concurrent_games, ConfigSelfPlay.mcts_iterations)
+    ConfigB200.games_per_iteration, ConfigB200.concurrent_games, ConfigSelfPlay.mcts_iterations = 40, 32, 16
+    try:
+        self_play.main(max_iterations=1)
+    finally:
+        ConfigB200.games_per_iteration, ConfigB200.concurrent_games, ConfigSelfPlay.mcts_iterations = saved
+    runs = os.listdir(os.path.join("results", "connect_n"))
+    assert len(runs) == 1 and runs[0].startswith("standalone_")
+    path = os.path.join("results", "connect_n", runs[0], "self_play", "iteration_0", "samples.npz")
+    data = np.load(path)
+    assert set(data.files) == {"states", "policies", "values"}
+    S = len(data["values"])
+    assert S > 100 and data["states"].shape == (S, 6, 7, 4) and data["states"].dtype == np.float32
+    assert data["policies"].shape == (S, 7) and data["policies"].dtype == np.float64
+    assert set(np.unique(data["values"])) <= {-1, 1}  # exclude_null_games: no zero rewards left

@@ -59,7 +59,8 @@ class TreeEngine:
     def __init__(self, rules=Rules(), n_trees=1, sims_per_move=250, *, eval_mode="external", prior_mode="f32",
                  move_mode="argmax", node_capacity=None, games_target=None, game_id_base=0, seed=0,
                  auto_restart=False, fin_capacity=None, max_free_sims=8, index_move_greedy=8, c_puct=1.5,
-                 pow_lut_len=None, device=None, inline_play=False):
+                 pow_lut_len=None, device=None, inline_play=False, dirichlet_noise=False, dirichlet_alpha=0.03,
+                 dirichlet_ratio=0.25):
         if not torch.cuda.is_available():
             raise NativeError("no CUDA device: the self-play engine has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -90,7 +91,8 @@ class TreeEngine:
             prior_mode={"f64": 0, "f32": 1}[prior_mode],
             move_mode={"argmax": 0, "host_uniforms": 1, "philox": 2}[move_mode],
             max_free_sims=int(max_free_sims), fin_capacity=int(fin_capacity), pow_lut_len=int(pow_lut_len),
-            auto_restart=int(auto_restart), inline_play=int(inline_play), c_puct=float(c_puct), seed=int(seed), game_id_base=int(game_id_base),
+            auto_restart=int(auto_restart), inline_play=int(inline_play), dirichlet_noise=int(dirichlet_noise),
+            dirichlet_alpha=float(dirichlet_alpha), dirichlet_ratio=float(dirichlet_ratio), c_puct=float(c_puct), seed=int(seed), game_id_base=int(game_id_base),
             games_target=int(games_target),
         )
         self.cfg = cfg

@@ -42,6 +42,9 @@ class AzConfig(ctypes.Structure):
         ("pow_lut_len", ctypes.c_int32),
         ("auto_restart", ctypes.c_int32),
         ("inline_play", ctypes.c_int32),
+        ("dirichlet_noise", ctypes.c_int32),
+        ("dirichlet_alpha", ctypes.c_double),
+        ("dirichlet_ratio", ctypes.c_double),
         ("c_puct", ctypes.c_double),
         ("seed", ctypes.c_uint64),
         ("game_id_base", ctypes.c_int64),
@@ -92,6 +95,7 @@ SYMBOLS = {
     "az_net_stem": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "az_net_heads": (ctypes.c_int, [_P, ctypes.POINTER(AzHeadWeights), _I, _I, _I, _I, _P, _P, _P]),
     "az_advance_fused": (ctypes.c_int, [_P, _P, ctypes.POINTER(AzHeadWeights), _P, _P, _P, _P, _P]),
+    "az_debug_dirichlet": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_double, _I, _I, _P, _P]),
     "az_debug_timeline": (ctypes.c_int, [_P, _P, _I]),
     "az_decode_samples": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
 }

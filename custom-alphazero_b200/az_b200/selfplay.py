@@ -73,7 +73,8 @@ class SelfPlayRunner:
     def __init__(self, rules=Rules(), n_trees=4096, sims_per_move=800, net=None, *, games_target=None,
                  game_id_base=0, seed=0, move_mode="philox", auto_restart=True, dtype=torch.bfloat16, unroll=8,
                  use_graph=True, max_free_sims=8, node_capacity=None, fin_capacity=None, device=None,
-                 index_move_greedy=8, groups=1, fused=True, extra_sims=0):
+                 index_move_greedy=8, groups=1, fused=True, extra_sims=0, dirichlet_noise=False, dirichlet_alpha=0.03,
+                 dirichlet_ratio=0.25):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.rules = rules
         T, A = int(n_trees), rules.n_actions
@@ -93,7 +94,8 @@ class SelfPlayRunner:
                              games_target=gi, game_id_base=game_id_base + g0, seed=seed, auto_restart=auto_restart,
                              max_free_sims=max_free_sims, node_capacity=node_capacity,
                              fin_capacity=None if fin_capacity is None else max(1, -(-fin_capacity // groups)),
-                             device=self.device, index_move_greedy=index_move_greedy, inline_play=True)
+                             device=self.device, index_move_greedy=index_move_greedy, inline_play=True,
+                             dirichlet_noise=dirichlet_noise, dirichlet_alpha=dirichlet_alpha, dirichlet_ratio=dirichlet_ratio)
             self.groups.append(_Group(eng, rules, dtype, self.device))
             t0 += ti
             g0 += gi

@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_play(Eng e, Aux aux, in
 // simulate until a leaf needs the evaluator: terminal leaves are finished on the spot, a spent budget is
 // turned into a move right here when inline_play allows (K6).  Returns 1 with the leaf position in
 // `leaf` when an evaluation is wanted, else 0.
-template <int NW, int KC, class R, class PriorFn>
+template <int NW, int KC, bool NOISE = false, class R, class PriorFn>
 __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& r, int t, WarpScratch& ws, int lane,
                                          bool have_eval, int prior_mode, double value, PriorFn prior_of, Pos<NW>& leaf,
                                          int submit = 1) {
@@ -455,7 +455,7 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
         if (pend || sims >= e.sims_target) break;
         Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
         int depth, term;
-        select_leaf<NW, KC>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags);
+        select_leaf<NW, KC, NOISE>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags, e.game_id[t], e.ply[t], sims);
         ndepth += depth;
         if (term) {  // mcts.py:179: terminal leaf, result 1 (win of the mover) or 0 (draw)
             backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
@@ -487,7 +487,7 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
     return pend;
 }
 
-template <int NW, int KC, class R>
+template <int NW, int KC, class R, bool NOISE = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     k_step(Eng e, Aux aux, const void* __restrict__ priors, const void* __restrict__ values, int eval_dtype, void* states,
            int state_dtype, int32_t* leaf_valid) {
@@ -502,15 +502,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     // the dtype of the evaluator output decides the arithmetic of normalize_probabilities, as in the
     // reference: float64 from infer_sample (factory.py:55), float32 from the model (mcts.py:131-137)
     if (priors == nullptr) {
-        pend = step_tree<NW, KC>(e, aux, r, t, ws, lane, false, AZ_PRIOR_F64, 0.0, [](int) { return 0.0; }, leaf);
+        pend = step_tree<NW, KC, NOISE>(e, aux, r, t, ws, lane, false, AZ_PRIOR_F64, 0.0, [](int) { return 0.0; }, leaf);
     } else if (eval_dtype == AZ_F64) {
         const double* p = static_cast<const double*>(priors) + (size_t)t * r.A;
-        pend = step_tree<NW, KC>(e, aux, r, t, ws, lane, true, AZ_PRIOR_F64, static_cast<const double*>(values)[t],
+        pend = step_tree<NW, KC, NOISE>(e, aux, r, t, ws, lane, true, AZ_PRIOR_F64, static_cast<const double*>(values)[t],
                                  [p](int a) { return p[a]; }, leaf);
     } else {
         const float* p = static_cast<const float*>(priors) + (size_t)t * r.A;
         // value.numpy().item() (mcts.py:136): the float32 value widened
-        pend = step_tree<NW, KC>(e, aux, r, t, ws, lane, true, AZ_PRIOR_F32, (double)static_cast<const float*>(values)[t],
+        pend = step_tree<NW, KC, NOISE>(e, aux, r, t, ws, lane, true, AZ_PRIOR_F32, (double)static_cast<const float*>(values)[t],
                                  [p](int a) { return (double)p[a]; }, leaf);
     }
     if (pend) {
@@ -537,7 +537,7 @@ struct StemParams {
     const float* b;  // [128]
 };
 
-template <int NW, int KC, class R>
+template <int NW, int KC, class R, bool NOISE = false>
 __global__ void __launch_bounds__(kAdvWarps * 32, 2)
     k_advance(Eng e, Aux aux, const __nv_bfloat16* __restrict__ x, HeadParams hp, StemParams sp,
               __nv_bfloat16* __restrict__ stem_out, int32_t* leaf_valid, unsigned long long* timeline) {
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(kAdvWarps * 32, 2)
     // ---- B: the tree step with the priors in registers (lane l holds actions l, l+32, ...)
     Pos<NW> leaf;
     const float p0 = pr[0], p1 = pr[1], p2 = pr[2], p3 = pr[3];
-    const int pend = step_tree<NW, KC>(e, aux, r, t, ws, lane, have_eval, AZ_PRIOR_F32, (double)value,
+    const int pend = step_tree<NW, KC, NOISE>(e, aux, r, t, ws, lane, have_eval, AZ_PRIOR_F32, (double)value,
                                        [p0, p1, p2, p3](int a) {
                                            const int m = a >> 5;
                                            return (double)(m == 0 ? p0 : (m == 1 ? p1 : (m == 2 ? p2 : p3)));
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(kAdvWarps * 32, 2)
 // leaf or spent the move budget).  Runs beside the tower on a forked stream: such trees keep finishing
 // terminal-leaf simulations and playing moves (up to e.max_free of them) until a leaf does need the net; that
 // leaf is parked (pending = 2) and submitted by the next az_advance_fused / az_step.
-template <int NW, int KC, class R>
+template <int NW, int KC, class R, bool NOISE = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_extra(Eng e, Aux aux) {
     __shared__ WarpScratch s_ws[kWarpsPerBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -783,11 +783,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_extra(Eng e, Aux aux) {
     if (e.pending[t] != 0 || (e.status[t] & AZ_PHASE_MASK) != AZ_PHASE_SEARCH) return;
     const auto r = RulesView<R>::get(e);
     Pos<NW> leaf;
-    step_tree<NW, KC>(e, aux, r, t, s_ws[warp], lane, false, AZ_PRIOR_F64, 0.0, [](int) { return 0.0; }, leaf, 2);
+    step_tree<NW, KC, NOISE>(e, aux, r, t, s_ws[warp], lane, false, AZ_PRIOR_F64, 0.0, [](int) { return 0.0; }, leaf, 2);
 }
 
 // ------------------------------------------------------------------------------------------ k_search
-template <int NW, int KC, class R>
+template <int NW, int KC, class R, bool NOISE = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
     __shared__ WarpScratch s_ws[kWarpsPerBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -809,7 +809,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search(Eng e) {
     while (sims < e.sims_target && !(flags & AZ_FLAG_POOL_OVERFLOW)) {
         Pos<NW> pos = root_pos;
         int depth, term;
-        select_leaf<NW, KC>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags);
+        select_leaf<NW, KC, NOISE>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags, e.game_id[t], e.ply[t], sims);
         ndepth += depth;
         if (term) {
             backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
@@ -948,6 +948,21 @@ __global__ void __launch_bounds__(128) k_decode(Rules r, int P, const uint64_t* 
     }
 }
 
+__global__ void k_debug_dirichlet(uint64_t seed, double alpha, int k, int n, double* out) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    for (int j0 = 0; j0 < k; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < k) out[(size_t)i * k + j] = gamma_variate(seed ^ 0xD1B54A32D192ED03ull, (uint32_t)i, 0u, 0u, (uint32_t)j, alpha);
+    }
+    __syncwarp();
+    double s = 0.0;
+    for (int j = lane; j < k; j += 32) s += out[(size_t)i * k + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    for (int j = lane; j < k; j += 32) out[(size_t)i * k + j] /= s;
+}
+
 }  // namespace az
 
 // ========================================================================================== C ABI
@@ -972,6 +987,8 @@ static int check_cfg(const az_config* c) {
     if (c->height * (c->width + 1) > 128) return fail(AZ_ERR_ARG, "board needs more than 128 bits%s");
     int m = c->width < c->height ? c->width : c->height;
     if (c->n_connect < 2 || c->n_connect > m) return fail(AZ_ERR_ARG, "n_connect must be in [2, min(W, H)]%s");
+    if (c->dirichlet_noise && (!(c->dirichlet_alpha > 0.0) || c->dirichlet_ratio < 0.0 || c->dirichlet_ratio > 1.0))
+        return fail(AZ_ERR_ARG, "dirichlet_alpha must be > 0 and dirichlet_ratio in [0, 1]%s");
     return AZ_OK;
 }
 
@@ -1070,6 +1087,9 @@ AZ_API int az_engine_create(const az_config* c, void* slab, size_t bytes, const 
     g.lut_len = c->pow_lut_len;
     g.auto_restart = c->auto_restart;
     g.inline_play = c->inline_play;
+    g.dirichlet = c->dirichlet_noise;
+    g.dir_alpha = c->dirichlet_alpha;
+    g.dir_ratio = c->dirichlet_ratio;
     g.c_puct = c->c_puct;
     g.seed = c->seed;
     g.game_base = c->game_id_base;
@@ -1151,15 +1171,22 @@ AZ_API int az_begin_search(az_engine* e, int32_t sims, void* stream) {
     return AZ_OK;
 }
 
+// Kernel variants: compile-time rules for the headline board; generic rules by bitboard words (NW) and children
+// chunks (KC); root-noise variants (generic rules only: the sampler would cost the fast path its registers).
 #define AZ_DISPATCH(kernel, ...)                                                                          \
     do {                                                                                                  \
         cudaStream_t s__ = static_cast<cudaStream_t>(stream);                                             \
         dim3 g__ = tree_grid(e), b__(kWarpsPerBlock * 32);                                                \
-        if (e->c4) kernel<1, 1, C4Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);                              \
-        else if (e->nw == 1 && e->kc == 1) kernel<1, 1, Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);        \
-        else if (e->nw == 1) kernel<1, 4, Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);                      \
-        else if (e->kc == 1) kernel<2, 1, Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);                      \
-        else kernel<2, 4, Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);                                      \
+        const bool nz__ = e->eng.dirichlet != 0;                                                          \
+        if (e->c4 && !nz__) kernel<1, 1, C4Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);                     \
+        else if (e->nw == 1 && e->kc == 1 && !nz__) kernel<1, 1, Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__); \
+        else if (e->nw == 1 && e->kc == 1) kernel<1, 1, Rules, true><<<g__, b__, 0, s__>>>(__VA_ARGS__);  \
+        else if (e->nw == 1 && !nz__) kernel<1, 4, Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);             \
+        else if (e->nw == 1) kernel<1, 4, Rules, true><<<g__, b__, 0, s__>>>(__VA_ARGS__);                \
+        else if (e->kc == 1 && !nz__) kernel<2, 1, Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);             \
+        else if (e->kc == 1) kernel<2, 1, Rules, true><<<g__, b__, 0, s__>>>(__VA_ARGS__);                \
+        else if (!nz__) kernel<2, 4, Rules><<<g__, b__, 0, s__>>>(__VA_ARGS__);                           \
+        else kernel<2, 4, Rules, true><<<g__, b__, 0, s__>>>(__VA_ARGS__);                                \
         AZ_CUDA(cudaGetLastError());                                                                      \
     } while (0)
 
@@ -1177,14 +1204,7 @@ AZ_API int az_extra_sims(az_engine* e, int32_t max_sims, void* stream) {
     if (!e || max_sims < 1) return fail(AZ_ERR_ARG, "az_extra_sims: bad argument%s");
     Eng g = e->eng;
     g.max_free = max_sims;
-    cudaStream_t s__ = static_cast<cudaStream_t>(stream);
-    dim3 g__ = tree_grid(e), b__(kWarpsPerBlock * 32);
-    if (e->c4) k_extra<1, 1, C4Rules><<<g__, b__, 0, s__>>>(g, e->aux);
-    else if (e->nw == 1 && e->kc == 1) k_extra<1, 1, Rules><<<g__, b__, 0, s__>>>(g, e->aux);
-    else if (e->nw == 1) k_extra<1, 4, Rules><<<g__, b__, 0, s__>>>(g, e->aux);
-    else if (e->kc == 1) k_extra<2, 1, Rules><<<g__, b__, 0, s__>>>(g, e->aux);
-    else k_extra<2, 4, Rules><<<g__, b__, 0, s__>>>(g, e->aux);
-    AZ_CUDA(cudaGetLastError());
+    AZ_DISPATCH(k_extra, g, e->aux);
     return AZ_OK;
 }
 
@@ -1200,7 +1220,16 @@ AZ_API int az_play(az_engine* e, int32_t greedy_override, int32_t move_mode_over
     if (!e) return fail(AZ_ERR_ARG, "null engine%s");
     int mode = move_mode_override >= 0 ? move_mode_override : e->eng.move_mode;
     if (mode < AZ_MOVE_ARGMAX || mode > AZ_MOVE_PHILOX) return fail(AZ_ERR_ARG, "az_play: bad move mode%s");
-    AZ_DISPATCH(k_play, e->eng, e->aux, greedy_override, mode);
+    {
+        cudaStream_t s__ = static_cast<cudaStream_t>(stream);
+        dim3 g__ = tree_grid(e), b__(kWarpsPerBlock * 32);
+        if (e->c4) k_play<1, 1, C4Rules><<<g__, b__, 0, s__>>>(e->eng, e->aux, greedy_override, mode);
+        else if (e->nw == 1 && e->kc == 1) k_play<1, 1, Rules><<<g__, b__, 0, s__>>>(e->eng, e->aux, greedy_override, mode);
+        else if (e->nw == 1) k_play<1, 4, Rules><<<g__, b__, 0, s__>>>(e->eng, e->aux, greedy_override, mode);
+        else if (e->kc == 1) k_play<2, 1, Rules><<<g__, b__, 0, s__>>>(e->eng, e->aux, greedy_override, mode);
+        else k_play<2, 4, Rules><<<g__, b__, 0, s__>>>(e->eng, e->aux, greedy_override, mode);
+        AZ_CUDA(cudaGetLastError());
+    }
     return AZ_OK;
 }
 
@@ -1287,17 +1316,22 @@ AZ_API int az_advance_fused(az_engine* e, const void* tower_out, const az_head_w
         tl = e->timeline + 2 * (e->timeline_next % e->timeline_slots);
         e->timeline_next += 1;
     }
-#define AZ_ADV(NWv, KCv, Rv)                                                                                         \
+#define AZ_ADV(NWv, KCv, Rv, NZv)                                                                                         \
     do {                                                                                                             \
-        auto kfn = k_advance<NWv, KCv, Rv>;                                                                          \
+        auto kfn = k_advance<NWv, KCv, Rv, NZv>;                                                                          \
         AZ_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
         kfn<<<grid, block, smem, s>>>(e->eng, e->aux, x, hp, sp, so, leaf_valid, tl);                                    \
     } while (0)
-    if (e->c4) AZ_ADV(1, 1, C4Rules);
-    else if (e->nw == 1 && e->kc == 1) AZ_ADV(1, 1, Rules);
-    else if (e->nw == 1) AZ_ADV(1, 4, Rules);
-    else if (e->kc == 1) AZ_ADV(2, 1, Rules);
-    else AZ_ADV(2, 4, Rules);
+    const bool nz = e->eng.dirichlet != 0;
+    if (e->c4 && !nz) AZ_ADV(1, 1, C4Rules, false);
+    else if (e->nw == 1 && e->kc == 1 && !nz) AZ_ADV(1, 1, Rules, false);
+    else if (e->nw == 1 && e->kc == 1) AZ_ADV(1, 1, Rules, true);
+    else if (e->nw == 1 && !nz) AZ_ADV(1, 4, Rules, false);
+    else if (e->nw == 1) AZ_ADV(1, 4, Rules, true);
+    else if (e->kc == 1 && !nz) AZ_ADV(2, 1, Rules, false);
+    else if (e->kc == 1) AZ_ADV(2, 1, Rules, true);
+    else if (!nz) AZ_ADV(2, 4, Rules, false);
+    else AZ_ADV(2, 4, Rules, true);
 #undef AZ_ADV
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
@@ -1308,5 +1342,13 @@ AZ_API int az_debug_timeline(az_engine* e, void* dev_slots, int32_t n_slots) {
     e->timeline = static_cast<unsigned long long*>(dev_slots);
     e->timeline_slots = dev_slots ? n_slots : 0;
     e->timeline_next = 0;
+    return AZ_OK;
+}
+
+AZ_API int az_debug_dirichlet(uint64_t seed, double alpha, int32_t k, int32_t n, double* out, void* stream) {
+    if (n == 0) return AZ_OK;
+    if (!out || k < 1 || k > AZ_MAX_ACTIONS || n < 0 || !(alpha > 0.0)) return fail(AZ_ERR_ARG, "az_debug_dirichlet: bad argument%s");
+    k_debug_dirichlet<<<(n + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(seed, alpha, k, n, out);
+    AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }

@@ -61,11 +61,62 @@ __device__ __forceinline__ void store_node(NodeA* p, const NodeA& r) {
     *reinterpret_cast<int4*>(p) = v;
 }
 
+// Philox4x32-10 block: 128 random bits for (key, counter)
+__device__ __forceinline__ uint4 philox4x32(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+        c0 = n0;
+        c1 = n1;
+        c2 = n2;
+        c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {  // [0, 1) with 53 bits, numpy's random_sample recipe
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+
+// One Gamma(alpha, 1) variate, any alpha > 0 (Marsaglia-Tsang squeeze; alpha < 1 through G(alpha + 1) * U^(1/alpha)).
+// Independent stream per (c0, c1, c2, lane-specific c3 base): used for the Dirichlet root noise (mcts.py:70-85).
+__device__ __forceinline__ double gamma_variate(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t stream,
+                                                double alpha) {
+    const double a = alpha < 1.0 ? alpha + 1.0 : alpha;
+    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    double g = d;
+    for (uint32_t it = 0; it < 64; ++it) {
+        const uint4 rb = philox4x32(seed, c0, c1, c2, (stream << 8) | (2 * it + 1));
+        const uint4 rc = philox4x32(seed, c0, c1, c2, (stream << 8) | (2 * it + 2));
+        const double u1 = u53(rb.x, rb.y), u2 = u53(rb.z, rb.w), u3 = u53(rc.x, rc.y);
+        const double x = sqrt(-2.0 * log(1.0 - u1)) * cospi(2.0 * u2);  // standard normal (Box-Muller)
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        if (log(1.0 - u3) < 0.5 * x * x + d - d * v + d * log(v)) {
+            g = d * v;
+            break;
+        }
+    }
+    if (alpha < 1.0) {
+        const uint4 rd = philox4x32(seed, c0, c1, c2, (stream << 8) | 255u);
+        g *= pow(1.0 - u53(rd.x, rd.y), 1.0 / alpha);  // U in (0, 1]
+    }
+    return g;
+}
+
 // Device view of the engine: rules, knobs and typed pointers into the slab (az_layout).
 struct Eng {
     Rules r;
     int T, C, P, F;  // trees, node capacity per half, max plies, finished-ring entries
     int sims_target, greedy_idx, eval_mode, prior_mode, move_mode, max_free, lut_len, auto_restart, inline_play;
+    int dirichlet;
+    double dir_alpha, dir_ratio;
     double c_puct;
     uint64_t seed;
     long long game_base, games_target;
@@ -127,9 +178,10 @@ __device__ __forceinline__ void store_pos(uint64_t* p, const Pos<NW>& v, int lan
 // K1 select (mcts.py:111-120).  pos: root position in, leaf position out.
 // Returns the leaf node; depth/ws.path receive the path; term = 0 none, 1 mover won, 2 draw.
 // ------------------------------------------------------------------------------------------
-template <int NW, int KC, class R>
+template <int NW, int KC, bool NOISE = false, class R>
 __device__ __forceinline__ int select_leaf(const Eng& e, const R& r, const NodeA* A, const double* Pr, int root, Pos<NW>& pos,
-                                           WarpScratch& ws, int lane, int& depth, int& term, uint32_t& flags) {
+                                           WarpScratch& ws, int lane, int& depth, int& term, uint32_t& flags,
+                                           long long noise_game = 0, int noise_ply = 0, int noise_sim = 0) {
     int node = root;
     uint32_t link = load_node(A + root).link;
     depth = 0;
@@ -165,6 +217,27 @@ __device__ __forceinline__ int select_leaf(const Eng& e, const R& r, const NodeA
                     prefetch_l2(Pr + cb + o);
                 }
             }
+        }
+        if (NOISE && depth == 0) {  // compiled only into the noise instantiations: the sampler is register-hungry
+            // get_best_edge_with_noise (mcts.py:70-85): at the root the prior is replaced, for this simulation only,
+            // by (1 - ratio) * prior + ratio * Dirichlet(alpha * 1_k); a Dirichlet draw is k Gamma(alpha) variates
+            // normalised by their sum
+            double gsum = 0.0, gam[KC];
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                const int j = lane + 32 * c;
+                gam[c] = j < k ? gamma_variate(e.seed ^ 0xD1B54A32D192ED03ull, (uint32_t)noise_game,
+                                               (uint32_t)((unsigned long long)noise_game >> 32),
+                                               ((uint32_t)noise_ply << 20) | (uint32_t)noise_sim, (uint32_t)j, e.dir_alpha)
+                               : 0.0;
+                gsum += gam[c];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(kFull, gsum, o);
+#pragma unroll
+            for (int c = 0; c < KC; ++c)
+                if (lane + 32 * c < k)
+                    pr[c] = __dadd_rn(__dmul_rn(1.0 - e.dir_ratio, pr[c]), __dmul_rn(e.dir_ratio, gam[c] / gsum));
         }
         const int total = __reduce_add_sync(kFull, ln);  // mcts.py:50: sum over the node's edges
         double s;
@@ -366,21 +439,8 @@ __device__ __forceinline__ double hash_value(uint64_t h) {
 // Philox4x32-10, counter (game id lo, game id hi, ply, 0), key = seed; 53-bit uniform in [0, 1)
 // built like numpy's random_sample: (a >> 5) * 2^26 + (b >> 6), / 2^53.
 __device__ __forceinline__ double philox_uniform(uint64_t seed, long long game, int ply) {
-    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)((uint64_t)game >> 32), c2 = (uint32_t)ply, c3 = 0;
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
-        c0 = n0;
-        c1 = n1;
-        c2 = n2;
-        c3 = n3;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    return ((double)(c0 >> 5) * 67108864.0 + (double)(c1 >> 6)) / 9007199254740992.0;
+    const uint4 rv = philox4x32(seed, (uint32_t)game, (uint32_t)((uint64_t)game >> 32), (uint32_t)ply, 0u);
+    return u53(rv.x, rv.y);
 }
 
 // K3: Board.full_state (board.py:83-98) of `pos` into out[H][W][4]; lanes stride over cells.

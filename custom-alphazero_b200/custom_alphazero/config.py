@@ -37,7 +37,7 @@ class ConfigConnectN:
 class ConfigMCTS:
     exploration_constant = 1.5
     index_move_greedy = 8  # plies from which the move is the most visited one
-    enable_dirichlet_noise = False  # not implemented on the GPU path (off in the reference too)
+    enable_dirichlet_noise = False  # off in the reference too; on the GPU the noise comes from a device Philox stream
     dirichlet_noise_value, dirichlet_noise_ratio = 0.03, 0.25
     use_solver = False
 

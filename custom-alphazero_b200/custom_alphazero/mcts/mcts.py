@@ -98,8 +98,8 @@ class MCTS:
                  model=None, use_solver: bool = False) -> None:
         if use_solver:
             raise NotImplementedError("the exact solver back-end is outside the B200 hot path (SURVEY 2 #12)")
-        if ConfigMCTS.enable_dirichlet_noise:
-            raise NotImplementedError("Dirichlet root noise is not implemented on the GPU path")
+        # ConfigMCTS.enable_dirichlet_noise (mcts.py:114-115): root noise is drawn on the device (same distribution as
+        # np.random.dirichlet, different stream: statistical parity only - SURVEY 8a row a5)
         self.board = deepcopy(board)
         self.all_possible_moves = all_possible_moves
         self.concurrency = concurrency
@@ -112,6 +112,10 @@ class MCTS:
                                   eval_mode="external", move_mode="host_uniforms", max_free_sims=64,
                                   index_move_greedy=ConfigMCTS.index_move_greedy,
                                   c_puct=ConfigMCTS.exploration_constant, games_target=1,
+                                  dirichlet_noise=bool(ConfigMCTS.enable_dirichlet_noise),
+                                  dirichlet_alpha=ConfigMCTS.dirichlet_noise_value,
+                                  dirichlet_ratio=ConfigMCTS.dirichlet_noise_ratio,
+                                  seed=int(np.random.randint(0, 2**31 - 1)) if ConfigMCTS.enable_dirichlet_noise else 0,
                                   pow_lut_len=self._rules.max_plies * 4096 + 2)
         dev = self._engine.device
         H, W, A = self._rules.height, self._rules.width, self._rules.n_actions

@@ -72,7 +72,9 @@ def _runner(net, games, game_id_base):
                        net=net, games_target=games, game_id_base=game_id_base, seed=ConfigB200.seed,
                        move_mode="philox", auto_restart=True, unroll=ConfigB200.graph_unroll,
                        max_free_sims=ConfigB200.max_free_sims, fin_capacity=games,
-                       index_move_greedy=ConfigMCTS.index_move_greedy)
+                       index_move_greedy=ConfigMCTS.index_move_greedy,
+                       dirichlet_noise=bool(ConfigMCTS.enable_dirichlet_noise), dirichlet_alpha=ConfigMCTS.dirichlet_noise_value,
+                       dirichlet_ratio=ConfigMCTS.dirichlet_noise_ratio)
     _live["runner"] = r
     return r
 

@@ -93,6 +93,12 @@ typedef struct az_config {
     int32_t inline_play;       /* 1: az_step itself plays the move (the az_play step with the self-play rules) the
                                   moment a tree's budget is spent, whenever the re-root fits in place; az_play
                                   then only serves trees that need the compaction path */
+    int32_t dirichlet_noise;   /* ConfigMCTS.enable_dirichlet_noise (mcts.py:70-85, off in the reference's config): at the
+                                  root every simulation scores the edges with (1 - ratio) * prior + ratio * Dir(alpha * 1_k),
+                                  drawn afresh each time (quirk Q4) from Philox(seed, game id, ply, simulation) - the same
+                                  distribution as np.random.dirichlet, not the same stream */
+    double dirichlet_alpha;    /* ConfigMCTS.dirichlet_noise_value (0.03) */
+    double dirichlet_ratio;    /* ConfigMCTS.dirichlet_noise_ratio (0.25) */
     double c_puct;             /* ConfigMCTS.exploration_constant */
     uint64_t seed;             /* Philox key for AZ_MOVE_PHILOX */
     int64_t game_id_base;      /* first global game id of this rank */
@@ -269,6 +275,10 @@ int az_net_heads(const void *dev_x, const az_head_weights *weights, int32_t n, i
  *   leaf_valid_out: dev int32 [T]: 1 = stem_out[tree] holds a fresh leaf. */
 int az_advance_fused(az_engine *e, const void *dev_tower_out, const az_head_weights *weights, const float *dev_stem_w,
                      const float *dev_stem_b, void *dev_stem_out, int32_t *dev_leaf_valid_out, void *stream);
+
+/* Test aid: n Dirichlet(alpha * 1_k) samples from the device sampler used for the root noise
+ * (out: dev double [n][k]); sample i uses the Philox counter (game = i, ply = 0, simulation = 0). */
+int az_debug_dirichlet(uint64_t seed, double alpha, int32_t k, int32_t n, double *dev_out, void *stream);
 
 /* Measurement aid: successive az_advance_fused launches record {first block start, last warp end} (globaltimer,
  * ns) into dev_slots[2 * (launch % n_slots)], which the caller initialises to {UINT64_MAX, 0}.  NULL switches it

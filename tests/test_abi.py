@@ -41,7 +41,7 @@ def _cfg(**kw):
 
     base = dict(abi_version=native.AZ_ABI_VERSION, width=7, height=6, n_connect=4, gravity=1, n_trees=4096,
                 node_capacity=22457, sims_per_move=800, index_move_greedy=8, eval_mode=0, prior_mode=1, move_mode=2,
-                max_free_sims=8, fin_capacity=8192, pow_lut_len=33602, auto_restart=1, inline_play=1, c_puct=1.5, seed=0,
+                max_free_sims=8, fin_capacity=8192, pow_lut_len=33602, auto_restart=1, inline_play=1, dirichlet_noise=0, dirichlet_alpha=0.03, dirichlet_ratio=0.25, c_puct=1.5, seed=0,
                 game_id_base=0, games_target=4096)
     base.update(kw)
     return native.AzConfig(**base)

@@ -351,3 +351,53 @@ def test_extreme_board_sizes_match_c_oracle(W, H, n, gravity):
         assert fin["len"][g] == k and fin["result"][g] == want["result"]
         np.testing.assert_array_equal(fin["action"][g][:k] & 0xFFFF, want["moves"])
         np.testing.assert_array_equal(fin["visits"][g][:k], want["visits"])
+
+
+# ------------------------------------------------------------------ Dirichlet root noise
+def test_dirichlet_sampler_has_the_right_distribution():
+    """The device sampler behind the root noise against the closed-form moments of Dirichlet(alpha * 1_k) and
+    against np.random.dirichlet itself (statistical parity: same distribution, different stream)."""
+    import ctypes
+
+    from az_b200 import engine, native
+
+    for alpha, k, n in ((0.03, 7, 40000), (1.0, 3, 20000), (0.3, 81, 4000)):
+        out = torch.zeros((n, k), dtype=torch.float64, device="cuda")
+        native.check(native.lib().az_debug_dirichlet(ctypes.c_uint64(123), alpha, k, n, engine._ptr(out), engine._stream()))
+        x = out.cpu().numpy()
+        assert np.isfinite(x).all() and (x >= 0).all() and np.allclose(x.sum(1), 1.0)
+        mean, var = 1.0 / k, (1.0 / k) * (1 - 1.0 / k) / (k * alpha + 1)
+        se_mean = np.sqrt(var / n)
+        assert np.abs(x.mean(0) - mean).max() < 5 * se_mean
+        assert np.abs(x.var(0) - var).max() < 0.08 * var + 5e-5
+        ref = np.random.RandomState(0).dirichlet(np.full(k, alpha), n)
+        # same shape of the distribution: quantiles of the first component agree with numpy's sampler
+        q = [0.5, 0.9, 0.99]
+        assert np.allclose(np.quantile(x[:, 0], q), np.quantile(ref[:, 0], q), atol=0.03)
+        assert abs((x.max(1) > 0.99).mean() - (ref.max(1) > 0.99).mean()) < 0.02  # mass on the corners (alpha << 1)
+
+
+def test_root_noise_plumbing():
+    """ratio = 0 goes through the noise kernels but must reproduce the golden game exactly; ratio = 0.25 changes
+    the search, keeps its invariants, depends on the seed and is reproducible for a seed."""
+    engine, _ = _engine_mod()
+    case = load_golden("game_6x7_250_hash")
+    rules = rules_of(case)
+    eng = engine.TreeEngine(rules, n_trees=2, sims_per_move=250, eval_mode="hash", prior_mode="f64", dirichlet_noise=True,
+                            dirichlet_ratio=0.0)
+    fin = _play_games(eng, rules.max_plies)
+    _check_against_golden(case, fin, 0)
+    runs = []
+    for seed in (1, 1, 2):
+        eng = engine.TreeEngine(rules, n_trees=2, sims_per_move=250, eval_mode="hash", prior_mode="f64", seed=seed,
+                                dirichlet_noise=True, dirichlet_alpha=0.03, dirichlet_ratio=0.25)
+        eng.search()
+        torch.cuda.synchronize()
+        eng.check_status()
+        n0, w0, p0 = eng.root_stats(0)
+        n1, _, _ = eng.root_stats(1)
+        assert sum(n0) == 249 and sum(n1) == 249 and p0 == case["plies"][0]["P"]  # stored priors are untouched
+        runs.append((n0, n1))
+    assert runs[0] == runs[1] and runs[0] != runs[2]
+    assert runs[0][0] != runs[0][1]  # different game ids draw different noise
+    assert runs[0][0] != case["plies"][0]["N"]

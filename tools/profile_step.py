@@ -13,7 +13,12 @@ r = selfplay.SelfPlayRunner(rules, n_trees=4096, sims_per_move=800, net=N.Policy
 r.run(9600); torch.cuda.synchronize()
 g = r.groups[0]
 g.tower_out = None
-for _ in range(12):
+for _ in range(10):
     r._advance(g)
 torch.cuda.synchronize()
+torch.cuda.nvtx.range_push("steady_advances")   # ncu --nvtx --nvtx-include "steady_advances/" profiles exactly these
+for _ in range(2):
+    r._advance(g)
+torch.cuda.synchronize()
+torch.cuda.nvtx.range_pop()
 print("done", r.totals())

@@ -307,8 +307,9 @@ def main():
         net_ms = a.elapsed_time(b) / n_rep
         ach = Tg * runner.flops_per_eval / (net_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_sustained"], "traffic": None,
-                "traffic_note": "library kernels; per-kernel DRAM bytes of the 3x3 convolutions are in profiles/ncu_full_summary_r1.csv",
+                "frac": ach / peaks["bf16_sustained"],
+                "traffic": 817.0e6 if (Tg == 4096 and RULES == (7, 6, 4, True)) else None,
+                "traffic_note": "DRAM bytes of the 12 tower convolutions per forward at 4096 positions (ncu, steady state, profiles/advance_traffic_r1.json); algorithmic in+out bytes are 1232 MB - the 126 MB L2 keeps part of every activation tensor on chip",
                 "kernel": "policy/value net forward timed alone: az_net_stem + 12 cuDNN tcgen05 implicit-GEMM convolutions (cutlass3x_sm100_tensorop, fused bias/ReLU/residual epilogues) + az_net_heads",
                 "flops_per_launch": Tg * runner.flops_per_eval, "positions_per_launch": Tg, "ms_per_launch": net_ms, "peak_source": peaks["source"] + ", sustained"}
         # the per-tree kernel alone (HBM bound): algorithmic bytes per tree and launch with the measured mean
@@ -354,8 +355,8 @@ def main():
         step_ms = a.elapsed_time(b) / n_rep
         ach_gbs = Tg * bytes_per_tree / (step_ms * 1e-3) / 1e9
         roof_tree = {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach_gbs / peaks["hbm_gbs"], "traffic": 82.8e6 if runner.fused else None,
-                     "traffic_source": "profiles/ncu_full_summary_r1.csv (dram read + write of k_advance, steady state)",
+                     "frac": ach_gbs / peaks["hbm_gbs"], "traffic": 89.7e6 if runner.fused else None,
+                     "traffic_source": "profiles/advance_traffic_r1.json (DRAM bytes of k_advance per launch, ncu, steady state)",
                      "kernel": kname, "bytes_per_tree": bytes_per_tree, "tree_bytes_per_sim": tree_bytes,
                      "mean_depth": d_bar, "mean_children": k_bar, "sims_per_evaluated_leaf": sims_per_tree,
                      "trees_per_launch": Tg, "ms_per_launch": step_ms, "peak_source": peaks["source"]}

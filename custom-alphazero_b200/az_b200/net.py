@@ -153,15 +153,6 @@ class InferenceNet(nn.Module):
         # fast path: custom stem/heads kernels + cuDNN fused-epilogue tower (GPU, bf16, 128 filters)
         self.fast = dev.type == "cuda" and dtype == torch.bfloat16 and net.filters == 128 and net.value_fc1.out_features == 256
         self._head_struct = None
-        # float32 shortcut weights / merged biases for az_net_block_tail (hand-written shortcut + add + ReLU)
-        self.tail_w32 = nn.ParameterList()
-        self.tail_b32 = nn.ParameterList()
-        for blk in net.blocks:
-            wpf, bpf = blk.proj.folded()
-            _, b2f = blk.c2.folded()
-            self.tail_w32.append(f32(wpf.reshape(wpf.shape[0], -1)))
-            self.tail_b32.append(f32(bpf + b2f))
-        self.custom_tail = False
         self.overlap_shortcut = False
         self._side = {}
 
@@ -238,21 +229,6 @@ class InferenceNet(nn.Module):
         side = self._side_stream(x.device) if self.overlap_shortcut else None
         for i in range(self.depth):
             w1, b1, w2, wp, b2p = self.block_params[5 * i: 5 * i + 5]
-            if self.custom_tail:
-                # library convolutions without the shortcut; az_net_block_tail does shortcut GEMM + add + bias + ReLU
-                from .engine import _ptr, _stream
-                from .native import check, lib
-
-                h = torch.cudnn_convolution_relu(x, w1, b1, one, one, one, 1)
-                c2 = F.conv2d(h, w2, None, padding=1)
-                xin = x.permute(0, 2, 3, 1)
-                c2m = c2.permute(0, 2, 3, 1)
-                assert xin.is_contiguous() and c2m.is_contiguous()
-                rows = c2m.shape[0] * c2m.shape[1] * c2m.shape[2]
-                check(lib().az_net_block_tail(_ptr(xin), _ptr(c2m), _ptr(self.tail_w32[i]), _ptr(self.tail_b32[i]), rows,
-                                              self.filters, _stream()))
-                x = c2
-                continue
             if side is not None:
                 # the bandwidth-bound 1x1 shortcut runs beside the compute-bound 3x3 on a forked stream
                 side.wait_stream(cur)

@@ -296,118 +296,3 @@ AZ_API int az_net_heads(const void* x, const az_head_weights* hw, int32_t n, int
     if (cudaGetLastError() != cudaSuccess) return fail_net(AZ_ERR_CUDA, "az_net_heads: launch failed");
     return AZ_OK;
 }
-
-namespace az {
-// ------------------------------------------------------------------------------------------ block tail
-// y = ReLU(c2 + x * Wp^T + b): the projection shortcut (Conv1x1 + BN of the block INPUT, base_layers.py:104-125), the
-// residual add and the activation in one pass over the data, instead of a library 1x1 convolution (read x, write p) plus
-// an add-ReLU epilogue that reads p back.  Bandwidth-bound (x and c2 in, y out; 5.6 GFLOP per 4096 positions), so the
-// GEMM rides mma.sync.  Both K (input channels) and N (output channels) are permuted inside the MMA so that lane (g, t4)
-// owns the 32 physical channels [32 t4, 32 t4 + 32) of rows g and g+8: every global access is a 128-bit vector and
-// a row is covered by its four lanes; the weight fragments are pre-packed per lane in shared memory.
-constexpr int kTailWarps = 8;
-
-__global__ void __launch_bounds__(kTailWarps * 32, 1) k_block_tail(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* c2y,
-                                                               const float* __restrict__ wp, const float* __restrict__ bias,
-                                                               int rows) {
-    constexpr int C = 128;
-    __shared__ uint2 s_b[8 * 16 * 32];  // [ks][nt][lane] -> {b0, b1} of the permuted weight matrix
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
-    for (int i = threadIdx.x; i < 8 * 16 * 32; i += blockDim.x) {
-        const int ln = i & 31, nt = (i >> 5) & 15, ks = i >> 9;
-        const int gg = ln >> 2, tt = ln & 3;
-        const int co = (gg >> 1) * 32 + nt * 2 + (gg & 1);  // physical output channel of logical column gg of n-tile nt
-        // logical k pair (2 tt, 2 tt + 1) (+8 for the second register) of k-step ks -> physical input channels
-        const int k0 = tt * 32 + ks * 4;
-        uint2 v;
-        v.x = pack_bf16(wp[co * C + k0], wp[co * C + k0 + 1]);
-        v.y = pack_bf16(wp[co * C + k0 + 2], wp[co * C + k0 + 3]);
-        s_b[i] = v;
-    }
-    __syncthreads();
-    const int pairs = (rows + 31) >> 5;  // two m-tiles (32 rows) per iteration
-    for (int it = blockIdx.x * kTailWarps + warp; it < pairs; it += gridDim.x * kTailWarps) {
-        const int r0 = it * 32;
-        // A fragments of both m-tiles: rows r0 + g, +8, +16, +24; lane's 64 contiguous bytes of each row
-        uint32_t a[2][8][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int hr = 0; hr < 2; ++hr) {
-                int row = r0 + mt * 16 + hr * 8 + g;
-                if (row >= rows) row = rows - 1;
-                const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)row * C + t4 * 32);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {  // 16 B = physical channels 8q..8q+7 of the lane's slice = k-steps 2q, 2q+1
-                    const uint4 v = src[q];
-                    a[mt][2 * q][hr] = v.x;          // k-step 2q,   first pair  (logical k 2t4, 2t4+1)
-                    a[mt][2 * q][hr + 2] = v.y;      // k-step 2q,   second pair (logical k +8)
-                    a[mt][2 * q + 1][hr] = v.z;      // k-step 2q+1, first pair
-                    a[mt][2 * q + 1][hr + 2] = v.w;  // k-step 2q+1, second pair
-                }
-            }
-#pragma unroll
-        for (int ng = 0; ng < 4; ++ng) {  // four n-tiles = 8 physical channels = one 128-bit vector per row and lane
-            float acc[2][4][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[mt][j][0] = acc[mt][j][1] = acc[mt][j][2] = acc[mt][j][3] = 0.f;
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint2 bq = s_b[((ks * 16 + ng * 4 + j) << 5) + lane];
-                    const uint32_t b2[2] = {bq.x, bq.y};
-                    mma_16816(acc[0][j], a[0][ks], b2);
-                    mma_16816(acc[1][j], a[1][ks], b2);
-                }
-            // epilogue: + c2 + bias, ReLU, in place
-            float bl[8];
-            {
-                const float4 b0 = reinterpret_cast<const float4*>(bias + t4 * 32 + ng * 8)[0];
-                const float4 b1 = reinterpret_cast<const float4*>(bias + t4 * 32 + ng * 8)[1];
-                bl[0] = b0.x; bl[1] = b0.y; bl[2] = b0.z; bl[3] = b0.w;
-                bl[4] = b1.x; bl[5] = b1.y; bl[6] = b1.z; bl[7] = b1.w;
-            }
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int hr = 0; hr < 2; ++hr) {
-                    const int row = r0 + mt * 16 + hr * 8 + g;
-                    if (row < rows) {
-                        uint4* p = reinterpret_cast<uint4*>(c2y + (size_t)row * C + t4 * 32 + ng * 8);
-                        const uint4 cv = *p;
-                        const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
-                        uint32_t ow[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {  // n-tile ng*4+j holds physical channels ng*8 + 2j, 2j+1
-                            const float c_lo = __uint_as_float(cw[j] << 16), c_hi = __uint_as_float(cw[j] & 0xffff0000u);
-                            const float lo = acc[mt][j][hr * 2 + 0] + c_lo + bl[2 * j];
-                            const float hi = acc[mt][j][hr * 2 + 1] + c_hi + bl[2 * j + 1];
-                            ow[j] = pack_bf16(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
-                        }
-                        *p = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                    }
-                }
-        }
-    }
-}
-}  // namespace az
-
-AZ_API int az_net_block_tail(const void* x, void* c2_inout, const float* wp, const float* bias, int64_t rows, int32_t C,
-                             void* stream) {
-    if (rows == 0) return AZ_OK;
-    if (!x || !c2_inout || !wp || !bias || rows < 0 || rows > 0x7fffffff) return fail_net(AZ_ERR_ARG, "az_net_block_tail: bad argument");
-    if (C != 128) return fail_net(AZ_ERR_ARG, "az_net_block_tail: built for 128 filters (config.py:71)");
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int pairs = (int)((rows + 31) / 32);
-    int grid = (pairs + kTailWarps - 1) / kTailWarps;
-    if (grid > sms) grid = sms;
-    k_block_tail<<<grid, kTailWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(c2_inout), wp, bias, (int)rows);
-    if (cudaGetLastError() != cudaSuccess) return fail_net(AZ_ERR_CUDA, "az_net_block_tail: launch failed");
-    return AZ_OK;
-}

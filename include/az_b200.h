@@ -267,12 +267,6 @@ int az_net_stem(const void *dev_states, const float *dev_w, const float *dev_b, 
 int az_net_heads(const void *dev_x, const az_head_weights *weights, int32_t n, int32_t cells, int32_t channels,
                  int32_t n_actions, float *dev_priors_out, float *dev_values_out, void *stream);
 
-/* Tail of an OuterConvBlock (base_layers.py:104-125): y = ReLU(c2 + Conv1x1(x) + bias), i.e. the projection shortcut of
- * the block input x, the residual add and the activation, in place on c2.  x, c2_inout: dev bf16 [rows][C] (NHWC pixels);
- * wp: dev float [C][C] (out, in; BN folded); bias: dev float [C] (shortcut bias + second convolution's bias). C = 128. */
-int az_net_block_tail(const void *dev_x, void *dev_c2_inout, const float *dev_wp, const float *dev_bias, int64_t rows,
-                      int32_t channels, void *stream);
-
 /* The three per-tree stages between two passes of the tower in ONE launch (one warp per tree):
  * az_net_heads on the tower output of each tree's pending leaf, az_step with those priors / value (kept in
  * registers), az_net_stem on the newly selected leaf.  Same results as the three calls in sequence.

@@ -232,3 +232,42 @@ def test_self_play_entry_point_writes_reference_format(tmp_path, monkeypatch, c4
     assert S > 100 and data["states"].shape == (S, 6, 7, 4) and data["states"].dtype == np.float32
     assert data["policies"].shape == (S, 7) and data["policies"].dtype == np.float64
     assert set(np.unique(data["values"])) <= {-1, 1}  # exclude_null_games: no zero rewards left
+
+
+def test_integration_md_binding_snippet_runs(c4):
+    """The ctypes stub printed in INTEGRATION.md section 3 is executed as written (only the library path is made
+    absolute): it must create an engine and drive az_step / az_play with a stand-in evaluator."""
+    import ctypes
+    import os
+    import re
+
+    from tests.helpers import ROOT
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if "class AzConfig" in b)
+    lib_path = os.path.join(ROOT, "custom-alphazero_b200", "libaz_b200.so")
+    stub = stub.replace('ctypes.CDLL("libaz_b200.so")', f'ctypes.CDLL("{lib_path}")')
+    ns = {}
+    exec(stub, ns)
+    assert ctypes.sizeof(ns["AzConfig"]) > 0
+    T, sims = 16, 12
+    h, slab, lay, cfg = ns["make_engine"](None, T, sims)
+    lib = ns["_lib"]
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    A = lay.n_actions
+    priors = torch.full((T, A), 1.0 / A, dtype=torch.float32, device="cuda")
+    values = torch.zeros(T, dtype=torch.float32, device="cuda")
+    states = torch.zeros((T, 6, 7, 4), dtype=torch.bfloat16, device="cuda")
+    valid = torch.zeros(T, dtype=torch.int32, device="cuda")
+    for _ in range(400):
+        assert lib.az_step(h, ptr(priors), ptr(values), 0, ptr(states), 2, ptr(valid), stream) == 0
+        assert lib.az_play(h, -1, -1, stream) == 0
+    torch.cuda.synchronize()
+    counters = slab[lay.counters: lay.counters + T * 8 * 8].view(torch.int64).view(T, 8).sum(0).tolist()
+    status = slab[lay.status: lay.status + 4 * T].view(torch.int32)
+    assert counters[0] >= 400 * T and counters[2] >= (400 // sims - 1) * T and counters[3] > 0  # sims, moves, games
+    assert int((status & ~0xFF).max()) == 0  # no error flags
+    st = states.float()
+    assert bool((st[..., 3] == 1).all()) and bool((st[..., :3].sum(-1) == 1).all())

@@ -60,7 +60,7 @@ class TreeEngine:
                  move_mode="argmax", node_capacity=None, games_target=None, game_id_base=0, seed=0,
                  auto_restart=False, fin_capacity=None, max_free_sims=8, index_move_greedy=8, c_puct=1.5,
                  pow_lut_len=None, device=None, inline_play=False, dirichlet_noise=False, dirichlet_alpha=0.03,
-                 dirichlet_ratio=0.25):
+                 dirichlet_ratio=0.25, eval_cache_log2=0):
         if not torch.cuda.is_available():
             raise NativeError("no CUDA device: the self-play engine has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -91,7 +91,8 @@ class TreeEngine:
             prior_mode={"f64": 0, "f32": 1}[prior_mode],
             move_mode={"argmax": 0, "host_uniforms": 1, "philox": 2}[move_mode],
             max_free_sims=int(max_free_sims), fin_capacity=int(fin_capacity), pow_lut_len=int(pow_lut_len),
-            auto_restart=int(auto_restart), inline_play=int(inline_play), dirichlet_noise=int(dirichlet_noise),
+            auto_restart=int(auto_restart), inline_play=int(inline_play), eval_cache_log2=int(eval_cache_log2),
+            dirichlet_noise=int(dirichlet_noise),
             dirichlet_alpha=float(dirichlet_alpha), dirichlet_ratio=float(dirichlet_ratio), c_puct=float(c_puct), seed=int(seed), game_id_base=int(game_id_base),
             games_target=int(games_target),
         )
@@ -183,6 +184,9 @@ class TreeEngine:
     def fin_clear(self):
         check(lib().az_fin_clear(self._h, _stream()))
 
+    def cache_clear(self):
+        check(lib().az_cache_clear(self._h, _stream()))
+
     # ------------------------------------------------------------------ host-side conveniences
     def set_uniforms(self, uniforms):
         """uniforms [T, <=P] float64: the np.random draws for AZ_MOVE_HOST_UNIFORMS."""
@@ -206,7 +210,7 @@ class TreeEngine:
     def totals(self):
         c = self.view("counters").sum(dim=0).tolist()
         return {"sims": c[0], "evals": c[1], "moves": c[2], "games": c[3], "depth_sum": c[4], "children": c[5],
-                "reroot_nodes": c[6]}
+                "reroot_nodes": c[6], "memo_hits": c[7]}
 
     def drain_finished(self):
         """Copies the finished-game ring to the host and empties it."""

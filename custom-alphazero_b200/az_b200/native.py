@@ -42,6 +42,7 @@ class AzConfig(ctypes.Structure):
         ("pow_lut_len", ctypes.c_int32),
         ("auto_restart", ctypes.c_int32),
         ("inline_play", ctypes.c_int32),
+        ("eval_cache_log2", ctypes.c_int32),
         ("dirichlet_noise", ctypes.c_int32),
         ("dirichlet_alpha", ctypes.c_double),
         ("dirichlet_ratio", ctypes.c_double),
@@ -56,6 +57,7 @@ LAYOUT_ARRAYS = [
     "status", "ply", "game_id", "root_board", "half", "root_node", "n_nodes", "sims_done", "pending", "path_len", "path",
     "leaf_board", "counters", "uniforms", "node_a", "node_p", "rec_visits", "rec_action", "rec_board", "rec_len",
     "result", "fin_count", "fin_game_id", "fin_len", "fin_result", "fin_visits", "fin_action", "fin_board", "pow_lut",
+    "cache_meta", "cache_key", "cache_val",
 ]
 
 
@@ -89,6 +91,7 @@ SYMBOLS = {
     "az_search": (ctypes.c_int, [_P, _P]),
     "az_play": (ctypes.c_int, [_P, _I, _I, _P]),
     "az_fin_clear": (ctypes.c_int, [_P, _P]),
+    "az_cache_clear": (ctypes.c_int, [_P, _P]),
     "az_env_play": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _P, _I, _P, _P, _P]),
     "az_env_legal": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _I, _P, _P]),
     "az_env_encode": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _I, _P, _P]),

@@ -74,7 +74,7 @@ class SelfPlayRunner:
                  game_id_base=0, seed=0, move_mode="philox", auto_restart=True, dtype=torch.bfloat16, unroll=8,
                  use_graph=True, max_free_sims=8, node_capacity=None, fin_capacity=None, device=None,
                  index_move_greedy=8, groups=1, fused=True, extra_sims=0, dirichlet_noise=False, dirichlet_alpha=0.03,
-                 dirichlet_ratio=0.25):
+                 dirichlet_ratio=0.25, eval_cache_log2=0):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.rules = rules
         T, A = int(n_trees), rules.n_actions
@@ -95,7 +95,8 @@ class SelfPlayRunner:
                              max_free_sims=max_free_sims, node_capacity=node_capacity,
                              fin_capacity=None if fin_capacity is None else max(1, -(-fin_capacity // groups)),
                              device=self.device, index_move_greedy=index_move_greedy, inline_play=True,
-                             dirichlet_noise=dirichlet_noise, dirichlet_alpha=dirichlet_alpha, dirichlet_ratio=dirichlet_ratio)
+                             dirichlet_noise=dirichlet_noise, dirichlet_alpha=dirichlet_alpha, dirichlet_ratio=dirichlet_ratio,
+                             eval_cache_log2=eval_cache_log2)
             self.groups.append(_Group(eng, rules, dtype, self.device))
             t0 += ti
             g0 += gi
@@ -277,8 +278,12 @@ class SelfPlayRunner:
         return out
 
     def load_weights(self, net: PolicyValueNet):
+        """New weights: refresh the folded inference copy and forget the memoised evaluations (the reference
+        resets plays_inferences when the best-model hash changes, self_play.py:142-150)."""
         self.fp32_net = net
         self.net.load_from(net)
+        for g in self.groups:
+            g.engine.cache_clear()
 
 
 def smoke_net_step():

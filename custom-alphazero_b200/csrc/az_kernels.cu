@@ -411,7 +411,7 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
     double* Pr = e.node_p + pool;
     int sims = e.sims_done[t];
     int root = e.root_node[t];
-    long long nsim = 0, neval = 0, ndepth = 0, nchild = 0;
+    long long nsim = 0, neval = 0, ndepth = 0, nchild = 0, nhit = 0;
     // pending: 0 = no leaf in flight, 1 = leaf handed to the evaluator, 2 = leaf selected by az_extra_sims but
     // not handed out yet (it is submitted by the next az_step / az_advance_fused, which finds no answer for it)
     const int was_pending = e.pending[t];
@@ -422,6 +422,8 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
         __syncwarp();
         const uint32_t link = expand_leaf<NW>(e, r, A, Pr, at, t, ws, lane, flags, prior_mode, prior_of);
         backup_path(A, root, ws, depth, -value, link, lane);  // mcts.py:175: value seen by the player who moved in
+        if (e.cache_meta && prior_mode == AZ_PRIOR_F32)  // memoise float32 evaluations (exact round trip)
+            cache_insert<NW>(e, r, at, lane, [&](int a) { return (float)prior_of(a); }, (float)value);
         ++sims;
         ++nsim;
         ++neval;
@@ -464,6 +466,21 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
             if (++freed >= e.max_free) break;
             continue;
         }
+        if (e.cache_meta) {  // plays_inferences (mcts.py:123-124): this position was evaluated before
+            float cv;
+            if (cache_lookup<NW>(e, r, pos, lane, ws.cpri, cv)) {
+                const float* cp = ws.cpri;
+                const uint32_t link = expand_leaf<NW>(e, r, A, Pr, pos, t, ws, lane, flags, AZ_PRIOR_F32,
+                                                      [cp](int a) { return (double)cp[a]; });
+                backup_path(A, root, ws, depth, -(double)cv, link, lane);
+                ++sims;
+                ++nsim;
+                ++nhit;
+                nchild += link >> 24;
+                if (++freed >= e.max_free) break;
+                continue;
+            }
+        }
         for (int i = lane; i < depth; i += 32) e.path[(size_t)t * kMaxDepth + i] = ws.path[i];
         store_pos<NW>(e.leaf_board + (size_t)t * 2 * NW, pos, lane);
         if (lane == 0) e.path_len[t] = depth;
@@ -475,6 +492,7 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
         bump(e.counters + (size_t)t * 8 + 1, neval);
         bump(e.counters + (size_t)t * 8 + 4, ndepth);
         bump(e.counters + (size_t)t * 8 + 5, nchild);
+        bump(e.counters + (size_t)t * 8 + 7, nhit);
         if (sims >= 0) {
             e.sims_done[t] = sims;
             e.pending[t] = pend ? submit : 0;
@@ -987,6 +1005,7 @@ static int check_cfg(const az_config* c) {
     if (c->height * (c->width + 1) > 128) return fail(AZ_ERR_ARG, "board needs more than 128 bits%s");
     int m = c->width < c->height ? c->width : c->height;
     if (c->n_connect < 2 || c->n_connect > m) return fail(AZ_ERR_ARG, "n_connect must be in [2, min(W, H)]%s");
+    if (c->eval_cache_log2 < 0 || c->eval_cache_log2 > 30) return fail(AZ_ERR_ARG, "eval_cache_log2 must be in [0, 30]%s");
     if (c->dirichlet_noise && (!(c->dirichlet_alpha > 0.0) || c->dirichlet_ratio < 0.0 || c->dirichlet_ratio > 1.0))
         return fail(AZ_ERR_ARG, "dirichlet_alpha must be > 0 and dirichlet_ratio in [0, 1]%s");
     return AZ_OK;
@@ -1050,6 +1069,12 @@ AZ_API int az_query_layout(const az_config* c, az_layout* L) {
     L->pow_lut = take(off, 8 * (size_t)c->pow_lut_len);
     L->rec_len = take(off, 4 * T);
     L->result = take(off, 4 * T);
+    if (c->eval_cache_log2 > 0) {
+        const size_t S = (size_t)1 << c->eval_cache_log2;
+        L->cache_meta = take(off, 4 * S);
+        L->cache_key = take(off, 8 * S * 2 * WD);
+        L->cache_val = take(off, 4 * S * (A + 1));
+    }
     L->total_bytes = (off + 255) & ~(size_t)255;
     return AZ_OK;
 }
@@ -1122,6 +1147,16 @@ AZ_API int az_engine_create(const az_config* c, void* slab, size_t bytes, const 
     g.fin_action = reinterpret_cast<int32_t*>(b + L.fin_action);
     g.fin_board = reinterpret_cast<uint64_t*>(b + L.fin_board);
     g.pow_lut = reinterpret_cast<const double*>(b + L.pow_lut);
+    g.cache_meta = nullptr;
+    g.cache_key = nullptr;
+    g.cache_val = nullptr;
+    g.cache_mask = 0;
+    if (c->eval_cache_log2 > 0) {
+        g.cache_meta = reinterpret_cast<unsigned int*>(b + L.cache_meta);
+        g.cache_key = reinterpret_cast<uint64_t*>(b + L.cache_key);
+        g.cache_val = reinterpret_cast<float*>(b + L.cache_val);
+        g.cache_mask = (1u << c->eval_cache_log2) - 1u;
+    }
     e->aux.rec_len = reinterpret_cast<int32_t*>(b + L.rec_len);
     e->aux.result = reinterpret_cast<int32_t*>(b + L.result);
     e->nw = L.words;
@@ -1350,5 +1385,13 @@ AZ_API int az_debug_dirichlet(uint64_t seed, double alpha, int32_t k, int32_t n,
     if (!out || k < 1 || k > AZ_MAX_ACTIONS || n < 0 || !(alpha > 0.0)) return fail(AZ_ERR_ARG, "az_debug_dirichlet: bad argument%s");
     k_debug_dirichlet<<<(n + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(seed, alpha, k, n, out);
     AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_cache_clear(az_engine* e, void* stream) {
+    if (!e) return fail(AZ_ERR_ARG, "null engine%s");
+    if (!e->eng.cache_meta) return AZ_OK;
+    AZ_CUDA(cudaMemsetAsync(e->eng.cache_meta, 0, sizeof(unsigned int) * ((size_t)e->eng.cache_mask + 1),
+                            static_cast<cudaStream_t>(stream)));
     return AZ_OK;
 }

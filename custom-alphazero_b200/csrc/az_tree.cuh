@@ -148,6 +148,11 @@ struct Eng {
     int32_t* fin_action;
     uint64_t* fin_board;
     const double* pow_lut;
+    // evaluation memo (null when off)
+    unsigned int* cache_meta;
+    uint64_t* cache_key;
+    float* cache_val;
+    unsigned int cache_mask;
 };
 
 // per-warp scratch in shared memory
@@ -156,6 +161,7 @@ struct WarpScratch {
     int32_t path[kMaxDepth];
     int32_t off[32];
     int32_t ob[32];
+    float cpri[kMaxActions];  // priors of an evaluation-memo hit
 };
 
 template <int NW>
@@ -392,6 +398,70 @@ __device__ __forceinline__ uint32_t expand_leaf(const Eng& e, const R& r, NodeA*
     }
     if (lane == 0) e.n_nodes[t] = base + k;
     return (uint32_t)base | ((uint32_t)k << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// Evaluation memo (plays_inferences of the reference, mcts.py:122-143): direct-mapped, shared by all trees,
+// lossy (a colliding insert overwrites).  Entries are guarded by a seqlock word so that a reader never combines
+// the key of one position with the numbers of another: writers take the slot with a CAS (or skip the insert),
+// readers re-check the version after reading and treat any change as a miss.  All table accesses bypass L1
+// (ld.cg / st.cg): other SMs write these lines during the same kernel.
+template <int NW>
+__device__ __forceinline__ unsigned int cache_slot(const Eng& e, const Pos<NW>& p) {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        h = (h ^ p.cur.w[i]) * 0xFF51AFD7ED558CCDull;
+        h = (h ^ (h >> 32) ^ p.opp.w[i]) * 0xC4CEB9FE1A85EC53ull;
+    }
+    h ^= h >> 29;
+    return (unsigned int)h & e.cache_mask;
+}
+
+// Insert (whole warp): prior_of(a) for a < A and the value.
+template <int NW, class R, typename PriorFn>
+__device__ __forceinline__ void cache_insert(const Eng& e, const R& r, const Pos<NW>& p, int lane, PriorFn prior_of, float value) {
+    const unsigned int s = cache_slot<NW>(e, p);
+    unsigned int m = 0;
+    int got = 0;
+    if (lane == 0) {
+        m = __ldcg(e.cache_meta + s);
+        got = !(m & 1u) && atomicCAS(e.cache_meta + s, m, m | 1u) == m;
+    }
+    got = __shfl_sync(kFull, got, 0);
+    if (!got) return;
+    uint64_t* key = e.cache_key + (size_t)s * 2 * NW;
+    float* val = e.cache_val + (size_t)s * (r.A + 1);
+    if (lane < 2 * NW) __stcg(key + lane, lane < NW ? p.cur.w[lane % NW] : p.opp.w[lane % NW]);
+    for (int a = lane; a < r.A; a += 32) __stcg(val + a, prior_of(a));
+    if (lane == 0) __stcg(val + r.A, value);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(e.cache_meta + s, (m | 1u) + 1u);  // even again, new version
+}
+
+// Lookup (whole warp): on a hit the priors land in out_priors[0..A) and value is set.
+template <int NW, class R>
+__device__ __forceinline__ bool cache_lookup(const Eng& e, const R& r, const Pos<NW>& p, int lane, float* out_priors,
+                                             float& value) {
+    const unsigned int s = cache_slot<NW>(e, p);
+    const unsigned int m1 = __ldcg(e.cache_meta + s);
+    if (m1 & 1u) return false;
+    const uint64_t* key = e.cache_key + (size_t)s * 2 * NW;
+    bool same = true;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) same = same && __ldcg(key + i) == p.cur.w[i] && __ldcg(key + NW + i) == p.opp.w[i];
+    if (!same || m1 == 0u) return false;  // version 0 = never written
+    const float* val = e.cache_val + (size_t)s * (r.A + 1);
+    for (int a = lane; a < r.A; a += 32) out_priors[a] = __ldcg(val + a);
+    const float v = __ldcg(val + r.A);
+    __threadfence();
+    const unsigned int m2 = __ldcg(e.cache_meta + s);
+    const bool ok = __all_sync(kFull, m2 == m1);
+    if (!ok) return false;
+    value = v;
+    __syncwarp();
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------

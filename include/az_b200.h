@@ -93,6 +93,11 @@ typedef struct az_config {
     int32_t inline_play;       /* 1: az_step itself plays the move (the az_play step with the self-play rules) the
                                   moment a tree's budget is spent, whenever the re-root fits in place; az_play
                                   then only serves trees that need the compaction path */
+    int32_t eval_cache_log2;   /* 0 = off; else the evaluation memo of the reference (plays_inferences, mcts.py:122-143) as a
+                                  direct-mapped table of 2^n entries shared by all trees: a leaf whose position was already
+                                  evaluated is expanded on the spot without the evaluator.  Results are identical with or
+                                  without it (the evaluator is a pure function of the position); only external evaluations
+                                  (az_step / az_advance_fused) are memoised.  az_cache_clear when the weights change. */
     int32_t dirichlet_noise;   /* ConfigMCTS.enable_dirichlet_noise (mcts.py:70-85, off in the reference's config): at the
                                   root every simulation scores the edges with (1 - ratio) * prior + ratio * Dir(alpha * 1_k),
                                   drawn afresh each time (quirk Q4) from Philox(seed, game id, ply, simulation) - the same
@@ -127,7 +132,7 @@ typedef struct az_layout {
     size_t path;        /* int32  [T][max_depth]  node indices root-child ... leaf */
     size_t leaf_board;  /* uint64 [T][2][WD] */
     size_t counters;    /* int64  [T][8]   cumulative: simulations, evaluations, moves, games finished, sum of
-                                           selection depths, children created, nodes copied by re-root, spare */
+                                           selection depths, children created, nodes copied by re-root, memo hits */
     size_t uniforms;    /* double [T][P]   AZ_MOVE_HOST_UNIFORMS draws */
     /* node pools: record A = {double W; int32 N; uint32 link}, link = first_child | k << 24, 0 = no edges */
     size_t node_a;      /* 16 B   [T][2][C] */
@@ -147,6 +152,10 @@ typedef struct az_layout {
     size_t fin_action;  /* int32  [F][P]     action | greedy << 16 */
     size_t fin_board;   /* uint64 [F][P][2][WD] */
     size_t pow_lut;     /* double [pow_lut_len] */
+    /* evaluation memo (eval_cache_log2 > 0): S = 2^n entries */
+    size_t cache_meta;  /* uint32 [S]   seqlock word: odd = being written, even = version */
+    size_t cache_key;   /* uint64 [S][2][WD]  position */
+    size_t cache_val;   /* float  [S][A + 1]  priors then value */
 } az_layout;
 
 typedef struct az_engine az_engine;
@@ -213,6 +222,10 @@ int az_search(az_engine *e, void *stream);
  * ply >= index_move_greedy, 0 / 1 = force; move_mode_override: -1 = cfg.move_mode.
  * Finished games are moved to the ring and, with auto_restart, replaced (play_game, self_play.py:59-78). */
 int az_play(az_engine *e, int32_t greedy_override, int32_t move_mode_override, void *stream);
+
+/* Forgets every memoised evaluation (the reference resets plays_inferences when the best-model hash changes,
+ * self_play.py:142-150). */
+int az_cache_clear(az_engine *e, void *stream);
 
 /* Empties the finished-game ring after the host copied it; trees in AZ_PHASE_STALLED hand their game over at
  * the next az_play. */

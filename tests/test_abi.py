@@ -41,7 +41,7 @@ def _cfg(**kw):
 
     base = dict(abi_version=native.AZ_ABI_VERSION, width=7, height=6, n_connect=4, gravity=1, n_trees=4096,
                 node_capacity=22457, sims_per_move=800, index_move_greedy=8, eval_mode=0, prior_mode=1, move_mode=2,
-                max_free_sims=8, fin_capacity=8192, pow_lut_len=33602, auto_restart=1, inline_play=1, dirichlet_noise=0, dirichlet_alpha=0.03, dirichlet_ratio=0.25, c_puct=1.5, seed=0,
+                max_free_sims=8, fin_capacity=8192, pow_lut_len=33602, auto_restart=1, inline_play=1, eval_cache_log2=0, dirichlet_noise=0, dirichlet_alpha=0.03, dirichlet_ratio=0.25, c_puct=1.5, seed=0,
                 game_id_base=0, games_target=4096)
     base.update(kw)
     return native.AzConfig(**base)
@@ -54,8 +54,15 @@ def test_layout_is_host_only_and_consistent():
     cfg = _cfg()
     native.check(native.lib().az_query_layout(ctypes.byref(cfg), ctypes.byref(lay)))
     assert (lay.n_actions, lay.max_plies, lay.words) == (7, 42, 1)
-    offs = [getattr(lay, n) for n in native.LAYOUT_ARRAYS]
+    core = [n for n in native.LAYOUT_ARRAYS if not n.startswith("cache_")]
+    offs = [getattr(lay, n) for n in core]
     assert len(set(offs)) == len(offs) and all(o % 256 == 0 for o in offs) and lay.total_bytes > max(offs)
+    assert lay.cache_meta == lay.cache_key == lay.cache_val == 0  # evaluation memo off: no table in the slab
+    cfg_memo = _cfg(eval_cache_log2=20)
+    lay2 = native.AzLayout()
+    native.check(native.lib().az_query_layout(ctypes.byref(cfg_memo), ctypes.byref(lay2)))
+    assert lay2.cache_meta > 0 and lay2.cache_key - lay2.cache_meta >= 4 << 20 and lay2.cache_val - lay2.cache_key >= 16 << 20
+    assert lay2.total_bytes - lay.total_bytes >= (4 + 16 + 32) << 20
     # node pools dominate: T * 2 halves * C * 24 B
     assert lay.node_p - lay.node_a >= 4096 * 2 * 22457 * 16
     cfg9 = _cfg(width=9, height=9, n_connect=5, gravity=0)

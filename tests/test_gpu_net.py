@@ -179,3 +179,37 @@ def test_games_do_not_depend_on_how_they_are_sharded():
     for g in range(G):
         assert whole[g][0] == parts[g][0] and whole[g][1] == parts[g][1], g
         assert whole[g][2] == parts[g][2] and whole[g][3] == parts[g][3], g
+
+
+def test_evaluation_memo_changes_nothing_but_the_number_of_evaluations():
+    """The reference memoises evaluations by position (plays_inferences, mcts.py:122-143).  With the device memo on,
+    every finished game must be identical to the run without it - the evaluator is a pure function of the position -
+    while a good share of the leaves no longer needs the net."""
+    from az_b200 import selfplay
+
+    engine, native, net = _mods()
+    rules = engine.Rules(7, 6, 4, True)
+    out = []
+    for log2, fused in ((0, True), (18, True), (18, False), (10, True)):
+        torch.manual_seed(0)
+        fp32 = net.randomise_bn(net.PolicyValueNet())
+        r = selfplay.SelfPlayRunner(rules, n_trees=128, sims_per_move=64, net=fp32, games_target=256, unroll=4, seed=5,
+                                    fused=fused, eval_cache_log2=log2)
+        r.run_until_done(poll_every=64, max_advances=400000)
+        fin = {k: v.cpu().numpy() for k, v in r.finished_device().items()}
+        order = np.argsort(fin["game_id"])
+        out.append(({k: v[order] for k, v in fin.items()}, r.totals()))
+    (a, ta) = out[0]
+    assert ta["memo_hits"] == 0
+    for b, tb in out[1:]:
+        assert tb["games"] == 256 and tb["sims"] == ta["sims"] and tb["moves"] == ta["moves"]
+        assert tb["memo_hits"] > 0 and tb["evals"] + tb["memo_hits"] == ta["evals"]
+        for k in ("game_id", "len", "result"):
+            np.testing.assert_array_equal(a[k], b[k])
+        for g in range(256):
+            n = a["len"][g]
+            np.testing.assert_array_equal(a["visits"][g][:n], b["visits"][g][:n])
+            np.testing.assert_array_equal(a["action"][g][:n], b["action"][g][:n])
+    # a big table hits more often than a tiny, collision-ridden one
+    assert out[1][1]["memo_hits"] > out[3][1]["memo_hits"] > 0
+    assert out[1][1]["memo_hits"] > 0.15 * ta["evals"]

@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--groups", type=int, default=1, help="tree slices advanced on parallel graph branches")
     ap.add_argument("--max-free", type=int, default=8)
     ap.add_argument("--no-fused", action="store_true", help="three-kernel route instead of az_advance_fused")
+    ap.add_argument("--memo-log2", type=int, default=0,
+                    help="evaluation memo (the reference's plays_inferences) with 2^n entries; 0 = off (headline)")
     ap.add_argument("--board", default="7x6", help="WxH (headline: 7x6); other boards are extra configurations (C4)")
     ap.add_argument("--connect", type=int, default=4)
     ap.add_argument("--no-gravity", action="store_true")
@@ -194,7 +196,8 @@ def main():
     fp32 = PolicyValueNet(rules.height, rules.width, rules.n_actions)
     runner = selfplay.SelfPlayRunner(rules, n_trees=T, sims_per_move=S, net=fp32, games_target=1 << 40,
                                      game_id_base=rank << 40, seed=1234, move_mode="philox", auto_restart=True,
-                                     unroll=args.unroll, fin_capacity=4 * T, groups=args.groups, max_free_sims=args.max_free, fused=not args.no_fused)
+                                     unroll=args.unroll, fin_capacity=4 * T, groups=args.groups, max_free_sims=args.max_free, fused=not args.no_fused,
+                                     eval_cache_log2=args.memo_log2)
     flat_dev = runner.net.flat_weights()  # what the trainer rank would broadcast after a training step
     n_w = flat_dev.numel()
 
@@ -368,10 +371,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{'C2' if RULES == (7, 6, 4, True) else 'C4'}: {T} concurrent {rules.height}x{rules.width} Connect-{rules.n} self-play games per GPU x {S} simulations/move, bf16 net leaf evaluation",
-                       "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "fused_advance": bool(runner.fused), "board": f"{rules.height}x{rules.width}", "n_connect": rules.n, "gravity": rules.gravity,
+                       "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "fused_advance": bool(runner.fused), "evaluation_memo_log2": args.memo_log2, "board": f"{rules.height}x{rules.width}", "n_connect": rules.n, "gravity": rules.gravity,
                        "net": f"4-block 128-filter projection-residual tower, {fp32.n_parameters()} params, random init",
                        "l2": "working set per advance (node pools ~GBs + 177 MB activations per conv) exceeds the 126 MB L2; no flush needed"},
-            "leaf_evals_per_sec": evals / ms * 1e3, "selfplay_moves_per_sec": moves / ms * 1e3,
+            "leaf_evals_per_sec": evals / ms * 1e3, "memo_hits_per_sec": (c1.get("memo_hits", 0) - c0.get("memo_hits", 0)) / ms * 1e3, "selfplay_moves_per_sec": moves / ms * 1e3,
             "games_finished": games,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(args.steps, 1),
                     "d2h_bytes_per_step": d2h // max(args.steps, 1),

@@ -1,0 +1,107 @@
+"""CPU suite for the chess row: the mailbox oracle against the published perft counts, and the
+DEVICE rules header (az_chess.cuh, compiled for the host by oracle/c/chess_hostcheck.cpp) against the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import chess_ref as cr
+
+
+@pytest.mark.parametrize("fen", list(cr.PERFT))
+def test_oracle_and_device_header_reproduce_published_perft(fen):
+    s = cr.from_fen(fen)
+    pos = cr.to_pos(s)
+    if not s.turn:  # the self-play path always has white to move: mirror black-to-move positions first
+        out = np.zeros(8, dtype=np.uint64)
+        cr.hlib().hc_mirror(cr._u64p(pos), cr._u64p(out))
+        pos = out
+    for depth, want in enumerate(cr.PERFT[fen][:3], 1):
+        assert cr.perft(s, depth) == want
+        assert cr.host_perft_mirrored(pos, depth) == want
+        if s.turn:
+            assert cr.perft(s, depth, mirrored=True) == want
+
+
+def test_deep_perft_startpos_and_kiwipete():
+    assert cr.perft(cr.start_state(), 4) == 197281
+    assert cr.host_perft_mirrored(cr.to_pos(cr.start_state()), 4) == 197281
+    kiwi = cr.from_fen("r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1")
+    assert cr.host_perft_mirrored(cr.to_pos(kiwi), 4) == 4085603
+
+
+def test_action_list_is_the_references_procedure():
+    acts = cr.all_possible_moves()
+    assert len(acts) == 1880
+    assert acts == sorted(set(acts), key=cr.move_key)
+    h = cr.hlib()
+    h.hc_act_move.restype = ctypes.c_int
+    h.hc_act_index.restype = ctypes.c_int
+    for i, (f, t, p) in enumerate(acts):
+        code = h.hc_act_move(i)
+        assert (code & 63, (code >> 6) & 63, cr.PROMO_LETTERS[code >> 12]) == (f, t, p)
+        assert h.hc_act_index(f, t) + cr.PROMO_LETTERS.index(p) == i
+    # first and last entries in the reference's order: a1 -> a2 ... h8 -> h7
+    assert cr.uci(acts[0]) == "a1a2" and cr.uci(acts[-1]) == "h8h7"
+
+
+def _lcg(seed):
+    s = (seed * 0x9E3779B97F4A7C15 + 1) % 2 ** 64
+    while True:
+        s = (s * 6364136223846793005 + 1442695040888963407) % 2 ** 64
+        yield s >> 33
+
+
+@pytest.mark.parametrize("keep", [True, False])
+def test_random_playouts_device_header_equals_oracle(keep):
+    acts = cr.all_possible_moves()
+    index = {m: i for i, m in enumerate(acts)}
+    n_pos = n_end = 0
+    for game in range(60):
+        rng = _lcg(game + (1000 if keep else 0))
+        s = cr.start_state()
+        pos = cr.to_pos(s)
+        for ply in range(300):
+            moves = cr.legal(s)
+            listed = sorted(index[m] for m in moves if m in index)
+            got, in_check, unlisted = cr.host_legal(pos)
+            assert got == listed, (game, ply)
+            assert unlisted == len(moves) - len(listed)
+            assert in_check == bool(cr.olib().co_in_check(ctypes.byref(s)))
+            assert cr.host_status(pos) == cr.status(s)
+            n_pos += 1
+            if cr.status(s) != 0:
+                n_end += 1
+                break
+            if not listed:  # only black promotions left (not in the action list): stop this playout
+                break
+            a = listed[next(rng) % len(listed)]
+            s = cr.push(s, acts[a], keep_same_player=keep)
+            code = acts[a][0] | acts[a][1] << 6 | cr.PROMO_LETTERS.index(acts[a][2]) << 12
+            pos = cr.host_play(pos, code, keep)
+            assert cr.states_equal(cr.from_pos(pos), s), (game, ply)
+            if keep:
+                assert s.turn == 1 and s.fullmove == 1
+    assert n_pos > 5000 and n_end >= 3
+
+
+def test_full_state_layout():
+    s = cr.start_state()
+    fs = cr.full_state(s, cr.selfplay_history())
+    assert fs.shape == (8, 8, 118)
+    cur = fs[:, :, 98:112]
+    assert cur[7, 4, 6] == 1 and cur[0, 4, 7] == 1      # white king e1 -> plane 6, black king e8 -> plane 13 - 6
+    assert cur[6, :, 1].sum() == 8 and cur[1, :, 12].sum() == 8  # pawns: white plane 1, black plane 12
+    assert cur[2:6, :, 0].sum() == 32 and cur[:, :, 13].sum() == 0
+    assert fs[:, :, :84].sum() == 0 and np.array_equal(fs[:, :, 84:98], cur)
+    assert [fs[0, 0, 112 + i] for i in range(6)] == [1, 1, 1, 1, 1, 0]
+    s2 = cr.push(s, (12, 28, ""), keep_same_player=True)  # e2e4 then mirror
+    assert s2.ep == (20 ^ 56) and s2.halfmove == 0 and cr.array_of(s2)[3, 4] == -1
+    assert cr.result(s2) is None
+    # fool's mate on the mirrored path: the side to move (always "white") is mated -> -1 (chess/board.py:183-187)
+    t = cr.start_state()
+    for u in ("f2f3", "e2e4", "g2g4", "d1h5"):
+        mv = (ord(u[0]) - 97 + 8 * (int(u[1]) - 1), ord(u[2]) - 97 + 8 * (int(u[3]) - 1), "")
+        assert mv in cr.legal(t), u
+        t = cr.push(t, mv, keep_same_player=True)
+    assert cr.status(t) == 1 and cr.result(t) == -1

@@ -17,6 +17,7 @@ AZ_F32, AZ_F64, AZ_BF16 = range(3)
 AZ_PHASE_IDLE, AZ_PHASE_SEARCH, AZ_PHASE_READY, AZ_PHASE_STALLED = range(4)
 AZ_PHASE_MASK = 0xFF
 AZ_FLAG_POOL_OVERFLOW, AZ_FLAG_LUT_OVERFLOW, AZ_FLAG_ILLEGAL = 1 << 8, 1 << 9, 1 << 10
+AZ_CHESS_ACTIONS, AZ_CHESS_MASK_WORDS, AZ_CHESS_PLANES = 1880, 30, 118
 
 
 class NativeError(RuntimeError):
@@ -101,6 +102,12 @@ SYMBOLS = {
     "az_debug_dirichlet": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_double, _I, _I, _P, _P]),
     "az_debug_timeline": (ctypes.c_int, [_P, _P, _I]),
     "az_decode_samples": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
+    # chess (az_chess_pos = 8 x uint64, passed as plain device pointers)
+    "az_chess_action_table": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint16)]),
+    "az_chess_legal": (ctypes.c_int, [_P, _I, _P, _P, _P, _P]),
+    "az_chess_play": (ctypes.c_int, [_P, _P, _I, _I, _P, _P, _P]),
+    "az_chess_encode": (ctypes.c_int, [_P, _P, _I, _I, _P, _P]),
+    "az_chess_perft": (ctypes.c_int, [_P, _I, _I, _P, _P]),
 }
 
 _lib = None

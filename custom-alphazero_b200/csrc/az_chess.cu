@@ -1,0 +1,270 @@
+// az_chess.cu - chess kernels and their C ABI (include/az_b200.h, section "chess").
+//
+//   k_chess_legal   Board.moves / legal_moves_mask / is_game_over (chess/board.py:46-48, :116-117, :178-190), thread per board
+//   k_chess_play    Board.play (chess/board.py:162-173): push + mirror, thread per board
+//   k_chess_encode  Board.full_state (chess/board.py:58-73): 118 planes, warp per board, coalesced writes
+//   k_chess_perft   move-path enumeration on the self-play path (move, mirror, move ...): the known-answer test of
+//                   the generator and its throughput measurement, thread per root position
+//   k_chess_search / k_chess_step / k_chess_move   warp-per-tree PUCT search over chess positions (further down)
+// Rules: az_chess.cuh.  Built for sm_100a only; there is no CPU implementation behind this ABI.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/az_b200.h"
+#include "az_chess.cuh"
+#include "az_tree.cuh"
+
+namespace az {
+int fail_net(int code, const char* msg);
+}
+
+namespace azc {
+
+static_assert(sizeof(Pos) == sizeof(az_chess_pos), "az_chess_pos mirrors azc::Pos");
+static_assert(kActions == AZ_CHESS_ACTIONS && kMaskWords == AZ_CHESS_MASK_WORDS && kPlanes == AZ_CHESS_PLANES, "header constants");
+
+#define AZC_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t err__ = (call);                                           \
+        if (err__ != cudaSuccess) {                                           \
+            char buf__[256];                                                  \
+            snprintf(buf__, sizeof(buf__), #call ": %s", cudaGetErrorString(err__)); \
+            return az::fail_net(AZ_ERR_CUDA, buf__);                          \
+        }                                                                     \
+    } while (0)
+
+__device__ __forceinline__ Pos load_cpos(const Pos* p) {
+    const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
+    ulonglong2 a = q[0], b = q[1], c = q[2], d = q[3];
+    Pos r;
+    r.pawns = a.x; r.knights = a.y; r.bishops = b.x; r.rooks = b.y;
+    r.queens = c.x; r.kings = c.y; r.white = d.x; r.meta = d.y;
+    return r;
+}
+__device__ __forceinline__ void store_cpos(Pos* p, const Pos& r) {
+    ulonglong2* q = reinterpret_cast<ulonglong2*>(p);
+    q[0] = make_ulonglong2(r.pawns, r.knights);
+    q[1] = make_ulonglong2(r.bishops, r.rooks);
+    q[2] = make_ulonglong2(r.queens, r.kings);
+    q[3] = make_ulonglong2(r.white, r.meta);
+}
+
+__global__ void __launch_bounds__(128) k_chess_legal(const Pos* pos, int n, u64* mask_out, int32_t* count_out,
+                                                      int32_t* status_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pos p = load_cpos(pos + i);
+    MoveMask mm;
+    int unlisted = 0;
+    GenInfo gi = legal_moves(p, mm, &unlisted);
+    if (mask_out)
+        for (int w = 0; w < kMaskWords; ++w) mask_out[(size_t)i * kMaskWords + w] = mm.w[w];
+    if (count_out) count_out[i] = gi.n_moves;
+    if (status_out) status_out[i] = game_status(p, gi) | (gi.in_check ? 4 : 0) | (unlisted << 8);
+}
+
+__global__ void __launch_bounds__(128) k_chess_play(const Pos* pos_in, const int32_t* actions, int n, int keep,
+                                                     Pos* pos_out, int32_t* status_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pos p = load_cpos(pos_in + i);
+    const int a = actions[i];
+    MoveMask mm;
+    legal_moves(p, mm, nullptr);
+    if (a < 0 || a >= kActions || !((mm.w[a >> 6] >> (a & 63)) & 1ull)) {
+        store_cpos(pos_out + i, p);  // python-chess raises on an illegal uci: the board stays as it was
+        status_out[i] = -1;
+        return;
+    }
+    const int mv = act_move(a);
+    Pos q = play(p, mv & 63, (mv >> 6) & 63, mv >> 12, keep != 0);
+    store_cpos(pos_out + i, q);
+    GenInfo gi = legal_moves(q, mm, nullptr);
+    status_out[i] = game_status(q, gi);
+}
+
+// The 8 deque entries of Board.full_state for `cur` (oldest first; entry 7 is the current state) into e8.
+// hist: 7 older entries or null for the self-play path's deque (six empty entries, then the state of the initial
+// position - see oracle/chess_ref.py on python-chess's mirror()).
+__device__ __forceinline__ void stage_history(const Pos& cur, const Pos* hist, Pos* e8, int lane) {
+    if (lane < 8) {
+        Pos e;
+        if (lane == 7) {
+            e = cur;
+            e.meta = (e.meta & ~META_REP) | META_VALID;  // is_repetition() needs the move stack: see az_chess.cuh
+        } else if (hist) {
+            e = load_cpos(hist + lane);
+        } else {
+            e = start_position();
+            e.meta = lane == 6 ? (e.meta | META_VALID) : 0;
+        }
+        e8[lane] = e;
+    }
+    __syncwarp();
+}
+
+// value of plane `pl` at square `sq` of Board.full_state (chess/board.py:58-73)
+__device__ __forceinline__ float plane_value(const Pos* e8, int sq, int pl) {
+    if (pl < 112) {
+        const int h = pl / 14, c = pl - h * 14;
+        const Pos& e = e8[h];
+        if (!(e.meta & META_VALID)) return 0.0f;
+        if (c == 13) return (e.meta & META_REP) ? 1.0f : 0.0f;
+        return piece_plane(piece_at(e, sq)) == c ? 1.0f : 0.0f;
+    }
+    const Pos& cur = e8[7];
+    const bool black = black_to_move(cur);
+    const int own_k = black ? 4 : 1, own_q = black ? 8 : 2, opp_k = black ? 1 : 4, opp_q = black ? 2 : 8;
+    switch (pl) {
+        case 112: return (cur.meta & own_q) ? 1.0f : 0.0f;
+        case 113: return (cur.meta & own_k) ? 1.0f : 0.0f;
+        case 114: return (cur.meta & opp_q) ? 1.0f : 0.0f;
+        case 115: return (cur.meta & opp_k) ? 1.0f : 0.0f;
+        case 116: return (float)fullmove(cur);
+        default: return (float)halfmove(cur);
+    }
+}
+
+// e8 in shared memory; out[8][8][118], lanes stride over the flat index so the stores coalesce
+template <typename T>
+__device__ __forceinline__ void encode_planes(const Pos* e8, T* out, int lane) {
+    for (int i = lane; i < 64 * kPlanes; i += 32) {
+        const int cell = i / kPlanes, pl = i - cell * kPlanes;
+        const int sq = ((7 - (cell >> 3)) << 3) | (cell & 7);  // array row 0 is rank 8 (chess/board.py:119-131)
+        out[i] = (T)plane_value(e8, sq, pl);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_chess_encode(const Pos* pos, const Pos* hist, int n, T* out) {
+    __shared__ Pos s_e[4][8];
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (i >= n) return;
+    const Pos cur = load_cpos(pos + i);
+    stage_history(cur, hist ? hist + (size_t)i * 7 : nullptr, s_e[warp], lane);
+    encode_planes<T>(s_e[warp], out + (size_t)i * 64 * kPlanes, lane);
+}
+
+constexpr int kPerftMaxDepth = 8;
+
+__global__ void __launch_bounds__(64) k_chess_perft(const Pos* pos, int n, int depth, unsigned long long* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pos st[kPerftMaxDepth];
+    MoveMask mm[kPerftMaxDepth];
+    int wi[kPerftMaxDepth];
+    u64 cur[kPerftMaxDepth];
+    Pos p = load_cpos(pos + i);
+    if (black_to_move(p)) p = mirror(p);
+    unsigned long long total = 0;
+    if (depth <= 0) {
+        out[i] = 1;
+        return;
+    }
+    st[0] = p;
+    GenInfo g0 = gen_white(st[0], mm[0]);
+    if (depth == 1) {
+        out[i] = (unsigned long long)g0.n_moves;
+        return;
+    }
+    int d = 0;
+    wi[0] = 0;
+    cur[0] = mm[0].w[0];
+    while (d >= 0) {
+        while (cur[d] == 0 && wi[d] + 1 < kMaskWords) cur[d] = mm[d].w[++wi[d]];
+        if (cur[d] == 0) {
+            --d;
+            continue;
+        }
+        const int a = wi[d] * 64 + lsb(cur[d]);
+        cur[d] &= cur[d] - 1;
+        const int mv = act_move(a);
+        Pos q = play(st[d], mv & 63, (mv >> 6) & 63, mv >> 12, true);
+        if (d + 2 == depth) {  // children of q are leaves: count them without visiting
+            MoveMask tmp;
+            total += (unsigned long long)gen_white(q, tmp).n_moves;
+        } else {
+            ++d;
+            st[d] = q;
+            gen_white(q, mm[d]);
+            wi[d] = 0;
+            cur[d] = mm[d].w[0];
+        }
+    }
+    out[i] = total;
+}
+
+static inline dim3 flat_grid(int n, int block) { return dim3((unsigned)((n + block - 1) / block)); }
+static int have_device() {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return az::fail_net(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback");
+    return AZ_OK;
+}
+
+}  // namespace azc
+
+using namespace azc;
+#define AZ_API extern "C" __attribute__((visibility("default")))
+
+AZ_API int az_chess_action_table(uint16_t* host_moves_out) {
+    if (!host_moves_out) return az::fail_net(AZ_ERR_ARG, "az_chess_action_table: null output");
+    for (int a = 0; a < kActions; ++a) host_moves_out[a] = (uint16_t)host_tables::ACT_MOVE[a];
+    return AZ_OK;
+}
+
+AZ_API int az_chess_legal(const az_chess_pos* pos, int32_t n, uint64_t* mask_out, int32_t* count_out, int32_t* status_out,
+                          void* stream) {
+    if (n == 0) return AZ_OK;
+    if (!pos || n < 0) return az::fail_net(AZ_ERR_ARG, "az_chess_legal: bad argument");
+    if (int rc = have_device()) return rc;
+    k_chess_legal<<<flat_grid(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const Pos*>(pos), n, reinterpret_cast<u64*>(mask_out), count_out, status_out);
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_chess_play(const az_chess_pos* pos_in, const int32_t* actions, int32_t n, int32_t keep_same_player,
+                         az_chess_pos* pos_out, int32_t* status_out, void* stream) {
+    if (n == 0) return AZ_OK;
+    if (!pos_in || !actions || !pos_out || !status_out || n < 0) return az::fail_net(AZ_ERR_ARG, "az_chess_play: bad argument");
+    if (int rc = have_device()) return rc;
+    k_chess_play<<<flat_grid(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const Pos*>(pos_in), actions, n, keep_same_player, reinterpret_cast<Pos*>(pos_out), status_out);
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_chess_encode(const az_chess_pos* pos, const az_chess_pos* history, int32_t n, int32_t dtype, void* states_out,
+                           void* stream) {
+    if (n == 0) return AZ_OK;
+    if (!pos || !states_out || n < 0 || (dtype != AZ_F32 && dtype != AZ_BF16))
+        return az::fail_net(AZ_ERR_ARG, "az_chess_encode: bad argument (dtype must be AZ_F32 or AZ_BF16)");
+    if (int rc = have_device()) return rc;
+    const dim3 grid = flat_grid(n * 32, 128);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == AZ_F32)
+        k_chess_encode<float><<<grid, 128, 0, s>>>(reinterpret_cast<const Pos*>(pos), reinterpret_cast<const Pos*>(history), n,
+                                                   static_cast<float*>(states_out));
+    else
+        k_chess_encode<__nv_bfloat16><<<grid, 128, 0, s>>>(reinterpret_cast<const Pos*>(pos),
+                                                           reinterpret_cast<const Pos*>(history), n,
+                                                           static_cast<__nv_bfloat16*>(states_out));
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_chess_perft(const az_chess_pos* pos, int32_t n, int32_t depth, uint64_t* nodes_out, void* stream) {
+    if (n == 0) return AZ_OK;
+    if (!pos || !nodes_out || n < 0 || depth < 0 || depth > kPerftMaxDepth)
+        return az::fail_net(AZ_ERR_ARG, "az_chess_perft: bad argument (depth 0..8)");
+    if (int rc = have_device()) return rc;
+    k_chess_perft<<<flat_grid(n, 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const Pos*>(pos), n, depth, reinterpret_cast<unsigned long long*>(nodes_out));
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}

@@ -1,7 +1,7 @@
 """Hyper-parameters the self-play hot path reads, under the reference's names.
 
 Same class / attribute names and default values as the reference's config.py (ConfigGeneral :7-16,
-ConfigSelfPlay :19-23, ConfigConnectN :38-47, ConfigMCTS :50-56, ConfigModel :59-71, ConfigServing
+ConfigSelfPlay :19-23, ConfigChess :26-35, ConfigConnectN :38-47, ConfigMCTS :50-56, ConfigModel :59-71, ConfigServing
 :74-95, ConfigPath :98-124), so code written against `custom_alphazero.config` keeps working; only the
 entries the hot path or its entry point touch are kept, plus the B200 knobs at the bottom.  As in the
 reference these are plain class attributes that may be patched before use.
@@ -9,7 +9,7 @@ reference these are plain class attributes that may be patched before use.
 
 
 class ConfigGeneral:
-    game = "connect_n"  # the B200 engine implements connect_n; "chess" is a later row
+    game = "connect_n"  # self_play / mcts drive connect_n; chess has its own environment and engine (custom_alphazero.chess, az_b200.chess)
     mono_process = False  # kept for API compatibility; games are a GPU batch, not processes
     concurrency = False
     http_inference = False
@@ -23,6 +23,14 @@ class ConfigSelfPlay:
     discounting_factor = 1  # 1 disables discounting (self_play.py:75-78)
     exclude_null_games = True  # drawn games contribute no samples (self_play.py:155-162)
     samples_checkpoint_frequency = 1
+
+
+class ConfigChess:
+    piece_symbols = [None, "p", "n", "b", "r", "q", "k"]
+    initial_board_fen = "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR"
+    initial_turn, initial_castling_rights, initial_ep_quare = "w", "KQkq", "-"
+    initial_halfmove_clock, initial_fullmove_number = "0", "1"
+    board_size, number_unique_pieces = 8, 12
 
 
 class ConfigConnectN:

@@ -298,6 +298,51 @@ int az_debug_dirichlet(uint64_t seed, double alpha, int32_t k, int32_t n, double
  * off.  The slot is chosen at launch (or graph-capture) time. */
 int az_debug_timeline(az_engine *e, void *dev_slots, int32_t n_slots);
 
+/* ---------------------------------------------------------------- chess ----
+ * The reference's chess environment (chess/board.py, chess/move.py, chess/utils.py) is a subclass of python-chess's
+ * Board; these entry points replace what it uses from it, batched over n boards.  A board is eight 64-bit words
+ * (square a1 = bit 0 ... h8 = bit 63, like python-chess): */
+#define AZ_CHESS_ACTIONS 1880  /* len(get_all_possible_moves()), chess/utils.py:11-32 */
+#define AZ_CHESS_MASK_WORDS 30 /* legal mask over the action list, 64 actions per word */
+#define AZ_CHESS_PLANES 118    /* Board.full_state channels, chess/board.py:58-73 */
+typedef struct az_chess_pos {
+    uint64_t pawns, knights, bishops, rooks, queens, kings; /* both colours */
+    uint64_t white;                                         /* squares of white pieces */
+    uint64_t meta; /* bits 0-3 castling rights (1 K, 2 Q, 4 k, 8 q); 4-10 en-passant square + 1 (0 none); 11 side to move
+                      (0 white); 16-31 halfmove clock; 32-47 fullmove number; 48 repetition flag and 49 valid flag of
+                      a history entry (az_chess_encode) */
+} az_chess_pos;
+
+/* get_all_possible_moves() (chess/utils.py:11-32) in the reference's order (chess/move.py:28-32):
+ * host_moves_out[a] = from | to << 6 | promo << 12, promo 0 none, 1 'b', 2 'n', 3 'q', 4 'r' (host memory, 1880 entries). */
+int az_chess_action_table(uint16_t *host_moves_out);
+
+/* Board.moves as Board.legal_moves_mask (chess/board.py:46-48, :116-117) + is_game_over / get_result (:178-190).
+ *   mask_out:   dev uint64 [n][30] or NULL: bit a = action a is legal for the side to move
+ *   count_out:  dev int32 [n] or NULL: number of legal moves (including black promotions, which the reference's action
+ *               list cannot express)
+ *   status_out: dev int32 [n] or NULL: bits 0-1: 0 ongoing, 1 checkmate (the side to move lost), 2 draw (insufficient
+ *               material, stalemate, 75-move rule); bit 2: side to move is in check; bits 8+: unlisted moves */
+int az_chess_legal(const az_chess_pos *dev_pos, int32_t n, uint64_t *dev_mask_out, int32_t *dev_count_out,
+                   int32_t *dev_status_out, void *stream);
+
+/* Board.play(move, keep_same_player) (chess/board.py:162-173): push_uci, then mirror() with the turn forced to white.
+ * actions: dev int32 [n] indices into the action list; status_out: dev int32 [n]: state of the NEW position as above
+ * (0 / 1 / 2), or -1 for an illegal action (board copied unchanged; python-chess raises). */
+int az_chess_play(const az_chess_pos *dev_pos_in, const int32_t *dev_actions, int32_t n, int32_t keep_same_player,
+                  az_chess_pos *dev_pos_out, int32_t *dev_status_out, void *stream);
+
+/* Board.full_state (chess/board.py:58-73): states_out dev [n][8][8][118] float32 (AZ_F32) or bf16 (AZ_BF16).
+ * history: dev az_chess_pos [n][7], the 7 older entries of Board.state_history (oldest first; an entry without the
+ * valid flag is the zero padding), or NULL for what the deque holds on the keep_same_player path. */
+int az_chess_encode(const az_chess_pos *dev_pos, const az_chess_pos *dev_history, int32_t n, int32_t dtype,
+                    void *dev_states_out, void *stream);
+
+/* Known-answer test and throughput measurement of the move generator: number of move paths of length `depth`
+ * (<= 8) from each position along the self-play path (move, mirror, move, ...), equal to the published perft counts.
+ * nodes_out: dev uint64 [n]. */
+int az_chess_perft(const az_chess_pos *dev_pos, int32_t n, int32_t depth, uint64_t *dev_nodes_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,26 @@ class AzLayout(ctypes.Structure):
     )
 
 
+class AzChessConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "abi_version", "n_trees", "node_capacity", "sims_per_move", "index_move_greedy", "eval_mode", "prior_mode",
+        "move_mode", "max_free_sims", "max_plies", "sample_capacity", "fin_capacity", "pow_lut_len", "auto_restart")] + [
+        ("c_puct", ctypes.c_double), ("seed", ctypes.c_uint64), ("game_id_base", ctypes.c_int64),
+        ("games_target", ctypes.c_int64)]
+
+
+CHESS_LAYOUT_ARRAYS = [
+    "status", "ply", "game_id", "root_pos", "half", "root_node", "n_nodes", "sims_done", "pending", "path_len", "path",
+    "leaf_pos", "leaf_mask", "counters", "uniforms", "node_a", "node_p", "node_m", "smp_count", "smp_game", "smp_ply",
+    "smp_pos", "smp_k", "smp_act", "smp_n", "smp_choice", "fin_count", "fin_game", "fin_len", "fin_result", "pow_lut",
+]
+AZ_CHESS_MAX_CHILDREN = 224
+
+
+class AzChessLayout(ctypes.Structure):
+    _fields_ = [("total_bytes", ctypes.c_size_t)] + [(n, ctypes.c_size_t) for n in CHESS_LAYOUT_ARRAYS]
+
+
 class AzHeadWeights(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("conv_w", "conv_b", "policy_w", "policy_b", "value1_w", "value1_b",
                                                 "value2_w", "value2_b")]
@@ -108,6 +128,18 @@ SYMBOLS = {
     "az_chess_play": (ctypes.c_int, [_P, _P, _I, _I, _P, _P, _P]),
     "az_chess_encode": (ctypes.c_int, [_P, _P, _I, _I, _P, _P]),
     "az_chess_perft": (ctypes.c_int, [_P, _I, _I, _P, _P]),
+    "az_chess_struct_sizes": (None, [ctypes.POINTER(_S), ctypes.POINTER(_S)]),
+    "az_chess_query_layout": (ctypes.c_int, [ctypes.POINTER(AzChessConfig), ctypes.POINTER(AzChessLayout)]),
+    "az_chess_engine_create": (ctypes.c_int, [ctypes.POINTER(AzChessConfig), _P, _S, _P, _P, ctypes.POINTER(_P)]),
+    "az_chess_engine_destroy": (None, [_P]),
+    "az_chess_reset_games": (ctypes.c_int, [_P, _P]),
+    "az_chess_set_roots": (ctypes.c_int, [_P, _P, _P, _I, _P]),
+    "az_chess_begin_search": (ctypes.c_int, [_P, _I, _P]),
+    "az_chess_search": (ctypes.c_int, [_P, _P]),
+    "az_chess_step": (ctypes.c_int, [_P, _P, _P, _I, _P, _P, _P]),
+    "az_chess_move": (ctypes.c_int, [_P, _I, _I, _P]),
+    "az_chess_rings_clear": (ctypes.c_int, [_P, _P]),
+    "az_chess_decode_samples": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _P, _P, _P]),
 }
 
 _lib = None
@@ -133,6 +165,9 @@ def lib():
         handle.az_struct_sizes(ctypes.byref(cs), ctypes.byref(ls))
         if cs.value != ctypes.sizeof(AzConfig) or ls.value != ctypes.sizeof(AzLayout):
             raise NativeError("az_config / az_layout mirror out of sync with include/az_b200.h")
+        handle.az_chess_struct_sizes(ctypes.byref(cs), ctypes.byref(ls))
+        if cs.value != ctypes.sizeof(AzChessConfig) or ls.value != ctypes.sizeof(AzChessLayout):
+            raise NativeError("az_chess_config / az_chess_layout mirror out of sync with include/az_b200.h")
         _lib = handle
     return _lib
 

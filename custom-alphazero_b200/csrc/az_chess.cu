@@ -198,6 +198,12 @@ __global__ void __launch_bounds__(64) k_chess_perft(const Pos* pos, int n, int d
     out[i] = total;
 }
 
+}  // namespace azc
+
+#include "az_chess_tree.cuh"
+
+namespace azc {
+
 static inline dim3 flat_grid(int n, int block) { return dim3((unsigned)((n + block - 1) / block)); }
 static int have_device() {
     int count = 0;
@@ -265,6 +271,236 @@ AZ_API int az_chess_perft(const az_chess_pos* pos, int32_t n, int32_t depth, uin
     if (int rc = have_device()) return rc;
     k_chess_perft<<<flat_grid(n, 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const Pos*>(pos), n, depth, reinterpret_cast<unsigned long long*>(nodes_out));
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------ chess search engine
+struct az_chess_engine {
+    az_chess_config cfg;
+    az_chess_layout lay;
+    CEng eng;
+};
+
+static size_t ctake(size_t& off, size_t bytes) {
+    size_t at = (off + 255) & ~(size_t)255;
+    off = at + bytes;
+    return at;
+}
+
+AZ_API void az_chess_struct_sizes(size_t* c, size_t* l) {
+    if (c) *c = sizeof(az_chess_config);
+    if (l) *l = sizeof(az_chess_layout);
+}
+
+AZ_API int az_chess_query_layout(const az_chess_config* c, az_chess_layout* L) {
+    if (!c || !L) return az::fail_net(AZ_ERR_ARG, "az_chess_query_layout: null argument");
+    if (c->abi_version != AZ_ABI_VERSION) return az::fail_net(AZ_ERR_ARG, "abi_version mismatch");
+    if (c->n_trees < 1 || c->node_capacity < 256 || c->node_capacity > 0xffffff || c->sims_per_move < 1 ||
+        c->max_free_sims < 1 || c->max_plies < 1 || c->sample_capacity < 1 || c->fin_capacity < 1 || c->pow_lut_len < 2)
+        return az::fail_net(AZ_ERR_ARG,
+                            "az_chess_config: n_trees / node_capacity (256 .. 2^24-1) / sims_per_move / max_free_sims / "
+                            "max_plies / sample_capacity / fin_capacity / pow_lut_len out of range");
+    if (c->eval_mode < AZ_EVAL_EXTERNAL || c->eval_mode > AZ_EVAL_HASH || c->move_mode < AZ_MOVE_ARGMAX ||
+        c->move_mode > AZ_MOVE_PHILOX || c->prior_mode < AZ_PRIOR_F64 || c->prior_mode > AZ_PRIOR_F32)
+        return az::fail_net(AZ_ERR_ARG, "az_chess_config: eval_mode / move_mode / prior_mode out of range");
+    memset(L, 0, sizeof(*L));
+    const size_t T = c->n_trees, C = c->node_capacity, S = c->sample_capacity, F = c->fin_capacity, P = c->max_plies;
+    const size_t K = kMaxKids, D = kCDepth, PB = sizeof(Pos);
+    size_t off = 0;
+    L->status = ctake(off, 4 * T);
+    L->ply = ctake(off, 4 * T);
+    L->game_id = ctake(off, 8 * T);
+    L->root_pos = ctake(off, PB * T);
+    L->half = ctake(off, 4 * T);
+    L->root_node = ctake(off, 4 * T);
+    L->n_nodes = ctake(off, 4 * T);
+    L->sims_done = ctake(off, 4 * T);
+    L->pending = ctake(off, 4 * T);
+    L->path_len = ctake(off, 4 * T);
+    L->path = ctake(off, 4 * T * D);
+    L->leaf_pos = ctake(off, PB * T);
+    L->leaf_mask = ctake(off, 8 * T * 32);
+    L->counters = ctake(off, 8 * T * 8);
+    L->uniforms = ctake(off, 8 * T * P);
+    L->node_a = ctake(off, 16 * T * 2 * C);
+    L->node_p = ctake(off, 8 * T * 2 * C);
+    L->node_m = ctake(off, 2 * T * 2 * C);
+    L->smp_count = ctake(off, 16);
+    L->smp_game = ctake(off, 8 * S);
+    L->smp_ply = ctake(off, 4 * S);
+    L->smp_pos = ctake(off, PB * S);
+    L->smp_k = ctake(off, 4 * S);
+    L->smp_act = ctake(off, 2 * S * K);
+    L->smp_n = ctake(off, 4 * S * K);
+    L->smp_choice = ctake(off, 4 * S);
+    L->fin_count = ctake(off, 16);
+    L->fin_game = ctake(off, 8 * F);
+    L->fin_len = ctake(off, 4 * F);
+    L->fin_result = ctake(off, 4 * F);
+    L->pow_lut = ctake(off, 8 * (size_t)c->pow_lut_len);
+    L->total_bytes = (off + 255) & ~(size_t)255;
+    return AZ_OK;
+}
+
+AZ_API int az_chess_reset_games(az_chess_engine* e, void* stream) {
+    if (!e) return az::fail_net(AZ_ERR_ARG, "null engine");
+    k_chess_reset<<<flat_grid(e->eng.T * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(e->eng);
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_chess_engine_create(const az_chess_config* c, void* slab, size_t bytes, const double* host_lut, void* stream,
+                                  az_chess_engine** out) {
+    if (!out) return az::fail_net(AZ_ERR_ARG, "null out");
+    *out = nullptr;
+    az_chess_layout L;
+    if (int rc = az_chess_query_layout(c, &L)) return rc;
+    if (int rc = have_device()) return rc;
+    if (!slab || !host_lut) return az::fail_net(AZ_ERR_ARG, "null slab / pow table");
+    if (bytes < L.total_bytes || (reinterpret_cast<uintptr_t>(slab) & 255))
+        return az::fail_net(AZ_ERR_SLAB, "slab too small or not 256-byte aligned");
+    az_chess_engine* e = new (std::nothrow) az_chess_engine();
+    if (!e) return az::fail_net(AZ_ERR_ARG, "out of host memory");
+    e->cfg = *c;
+    e->lay = L;
+    char* b = static_cast<char*>(slab);
+    CEng& g = e->eng;
+    g.T = c->n_trees;
+    g.C = c->node_capacity;
+    g.S = c->sample_capacity;
+    g.F = c->fin_capacity;
+    g.P = c->max_plies;
+    g.sims_target = c->sims_per_move;
+    g.greedy_idx = c->index_move_greedy;
+    g.eval_mode = c->eval_mode;
+    g.prior_mode = c->prior_mode;
+    g.move_mode = c->move_mode;
+    g.max_free = c->max_free_sims;
+    g.lut_len = c->pow_lut_len;
+    g.auto_restart = c->auto_restart;
+    g.c_puct = c->c_puct;
+    g.seed = c->seed;
+    g.game_base = c->game_id_base;
+    g.games_target = c->games_target;
+#define AZC_PTR(field, type) g.field = reinterpret_cast<type*>(b + L.field)
+    AZC_PTR(status, int32_t);
+    AZC_PTR(ply, int32_t);
+    AZC_PTR(game_id, long long);
+    AZC_PTR(root_pos, Pos);
+    AZC_PTR(half, int32_t);
+    AZC_PTR(root_node, int32_t);
+    AZC_PTR(n_nodes, int32_t);
+    AZC_PTR(sims_done, int32_t);
+    AZC_PTR(pending, int32_t);
+    AZC_PTR(path_len, int32_t);
+    AZC_PTR(path, int32_t);
+    AZC_PTR(leaf_pos, Pos);
+    AZC_PTR(leaf_mask, u64);
+    AZC_PTR(counters, long long);
+    AZC_PTR(uniforms, double);
+    AZC_PTR(node_a, NodeA);
+    AZC_PTR(node_p, double);
+    AZC_PTR(node_m, uint16_t);
+    AZC_PTR(smp_count, int32_t);
+    AZC_PTR(smp_game, long long);
+    AZC_PTR(smp_ply, int32_t);
+    AZC_PTR(smp_pos, Pos);
+    AZC_PTR(smp_k, int32_t);
+    AZC_PTR(smp_act, uint16_t);
+    AZC_PTR(smp_n, int32_t);
+    AZC_PTR(smp_choice, int32_t);
+    AZC_PTR(fin_count, int32_t);
+    AZC_PTR(fin_game, long long);
+    AZC_PTR(fin_len, int32_t);
+    AZC_PTR(fin_result, int32_t);
+#undef AZC_PTR
+    g.games_started = reinterpret_cast<unsigned long long*>(b + L.fin_count + 8);
+    g.pow_lut = reinterpret_cast<const double*>(b + L.pow_lut);
+    cudaError_t err = cudaMemcpyAsync(b + L.pow_lut, host_lut, 8 * (size_t)c->pow_lut_len, cudaMemcpyHostToDevice,
+                                      static_cast<cudaStream_t>(stream));
+    if (err == cudaSuccess) err = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));  // host_lut may be freed
+    if (err != cudaSuccess) {
+        delete e;
+        return az::fail_net(AZ_ERR_CUDA, cudaGetErrorString(err));
+    }
+    *out = e;
+    return az_chess_reset_games(e, stream);
+}
+
+AZ_API void az_chess_engine_destroy(az_chess_engine* e) { delete e; }
+
+static inline dim3 ctree_grid(const az_chess_engine* e) { return dim3((unsigned)((e->eng.T + kCWarps - 1) / kCWarps)); }
+
+AZ_API int az_chess_set_roots(az_chess_engine* e, const int32_t* ids, const az_chess_pos* positions, int32_t n, void* stream) {
+    if (!e) return az::fail_net(AZ_ERR_ARG, "null engine");
+    if (n == 0) return AZ_OK;
+    if (!ids || !positions || n < 0) return az::fail_net(AZ_ERR_ARG, "az_chess_set_roots: bad argument");
+    k_chess_set_roots<<<flat_grid(n * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        e->eng, ids, reinterpret_cast<const Pos*>(positions), n);
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_chess_begin_search(az_chess_engine* e, int32_t sims, void* stream) {
+    if (!e || sims < 0) return az::fail_net(AZ_ERR_ARG, "az_chess_begin_search: bad argument");
+    if (sims > 0) e->eng.sims_target = sims;
+    k_chess_begin<<<flat_grid(e->eng.T, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(e->eng);
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_chess_search(az_chess_engine* e, void* stream) {
+    if (!e) return az::fail_net(AZ_ERR_ARG, "null engine");
+    if (e->eng.eval_mode == AZ_EVAL_EXTERNAL)
+        return az::fail_net(AZ_ERR_ARG, "az_chess_search needs an in-kernel evaluator (eval_mode uniform / hash); use az_chess_step");
+    k_chess_search<<<ctree_grid(e), kCWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(e->eng);
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_chess_step(az_chess_engine* e, const void* priors, const void* values, int32_t eval_dtype, void* states_out,
+                         int32_t* leaf_valid_out, void* stream) {
+    if (!e || !states_out || !leaf_valid_out) return az::fail_net(AZ_ERR_ARG, "az_chess_step: null argument");
+    if ((priors == nullptr) != (values == nullptr)) return az::fail_net(AZ_ERR_ARG, "az_chess_step: priors and values go together");
+    if (eval_dtype != AZ_F32 && eval_dtype != AZ_F64) return az::fail_net(AZ_ERR_ARG, "az_chess_step: eval_dtype must be AZ_F32 or AZ_F64");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int have = priors != nullptr;
+    __nv_bfloat16* so = static_cast<__nv_bfloat16*>(states_out);
+    if (eval_dtype == AZ_F32)
+        k_chess_step<float><<<ctree_grid(e), kCWarps * 32, 0, s>>>(e->eng, static_cast<const float*>(priors),
+                                                                  static_cast<const float*>(values), have, so, leaf_valid_out);
+    else
+        k_chess_step<double><<<ctree_grid(e), kCWarps * 32, 0, s>>>(e->eng, static_cast<const double*>(priors),
+                                                                   static_cast<const double*>(values), have, so, leaf_valid_out);
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_chess_move(az_chess_engine* e, int32_t greedy_override, int32_t move_mode_override, void* stream) {
+    if (!e) return az::fail_net(AZ_ERR_ARG, "null engine");
+    const int mode = move_mode_override >= 0 ? move_mode_override : e->eng.move_mode;
+    if (mode > AZ_MOVE_PHILOX) return az::fail_net(AZ_ERR_ARG, "az_chess_move: bad move mode");
+    k_chess_move<<<ctree_grid(e), kCWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(e->eng, greedy_override, mode);
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_chess_rings_clear(az_chess_engine* e, void* stream) {
+    if (!e) return az::fail_net(AZ_ERR_ARG, "null engine");
+    k_chess_rings_clear<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(e->eng);
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_chess_decode_samples(const az_chess_pos* pos, const int32_t* k, const uint16_t* act, const int32_t* nv,
+                                   const int32_t* choice, int32_t n, float* states_out, double* policies_out, void* stream) {
+    if (n == 0) return AZ_OK;
+    if (!pos || !k || !act || !nv || !choice || !states_out || !policies_out || n < 0)
+        return az::fail_net(AZ_ERR_ARG, "az_chess_decode_samples: bad argument");
+    if (int rc = have_device()) return rc;
+    k_chess_decode<<<flat_grid(n * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const Pos*>(pos), k, act, nv, choice, n, states_out, policies_out);
     AZC_CUDA(cudaGetLastError());
     return AZ_OK;
 }

@@ -343,6 +343,109 @@ int az_chess_encode(const az_chess_pos *dev_pos, const az_chess_pos *dev_history
  * nodes_out: dev uint64 [n]. */
 int az_chess_perft(const az_chess_pos *dev_pos, int32_t n, int32_t depth, uint64_t *dev_nodes_out, void *stream);
 
+/* ---- chess search engine: the same warp-per-tree PUCT search (mcts/mcts.py:39-222) over chess positions ----
+ * One warp owns one game tree.  A node is {double W; int32 N; uint32 link} + double prior + uint16 action (the move
+ * INTO the node as an index into the action list); children of a node are contiguous, 8-aligned, in ascending action
+ * order, and get their priors by action (the reference pairs p[legal_mask] with python-chess's generation order,
+ * which cannot be pinned here - see DESIGN.md).  The position is replayed in registers while descending (move +
+ * mirror per level); leaves are classified by the legal-move generator (checkmate: +1 for the player who moved in,
+ * any draw: 0; mcts.py:179 with the Connect-N meaning of get_result(keep_same_player=True)).  Selection arithmetic,
+ * tie-break, backup, root policy, move sampling and re-root are those of az_step / az_play.
+ * Finished plies go to a sample ring (one entry per ply: parent position, legal actions, visit counts, chosen
+ * action), finished games to a small ring (game id, length, result); the host joins them by game id to give every
+ * sample its value (self_play.py:66-78). */
+#define AZ_CHESS_MAX_CHILDREN 224 /* >= 218, the most legal moves a chess position can have */
+typedef struct az_chess_config {
+    int32_t abi_version;       /* AZ_ABI_VERSION */
+    int32_t n_trees;           /* concurrent games (one warp each) */
+    int32_t node_capacity;     /* nodes per tree per pool half */
+    int32_t sims_per_move;     /* ConfigSelfPlay.mcts_iterations */
+    int32_t index_move_greedy; /* ConfigMCTS.index_move_greedy */
+    int32_t eval_mode;         /* AZ_EVAL_*: external (az_chess_step) or the in-kernel uniform / hash evaluators */
+    int32_t prior_mode;        /* AZ_PRIOR_* of the in-kernel evaluators; az_chess_step follows eval_dtype */
+    int32_t move_mode;         /* AZ_MOVE_* */
+    int32_t max_free_sims;     /* simulations ending in a terminal leaf one az_chess_step may run per tree */
+    int32_t max_plies;         /* a game still running after this many plies is recorded as a draw (the reference has
+                                  no cut-off besides the 75-move rule); also the row length of `uniforms` */
+    int32_t sample_capacity;   /* entries of the sample ring */
+    int32_t fin_capacity;      /* entries of the finished-game ring */
+    int32_t pow_lut_len;       /* entries of the host-built table n -> n ** 0.5 */
+    int32_t auto_restart;      /* 1: a finished game is replaced by the next game id while any remain */
+    double c_puct;             /* ConfigMCTS.exploration_constant */
+    uint64_t seed;             /* Philox key for AZ_MOVE_PHILOX */
+    int64_t game_id_base;      /* first global game id of this rank */
+    int64_t games_target;      /* games this rank may start in total */
+} az_chess_config;
+
+/* Byte offsets into the caller-provided slab.  T = n_trees, C = node_capacity, S = sample_capacity, F = fin_capacity,
+ * P = max_plies, K = AZ_CHESS_MAX_CHILDREN, D = AZ_MAX_DEPTH. */
+typedef struct az_chess_layout {
+    size_t total_bytes;
+    size_t status;     /* int32 [T]  AZ_PHASE_* | AZ_FLAG_* */
+    size_t ply;        /* int32 [T] */
+    size_t game_id;    /* int64 [T] */
+    size_t root_pos;   /* az_chess_pos [T]  white (the side to move) at the bottom */
+    size_t half;       /* int32 [T] */
+    size_t root_node;  /* int32 [T] */
+    size_t n_nodes;    /* int32 [T] */
+    size_t sims_done;  /* int32 [T] */
+    size_t pending;    /* int32 [T]  1 = a leaf awaits its evaluation */
+    size_t path_len;   /* int32 [T] */
+    size_t path;       /* int32 [T][D] */
+    size_t leaf_pos;   /* az_chess_pos [T] */
+    size_t leaf_mask;  /* uint64 [T][32]  legal mask of the pending leaf (30 words used) */
+    size_t counters;   /* int64 [T][8]  simulations, evaluations, moves, games finished, sum of depths, children
+                                        created, nodes copied by re-root, pool high-water mark */
+    size_t uniforms;   /* double [T][P]  AZ_MOVE_HOST_UNIFORMS draws */
+    size_t node_a;     /* 16 B   [T][2][C] */
+    size_t node_p;     /* double [T][2][C] */
+    size_t node_m;     /* uint16 [T][2][C] */
+    size_t smp_count;  /* int32 [1] */
+    size_t smp_game;   /* int64 [S] */
+    size_t smp_ply;    /* int32 [S] */
+    size_t smp_pos;    /* az_chess_pos [S]  parent position of the ply */
+    size_t smp_k;      /* int32 [S]  legal moves */
+    size_t smp_act;    /* uint16 [S][K]  their action indices, ascending */
+    size_t smp_n;      /* int32 [S][K]  root visit counts */
+    size_t smp_choice; /* int32 [S]  chosen action | greedy << 16 */
+    size_t fin_count;  /* int32 [1] (+ games_started int64 at fin_count + 8) */
+    size_t fin_game;   /* int64 [F] */
+    size_t fin_len;    /* int32 [F] */
+    size_t fin_result; /* int32 [F]  1 = the player who moved last won, 0 = draw */
+    size_t pow_lut;    /* double [pow_lut_len] */
+} az_chess_layout;
+
+typedef struct az_chess_engine az_chess_engine;
+void az_chess_struct_sizes(size_t *config_bytes, size_t *layout_bytes);
+int az_chess_query_layout(const az_chess_config *cfg, az_chess_layout *out);
+int az_chess_engine_create(const az_chess_config *cfg, void *dev_slab, size_t slab_bytes, const double *host_pow_lut,
+                           void *stream, az_chess_engine **out);
+void az_chess_engine_destroy(az_chess_engine *e);
+/* every tree starts game `game_id_base + tree` from the initial position (MCTS.__init__ / initialize_root) */
+int az_chess_reset_games(az_chess_engine *e, void *stream);
+/* trees tree_ids[i] get the root position positions[i] (white to move) and a fresh tree */
+int az_chess_set_roots(az_chess_engine *e, const int32_t *dev_tree_ids, const az_chess_pos *dev_positions, int32_t n,
+                       void *stream);
+/* MCTS.search(sims) is about to run on every live tree: simulation counters to zero, budget = sims (0 keeps it) */
+int az_chess_begin_search(az_chess_engine *e, int32_t sims, void *stream);
+/* all remaining simulations of the move with the in-kernel evaluator (eval_mode uniform / hash) */
+int az_chess_search(az_chess_engine *e, void *stream);
+/* one lock-step advance with an external evaluator, like az_step: consume priors dev [T][1880] / values dev [T]
+ * (AZ_F32 or AZ_F64; ignored for trees without a pending leaf), simulate up to the next leaf, write its 118 planes
+ * to states_out dev bf16 [T][8][8][118] and leaf_valid_out dev int32 [T]. */
+int az_chess_step(az_chess_engine *e, const void *dev_priors, const void *dev_values, int32_t eval_dtype,
+                  void *dev_states_out, int32_t *dev_leaf_valid_out, void *stream);
+/* MCTS.play for every tree whose budget is spent: sample-ring entry, move, re-root (in place, or compacted into the
+ * other pool half), game end -> finished ring + next game.  greedy_override / move_mode_override: -1 = configured. */
+int az_chess_move(az_chess_engine *e, int32_t greedy_override, int32_t move_mode_override, void *stream);
+/* the host has read the rings: both counts back to zero */
+int az_chess_rings_clear(az_chess_engine *e, void *stream);
+/* sample-ring entries -> training arrays (self_play.py:63-66): states_out dev float32 [n][8][8][118] of the parent
+ * positions, policies_out dev float64 [n][1880] = N / sum N, or one-hot at the first maximum for greedy plies. */
+int az_chess_decode_samples(const az_chess_pos *dev_pos, const int32_t *dev_k, const uint16_t *dev_act,
+                            const int32_t *dev_n, const int32_t *dev_choice, int32_t n, float *dev_states_out,
+                            double *dev_policies_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -316,3 +316,51 @@ def host_status(pos):
 
 def host_perft_mirrored(pos, depth):
     return int(hlib().hc_perft_mirrored(_u64p(pos), depth))
+
+
+# ---------------------------------------------------------------- MCTS over chess (oracle/c/chess_oracle.c: co_mcts_game)
+class CoMctsCfg(ctypes.Structure):
+    _fields_ = [("eval_kind", ctypes.c_int32), ("prior_mode", ctypes.c_int32), ("sims", ctypes.c_int32),
+                ("greedy_idx", ctypes.c_int32), ("max_plies", ctypes.c_int32), ("c_puct", ctypes.c_double)]
+
+
+_act_index = None
+
+
+def act_index_table():
+    """int16 [4096]: index of the promotion-less move joining two squares in all_possible_moves(), -1 if none."""
+    global _act_index
+    if _act_index is None:
+        t = np.full(4096, -1, dtype=np.int16)
+        for i, (f, to, p) in enumerate(all_possible_moves()):
+            if p == "":
+                t[f * 64 + to] = i
+        _act_index = t
+    return _act_index
+
+
+def mcts_game(start=None, sims=100, evaluator="uniform", prior_mode="f64", greedy_idx=8, max_plies=512, c_puct=1.5,
+              uniforms=None):
+    """One self-play game by the C oracle.  Returns dict(k, act, n, choice [plies...], result, sims, evals)."""
+    L = olib()
+    L.co_mcts_game.restype = ctypes.c_int
+    start = start_state() if start is None else start
+    cfg = CoMctsCfg({"uniform": 0, "hash": 1}[evaluator], {"f64": 0, "f32": 1}[prior_mode], sims, greedy_idx, max_plies, c_puct)
+    P = max_plies
+    out_k = np.zeros(P, dtype=np.int32)
+    out_act = np.zeros((P, 224), dtype=np.uint16)
+    out_n = np.zeros((P, 224), dtype=np.int32)
+    out_choice = np.zeros(P, dtype=np.int32)
+    result = ctypes.c_int32(0)
+    counters = (ctypes.c_longlong * 2)()
+    table = act_index_table()
+    u = None
+    if uniforms is not None:
+        u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64))
+        assert len(u) >= P
+    vp = ctypes.c_void_p
+    plies = L.co_mcts_game(ctypes.byref(cfg), ctypes.byref(start), vp(table.ctypes.data),
+                           vp(u.ctypes.data) if u is not None else vp(None), vp(out_k.ctypes.data), vp(out_act.ctypes.data),
+                           vp(out_n.ctypes.data), vp(out_choice.ctypes.data), ctypes.byref(result), counters)
+    return dict(plies=plies, k=out_k[:plies], act=out_act[:plies], n=out_n[:plies], choice=out_choice[:plies],
+                result=result.value, sims=counters[0], evals=counters[1])

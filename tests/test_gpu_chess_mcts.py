@@ -1,0 +1,172 @@
+"""GPU parity tests of the chess search engine (az_chess_search / az_chess_step / az_chess_move) against the C oracle's
+MCTS over the mailbox rules (oracle/c/chess_oracle.c: co_mcts_game): per ply the legal actions, root visit counts
+and chosen move must be identical, for whole games, with the in-kernel evaluators and through the external route."""
+import numpy as np
+import pytest
+
+from oracle import chess_ref as cr
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+MASK = (1 << 64) - 1
+
+
+def _play_games(eng, max_iters, route="search", evaluator=None):
+    """Runs every tree to the end of its game; returns {game: [(k, act, n, choice)...]}, {game: (len, result)}."""
+    from az_b200 import native
+
+    per_game, fin = {}, {}
+    T = eng.n_trees
+    states = torch.zeros((T, 8, 8, 118), dtype=torch.bfloat16, device=eng.device)
+    valid = torch.zeros(T, dtype=torch.int32, device=eng.device)
+    for _ in range(max_iters):
+        ph = eng.phases()
+        if bool((ph == native.AZ_PHASE_IDLE).all()):
+            break
+        if route == "search":
+            eng.search()
+        else:
+            pri = val = None
+            for _adv in range(100000):
+                eng.step(pri, val, states, valid)
+                if bool((eng.phases() != native.AZ_PHASE_SEARCH).all()):
+                    break
+                pri, val = evaluator(eng, states, valid) if bool(valid.any()) else (None, None)
+        eng.check_status()
+        eng.move()
+        eng.check_status()
+        d = eng.drain()
+        for i in range(len(d["k"])):
+            per_game.setdefault(int(d["game"][i]), []).append(
+                (int(d["ply"][i]), int(d["k"][i]), d["act"][i].copy(), d["n"][i].copy(), int(d["choice"][i])))
+        for g, ln, r in zip(d["fin_game"], d["fin_len"], d["fin_result"]):
+            fin[int(g)] = (int(ln), int(r))
+    return per_game, fin
+
+
+def _assert_game_equals(plies, fin, want):
+    assert fin == (want["plies"], want["result"])
+    assert [p[0] for p in plies] == list(range(want["plies"]))
+    for ply, k, act, n, choice in plies:
+        assert k == int(want["k"][ply]), ply
+        assert np.array_equal(act[:k], want["act"][ply][:k]), ply
+        assert np.array_equal(n[:k], want["n"][ply][:k]), (ply, n[:k], want["n"][ply][:k])
+        assert choice == int(want["choice"][ply]), ply
+
+
+@pytest.mark.parametrize("evaluator,prior_mode,sims,max_plies", [
+    ("hash", "f64", 60, 60), ("uniform", "f64", 100, 16), ("hash", "f32", 40, 300), ("uniform", "f32", 64, 10)])
+def test_in_kernel_search_reproduces_the_oracle_game(evaluator, prior_mode, sims, max_plies):
+    from az_b200.chess_engine import ChessTreeEngine
+
+    want = cr.mcts_game(sims=sims, evaluator=evaluator, prior_mode=prior_mode, max_plies=max_plies)
+    eng = ChessTreeEngine(n_trees=5, sims_per_move=sims, eval_mode=evaluator, prior_mode=prior_mode, max_plies=max_plies)
+    per_game, fin = _play_games(eng, max_plies + 2)
+    assert sorted(per_game) == list(range(5))
+    for g in range(5):
+        _assert_game_equals(per_game[g], fin[g], want)
+    tot = eng.totals()
+    assert tot["sims"] == 5 * want["sims"] and tot["evals"] == 5 * want["evals"] and tot["games"] == 5
+
+
+def test_sampled_moves_and_compaction():
+    """np.random.choice semantics with host-supplied draws, a different game in every tree; pools so small that every
+    re-root takes the compaction path must give the same games as roomy pools."""
+    from az_b200.chess_engine import ChessTreeEngine
+
+    T, sims, P = 6, 48, 80
+    rs = np.random.RandomState(5)
+    u = rs.random_sample((T, P))
+    wants = [cr.mcts_game(sims=sims, evaluator="hash", max_plies=P, uniforms=u[t], greedy_idx=30) for t in range(T)]
+    assert len({tuple(w["choice"][:6]) for w in wants}) > 1
+    for cap in (None, 8192):
+        eng = ChessTreeEngine(n_trees=T, sims_per_move=sims, eval_mode="hash", prior_mode="f64", move_mode="host_uniforms",
+                              max_plies=P, index_move_greedy=30, node_capacity=cap)
+        eng.set_uniforms(u)
+        per_game, fin = _play_games(eng, P + 2)
+        for t in range(T):
+            _assert_game_equals(per_game[t], fin[t], wants[t])
+        if cap is not None:
+            assert eng.totals()["reroot_nodes"] > 0
+
+
+def _host_hash_evaluator(eng, states, valid):
+    """The hash evaluator computed on the host from the leaf positions the engine stored (float64 priors)."""
+    from az_b200 import chess
+
+    pos = eng.view("leaf_pos").cpu().numpy().view(np.uint64)
+    T = eng.n_trees
+    pri = np.zeros((T, 1880), dtype=np.float64)
+    val = np.zeros(T, dtype=np.float64)
+    v = valid.cpu().numpy()
+    # the planes handed to the evaluator are those of the stored leaf
+    idx = np.nonzero(v)[0]
+    if len(idx):
+        enc = chess.chess_encode(pos[idx])
+        got = states[torch.as_tensor(idx, device=states.device)].float().cpu().numpy()
+        assert np.array_equal(got, enc)
+    a = np.arange(1880, dtype=np.uint64)
+    for t in idx:
+        s = cr.from_pos(pos[t])
+        h = 0xCBF29CE484222325
+        for sq in range(64):
+            h = ((h ^ (s.sq[sq] + 7)) * 0x100000001B3) & MASK
+        h = ((h ^ ((s.castling & 15) | ((s.ep + 1) << 4))) * 0x100000001B3) & MASK
+        with np.errstate(over="ignore"):
+            m = (np.uint64(h) ^ (a * np.uint64(0x9E3779B97F4A7C15))) * np.uint64(0xFF51AFD7ED558CCD)
+        pri[t] = ((m >> np.uint64(40)) % np.uint64(1000) + np.uint64(1)).astype(np.float64)
+        val[t] = (float((h >> 20) % 2001) - 1000.0) / 1000.0
+    return (torch.as_tensor(pri, device=states.device), torch.as_tensor(val, device=states.device))
+
+
+def test_external_route_equals_the_oracle():
+    from az_b200.chess_engine import ChessTreeEngine
+
+    sims, P = 30, 24
+    want = cr.mcts_game(sims=sims, evaluator="hash", prior_mode="f64", max_plies=P)
+    eng = ChessTreeEngine(n_trees=3, sims_per_move=sims, eval_mode="external", max_plies=P, max_free_sims=2)
+    per_game, fin = _play_games(eng, P + 2, route="step", evaluator=_host_hash_evaluator)
+    for g in range(3):
+        _assert_game_equals(per_game[g], fin[g], want)
+
+
+def test_refill_and_decoded_samples():
+    """auto_restart keeps the batch full; decoded policies / values follow self_play.py:63-78."""
+    from az_b200 import chess
+    from az_b200.chess_engine import ChessTreeEngine, decode_samples, sample_values
+
+    sims, P, G = 24, 12, 7
+    eng = ChessTreeEngine(n_trees=3, sims_per_move=sims, eval_mode="hash", prior_mode="f64", max_plies=P, games_target=G,
+                          auto_restart=True, index_move_greedy=4)
+    want = cr.mcts_game(sims=sims, evaluator="hash", max_plies=P, greedy_idx=4)
+    per_game, fin = _play_games(eng, 10 * P)
+    assert sorted(fin) == list(range(G)) and sorted(per_game) == list(range(G))
+    for g in range(G):
+        _assert_game_equals(per_game[g], fin[g], want)
+    # one game's samples through the decoder
+    plies = per_game[0]
+    d = {"pos": None, "k": np.array([p[1] for p in plies], dtype=np.int32),
+         "act": np.stack([p[2] for p in plies]), "n": np.stack([p[3] for p in plies]),
+         "choice": np.array([p[4] for p in plies], dtype=np.int32), "game": np.zeros(len(plies), dtype=np.int64),
+         "ply": np.arange(len(plies), dtype=np.int32), "fin_game": np.array([0]), "fin_len": np.array([fin[0][0]]),
+         "fin_result": np.array([fin[0][1]])}
+    # parent positions: replay the chosen moves from the start position with the environment kernel
+    pos = [chess.position_from_fen()]
+    for p in plies[:-1]:
+        nxt, st = chess.chess_play(pos[-1][None], np.array([p[4] & 0xFFFF], dtype=np.int32))
+        pos.append(nxt[0])
+    d["pos"] = np.stack(pos)
+    states, policies = decode_samples(d)
+    assert np.array_equal(states.cpu().numpy(), chess.chess_encode(d["pos"]))
+    pol = policies.cpu().numpy()
+    for i, (ply, k, act, n, choice) in enumerate(plies):
+        ref = np.zeros(1880)
+        if choice >> 16:
+            ref[act[int(np.argmax(n[:k]))]] = 1.0
+        else:
+            ref[act[:k].astype(np.int64)] = n[:k] / n[:k].sum()
+        assert np.array_equal(pol[i], ref), i
+    vals, known = sample_values(d)
+    L, r = fin[0]
+    assert known.all() and list(vals) == [r * (1 if (L - 1 - i) % 2 == 0 else -1) for i in range(L)]

@@ -153,7 +153,15 @@ def main():
     ap.add_argument("--board", default="7x6", help="WxH (headline: 7x6); other boards are extra configurations (C4)")
     ap.add_argument("--connect", type=int, default=4)
     ap.add_argument("--no-gravity", action="store_true")
+    ap.add_argument("--game", default="connect_n", choices=["connect_n", "chess"],
+                    help="chess = BASELINE config C5 (tools/bench_chess.py); the headline metric is connect_n")
+    ap.add_argument("--max-plies", type=int, default=512, help="chess: a game still running after this many plies is a draw")
     args = ap.parse_args()
+    if args.game == "chess":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_chess
+
+        return bench_chess.main(args, ClockSampler, load_peaks)
     global RULES
     bw, bh = (int(v) for v in args.board.lower().split("x"))
     RULES = (bw, bh, args.connect, not args.no_gravity)

@@ -22,10 +22,10 @@ BN_EPS = 1e-3
 BN_MOMENTUM = 0.01  # Keras momentum 0.99
 
 
-def flops_per_eval(height, width, n_actions, filters=128, depth=4):
+def flops_per_eval(height, width, n_actions, filters=128, depth=4, in_planes=4):
     """2 * MAC over the layers above: 105 037 976 at 6x7 / A=7."""
     px = height * width
-    macs = px * 9 * 4 * filters
+    macs = px * 9 * in_planes * filters
     macs += depth * (2 * px * 9 * filters * filters + px * filters * filters)
     macs += px * filters * 2 + 2 * px * n_actions
     macs += px * filters * 1 + px * 256 + 256
@@ -67,10 +67,11 @@ class ResBlock(nn.Module):
 class PolicyValueNet(nn.Module):
     """Trainable fp32 module (the checker for the bf16 inference path and the thing a trainer updates)."""
 
-    def __init__(self, height=6, width=7, n_actions=7, filters=128, depth=4):
+    def __init__(self, height=6, width=7, n_actions=7, filters=128, depth=4, in_planes=4):
         super().__init__()
         self.height, self.width, self.n_actions, self.filters, self.depth = height, width, n_actions, filters, depth
-        self.stem = ConvBN(4, filters, 3, relu=True)
+        self.in_planes = in_planes  # 4 for Connect-N (board.py:83-98), 118 for chess (chess/board.py:58-73)
+        self.stem = ConvBN(in_planes, filters, 3, relu=True)
         self.blocks = nn.ModuleList([ResBlock(filters) for _ in range(depth)])
         self.policy_conv = ConvBN(filters, 2, 1, relu=True)
         self.policy_fc = nn.Linear(2 * height * width, n_actions)
@@ -122,6 +123,12 @@ class InferenceNet(nn.Module):
                     nn.Parameter(b.detach().to(device=device, dtype=dtype), requires_grad=False))
 
         self.stem_w, self.stem_b = conv_params(net.stem)
+        # cuDNN's tensor-core kernels want the channel count a multiple of 8 (bf16): the chess input (118 planes) is
+        # padded to 120 with zero planes against zero weights
+        self.in_pad = (-net.in_planes) % 8
+        if self.in_pad:
+            wpad = F.pad(self.stem_w.data.contiguous(), (0, 0, 0, 0, 0, self.in_pad)).contiguous(memory_format=cl)
+            self.stem_w_pad = nn.Parameter(wpad, requires_grad=False)
         self.block_params = nn.ParameterList()
         for blk in net.blocks:
             w1, b1 = conv_params(blk.c1)
@@ -151,7 +158,8 @@ class InferenceNet(nn.Module):
         self.filters = net.filters
         dev = torch.device(device)
         # fast path: custom stem/heads kernels + cuDNN fused-epilogue tower (GPU, bf16, 128 filters)
-        self.fast = dev.type == "cuda" and dtype == torch.bfloat16 and net.filters == 128 and net.value_fc1.out_features == 256
+        self.fast = (dev.type == "cuda" and dtype == torch.bfloat16 and net.filters == 128 and net.value_fc1.out_features == 256
+                     and net.in_planes == 4 and net.n_actions <= 128)
         self._head_struct = None
         self.overlap_shortcut = False
         self._side = {}
@@ -180,14 +188,24 @@ class InferenceNet(nn.Module):
             return self._forward_fast(x_nhwc, priors_out, values_out)
         B = x_nhwc.shape[0]
         x = x_nhwc.to(self.dtype).permute(0, 3, 1, 2)
-        x = F.relu_(F.conv2d(x, self.stem_w, self.stem_b, padding=1))
-        for i in range(self.depth):
-            w1, b1, w2, wp, b2p = self.block_params[5 * i: 5 * i + 5]
-            h = F.relu_(F.conv2d(x, w1, b1, padding=1))
-            y = F.conv2d(h, w2, b2p, padding=1)
-            y += F.conv2d(x, wp)
-            x = F.relu_(y)
-        xf = x.permute(0, 2, 3, 1).float()  # [B, H, W, C]
+        if x.is_cuda and self.dtype == torch.bfloat16:
+            # other input planes / action spaces (chess: 118 planes, 1 880 actions): library stem, the same cuDNN
+            # fused-epilogue tower as the fast path, heads through cuBLAS
+            if self.in_pad:
+                x = F.pad(x_nhwc.to(self.dtype), (0, self.in_pad)).permute(0, 3, 1, 2)
+            h0 = torch.cudnn_convolution_relu(x.contiguous(memory_format=torch.channels_last),
+                                              self.stem_w_pad if self.in_pad else self.stem_w, self.stem_b,
+                                              (1, 1), (1, 1), (1, 1), 1)
+            xf = self.tower(h0.permute(0, 2, 3, 1)).float()
+        else:
+            x = F.relu_(F.conv2d(x, self.stem_w, self.stem_b, padding=1))
+            for i in range(self.depth):
+                w1, b1, w2, wp, b2p = self.block_params[5 * i: 5 * i + 5]
+                h = F.relu_(F.conv2d(x, w1, b1, padding=1))
+                y = F.conv2d(h, w2, b2p, padding=1)
+                y += F.conv2d(x, wp)
+                x = F.relu_(y)
+            xf = x.permute(0, 2, 3, 1).float()  # [B, H, W, C]
         hd = F.relu_(F.linear(xf, self.head_w32, self.head_b32))  # 1x1 convs: [B, H, W, 3]
         p = hd[..., :2].reshape(B, -1)
         v = hd[..., 2].reshape(B, -1)

@@ -170,3 +170,37 @@ def test_refill_and_decoded_samples():
     vals, known = sample_values(d)
     L, r = fin[0]
     assert known.all() and list(vals) == [r * (1 if (L - 1 - i) % 2 == 0 else -1) for i in range(L)]
+
+
+def test_chess_net_bf16_against_fp32():
+    """The chess-shaped net (8x8x118 -> 1 880 actions): bf16 GPU path (cuDNN tower) against the fp32 module."""
+    from az_b200.chess_selfplay import chess_net
+    from az_b200.net import InferenceNet, randomise_bn
+
+    torch.manual_seed(1)
+    net = randomise_bn(chess_net()).eval()
+    x = (torch.rand(64, 8, 8, 118) < 0.1).float()
+    with torch.no_grad():
+        p32, v32 = net(x)
+    inf = InferenceNet(net, dtype=torch.bfloat16, device="cuda")
+    p16, v16 = inf(x.cuda().to(torch.bfloat16))
+    dp = (p16.cpu() - p32).abs().max().item()
+    dv = (v16.cpu() - v32.reshape(-1)).abs().max().item()
+    assert p16.shape == (64, 1880) and abs(float(p16.sum()) - 64.0) < 1e-2
+    assert dp < 2e-2 and dv < 8e-2, (dp, dv)  # bf16 activations through 13 convolutions; tolerance as tests/test_gpu_net.py
+
+
+def test_chess_selfplay_runner_with_the_net():
+    """Tiny end-to-end: 16 trees, 12 simulations per move, games cut at 10 plies, bf16 net, CUDA graph."""
+    from az_b200.chess_selfplay import ChessSelfPlayRunner
+
+    torch.manual_seed(0)
+    r = ChessSelfPlayRunner(n_trees=16, sims_per_move=12, games_target=24, max_plies=10, unroll=4)
+    states, policies, values, known = r.run_until_done(poll_every=32, max_advances=20000)
+    tot = r.totals()
+    assert tot["games"] == 24 and tot["moves"] == 240 and states.shape == (240, 8, 8, 118) and policies.shape == (240, 1880)
+    assert known.all() and np.allclose(policies.sum(-1), 1.0) and set(np.unique(values)).issubset({-1, 0, 1})
+    assert tot["sims"] >= 240 * 12
+    # planes of a first ply: the start position in the last history slot and in the "initial position" slot
+    first = states[np.nonzero(np.abs(states[:, :, :, 84:98] - states[:, :, :, 98:112]).sum((1, 2, 3)) == 0)[0]]
+    assert len(first) == 24

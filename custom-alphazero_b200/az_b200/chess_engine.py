@@ -122,16 +122,17 @@ class ChessTreeEngine:
 
     def step(self, priors, values, states_out, leaf_valid_out):
         """One lock-step advance.  priors [T, 1880] / values [T] float32 or float64 (or None on the first call);
-        states_out bf16 [T, 8, 8, 118]; leaf_valid_out int32 [T]."""
+        states_out bf16 [T, 8, 8, 118 or more]; leaf_valid_out int32 [T]."""
         eval_dtype = native.AZ_F32
         if priors is not None:
             assert priors.is_contiguous() and values.is_contiguous() and priors.dtype == values.dtype
             assert priors.shape == (self.n_trees, N_ACTIONS)
             eval_dtype = {torch.float32: native.AZ_F32, torch.float64: native.AZ_F64}[priors.dtype]
         assert states_out.dtype == torch.bfloat16 and states_out.is_contiguous() and leaf_valid_out.dtype == torch.int32
-        assert states_out.shape == (self.n_trees, 8, 8, PLANES)
-        check(lib().az_chess_step(self._h, _ptr(priors), _ptr(values), eval_dtype, _ptr(states_out), _ptr(leaf_valid_out),
-                                  _stream()))
+        stride = states_out.shape[-1]  # >= 118: extra planes are written as zeros (channel padding for the stem)
+        assert states_out.shape == (self.n_trees, 8, 8, stride) and stride >= PLANES
+        check(lib().az_chess_step(self._h, _ptr(priors), _ptr(values), eval_dtype, _ptr(states_out), stride,
+                                  _ptr(leaf_valid_out), _stream()))
 
     def move(self, greedy=None, move_mode=None):
         g = -1 if greedy is None else int(bool(greedy))

@@ -40,7 +40,8 @@ class ChessSelfPlayRunner:
                                       max_plies=max_plies, sample_capacity=sample_capacity, device=self.device,
                                       index_move_greedy=index_move_greedy)
         self.n_trees = T
-        self.states = torch.zeros((T, 8, 8, PLANES), dtype=torch.bfloat16, device=self.device)
+        # the step kernel writes the planes with the channel padding the tensor-core stem wants (118 -> 120)
+        self.states = torch.zeros((T, 8, 8, PLANES + self.net.in_pad), dtype=torch.bfloat16, device=self.device)
         self.valid = torch.zeros(T, dtype=torch.int32, device=self.device)
         self.priors = torch.zeros((T, N_ACTIONS), dtype=torch.float32, device=self.device)
         self.values = torch.zeros(T, dtype=torch.float32, device=self.device)

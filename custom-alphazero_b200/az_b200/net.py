@@ -148,6 +148,9 @@ class InferenceNet(nn.Module):
         self.head_w32 = f32(torch.cat([pw, vw], 0).reshape(3, -1))
         self.head_b32 = f32(torch.cat([pb, vb], 0))
         self.pfc_w, self.pfc_b = f32(net.policy_fc.weight), f32(net.policy_fc.bias)
+        if net.n_actions > 128:
+            self.pfc_w16 = nn.Parameter(net.policy_fc.weight.detach().to(device=device, dtype=torch.bfloat16).contiguous(),
+                                        requires_grad=False)
         self.v1_w, self.v1_b = f32(net.value_fc1.weight), f32(net.value_fc1.bias)
         # az_net_heads wants the policy rows padded to an odd stride and the value weights transposed
         # (bank-conflict-free shared memory images that the kernel copies verbatim)
@@ -191,12 +194,22 @@ class InferenceNet(nn.Module):
         if x.is_cuda and self.dtype == torch.bfloat16:
             # other input planes / action spaces (chess: 118 planes, 1 880 actions): library stem, the same cuDNN
             # fused-epilogue tower as the fast path, heads through cuBLAS
-            if self.in_pad:
+            if self.in_pad and x_nhwc.shape[-1] != self.stem_w_pad.shape[1]:  # not padded by the producer already
                 x = F.pad(x_nhwc.to(self.dtype), (0, self.in_pad)).permute(0, 3, 1, 2)
             h0 = torch.cudnn_convolution_relu(x.contiguous(memory_format=torch.channels_last),
                                               self.stem_w_pad if self.in_pad else self.stem_w, self.stem_b,
                                               (1, 1), (1, 1), (1, 1), 1)
-            xf = self.tower(h0.permute(0, 2, 3, 1)).float()
+            xm = self.tower(h0.permute(0, 2, 3, 1))
+            hd = torch.empty((B, self.height, self.width, 3), dtype=torch.float32, device=xm.device)
+            if self.filters == 128:  # hand-written: one pass over the tower output, float32 accumulation
+                from .engine import _ptr, _stream
+                from .native import check, lib
+
+                check(lib().az_net_head_convs(_ptr(xm), _ptr(self.head_w32), _ptr(self.head_b32), B,
+                                              self.height * self.width, self.filters, _ptr(hd), _stream()))
+            else:
+                hd = F.relu_(F.linear(xm.float(), self.head_w32, self.head_b32))
+            xf = None
         else:
             x = F.relu_(F.conv2d(x, self.stem_w, self.stem_b, padding=1))
             for i in range(self.depth):
@@ -206,10 +219,16 @@ class InferenceNet(nn.Module):
                 y += F.conv2d(x, wp)
                 x = F.relu_(y)
             xf = x.permute(0, 2, 3, 1).float()  # [B, H, W, C]
-        hd = F.relu_(F.linear(xf, self.head_w32, self.head_b32))  # 1x1 convs: [B, H, W, 3]
+        if xf is not None:
+            hd = F.relu_(F.linear(xf, self.head_w32, self.head_b32))  # 1x1 convs: [B, H, W, 3]
         p = hd[..., :2].reshape(B, -1)
         v = hd[..., 2].reshape(B, -1)
-        policy = torch.softmax(F.linear(p, self.pfc_w, self.pfc_b), dim=-1)
+        if xf is None and self.n_actions > 128:
+            # wide policy layer (chess: 128 -> 1 880): bf16 operands on the tensor cores, float32 accumulation and softmax
+            logits = F.linear(p.to(torch.bfloat16), self.pfc_w16).float() + self.pfc_b
+        else:
+            logits = F.linear(p, self.pfc_w, self.pfc_b)
+        policy = torch.softmax(logits, dim=-1)
         value = torch.tanh(F.linear(F.relu_(F.linear(v, self.v1_w, self.v1_b)), self.v2_w, self.v2_b)).reshape(B)
         if priors_out is not None:
             priors_out.copy_(policy)

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -107,36 +108,56 @@ __device__ __forceinline__ void stage_history(const Pos& cur, const Pos* hist, P
     __syncwarp();
 }
 
-// value of plane `pl` at square `sq` of Board.full_state (chess/board.py:58-73)
-__device__ __forceinline__ float plane_value(const Pos* e8, int sq, int pl) {
-    if (pl < 112) {
-        const int h = pl / 14, c = pl - h * 14;
-        const Pos& e = e8[h];
-        if (!(e.meta & META_VALID)) return 0.0f;
-        if (c == 13) return (e.meta & META_REP) ? 1.0f : 0.0f;
-        return piece_plane(piece_at(e, sq)) == c ? 1.0f : 0.0f;
+template <typename T>
+__device__ __forceinline__ T plane_cast(float v);
+template <>
+__device__ __forceinline__ float plane_cast<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 plane_cast<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+// Board.full_state (chess/board.py:58-73) of the deque e8 (shared memory) into out[8][8][stride], stride >= 118 and
+// 16-byte rows (stride * sizeof(T) % 16 == 0) or stride == 118.  Almost every value is zero (per cell at most one piece
+// plane and one repetition plane per deque entry plus the six scalar planes), so the warp first clears the block with
+// coalesced 128-bit stores and then each lane scatters the few non-zero values of its two cells.
+template <typename T>
+__device__ __forceinline__ void encode_planes_strided(const Pos* e8, T* out, int lane, int stride) {
+    const int total = 64 * stride;  // elements; the block starts 16-byte aligned (n * 64 * stride * sizeof(T))
+    constexpr int per16 = 16 / (int)sizeof(T);
+    if ((total % per16) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        uint4* o4 = reinterpret_cast<uint4*>(out);
+        for (int i = lane; i < total / per16; i += 32) o4[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+        for (int i = lane; i < total; i += 32) out[i] = plane_cast<T>(0.0f);
     }
+    __syncwarp();
     const Pos& cur = e8[7];
     const bool black = black_to_move(cur);
     const int own_k = black ? 4 : 1, own_q = black ? 8 : 2, opp_k = black ? 1 : 4, opp_q = black ? 2 : 8;
-    switch (pl) {
-        case 112: return (cur.meta & own_q) ? 1.0f : 0.0f;
-        case 113: return (cur.meta & own_k) ? 1.0f : 0.0f;
-        case 114: return (cur.meta & opp_q) ? 1.0f : 0.0f;
-        case 115: return (cur.meta & opp_k) ? 1.0f : 0.0f;
-        case 116: return (float)fullmove(cur);
-        default: return (float)halfmove(cur);
+    const T one = plane_cast<T>(1.0f);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int cell = lane + 32 * half;
+        const int sq = ((7 - (cell >> 3)) << 3) | (cell & 7);  // array row 0 is rank 8 (chess/board.py:119-131)
+        T* row = out + (size_t)cell * stride;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const Pos& e = e8[h];
+            if (!(e.meta & META_VALID)) continue;
+            row[h * 14 + piece_plane(piece_at(e, sq))] = one;  // plane 0 = empty square
+            if (e.meta & META_REP) row[h * 14 + 13] = one;
+        }
+        if (cur.meta & own_q) row[112] = one;
+        if (cur.meta & own_k) row[113] = one;
+        if (cur.meta & opp_q) row[114] = one;
+        if (cur.meta & opp_k) row[115] = one;
+        row[116] = plane_cast<T>((float)fullmove(cur));
+        row[117] = plane_cast<T>((float)halfmove(cur));
     }
 }
 
-// e8 in shared memory; out[8][8][118], lanes stride over the flat index so the stores coalesce
 template <typename T>
 __device__ __forceinline__ void encode_planes(const Pos* e8, T* out, int lane) {
-    for (int i = lane; i < 64 * kPlanes; i += 32) {
-        const int cell = i / kPlanes, pl = i - cell * kPlanes;
-        const int sq = ((7 - (cell >> 3)) << 3) | (cell & 7);  // array row 0 is rank 8 (chess/board.py:119-131)
-        out[i] = (T)plane_value(e8, sq, pl);
-    }
+    encode_planes_strided<T>(e8, out, lane, kPlanes);
 }
 
 template <typename T>
@@ -460,19 +481,30 @@ AZ_API int az_chess_search(az_chess_engine* e, void* stream) {
 }
 
 AZ_API int az_chess_step(az_chess_engine* e, const void* priors, const void* values, int32_t eval_dtype, void* states_out,
-                         int32_t* leaf_valid_out, void* stream) {
+                         int32_t plane_stride, int32_t* leaf_valid_out, void* stream) {
     if (!e || !states_out || !leaf_valid_out) return az::fail_net(AZ_ERR_ARG, "az_chess_step: null argument");
+    if (plane_stride < kPlanes || plane_stride > 256) return az::fail_net(AZ_ERR_ARG, "az_chess_step: plane_stride must be in [118, 256]");
     if ((priors == nullptr) != (values == nullptr)) return az::fail_net(AZ_ERR_ARG, "az_chess_step: priors and values go together");
     if (eval_dtype != AZ_F32 && eval_dtype != AZ_F64) return az::fail_net(AZ_ERR_ARG, "az_chess_step: eval_dtype must be AZ_F32 or AZ_F64");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int have = priors != nullptr;
     __nv_bfloat16* so = static_cast<__nv_bfloat16*>(states_out);
-    if (eval_dtype == AZ_F32)
-        k_chess_step<float><<<ctree_grid(e), kCWarps * 32, 0, s>>>(e->eng, static_cast<const float*>(priors),
-                                                                  static_cast<const float*>(values), have, so, leaf_valid_out);
-    else
-        k_chess_step<double><<<ctree_grid(e), kCWarps * 32, 0, s>>>(e->eng, static_cast<const double*>(priors),
-                                                                   static_cast<const double*>(values), have, so, leaf_valid_out);
+    static const int minb = [] {
+        // 4 (default) = 112 registers, no spills, two waves of warps at 4096 trees; 7 = 72 registers with spills, one
+        // wave.  Measured on B200 at 4096 trees x 800 simulations: 4.45 vs 4.43 M simulations/s (profiles/README.md).
+        const char* v = getenv("AZ_CHESS_STEP_BLOCKS");
+        return v ? atoi(v) : 4;
+    }();
+    const dim3 grid = ctree_grid(e);
+#define AZC_STEP(PT, MINB)                                                                                              \
+    k_chess_step<PT, MINB><<<grid, kCWarps * 32, 0, s>>>(e->eng, static_cast<const PT*>(priors), static_cast<const PT*>(values), \
+                                                         have, so, plane_stride, leaf_valid_out)
+    if (eval_dtype == AZ_F32) {
+        if (minb <= 4) AZC_STEP(float, 4); else AZC_STEP(float, 7);
+    } else {
+        if (minb <= 4) AZC_STEP(double, 4); else AZC_STEP(double, 7);
+    }
+#undef AZC_STEP
     AZC_CUDA(cudaGetLastError());
     return AZ_OK;
 }

@@ -382,9 +382,11 @@ __global__ void __launch_bounds__(kCWarps * 32) k_chess_search(CEng e) {
     c_step_tree<false>(e, t, s_ws[warp], lane, false, 0.0, e.prior_mode, [](int) { return 0.0; }, dummy);
 }
 
-template <typename PT>
-__global__ void __launch_bounds__(kCWarps * 32) k_chess_step(CEng e, const PT* priors, const PT* values, int have_eval,
-                                                             __nv_bfloat16* states_out, int32_t* leaf_valid) {
+// MINB = resident blocks per SM the register allocation aims for: 7 x 4 warps = 28 warps hold 4096 trees on 148 SMs in
+// one wave (72 registers, some spills); 4 keeps everything in registers (112) but needs two waves.
+template <typename PT, int MINB>
+__global__ void __launch_bounds__(kCWarps * 32, MINB) k_chess_step(CEng e, const PT* priors, const PT* values, int have_eval,
+                                                             __nv_bfloat16* states_out, int plane_stride, int32_t* leaf_valid) {
     __shared__ CScratch s_ws[kCWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * kCWarps + warp;
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(kCWarps * 32) k_chess_step(CEng e, const PT* p
     if (lane == 0) leaf_valid[t] = want;
     if (want) {
         stage_history(leaf, nullptr, ws.e8, lane);
-        encode_planes<__nv_bfloat16>(ws.e8, states_out + (size_t)t * 64 * kPlanes, lane);
+        encode_planes_strided<__nv_bfloat16>(ws.e8, states_out + (size_t)t * 64 * plane_stride, lane, plane_stride);
     }
 }
 

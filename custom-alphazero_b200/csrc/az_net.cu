@@ -248,6 +248,56 @@ __global__ void __launch_bounds__(kHeadWarps * 32) k_heads(const __nv_bfloat16* 
     }
 }
 
+// ------------------------------------------------------------------------------------------ head convolutions alone
+// The two 1x1 head convolutions (policy: 2 planes, value: 1 plane; model.py:76-80, :114-118) + ReLU on the tower
+// output, for shapes az_net_heads does not cover (chess: 64 cells, 1 880 actions - the dense layers then run through
+// cuBLAS).  Bandwidth bound: every activation is read once with 128-bit loads; a half-warp owns one cell (16 lanes x
+// 8 channels), three dot products in float32, reduced by shuffles.  x [rows][128] bf16 -> out [rows][3] float32.
+__global__ void __launch_bounds__(256) k_head_convs(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                    const float* __restrict__ b, long long rows, float* __restrict__ out) {
+    __shared__ float sw[3 * 128];
+    for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int l16 = threadIdx.x & 15, sub = (threadIdx.x & 31) >> 4;
+    float wr[3][8];
+#pragma unroll
+    for (int o = 0; o < 3; ++o)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) wr[o][c] = sw[o * 128 + 8 * l16 + c];
+    const float b0 = b[0], b1 = b[1], b2 = b[2];
+    const long long warp = (long long)(blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = (long long)(gridDim.x * blockDim.x) >> 5;
+    for (long long base = 2 * warp; base < rows; base += 2 * n_warps) {  // two cells per warp and iteration
+        const long long row = base + sub;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        if (row < rows) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(x + row * 128) + l16);
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float lo = __uint_as_float(u[j] << 16), hi = __uint_as_float(u[j] & 0xffff0000u);
+                a0 = fmaf(lo, wr[0][2 * j], a0);
+                a0 = fmaf(hi, wr[0][2 * j + 1], a0);
+                a1 = fmaf(lo, wr[1][2 * j], a1);
+                a1 = fmaf(hi, wr[1][2 * j + 1], a1);
+                a2 = fmaf(lo, wr[2][2 * j], a2);
+                a2 = fmaf(hi, wr[2][2 * j + 1], a2);
+            }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (l16 == 0 && row < rows) {
+            out[row * 3 + 0] = fmaxf(a0 + b0, 0.f);
+            out[row * 3 + 1] = fmaxf(a1 + b1, 0.f);
+            out[row * 3 + 2] = fmaxf(a2 + b2, 0.f);
+        }
+    }
+}
+
 }  // namespace az
 
 using namespace az;
@@ -294,5 +344,22 @@ AZ_API int az_net_heads(const void* x, const az_head_weights* hw, int32_t n, int
     k_heads<128><<<grid, kHeadWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), hp, priors, values);
     if (cudaGetLastError() != cudaSuccess) return fail_net(AZ_ERR_CUDA, "az_net_heads: launch failed");
+    return AZ_OK;
+}
+
+AZ_API int az_net_head_convs(const void* x, const float* conv_w, const float* conv_b, int32_t n, int32_t cells, int32_t C,
+                             float* out, void* stream) {
+    if (n == 0) return AZ_OK;
+    if (!x || !conv_w || !conv_b || !out || n < 0 || cells < 1) return fail_net(AZ_ERR_ARG, "az_net_head_convs: bad argument");
+    if (C != 128) return fail_net(AZ_ERR_ARG, "az_net_head_convs: built for 128 filters (config.py:71)");
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail_net(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback");
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long rows = (long long)n * cells;
+    long long grid = (rows + 15) / 16;  // 8 warps x 2 cells per block and iteration
+    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+    k_head_convs<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), conv_w,
+                                                                               conv_b, rows, out);
+    if (cudaGetLastError() != cudaSuccess) return fail_net(AZ_ERR_CUDA, "az_net_head_convs: launch failed");
     return AZ_OK;
 }

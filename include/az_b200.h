@@ -280,6 +280,13 @@ int az_net_stem(const void *dev_states, const float *dev_w, const float *dev_b, 
 int az_net_heads(const void *dev_x, const az_head_weights *weights, int32_t n, int32_t cells, int32_t channels,
                  int32_t n_actions, float *dev_priors_out, float *dev_values_out, void *stream);
 
+/* Only the two 1x1 head convolutions + BN + ReLU (model.py:76-80, :114-118) of az_net_heads, for shapes whose dense
+ * layers do not fit its shared memory (chess: 64 cells x 1 880 actions; they then run through cuBLAS).
+ * x: dev bf16 [n][cells][C]; conv_w: dev float [3][C] (rows 0-1 policy, row 2 value); conv_b: dev float [3];
+ * out: dev float [n][cells][3]. */
+int az_net_head_convs(const void *dev_x, const float *dev_conv_w, const float *dev_conv_b, int32_t n, int32_t cells,
+                      int32_t channels, float *dev_out, void *stream);
+
 /* The three per-tree stages between two passes of the tower in ONE launch (one warp per tree):
  * az_net_heads on the tower output of each tree's pending leaf, az_step with those priors / value (kept in
  * registers), az_net_stem on the newly selected leaf.  Same results as the three calls in sequence.
@@ -432,9 +439,10 @@ int az_chess_begin_search(az_chess_engine *e, int32_t sims, void *stream);
 int az_chess_search(az_chess_engine *e, void *stream);
 /* one lock-step advance with an external evaluator, like az_step: consume priors dev [T][1880] / values dev [T]
  * (AZ_F32 or AZ_F64; ignored for trees without a pending leaf), simulate up to the next leaf, write its 118 planes
- * to states_out dev bf16 [T][8][8][118] and leaf_valid_out dev int32 [T]. */
+ * to states_out dev bf16 [T][8][8][plane_stride] (plane_stride >= 118; the planes beyond 118 are written as zeros so a
+ * tensor-core stem can read a channel count that is a multiple of 8 in place) and leaf_valid_out dev int32 [T]. */
 int az_chess_step(az_chess_engine *e, const void *dev_priors, const void *dev_values, int32_t eval_dtype,
-                  void *dev_states_out, int32_t *dev_leaf_valid_out, void *stream);
+                  void *dev_states_out, int32_t plane_stride, int32_t *dev_leaf_valid_out, void *stream);
 /* MCTS.play for every tree whose budget is spent: sample-ring entry, move, re-root (in place, or compacted into the
  * other pool half), game end -> finished ring + next game.  greedy_override / move_mode_override: -1 = configured. */
 int az_chess_move(az_chess_engine *e, int32_t greedy_override, int32_t move_mode_override, void *stream);

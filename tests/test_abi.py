@@ -103,3 +103,68 @@ def test_no_cpu_fallback():
     h = ctypes.c_void_p()
     rc = native.lib().az_engine_create(ctypes.byref(cfg), buf, 256, lut, None, ctypes.byref(h))
     assert rc == native.AZ_ERR_NO_DEVICE and h.value is None
+
+
+def _chess_cfg(**kw):
+    from az_b200 import native
+
+    base = dict(abi_version=native.AZ_ABI_VERSION, n_trees=1024, node_capacity=60000, sims_per_move=200, index_move_greedy=8,
+                eval_mode=0, prior_mode=1, move_mode=2, max_free_sims=8, max_plies=512, sample_capacity=8192,
+                fin_capacity=2048, pow_lut_len=80002, auto_restart=1, c_puct=1.5, seed=0, game_id_base=0, games_target=1024)
+    base.update(kw)
+    return native.AzChessConfig(**base)
+
+
+def test_chess_layout_and_action_table_are_host_only():
+    """The chess engine's layout query and the action list need no device; the struct mirrors match."""
+    from az_b200 import chess, native
+
+    cs, ls = ctypes.c_size_t(), ctypes.c_size_t()
+    native.lib().az_chess_struct_sizes(ctypes.byref(cs), ctypes.byref(ls))
+    assert cs.value == ctypes.sizeof(native.AzChessConfig) and ls.value == ctypes.sizeof(native.AzChessLayout)
+    lay = native.AzChessLayout()
+    cfg = _chess_cfg()
+    native.check(native.lib().az_chess_query_layout(ctypes.byref(cfg), ctypes.byref(lay)))
+    offs = [getattr(lay, n) for n in native.CHESS_LAYOUT_ARRAYS]
+    assert len(set(offs)) == len(offs) and all(o % 256 == 0 for o in offs) and lay.total_bytes > max(offs)
+    assert lay.node_p - lay.node_a >= 1024 * 2 * 60000 * 16 and lay.node_m - lay.node_p >= 1024 * 2 * 60000 * 8
+    assert lay.smp_n - lay.smp_act >= 8192 * 224 * 2
+    for bad in (dict(node_capacity=100), dict(node_capacity=1 << 24), dict(n_trees=0), dict(max_plies=0),
+                dict(eval_mode=3), dict(abi_version=7), dict(sample_capacity=0)):
+        rc = native.lib().az_chess_query_layout(ctypes.byref(_chess_cfg(**bad)), ctypes.byref(lay))
+        assert rc == native.AZ_ERR_ARG and native.lib().az_last_error()
+    table = chess.action_table()
+    assert table.shape == (1880,) and chess.action_uci(0) == "a1a2" and chess.uci_action("e7e8q") >= 0
+    assert chess.uci_action("e2e4") == int(table.tolist().index(12 | 28 << 6))
+
+
+def test_chess_has_no_cpu_fallback():
+    import numpy as np
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from az_b200 import chess, chess_engine, native
+
+    start = chess.position_from_fen()
+    for call in (lambda: chess.chess_legal(start[None]), lambda: chess.chess_play(start[None], [0]),
+                 lambda: chess.chess_encode(start[None]), lambda: chess.chess_perft(start[None], 2),
+                 lambda: chess_engine.ChessTreeEngine(n_trees=2, sims_per_move=4)):
+        with pytest.raises(native.NativeError):
+            call()
+    # straight through the ABI: AZ_ERR_NO_DEVICE, not a silent success
+    buf = (ctypes.c_uint64 * 8)(*[int(x) for x in start])
+    out = (ctypes.c_uint64 * 1)()
+    assert native.lib().az_chess_perft(buf, 1, 2, out, None) == native.AZ_ERR_NO_DEVICE
+    cfg = _chess_cfg(n_trees=2, node_capacity=256, sample_capacity=4, fin_capacity=2, pow_lut_len=8, games_target=2)
+    slab = (ctypes.c_char * 256)()
+    lut = (ctypes.c_double * 8)()
+    h = ctypes.c_void_p()
+    rc = native.lib().az_chess_engine_create(ctypes.byref(cfg), slab, 256, lut, None, ctypes.byref(h))
+    assert rc == native.AZ_ERR_NO_DEVICE and h.value is None
+    # the drop-in classes are GPU-backed too
+    from custom_alphazero.chess.board import Board
+
+    with pytest.raises(native.NativeError):
+        Board().moves
+    assert np.array_equal(Board().array[7], [4, 2, 3, 5, 6, 3, 2, 4])  # the array itself is data-format glue

@@ -18,7 +18,7 @@ def _play_games(eng, max_iters, route="search", evaluator=None):
 
     per_game, fin = {}, {}
     T = eng.n_trees
-    states = torch.zeros((T, 8, 8, 118), dtype=torch.bfloat16, device=eng.device)
+    states = torch.full((T, 8, 8, 120), 7.0, dtype=torch.bfloat16, device=eng.device)  # 2 pad planes: must come back as zeros
     valid = torch.zeros(T, dtype=torch.int32, device=eng.device)
     for _ in range(max_iters):
         ph = eng.phases()
@@ -105,7 +105,7 @@ def _host_hash_evaluator(eng, states, valid):
     if len(idx):
         enc = chess.chess_encode(pos[idx])
         got = states[torch.as_tensor(idx, device=states.device)].float().cpu().numpy()
-        assert np.array_equal(got, enc)
+        assert np.array_equal(got[..., :118], enc) and not got[..., 118:].any()
     a = np.arange(1880, dtype=np.uint64)
     for t in idx:
         s = cr.from_pos(pos[t])

@@ -23,4 +23,9 @@ Files
                   Python port cannot finish in seconds; built by oracle/Makefile into
                   oracle/_build/libaz_oracle.so
   c_oracle.py     ctypes loader for the C restatement
+  c/chess_oracle.c    chess: mailbox rules + the reference's MCTS over them.  PARITY UNPINNED against
+                      python-chess (the reference's third-party rules engine, absent here); pinned on published perft
+                      counts (tests/test_chess_oracle.py)
+  chess_ref.py        the reference's own chess layer restated (array, planes, play + mirror, action list) + loaders
+  c/chess_hostcheck.cpp  the DEVICE rules header compiled for the host so the CPU suite can compare it with the oracle
 """

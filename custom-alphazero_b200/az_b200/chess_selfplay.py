@@ -132,3 +132,27 @@ class ChessSelfPlayRunner:
     def load_weights(self, net: PolicyValueNet):
         self.fp32_net = net
         self.net.load_from(net)
+
+
+def chess_training_loop(runner: ChessSelfPlayRunner, trainer, window, iterations, train_steps_per_iteration=1,
+                        exclude_null_games=True, rng=np.random, log=None, max_advances=None):
+    """Self-play -> samples -> train -> new weights for chess on one rank: the loop of train.selfplay_training_loop
+    (reference train.py:16-84, self_play.py:122-188) with the chess runner's sample ring in place of the finished-game
+    records.  Drawn games contribute no samples when exclude_null_games (self_play.py:155-162)."""
+    history = []
+    for it in range(iterations):
+        runner.engine.reset()  # the runner's games_target games, every iteration
+        runner.valid.zero_()
+        runner._games.clear()
+        states, policies, values, known = runner.run_until_done(max_advances=max_advances)
+        keep = known & ((values != 0) if exclude_null_games else np.ones(len(values), dtype=bool))
+        window.append(states[keep], policies[keep], values[keep])
+        if window.ready():
+            for _ in range(train_steps_per_iteration):
+                from .train import BATCH_SIZE
+
+                history.append(trainer.train_step(*window.sample(min(BATCH_SIZE, len(window)), rng=rng)))
+            runner.load_weights(trainer.net)
+        if log is not None:
+            log(it, len(window), history[-1] if history else None)
+    return history

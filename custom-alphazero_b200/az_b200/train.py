@@ -40,9 +40,9 @@ def learning_rate_for(steps):
 class ReplayWindow:
     """train.py:16-38: append, keep the last `capacity` samples."""
 
-    def __init__(self, height, width, n_actions, capacity=WINDOW):
+    def __init__(self, height, width, n_actions, capacity=WINDOW, planes=4):
         self.capacity = capacity
-        self.states = np.empty((0, height, width, 4), dtype=np.float32)
+        self.states = np.empty((0, height, width, planes), dtype=np.float32)  # 4 planes Connect-N, 118 chess
         self.policies = np.empty((0, n_actions), dtype=np.float64)
         self.values = np.empty(0, dtype=np.float64)
 

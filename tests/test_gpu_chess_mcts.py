@@ -204,3 +204,45 @@ def test_chess_selfplay_runner_with_the_net():
     # planes of a first ply: the start position in the last history slot and in the "initial position" slot
     first = states[np.nonzero(np.abs(states[:, :, :, 84:98] - states[:, :, :, 98:112]).sum((1, 2, 3)) == 0)[0]]
     assert len(first) == 24
+
+
+def test_sharding_invariance():
+    """A game's moves depend on (seed, game id, ply) only: trees hosted by another engine / rank replay the same games."""
+    from az_b200.chess_engine import ChessTreeEngine
+
+    kw = dict(sims_per_move=24, eval_mode="hash", prior_mode="f64", move_mode="philox", max_plies=14, seed=99,
+              index_move_greedy=30)
+    whole, fin_w = _play_games(ChessTreeEngine(n_trees=4, **kw), 16)
+    part, fin_p = _play_games(ChessTreeEngine(n_trees=2, game_id_base=2, **kw), 16)
+    assert sorted(part) == [2, 3]
+    for g in (2, 3):
+        assert fin_w[g] == fin_p[g]
+        assert [(p[0], p[1], p[4]) for p in whole[g]] == [(p[0], p[1], p[4]) for p in part[g]]
+        assert all(np.array_equal(a[3], b[3]) for a, b in zip(whole[g], part[g]))
+    assert [p[4] for p in whole[0]] != [p[4] for p in whole[1]]  # different games really differ
+
+
+def test_chess_closed_loop_trains():
+    """Self-play -> sample ring -> replay window -> SGD step (the reference's losses) -> new weights in the runner."""
+    from az_b200.chess_selfplay import ChessSelfPlayRunner, chess_net, chess_training_loop
+    from az_b200.train import ReplayWindow, Trainer
+
+    torch.manual_seed(0)
+    net = chess_net()
+    runner = ChessSelfPlayRunner(n_trees=16, sims_per_move=8, net=net, games_target=16, max_plies=8, unroll=4,
+                                 auto_restart=False)
+    trainer = Trainer(net)
+    window = ReplayWindow(8, 8, 1880, capacity=512, planes=118)
+    before = runner.net.flat_weights().clone()
+    import az_b200.train as T
+
+    old_min, old_batch = T.MIN_TRAINING_SIZE, T.BATCH_SIZE
+    T.MIN_TRAINING_SIZE = 64
+    try:
+        hist = chess_training_loop(runner, trainer, window, iterations=2, exclude_null_games=False,
+                                   rng=np.random.RandomState(0), max_advances=4000)
+    finally:
+        T.MIN_TRAINING_SIZE, T.BATCH_SIZE = old_min, old_batch
+    assert len(window) == 256 and len(hist) >= 1 and all(np.isfinite(h["loss"]) for h in hist)
+    assert hist[0]["policy_loss"] > 1.0  # cross-entropy against visit distributions over ~20 legal moves
+    assert not torch.equal(before, runner.net.flat_weights())

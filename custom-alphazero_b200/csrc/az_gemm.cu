@@ -1,0 +1,221 @@
+// az_gemm.cu - the tower's 1x1 projection shortcut (base_layers.py:105-113 of the reference) as a hand-written
+// tcgen05 GEMM for sm_100a:   Y[rows][128] = X[rows][128] . W[128][128]^T   (bf16 in, float32 accumulate, bf16 out)
+//
+// The shortcut is bandwidth bound (33 kFLOP against 512 B of traffic per cell).  Measured on B200 at 172 032 cells with
+// the input still in L2 (tools/explore_conv1x1.py): this kernel 14.2 us = 6.2 TB/s of algorithmic traffic (0.96 of the
+// measured HBM peak), cuDNN's 1x1 convolution 12.9 us; inside the tower cuDNN's is 2 us faster per call, so the tower
+// uses this kernel only on request (AZ_TC_SHORTCUT=1).  Design:
+//   * persistent CTAs (2 per SM), the 32 KB weight matrix staged once per CTA in the canonical K-major SWIZZLE_128B
+//     layout, activation tiles of 128 cells streamed with cp.async into a double buffer in the same layout
+//     (16-byte chunk c of row r lands at chunk c ^ (r & 7) of its 128-byte row; 8-row groups are 1024 B apart);
+//   * one elected thread issues 8 tcgen05.mma (M = 128, N = 128, K = 16 each) per tile into a 128-column TMEM
+//     accumulator and commits to an mbarrier; the next tile's cp.async is already in flight underneath;
+//   * epilogue: the four warps read their 32 TMEM lanes with tcgen05.ld (32x32b.x32), pack to bf16, stage the tile in
+//     the shared-memory buffer the MMA has just finished with (XOR-swizzled, conflict free) and write it out with
+//     fully coalesced 128-bit stores.
+// No TMA descriptors are needed (rows are 256 B and contiguous), so nothing here depends on the driver API.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/az_b200.h"
+
+namespace az {
+int fail_net(int code, const char* msg);
+
+namespace gemm {
+
+constexpr int kC = 128;              // channels in and out (config.py:71)
+constexpr int kTileM = 128;          // cells per tile = UMMA M
+constexpr int kKBlockBytes = 16384;  // one 64-channel K block of a 128-row tile: 128 rows x 128 B
+constexpr int kTileBytes = 2 * kKBlockBytes;
+constexpr int kSmemBytes = 3 * kTileBytes + 1024;  // W + two activation buffers + alignment slack
+constexpr uint32_t kTmemCols = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits 0-13,
+// leading byte offset (unused for swizzled K-major) bits 16-29, stride byte offset = 1024 B between 8-row groups in
+// bits 32-45, descriptor version 1 in bits 46-47, layout type 2 (SWIZZLE_128B) in bits 61-63.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffff) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bit 4), A = B = BF16 (bits 7, 10), both K-major,
+// N >> 3 in bits 17-22, M >> 4 in bits 24-28
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kC >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 24)) __trap();  // a lost arrival must fail loudly, never hang the GPU
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// position of 16-byte chunk c (0..15) of row r (0..127) inside a tile in the UMMA layout
+__device__ __forceinline__ uint32_t umma_chunk_offset(int r, int c) {
+    return (uint32_t)((c >> 3) * kKBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + (((c & 7) ^ (r & 7)) << 4));
+}
+// ... and inside the row-major staging tile of the epilogue (256 B rows, chunks XOR-ed with the row: conflict free)
+__device__ __forceinline__ uint32_t stage_chunk_offset(int r, int c) { return (uint32_t)(r * 256 + ((c ^ (r & 15)) << 4)); }
+
+__device__ __forceinline__ void load_tile_async(uint32_t sdst, const __nv_bfloat16* x, long long row0, long long rows, int tid) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int idx = tid + 128 * i, r = idx >> 4, c = idx & 15;
+        const long long row = row0 + r;
+        const uint32_t dst = sdst + umma_chunk_offset(r, c);
+        const __nv_bfloat16* src = x + (row < rows ? row : rows - 1) * kC + c * 8;
+        const int bytes = row < rows ? 16 : 0;  // rows past the end are zero-filled
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+__global__ void __launch_bounds__(128, 2) k_conv1x1(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                    __nv_bfloat16* __restrict__ y, long long rows, int n_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-byte aligned tiles
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sW = base, sA0 = base + kTileBytes;
+    const uint32_t bar = smem_u32(&s_bar);
+
+    // one-time: weights -> UMMA layout (row = output channel, K = input channel), TMEM, barrier
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int idx = tid + 128 * i, r = idx >> 4, c = idx & 15;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + r * kC) + c);
+        *reinterpret_cast<uint4*>(gen + umma_chunk_offset(r, c)) = v;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    int tile = blockIdx.x, buf = 0;
+    if (tile < n_tiles) load_tile_async(sA0, x, (long long)tile * kTileM, rows, tid);
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    uint32_t phase = 0;
+
+    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        const uint32_t sA = sA0 + buf * kTileBytes;
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+        const int next = tile + gridDim.x;
+        if (next < n_tiles) load_tile_async(sA0 + (buf ^ 1) * kTileBytes, x, (long long)next * kTileM, rows, tid);
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < kC / 16; ++k) {  // UMMA K = 16 bf16 = 32 B: step inside the 128-byte swizzle row
+                const uint32_t koff = (uint32_t)((k >> 2) * kKBlockBytes + (k & 3) * 32);
+                mma_bf16(tmem, umma_desc(sA + koff), umma_desc(sW + koff), k > 0);
+            }
+            // arrives on the barrier when the MMAs above have finished (implies tcgen05.fence::before_thread_sync)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        // epilogue: thread = row (TMEM lane) warp * 32 + lane; 4 x 32 columns
+        uint8_t* stage = gen + (sA - base);
+        const int r = warp * 32 + lane;
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // 8 columns = one 16-byte chunk of bf16
+                uint4 o;
+                o.x = pack_bf16(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+                o.y = pack_bf16(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+                o.z = pack_bf16(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+                o.w = pack_bf16(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+                *reinterpret_cast<uint4*>(stage + stage_chunk_offset(r, cb * 4 + q)) = o;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();  // staging complete; TMEM reads done before the next tile's MMA overwrites the accumulator
+        const long long row0 = (long long)tile * kTileM;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {  // a warp writes two whole rows (512 contiguous bytes) per instruction
+            const int idx = tid + 128 * i, rr = idx >> 4, c = idx & 15;
+            if (row0 + rr < rows)
+                *(reinterpret_cast<uint4*>(y + (row0 + rr) * kC) + c) =
+                    *reinterpret_cast<const uint4*>(stage + stage_chunk_offset(rr, c));  // default policy: the next convolution reads y from L2
+        }
+        // the staging buffer is refilled by cp.async two iterations from now, after the __syncthreads at the loop top
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kTmemCols) : "memory");
+}
+
+}  // namespace gemm
+}  // namespace az
+
+extern "C" __attribute__((visibility("default"))) int az_net_conv1x1(const void* x, const void* w, int64_t rows, int32_t channels,
+                                                                      void* y, void* stream) {
+    using namespace az::gemm;
+    if (rows == 0) return AZ_OK;
+    if (!x || !w || !y || rows < 0) return az::fail_net(AZ_ERR_ARG, "az_net_conv1x1: bad argument");
+    if (channels != kC) return az::fail_net(AZ_ERR_ARG, "az_net_conv1x1: built for 128 filters (config.py:71)");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15)
+        return az::fail_net(AZ_ERR_ARG, "az_net_conv1x1: pointers must be 16-byte aligned");
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return az::fail_net(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback");
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_conv1x1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+            return az::fail_net(AZ_ERR_CUDA, "az_net_conv1x1: shared memory request refused");
+        configured = true;
+    }
+    const long long n_tiles = (rows + kTileM - 1) / kTileM;
+    long long grid = n_tiles < 2LL * sms ? n_tiles : 2LL * sms;
+    k_conv1x1<<<(unsigned)grid, 128, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(y), rows,
+        (int)n_tiles);
+    if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_conv1x1: launch failed");
+    return AZ_OK;
+}

@@ -280,6 +280,13 @@ int az_net_stem(const void *dev_states, const float *dev_w, const float *dev_b, 
 int az_net_heads(const void *dev_x, const az_head_weights *weights, int32_t n, int32_t cells, int32_t channels,
                  int32_t n_actions, float *dev_priors_out, float *dev_values_out, void *stream);
 
+/* The 1x1 projection shortcut of a residual block (model/tensorflow/base_layers.py:105-113, BN folded):
+ * y[rows][128] = x[rows][128] . w[128][128]^T, bf16 in / float32 accumulate / bf16 out, no bias (the caller folds it
+ * into the bias of the convolution that consumes y).  Hand-written tcgen05 GEMM (csrc/az_gemm.cu).
+ * x, y: dev bf16 [rows][channels] (NHWC activations flattened over cells); w: dev bf16 [channels out][channels in];
+ * all 16-byte aligned; channels must be 128. */
+int az_net_conv1x1(const void *dev_x, const void *dev_w, int64_t rows, int32_t channels, void *dev_y, void *stream);
+
 /* Only the two 1x1 head convolutions + BN + ReLU (model.py:76-80, :114-118) of az_net_heads, for shapes whose dense
  * layers do not fit its shared memory (chess: 64 cells x 1 880 actions; they then run through cuBLAS).
  * x: dev bf16 [n][cells][C]; conv_w: dev float [3][C] (rows 0-1 policy, row 2 value); conv_b: dev float [3];

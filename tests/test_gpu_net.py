@@ -213,3 +213,47 @@ def test_evaluation_memo_changes_nothing_but_the_number_of_evaluations():
     # a big table hits more often than a tiny, collision-ridden one
     assert out[1][1]["memo_hits"] > out[3][1]["memo_hits"] > 0
     assert out[1][1]["memo_hits"] > 0.15 * ta["evals"]
+
+
+def test_tcgen05_shortcut_gemm_matches_the_library():
+    """az_net_conv1x1 (hand-written tcgen05 GEMM) against the same product in float32 and against cuDNN's bf16 result."""
+    import ctypes
+
+    from az_b200 import native
+
+    torch.manual_seed(3)
+    lib = native.lib()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    w = (torch.randn(128, 128, device="cuda") * 0.1).to(torch.bfloat16).contiguous()
+    for rows in (128, 1, 127, 129, 4096 * 42, 300 * 128 + 77):
+        x = torch.randn(rows, 128, device="cuda").to(torch.bfloat16).contiguous()
+        y = torch.full((rows + 1, 128), 7.0, device="cuda", dtype=torch.bfloat16)  # one guard row
+        native.check(lib.az_net_conv1x1(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(w.data_ptr()), rows, 128,
+                                        ctypes.c_void_p(y.data_ptr()), stream))
+        torch.cuda.synchronize()
+        ref = x.float() @ w.float().t()
+        err = (y[:rows].float() - ref).abs().max().item()
+        assert err <= 2.0 ** -7 * max(1.0, ref.abs().max().item()), (rows, err)  # bf16 output rounding only
+        assert bool((y[rows] == 7.0).all()), rows  # nothing written past the last row
+    # every row and column really lands where it should: a one-hot probe
+    x = torch.zeros(256, 128, device="cuda", dtype=torch.bfloat16)
+    x[torch.arange(256), torch.arange(256) % 128] = 1.0
+    y = torch.empty_like(x)
+    native.check(lib.az_net_conv1x1(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(w.data_ptr()), 256, 128,
+                                    ctypes.c_void_p(y.data_ptr()), stream))
+    assert torch.equal(y, w.t()[torch.arange(256) % 128])
+
+
+def test_tower_with_tcgen05_shortcut_equals_cudnn_tower():
+    from az_b200.net import InferenceNet, PolicyValueNet, randomise_bn
+
+    torch.manual_seed(5)
+    net = randomise_bn(PolicyValueNet()).eval()
+    inf = InferenceNet(net, dtype=torch.bfloat16, device="cuda")
+    h0 = torch.randn(777, 6, 7, 128, device="cuda").to(torch.bfloat16)
+    inf.tc_shortcut = True
+    a = inf.tower(h0).float()
+    inf.tc_shortcut = False
+    b = inf.tower(h0).float()
+    scale = b.abs().max().item()
+    assert (a - b).abs().max().item() <= 0.02 * scale  # two bf16 roundings of the shortcut per block, different order

@@ -30,9 +30,11 @@
 
 #if defined(__CUDACC__)
 #define AZC_HD __host__ __device__ __forceinline__
+#define AZC_HDM __host__ __device__ __forceinline__ /* member functions */
 #define AZC_TABLE static __device__ const
 #else
 #define AZC_HD static inline
+#define AZC_HDM inline
 #define AZC_TABLE static const
 #endif
 
@@ -222,13 +224,34 @@ AZC_HD void emit(MoveMask& m, int from, int to, int promo) {
     int a = act_index(from, to) + promo;
     m.w[a >> 6] |= 1ull << (a & 63);
 }
-AZC_HD void emit_targets(MoveMask& m, int from, u64 targets) {
-    while (targets) {
-        int to = lsb(targets);
-        targets &= targets - 1;
-        emit(m, from, to, 0);
+
+// Where generated moves go.  MaskSink: one thread fills a private MoveMask (thread-per-board kernels, host build).
+// The tree kernels use a warp-collective sink instead (az_chess_tree.cuh: the lanes share out the targets of a piece).
+struct MaskSink {
+    MoveMask& m;
+    AZC_HDM void clear() { mask_clear(m); }
+    AZC_HDM void one(int from, int to, int promo) { emit(m, from, to, promo); }
+    AZC_HDM void targets(int from, u64 t) {
+        while (t) {
+            int to = lsb(t);
+            t &= t - 1;
+            emit(m, from, to, 0);
+        }
     }
-}
+    // pawn targets: a move onto the eighth rank is four promotions
+    AZC_HDM void pawn_targets(int from, u64 t) {
+        while (t) {
+            int to = lsb(t);
+            t &= t - 1;
+            if (to >= 56) {
+                for (int pr = 1; pr <= 4; ++pr) emit(m, from, to, pr);
+            } else {
+                emit(m, from, to, 0);
+            }
+        }
+    }
+    AZC_HDM int count() { return mask_count(m); }
+};
 
 struct GenInfo {
     int n_moves;
@@ -239,8 +262,9 @@ struct GenInfo {
 // move are mirrored by the caller, see legal_moves below).  Returns the number of moves and whether the king is
 // in check.  A position without a white king (the reference builds such boards for its action list,
 // chess/utils.py:14-29) generates pseudo-legal moves, like python-chess does.
-AZC_HD GenInfo gen_white(const Pos& p, MoveMask& out) {
-    mask_clear(out);
+template <class Sink>
+AZC_HD GenInfo gen_white_to(const Pos& p, Sink& out) {
+    out.clear();
     GenInfo gi;
     gi.n_moves = 0;
     gi.in_check = false;
@@ -303,26 +327,26 @@ AZC_HD GenInfo gen_white(const Pos& p, MoveMask& out) {
 
     // king
     if (has_king) {
-        emit_targets(out, ksq, king_attacks(kbb) & ~us & ~danger);
+        out.targets(ksq, king_attacks(kbb) & ~us & ~danger);
         if (!gi.in_check && ksq == 4) {
             // castling (standard chess): rights, empty squares between king and rook, king path not attacked
-            if ((p.meta & 1) && (p.rooks & us & bit(7)) && !(occ & 0x60ull) && !(danger & 0x70ull)) emit(out, 4, 6, 0);
-            if ((p.meta & 2) && (p.rooks & us & bit(0)) && !(occ & 0x0eull) && !(danger & 0x1cull)) emit(out, 4, 2, 0);
+            if ((p.meta & 1) && (p.rooks & us & bit(7)) && !(occ & 0x60ull) && !(danger & 0x70ull)) out.one(4, 6, 0);
+            if ((p.meta & 2) && (p.rooks & us & bit(0)) && !(occ & 0x0eull) && !(danger & 0x1cull)) out.one(4, 2, 0);
         }
     }
     if (check_mask) {
         const u64 tmask = ~us & check_mask;
         for (u64 b = p.knights & us & ~pinned; b; b &= b - 1) {
             int from = lsb(b);
-            emit_targets(out, from, knight_attacks(bit(from)) & tmask);
+            out.targets(from, knight_attacks(bit(from)) & tmask);
         }
         for (u64 b = (p.bishops | p.queens) & us; b; b &= b - 1) {
             int from = lsb(b);
-            emit_targets(out, from, bishop_attacks(occ, from) & tmask & pin_line(from));
+            out.targets(from, bishop_attacks(occ, from) & tmask & pin_line(from));
         }
         for (u64 b = (p.rooks | p.queens) & us; b; b &= b - 1) {
             int from = lsb(b);
-            emit_targets(out, from, rook_attacks(occ, from) & tmask & pin_line(from));
+            out.targets(from, rook_attacks(occ, from) & tmask & pin_line(from));
         }
         // pawns
         for (u64 b = p.pawns & us; b; b &= b - 1) {
@@ -332,15 +356,7 @@ AZC_HD GenInfo gen_white(const Pos& p, MoveMask& out) {
             t |= ((t & RANK_3) << 8) & ~occ;
             t |= (((f << 7) & ~FILE_H) | ((f << 9) & ~FILE_A)) & them;
             t &= check_mask & pl;
-            while (t) {
-                int to = lsb(t);
-                t &= t - 1;
-                if (to >= 56) {
-                    for (int pr = 1; pr <= 4; ++pr) emit(out, from, to, pr);
-                } else {
-                    emit(out, from, to, 0);
-                }
-            }
+            out.pawn_targets(from, t);
         }
     }
     // en passant: rare, so legality is checked by playing it on the occupancy
@@ -358,11 +374,16 @@ AZC_HD GenInfo gen_white(const Pos& p, MoveMask& out) {
                 q.pawns &= ~cap;
                 ok = attackers_to(q, ksq, occ2, false) == 0;
             }
-            if (ok) emit(out, from, ep, 0);
+            if (ok) out.one(from, ep, 0);
         }
     }
-    gi.n_moves = mask_count(out);
+    gi.n_moves = out.count();
     return gi;
+}
+
+AZC_HD GenInfo gen_white(const Pos& p, MoveMask& out) {
+    MaskSink sink{out};
+    return gen_white_to(p, sink);
 }
 
 // Plays a move of WHITE given as from / to / promo (promo 0 none, 1 bishop, 2 knight, 3 queen, 4 rook - the

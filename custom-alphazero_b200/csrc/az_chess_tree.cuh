@@ -262,17 +262,42 @@ __device__ __forceinline__ uint64_t c_hash_position(const Pos& p) {
     return h;
 }
 
-// leaf classification: fills ws.mask, returns game_status (0 ongoing, 1 checkmate, 2 draw)
-__device__ __forceinline__ int c_classify(const Pos& pos, CScratch& ws, int lane) {
-    MoveMask mm;
-    const GenInfo gi = gen_white(pos, mm);
-    __syncwarp();
-    if (lane == 0) {
-#pragma unroll
-        for (int w = 0; w < kMaskWords; ++w) ws.mask[w] = mm.w[w];
-        ws.mask[30] = 0;
-        ws.mask[31] = 0;
+// Warp-collective move sink: every lane runs the generator on the same position (one instruction stream), and when a
+// piece's target set is known the lanes share out its moves - lane j takes the j-th target, looks up the action index
+// and sets its bit in the shared-memory mask - instead of each lane walking all targets.
+struct WarpSink {
+    uint32_t* m32;  // ws.mask viewed as 64 x 32-bit words
+    int lane;
+    __device__ __forceinline__ void clear() {
+        m32[lane] = 0u;
+        m32[lane + 32] = 0u;
+        __syncwarp();
     }
+    __device__ __forceinline__ void set(int a) { atomicOr(m32 + (a >> 5), 1u << (a & 31)); }
+    __device__ __forceinline__ void one(int from, int to, int promo) {
+        if (lane == 0) set(act_index(from, to) + promo);
+    }
+    __device__ __forceinline__ void targets(int from, u64 t) {
+        if (lane < popc(t)) set(act_index(from, az::nth_set64(t, lane)));
+    }
+    __device__ __forceinline__ void pawn_targets(int from, u64 t) {  // at most 3 targets, promotions x 4
+        if (lane < 4 * popc(t)) {
+            const int to = az::nth_set64(t, lane >> 2), pr = lane & 3;
+            if (to >= 56) set(act_index(from, to) + pr + 1);
+            else if (pr == 0) set(act_index(from, to));
+        }
+    }
+    __device__ __forceinline__ int count() {
+        __syncwarp();
+        return __reduce_add_sync(kFull, __popc(m32[lane]) + __popc(m32[lane + 32]));
+    }
+};
+
+// leaf classification: fills ws.mask (legal moves as a mask over the action list), returns game_status
+// (0 ongoing, 1 checkmate, 2 draw)
+__device__ __forceinline__ int c_classify(const Pos& pos, CScratch& ws, int lane) {
+    WarpSink sink{reinterpret_cast<uint32_t*>(ws.mask), lane};
+    const GenInfo gi = gen_white_to(pos, sink);
     __syncwarp();
     return game_status(pos, gi);
 }

@@ -23,7 +23,13 @@ from custom_alphazero.config import ConfigGeneral, ConfigMCTS, ConfigSelfPlay
 from custom_alphazero.mcts.utils import normalize_probabilities  # noqa: F401  (re-exported like the reference)
 from custom_alphazero.serving.factory import infer_sample
 
-if ConfigGeneral.game == "connect_n":
+if ConfigGeneral.game == "chess":  # mcts.py:12-14 of the reference
+    # The module imports like the reference's; the search object below drives the Connect-N engine, chess searches run
+    # through az_b200.chess_engine.ChessTreeEngine / chess_selfplay (the reference's own MCTS cannot finish a chess
+    # simulation: mcts.py:179 passes keep_same_player to a Board.get_result that does not take it).
+    from custom_alphazero.chess.board import Board
+    from custom_alphazero.chess.move import Move
+elif ConfigGeneral.game == "connect_n":
     from custom_alphazero.connect_n.board import Board
     from custom_alphazero.connect_n.move import Move
 else:
@@ -98,6 +104,8 @@ class MCTS:
                  model=None, use_solver: bool = False) -> None:
         if use_solver:
             raise NotImplementedError("the exact solver back-end is outside the B200 hot path (SURVEY 2 #12)")
+        if ConfigGeneral.game != "connect_n":
+            raise NotImplementedError("this search object drives the Connect-N engine; chess: az_b200.chess_engine")
         # ConfigMCTS.enable_dirichlet_noise (mcts.py:114-115): root noise is drawn on the device (same distribution as
         # np.random.dirichlet, different stream: statistical parity only - SURVEY 8a row a5)
         self.board = deepcopy(board)

@@ -21,7 +21,11 @@ from custom_alphazero.mcts.mcts import MCTS
 from custom_alphazero.serving.factory import append_queue, get_run_id
 from custom_alphazero.utils import HostModel, best_saved_model, best_saved_model_hash, reset_plays_inferences_dict
 
-if ConfigGeneral.game == "connect_n":
+if ConfigGeneral.game == "chess":  # self_play.py:24-27 of the reference
+    from custom_alphazero.chess.board import Board
+    from custom_alphazero.chess.move import Move
+    from custom_alphazero.chess.utils import get_all_possible_moves
+elif ConfigGeneral.game == "connect_n":
     from custom_alphazero.connect_n.board import Board
     from custom_alphazero.connect_n.move import Move
 
@@ -44,6 +48,10 @@ def play_game(process_id: int, all_possible_moves: List[Move], mcts_iterations: 
     """One game through the drop-in MCTS class; signature and return values of the reference's play_game
     (self_play.py:37-82): states [T, H, W, 4] float32 (positions BEFORE each move), policies [T, A] float64,
     rewards [T], and the search object with its model detached."""
+    if ConfigGeneral.game == "chess":
+        # the reference's own chess path cannot finish a game inside its MCTS (mcts.py:179 passes keep_same_player to a
+        # Board.get_result that does not take it); chess self-play goes through play() / az_b200.chess_selfplay
+        raise NotImplementedError("play_game drives the Connect-N search object; for chess use play()")
     np.random.seed(int((process_id + 1) * time.time()) % (2**32 - 1))  # every worker samples differently
     evaluator = None if ConfigGeneral.http_inference else HostModel(best_saved_model(run_id))
     search = MCTS(board=Board(), all_possible_moves=all_possible_moves, concurrency=ConfigGeneral.concurrency,
@@ -84,11 +92,29 @@ def play(run_id: str, plays_inferences: Optional[Dict[str, Tuple[np.ndarray, flo
     """One self-play iteration on the GPU.  plays_inferences is accepted for signature compatibility:
     the evaluation cache of the reference only saves CPU net calls and never changes results."""
     games = ConfigB200.games_per_iteration
+    if ConfigGeneral.game == "chess":
+        return _play_chess(run_id, games, iteration)
     runner = _runner(best_saved_model(run_id), games, game_id_base=iteration * games)
     runner.run_until_done()
     states, policies, rewards = runner.collect()
     rewards = rewards * ConfigSelfPlay.discounting_factor ** 0  # discounting_factor == 1 in the reference config
     return states, policies, rewards, []
+
+
+def _play_chess(run_id: str, games: int, iteration: int):
+    """The same iteration for chess: ChessSelfPlayRunner (az_chess_step / az_chess_move around the bf16 net); states
+    float32 [S, 8, 8, 118], policies float64 [S, 1880], rewards int [S] of the finished games."""
+    from az_b200.chess_selfplay import ChessSelfPlayRunner
+
+    _live.clear()
+    r = ChessSelfPlayRunner(n_trees=min(ConfigB200.concurrent_games, games), sims_per_move=ConfigSelfPlay.mcts_iterations,
+                            net=best_saved_model(run_id), games_target=games, game_id_base=iteration * games,
+                            seed=ConfigB200.seed, move_mode="philox", auto_restart=True, unroll=ConfigB200.graph_unroll,
+                            max_free_sims=ConfigB200.max_free_sims, index_move_greedy=ConfigMCTS.index_move_greedy,
+                            max_plies=ConfigB200.chess_max_plies)
+    _live["runner"] = r
+    states, policies, rewards, known = r.run_until_done()
+    return states[known], policies[known], rewards[known].astype(np.int64), []
 
 
 def main(max_iterations: Optional[int] = None):

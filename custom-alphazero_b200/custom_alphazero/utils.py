@@ -47,8 +47,15 @@ def load_with_meta(net: PolicyValueNet, path: str) -> dict:
 
 
 def init_model(path: Optional[str] = None) -> PolicyValueNet:
-    A = len(Board.get_all_possible_moves())
-    net = PolicyValueNet(ConfigConnectN.board_height, ConfigConnectN.board_width, A, ConfigModel.filters, ConfigModel.depth)
+    from custom_alphazero.config import ConfigGeneral
+
+    if ConfigGeneral.game == "chess":  # 8x8x118 planes in, one output per entry of chess.utils.get_all_possible_moves()
+        from az_b200.chess import N_ACTIONS, PLANES
+
+        net = PolicyValueNet(8, 8, N_ACTIONS, ConfigModel.filters, ConfigModel.depth, in_planes=PLANES)
+    else:
+        A = len(Board.get_all_possible_moves())
+        net = PolicyValueNet(ConfigConnectN.board_height, ConfigConnectN.board_width, A, ConfigModel.filters, ConfigModel.depth)
     if path is not None:
         load_with_meta(net, path)
     return net.eval()

@@ -246,3 +246,38 @@ def test_chess_closed_loop_trains():
     assert len(window) == 256 and len(hist) >= 1 and all(np.isfinite(h["loss"]) for h in hist)
     assert hist[0]["policy_loss"] > 1.0  # cross-entropy against visit distributions over ~20 legal moves
     assert not torch.equal(before, runner.net.flat_weights())
+
+
+def test_entry_point_plays_chess(tmp_path, monkeypatch):
+    """`python -m custom_alphazero.self_play` with ConfigGeneral.game = "chess": one stand-alone iteration writes
+    samples.npz with the reference's keys and the chess shapes."""
+    import importlib
+    import sys
+
+    from custom_alphazero import config
+
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(config.ConfigGeneral, "game", "chess")
+    monkeypatch.setattr(config.ConfigSelfPlay, "mcts_iterations", 8)
+    monkeypatch.setattr(config.ConfigSelfPlay, "exclude_null_games", False)
+    monkeypatch.setattr(config.ConfigB200, "concurrent_games", 8)
+    monkeypatch.setattr(config.ConfigB200, "games_per_iteration", 12)
+    monkeypatch.setattr(config.ConfigB200, "chess_max_plies", 6)
+    monkeypatch.setattr(config.ConfigB200, "graph_unroll", 2)
+    monkeypatch.setattr(config.ConfigServing, "serving_address", "http://127.0.0.1:9")  # nothing listens: stand-alone
+    for name in ("custom_alphazero.self_play", "custom_alphazero.mcts.mcts"):
+        sys.modules.pop(name, None)
+    sp = importlib.import_module("custom_alphazero.self_play")
+    try:
+        assert sp.Board.__module__ == "custom_alphazero.chess.board" and len(sp.get_all_possible_moves()) == 1880
+        sp.main(max_iterations=1)
+        files = list(tmp_path.rglob("samples.npz"))
+        assert len(files) == 1 and "chess" in str(files[0])
+        data = np.load(files[0])
+        assert set(data.files) == {"states", "policies", "values"}
+        assert data["states"].shape == (72, 8, 8, 118) and data["policies"].shape == (72, 1880) and len(data["values"]) == 72
+        with pytest.raises(NotImplementedError):
+            sp.play_game(0, [], 8, "x")
+    finally:
+        for name in ("custom_alphazero.self_play", "custom_alphazero.mcts.mcts"):
+            sys.modules.pop(name, None)  # the next importer gets the Connect-N flavour again

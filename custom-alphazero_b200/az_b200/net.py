@@ -149,8 +149,13 @@ class InferenceNet(nn.Module):
         self.head_b32 = f32(torch.cat([pb, vb], 0))
         self.pfc_w, self.pfc_b = f32(net.policy_fc.weight), f32(net.policy_fc.bias)
         if net.n_actions > 128:
-            self.pfc_w16 = nn.Parameter(net.policy_fc.weight.detach().to(device=device, dtype=torch.bfloat16).contiguous(),
-                                        requires_grad=False)
+            # wide policy layer (chess): bf16 operands for the tensor cores, rows padded to a multiple of 128 for
+            # az_net_dense_heads; the value hidden layer likewise
+            w16 = net.policy_fc.weight.detach().to(device=device, dtype=torch.bfloat16)
+            self.pfc_w16 = nn.Parameter(F.pad(w16, (0, 0, 0, (-net.n_actions) % 128)).contiguous(), requires_grad=False)
+            self.v1_w16 = nn.Parameter(net.value_fc1.weight.detach().to(device=device, dtype=torch.bfloat16).contiguous(),
+                                       requires_grad=False)
+        self.fused_dense_heads = True  # az_net_dense_heads where it applies (GPU, 64 cells, wide policy); else cuBLAS
         self.v1_w, self.v1_b = f32(net.value_fc1.weight), f32(net.value_fc1.bias)
         # az_net_heads wants the policy rows padded to an odd stride and the value weights transposed
         # (bank-conflict-free shared memory images that the kernel copies verbatim)
@@ -228,11 +233,24 @@ class InferenceNet(nn.Module):
             xf = x.permute(0, 2, 3, 1).float()  # [B, H, W, C]
         if xf is not None:
             hd = F.relu_(F.linear(xf, self.head_w32, self.head_b32))  # 1x1 convs: [B, H, W, 3]
+        if (xf is None and self.n_actions > 128 and self.fused_dense_heads and self.filters == 128
+                and self.height * self.width == 64 and self.n_actions % 4 == 0 and self.v1_w.shape[0] == 256):
+            # chess: both heads' dense layers, softmax and tanh in one tcgen05 kernel
+            from .engine import _ptr, _stream
+            from .native import check, lib
+
+            if priors_out is None:
+                priors_out = torch.empty((B, self.n_actions), dtype=torch.float32, device=hd.device)
+                values_out = torch.empty(B, dtype=torch.float32, device=hd.device)
+            check(lib().az_net_dense_heads(_ptr(hd), _ptr(self.pfc_w16), _ptr(self.pfc_b), _ptr(self.v1_w16), _ptr(self.v1_b),
+                                           _ptr(self.v2_w), _ptr(self.v2_b), B, 64, self.n_actions, _ptr(priors_out),
+                                           _ptr(values_out), _stream()))
+            return priors_out, values_out
         p = hd[..., :2].reshape(B, -1)
         v = hd[..., 2].reshape(B, -1)
         if xf is None and self.n_actions > 128:
-            # wide policy layer (chess: 128 -> 1 880): bf16 operands on the tensor cores, float32 accumulation and softmax
-            logits = F.linear(p.to(torch.bfloat16), self.pfc_w16).float() + self.pfc_b
+            # wide policy layer without the fused kernel: bf16 operands on the tensor cores, float32 accumulation and softmax
+            logits = F.linear(p.to(torch.bfloat16), self.pfc_w16[: self.n_actions]).float() + self.pfc_b
         else:
             logits = F.linear(p, self.pfc_w, self.pfc_b)
         policy = torch.softmax(logits, dim=-1)

@@ -191,6 +191,228 @@ __global__ void __launch_bounds__(128, 2) k_conv1x1(const __nv_bfloat16* __restr
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kTmemCols) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Dense head layers for wide action spaces (chess: Dense(1880) + softmax on the 128 policy features, Dense(256) + ReLU
+// + Dense(1) + tanh on the 64 value features; model/tensorflow/model.py:86-103, 129-149) as ONE tcgen05 kernel.
+// A tile is 128 positions = the 128 TMEM lanes, so a thread owns a whole output row: bias, ReLU, the value layer's
+// second dot product and the softmax statistics (running maximum and sum over the 15 chunks of 128 logits) are
+// per-thread scalars - no shuffles, no shared-memory reductions.  The policy GEMM is simply issued twice (it is 0.5
+// GFLOP for 4096 positions): pass 1 collects max / sum, pass 2 writes exp(l - max) / sum, staged through shared
+// memory so that the 30 MB of priors leave in coalesced 128-bit stores.  Replaces eleven library kernels (bf16 cast,
+// cuBLAS GEMMs, bias add, float conversion, softmax, value MLP): 116 us -> see profiles/README.md.
+constexpr int kHA_P = 0;                 // policy features  [128 rows][128 K] bf16, two K blocks
+constexpr int kHA_V = 32768;             // value features   [128 rows][ 64 K] bf16
+constexpr int kHW_V = 49152;             // value fc1        [256 rows][ 64 K] bf16
+constexpr int kHW_0 = 81920;             // policy weight chunk, double buffered [128 rows][128 K] bf16
+constexpr int kHStage = 147456;          // [128 rows][128] float32 staging of one output chunk
+constexpr int kHeadsSmem = kHStage + 65536 + 1024;
+constexpr uint32_t kHeadsTmemCols = 512;  // columns 0-127 policy chunk, 256-511 value hidden layer
+
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_i(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+          "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void commit_to(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+
+struct DenseHeadParams {
+    const float* hd;           // [n][64][3] ReLU'd head-convolution outputs (az_net_head_convs)
+    const __nv_bfloat16* wp;   // [n_chunks * 128][128] policy weights, rows beyond n_actions are zero
+    const float* bp;           // [n_actions]
+    const __nv_bfloat16* w1;   // [256][64] value fc1
+    const float* b1;           // [256]
+    const float* w2;           // [256] value fc2
+    const float* b2;           // [1]
+    float* priors;             // [n][n_actions]
+    float* values;             // [n]
+    int n, n_actions, n_chunks;
+};
+
+__global__ void __launch_bounds__(128, 1) k_dense_heads(DenseHeadParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar = smem_u32(&s_bar);
+    const long long row0 = (long long)blockIdx.x * 128;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)),
+                     "n"(kHeadsTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    // weights in flight: value fc1 (256 rows x 128 B) and the first policy chunk
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int idx = tid + 128 * i, r = idx >> 3, c = idx & 7;
+        const uint32_t dst = base + kHW_V + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(P.w1 + r * 64 + c * 8) : "memory");
+    }
+    load_tile_async(base + kHW_0, P.wp, 0, (long long)P.n_chunks * 128, tid);
+    // features: hd [row][cell][plane] float32 -> bf16 operands (policy K index = cell * 2 + plane, the NHWC flatten
+    // order of the Dense layer; value K index = cell), coalesced reads, scattered 2-byte shared-memory stores
+    for (int it = 0; it < 192; ++it) {
+        const int li = tid + 128 * it, r = li / 192, rem = li - r * 192, cell = rem / 3, plane = rem - cell * 3;
+        const long long row = row0 + r;
+        const float f = row < P.n ? __ldg(P.hd + row * 192 + rem) : 0.0f;
+        const __nv_bfloat16 h = __float2bfloat16(f);
+        uint32_t off;
+        if (plane < 2) {
+            const int k = cell * 2 + plane;
+            off = kHA_P + umma_chunk_offset(r, k >> 3) + (uint32_t)((k & 7) * 2);
+        } else {
+            off = kHA_V + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((cell >> 3) ^ (r & 7)) << 4) + (cell & 7) * 2);
+        }
+        *reinterpret_cast<__nv_bfloat16*>(gen + off) = h;
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t phase = 0;
+    const int r = tid;
+    const long long row = row0 + r;
+
+    // ---- value head: hidden = relu(features . W1^T + b1) in TMEM columns 256-511, value = tanh(hidden . w2 + b2)
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            mma_bf16_i(tmem + 256, umma_desc(base + kHA_V + k * 32), umma_desc(base + kHW_V + k * 32), idesc_bf16(128, 256), k > 0);
+        commit_to(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    {
+        float acc = 0.0f;
+#pragma unroll 1
+        for (int cb = 0; cb < 8; ++cb) {
+            uint32_t v[32];
+            tmem_ld32(tmem + lane_base + 256 + cb * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = cb * 32 + j;
+                acc = fmaf(fmaxf(__uint_as_float(v[j]) + __ldg(P.b1 + col), 0.0f), __ldg(P.w2 + col), acc);
+            }
+        }
+        if (row < P.n) P.values[row] = tanhf(acc + __ldg(P.b2));
+    }
+
+    // ---- policy head: two passes over the chunks of 128 logits
+    float m = -INFINITY, ssum = 0.0f, inv = 0.0f;
+    int counter = 0;
+    const int total = 2 * P.n_chunks;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+        for (int c = 0; c < P.n_chunks; ++c, ++counter) {
+            const uint32_t sW = base + kHW_0 + (uint32_t)(counter & 1) * kTileBytes;
+            asm volatile("cp.async.wait_all;\n" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncthreads();  // this chunk's weights landed; everybody is done with the previous accumulator and staging
+            if (counter + 1 < total) {
+                const int nc = (c + 1 == P.n_chunks) ? 0 : c + 1;
+                load_tile_async(base + kHW_0 + (uint32_t)((counter + 1) & 1) * kTileBytes, P.wp, (long long)nc * 128,
+                                (long long)P.n_chunks * 128, tid);
+            }
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t koff = (uint32_t)((k >> 2) * kKBlockBytes + (k & 3) * 32);
+                    mma_bf16_i(tmem, umma_desc(base + kHA_P + koff), umma_desc(sW + koff), idesc_bf16(128, 128), k > 0);
+                }
+                commit_to(bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const int col0 = c * 128;
+#pragma unroll 1
+            for (int cb = 0; cb < 4; ++cb) {
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_base + cb * 32, v);
+                float l[32];
+                float bmax = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = col0 + cb * 32 + j;
+                    l[j] = col < P.n_actions ? __uint_as_float(v[j]) + __ldg(P.bp + col) : -INFINITY;
+                    bmax = fmaxf(bmax, l[j]);
+                }
+                if (pass == 0) {
+                    if (bmax > -INFINITY) {
+                        const float mn = fmaxf(m, bmax);
+                        float part = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) part += __expf(l[j] - mn);
+                        ssum = ssum * __expf(m - mn) + part;
+                        m = mn;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 o;
+                        o.x = __expf(l[4 * q + 0] - m) * inv;
+                        o.y = __expf(l[4 * q + 1] - m) * inv;
+                        o.z = __expf(l[4 * q + 2] - m) * inv;
+                        o.w = __expf(l[4 * q + 3] - m) * inv;
+                        const int ch = cb * 8 + q;
+                        *reinterpret_cast<float4*>(gen + kHStage + r * 512 + ((ch ^ (r & 31)) << 4)) = o;
+                    }
+                }
+            }
+            if (pass == 1) {
+                __syncthreads();
+#pragma unroll 4
+                for (int i = 0; i < 32; ++i) {  // one warp instruction = one whole row of the chunk (512 contiguous bytes)
+                    const int idx = tid + 128 * i, rr = idx >> 5, ch = idx & 31;
+                    const int col = col0 + ch * 4;
+                    if (row0 + rr < P.n && col < P.n_actions)
+                        *reinterpret_cast<float4*>(P.priors + (row0 + rr) * P.n_actions + col) =
+                            *reinterpret_cast<const float4*>(gen + kHStage + rr * 512 + ((ch ^ (rr & 31)) << 4));
+                }
+            }
+        }
+        if (pass == 0) inv = 1.0f / ssum;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kHeadsTmemCols) : "memory");
+}
+
 }  // namespace gemm
 }  // namespace az
 
@@ -217,5 +439,33 @@ extern "C" __attribute__((visibility("default"))) int az_net_conv1x1(const void*
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(y), rows,
         (int)n_tiles);
     if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_conv1x1: launch failed");
+    return AZ_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int az_net_dense_heads(const float* hd, const void* policy_w, const float* policy_b,
+                                                                          const void* value1_w, const float* value1_b,
+                                                                          const float* value2_w, const float* value2_b, int32_t n,
+                                                                          int32_t cells, int32_t n_actions, float* priors,
+                                                                          float* values, void* stream) {
+    using namespace az::gemm;
+    if (n == 0) return AZ_OK;
+    if (!hd || !policy_w || !policy_b || !value1_w || !value1_b || !value2_w || !value2_b || !priors || !values || n < 0)
+        return az::fail_net(AZ_ERR_ARG, "az_net_dense_heads: bad argument");
+    if (cells != 64 || n_actions < 1 || n_actions > 4096 || (n_actions & 3))
+        return az::fail_net(AZ_ERR_ARG, "az_net_dense_heads: built for 64 cells (8x8 boards) and a multiple of 4 actions <= 4096");
+    if ((reinterpret_cast<uintptr_t>(policy_w) | reinterpret_cast<uintptr_t>(value1_w) | reinterpret_cast<uintptr_t>(priors)) & 15)
+        return az::fail_net(AZ_ERR_ARG, "az_net_dense_heads: weights and priors must be 16-byte aligned");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return az::fail_net(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback");
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_dense_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadsSmem) != cudaSuccess)
+            return az::fail_net(AZ_ERR_CUDA, "az_net_dense_heads: shared memory request refused");
+        configured = true;
+    }
+    DenseHeadParams P{hd, static_cast<const __nv_bfloat16*>(policy_w), policy_b, static_cast<const __nv_bfloat16*>(value1_w),
+                      value1_b, value2_w, value2_b, priors, values, n, n_actions, (n_actions + 127) / 128};
+    k_dense_heads<<<(unsigned)((n + 127) / 128), 128, kHeadsSmem, static_cast<cudaStream_t>(stream)>>>(P);
+    if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_dense_heads: launch failed");
     return AZ_OK;
 }

@@ -294,6 +294,16 @@ int az_net_conv1x1(const void *dev_x, const void *dev_w, int64_t rows, int32_t c
 int az_net_head_convs(const void *dev_x, const float *dev_conv_w, const float *dev_conv_b, int32_t n, int32_t cells,
                       int32_t channels, float *dev_out, void *stream);
 
+/* The dense layers of both heads for wide action spaces (chess) in one tcgen05 kernel (csrc/az_gemm.cu): policy
+ * Dense(A) + softmax (model/tensorflow/model.py:86-103) and value Dense(256) + ReLU + Dense(1) + tanh (:129-149) on
+ * the output of az_net_head_convs.
+ *   hd: dev float [n][cells][3]; policy_w: dev bf16 [ceil(A / 128) * 128][2 * cells], rows >= A zero; policy_b: dev float [A];
+ *   value1_w: dev bf16 [256][cells]; value1_b: dev float [256]; value2_w: dev float [256]; value2_b: dev float [1];
+ *   priors_out: dev float [n][A]; values_out: dev float [n].  cells must be 64, A a multiple of 4. */
+int az_net_dense_heads(const float *dev_hd, const void *dev_policy_w, const float *dev_policy_b, const void *dev_value1_w,
+                       const float *dev_value1_b, const float *dev_value2_w, const float *dev_value2_b, int32_t n,
+                       int32_t cells, int32_t n_actions, float *dev_priors_out, float *dev_values_out, void *stream);
+
 /* The three per-tree stages between two passes of the tower in ONE launch (one warp per tree):
  * az_net_heads on the tower output of each tree's pending leaf, az_step with those priors / value (kept in
  * registers), az_net_stem on the newly selected leaf.  Same results as the three calls in sequence.

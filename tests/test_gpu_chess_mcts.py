@@ -281,3 +281,41 @@ def test_entry_point_plays_chess(tmp_path, monkeypatch):
     finally:
         for name in ("custom_alphazero.self_play", "custom_alphazero.mcts.mcts"):
             sys.modules.pop(name, None)  # the next importer gets the Connect-N flavour again
+
+
+def test_fused_dense_heads_against_float64():
+    """az_net_dense_heads (tcgen05: policy GEMM + softmax, value MLP + tanh) against the same arithmetic in float64 on
+    the operands the kernel sees (bf16-rounded features and weights, float32 biases)."""
+    import ctypes
+
+    from az_b200 import native
+
+    torch.manual_seed(2)
+    A = 1880
+    lib = native.lib()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    wp = (torch.randn(A, 128, device="cuda") * 0.5).to(torch.bfloat16)
+    wp_pad = torch.cat([wp, torch.zeros(1920 - A, 128, device="cuda", dtype=torch.bfloat16)]).contiguous()
+    bp = torch.rand(A, device="cuda") * 2 - 1
+    w1 = (torch.randn(256, 64, device="cuda") * 0.2).to(torch.bfloat16).contiguous()
+    b1 = torch.rand(256, device="cuda") - 0.5
+    w2 = torch.randn(256, device="cuda") * 0.2
+    b2 = torch.tensor([0.1], device="cuda")
+    for n in (4096, 1, 127, 129, 300):
+        hd = torch.relu(torch.randn(n, 64, 3, device="cuda")).contiguous()
+        priors = torch.full((n + 1, A), 7.0, device="cuda")
+        values = torch.full((n + 1,), 7.0, device="cuda")
+        native.check(lib.az_net_dense_heads(P(hd), P(wp_pad), P(bp), P(w1), P(b1), P(w2), P(b2), n, 64, A, P(priors), P(values),
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        f = hd.to(torch.bfloat16).double()
+        pf = f[:, :, :2].reshape(n, 128)            # Keras Flatten on [cells][2 planes]
+        vf = f[:, :, 2]
+        ref_p = torch.softmax(pf @ wp.double().t() + bp.double(), dim=-1)
+        ref_v = torch.tanh(torch.relu(vf @ w1.double().t() + b1.double()) @ w2.double() + b2.double())
+        dp = (priors[:n].double() - ref_p).abs().max().item()
+        dv = (values[:n].double() - ref_v).abs().max().item()
+        assert dp <= 2e-6 + 2e-5 * ref_p.max().item(), (n, dp, ref_p.max().item())
+        assert dv <= 2e-5, (n, dv)
+        assert bool((priors[n] == 7.0).all()) and float(values[n]) == 7.0  # nothing written past the last row
+        assert float(ref_p.max()) > 50.0 / A  # sharp rows: the softmax statistics really matter

@@ -18,6 +18,7 @@ AZ_PHASE_IDLE, AZ_PHASE_SEARCH, AZ_PHASE_READY, AZ_PHASE_STALLED = range(4)
 AZ_PHASE_MASK = 0xFF
 AZ_FLAG_POOL_OVERFLOW, AZ_FLAG_LUT_OVERFLOW, AZ_FLAG_ILLEGAL = 1 << 8, 1 << 9, 1 << 10
 AZ_CHESS_ACTIONS, AZ_CHESS_MASK_WORDS, AZ_CHESS_PLANES = 1880, 30, 118
+AZ_DENSE_HEAD_SPLITS = 4
 
 
 class NativeError(RuntimeError):
@@ -119,7 +120,7 @@ SYMBOLS = {
     "az_net_stem": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "az_net_heads": (ctypes.c_int, [_P, ctypes.POINTER(AzHeadWeights), _I, _I, _I, _I, _P, _P, _P]),
     "az_net_conv1x1": (ctypes.c_int, [_P, _P, ctypes.c_int64, _I, _P, _P]),
-    "az_net_dense_heads": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "az_net_dense_heads": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "az_net_head_convs": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "az_advance_fused": (ctypes.c_int, [_P, _P, ctypes.POINTER(AzHeadWeights), _P, _P, _P, _P, _P]),
     "az_debug_dirichlet": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_double, _I, _I, _P, _P]),

@@ -242,9 +242,12 @@ class InferenceNet(nn.Module):
             if priors_out is None:
                 priors_out = torch.empty((B, self.n_actions), dtype=torch.float32, device=hd.device)
                 values_out = torch.empty(B, dtype=torch.float32, device=hd.device)
+            from .native import AZ_DENSE_HEAD_SPLITS
+
+            scratch = torch.empty((B, AZ_DENSE_HEAD_SPLITS, 2), dtype=torch.float32, device=hd.device)
             check(lib().az_net_dense_heads(_ptr(hd), _ptr(self.pfc_w16), _ptr(self.pfc_b), _ptr(self.v1_w16), _ptr(self.v1_b),
                                            _ptr(self.v2_w), _ptr(self.v2_b), B, 64, self.n_actions, _ptr(priors_out),
-                                           _ptr(values_out), _stream()))
+                                           _ptr(values_out), _ptr(scratch), _stream()))
             return priors_out, values_out
         p = hd[..., :2].reshape(B, -1)
         v = hd[..., 2].reshape(B, -1)

@@ -246,14 +246,21 @@ struct DenseHeadParams {
     const float* b2;           // [1]
     float* priors;             // [n][n_actions]
     float* values;             // [n]
-    int n, n_actions, n_chunks;
+    float2* stats;             // [n][n_splits] partial softmax statistics (running maximum, sum of exp) per column split
+    int n, n_actions, n_chunks, chunks_per_split, n_splits;
 };
 
+// grid = (row tiles of 128 positions, column splits).  PASS 0 computes this split's logits and leaves their (max, sum
+// exp) in P.stats (split 0 also does the value head); PASS 1 combines the splits' statistics, recomputes the logits and
+// writes the normalised priors.  Thread-per-row alone would be 4096 threads for 7.7 M logits: the column splits are
+// what fills the 148 SMs.
+template <int PASS>
 __global__ void __launch_bounds__(128, 1) k_dense_heads(DenseHeadParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ float s_bias[8 * 128];  // chunks_per_split <= 8
+    const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bar = smem_u32(&s_bar);
@@ -276,22 +283,48 @@ __global__ void __launch_bounds__(128, 1) k_dense_heads(DenseHeadParams P) {
         const uint32_t dst = base + kHW_V + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(P.w1 + r * 64 + c * 8) : "memory");
     }
-    load_tile_async(base + kHW_0, P.wp, 0, (long long)P.n_chunks * 128, tid);
+    const int c_begin = blockIdx.y * P.chunks_per_split;
+    const int c_end = min(P.n_chunks, c_begin + P.chunks_per_split);
+    const bool do_value = PASS == 0 && blockIdx.y == 0;
+    load_tile_async(base + kHW_0, P.wp, (long long)c_begin * 128, (long long)P.n_chunks * 128, tid);
+    // this split's slice of the policy bias -> shared memory (read 128 times per chunk by every thread)
+    for (int i = tid; i < (c_end - c_begin) * 128; i += 128) {
+        const int col = c_begin * 128 + i;
+        s_bias[i] = col < P.n_actions ? __ldg(P.bp + col) : 0.0f;
+    }
     // features: hd [row][cell][plane] float32 -> bf16 operands (policy K index = cell * 2 + plane, the NHWC flatten
-    // order of the Dense layer; value K index = cell), coalesced reads, scattered 2-byte shared-memory stores
-    for (int it = 0; it < 192; ++it) {
-        const int li = tid + 128 * it, r = li / 192, rem = li - r * 192, cell = rem / 3, plane = rem - cell * 3;
-        const long long row = row0 + r;
-        const float f = row < P.n ? __ldg(P.hd + row * 192 + rem) : 0.0f;
-        const __nv_bfloat16 h = __float2bfloat16(f);
-        uint32_t off;
-        if (plane < 2) {
-            const int k = cell * 2 + plane;
-            off = kHA_P + umma_chunk_offset(r, k >> 3) + (uint32_t)((k & 7) * 2);
-        } else {
-            off = kHA_V + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((cell >> 3) ^ (r & 7)) << 4) + (cell & 7) * 2);
+    // order of the Dense layer; value K index = cell).  The tile's 128 x 192 floats are contiguous: 128-bit loads, twelve
+    // in flight per thread, then scattered 2-byte shared-memory stores.
+    {
+        const float4* src = reinterpret_cast<const float4*>(P.hd + row0 * 192);
+        const long long valid4 = (min((long long)P.n, row0 + 128) - row0) * 48;  // float4s of the tile that exist
+#pragma unroll 1
+        for (int it0 = 0; it0 < 48; it0 += 12) {
+            float4 f[12];
+#pragma unroll
+            for (int u = 0; u < 12; ++u) {
+                const int i4 = tid + 128 * (it0 + u);
+                f[u] = i4 < valid4 ? __ldg(src + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 12; ++u) {
+                const int i4 = tid + 128 * (it0 + u);
+                const float vals[4] = {f[u].x, f[u].y, f[u].z, f[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int li = i4 * 4 + e, r = li / 192, rem = li - r * 192, cell = rem / 3, plane = rem - cell * 3;
+                    uint32_t off;
+                    if (plane < 2) {
+                        const int k = cell * 2 + plane;
+                        off = kHA_P + umma_chunk_offset(r, k >> 3) + (uint32_t)((k & 7) * 2);
+                    } else {
+                        if (!do_value) continue;
+                        off = kHA_V + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((cell >> 3) ^ (r & 7)) << 4) + (cell & 7) * 2);
+                    }
+                    *reinterpret_cast<__nv_bfloat16*>(gen + off) = __float2bfloat16(vals[e]);
+                }
+            }
         }
-        *reinterpret_cast<__nv_bfloat16*>(gen + off) = h;
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -305,6 +338,7 @@ __global__ void __launch_bounds__(128, 1) k_dense_heads(DenseHeadParams P) {
     const long long row = row0 + r;
 
     // ---- value head: hidden = relu(features . W1^T + b1) in TMEM columns 256-511, value = tanh(hidden . w2 + b2)
+    if (do_value) {
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -328,25 +362,33 @@ __global__ void __launch_bounds__(128, 1) k_dense_heads(DenseHeadParams P) {
         }
         if (row < P.n) P.values[row] = tanhf(acc + __ldg(P.b2));
     }
+    }
 
-    // ---- policy head: two passes over the chunks of 128 logits
+    // ---- policy head: this split's chunks of 128 logits
     float m = -INFINITY, ssum = 0.0f, inv = 0.0f;
+    if (PASS == 1 && row < P.n) {  // combine the splits' statistics of this row
+        for (int sp = 0; sp < P.n_splits; ++sp) m = fmaxf(m, P.stats[row * P.n_splits + sp].x);
+        for (int sp = 0; sp < P.n_splits; ++sp) {
+            const float2 st = P.stats[row * P.n_splits + sp];
+            if (st.x > -INFINITY) ssum += st.y * __expf(st.x - m);
+        }
+        inv = 1.0f / ssum;
+        ssum = 0.0f;
+    }
     int counter = 0;
-    const int total = 2 * P.n_chunks;
+    const int total = c_end - c_begin;
+    constexpr int pass = PASS;
+    {
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll 1
-        for (int c = 0; c < P.n_chunks; ++c, ++counter) {
+        for (int c = c_begin; c < c_end; ++c, ++counter) {
             const uint32_t sW = base + kHW_0 + (uint32_t)(counter & 1) * kTileBytes;
             asm volatile("cp.async.wait_all;\n" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             __syncthreads();  // this chunk's weights landed; everybody is done with the previous accumulator and staging
-            if (counter + 1 < total) {
-                const int nc = (c + 1 == P.n_chunks) ? 0 : c + 1;
-                load_tile_async(base + kHW_0 + (uint32_t)((counter + 1) & 1) * kTileBytes, P.wp, (long long)nc * 128,
+            if (counter + 1 < total)
+                load_tile_async(base + kHW_0 + (uint32_t)((counter + 1) & 1) * kTileBytes, P.wp, (long long)(c + 1) * 128,
                                 (long long)P.n_chunks * 128, tid);
-            }
             if (tid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
@@ -369,7 +411,7 @@ __global__ void __launch_bounds__(128, 1) k_dense_heads(DenseHeadParams P) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int col = col0 + cb * 32 + j;
-                    l[j] = col < P.n_actions ? __uint_as_float(v[j]) + __ldg(P.bp + col) : -INFINITY;
+                    l[j] = col < P.n_actions ? __uint_as_float(v[j]) + s_bias[col - c_begin * 128] : -INFINITY;
                     bmax = fmaxf(bmax, l[j]);
                 }
                 if (pass == 0) {
@@ -406,8 +448,8 @@ __global__ void __launch_bounds__(128, 1) k_dense_heads(DenseHeadParams P) {
                 }
             }
         }
-        if (pass == 0) inv = 1.0f / ssum;
     }
+    if (PASS == 0 && row < P.n) P.stats[row * P.n_splits + blockIdx.y] = make_float2(m, ssum);
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kHeadsTmemCols) : "memory");
@@ -446,10 +488,11 @@ extern "C" __attribute__((visibility("default"))) int az_net_dense_heads(const f
                                                                           const void* value1_w, const float* value1_b,
                                                                           const float* value2_w, const float* value2_b, int32_t n,
                                                                           int32_t cells, int32_t n_actions, float* priors,
-                                                                          float* values, void* stream) {
+                                                                          float* values, float* stats_scratch, void* stream) {
     using namespace az::gemm;
     if (n == 0) return AZ_OK;
-    if (!hd || !policy_w || !policy_b || !value1_w || !value1_b || !value2_w || !value2_b || !priors || !values || n < 0)
+    if (!hd || !policy_w || !policy_b || !value1_w || !value1_b || !value2_w || !value2_b || !priors || !values ||
+        !stats_scratch || n < 0)
         return az::fail_net(AZ_ERR_ARG, "az_net_dense_heads: bad argument");
     if (cells != 64 || n_actions < 1 || n_actions > 4096 || (n_actions & 3))
         return az::fail_net(AZ_ERR_ARG, "az_net_dense_heads: built for 64 cells (8x8 boards) and a multiple of 4 actions <= 4096");
@@ -459,13 +502,21 @@ extern "C" __attribute__((visibility("default"))) int az_net_dense_heads(const f
     if (cudaGetDevice(&dev) != cudaSuccess) return az::fail_net(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback");
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_dense_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadsSmem) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_dense_heads<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadsSmem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_dense_heads<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadsSmem) != cudaSuccess)
             return az::fail_net(AZ_ERR_CUDA, "az_net_dense_heads: shared memory request refused");
         configured = true;
     }
+    if (reinterpret_cast<uintptr_t>(stats_scratch) & 7) return az::fail_net(AZ_ERR_ARG, "az_net_dense_heads: scratch must be 8-byte aligned");
+    const int n_chunks = (n_actions + 127) / 128, n_splits = AZ_DENSE_HEAD_SPLITS;
+    const int cps = (n_chunks + n_splits - 1) / n_splits;  // <= 8 since n_actions <= 4096
     DenseHeadParams P{hd, static_cast<const __nv_bfloat16*>(policy_w), policy_b, static_cast<const __nv_bfloat16*>(value1_w),
-                      value1_b, value2_w, value2_b, priors, values, n, n_actions, (n_actions + 127) / 128};
-    k_dense_heads<<<(unsigned)((n + 127) / 128), 128, kHeadsSmem, static_cast<cudaStream_t>(stream)>>>(P);
+                      value1_b, value2_w, value2_b, priors, values, reinterpret_cast<float2*>(stats_scratch), n, n_actions,
+                      n_chunks, cps, n_splits};
+    const dim3 grid((unsigned)((n + 127) / 128), (unsigned)n_splits);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    k_dense_heads<0><<<grid, 128, kHeadsSmem, s>>>(P);
+    k_dense_heads<1><<<grid, 128, kHeadsSmem, s>>>(P);
     if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_dense_heads: launch failed");
     return AZ_OK;
 }

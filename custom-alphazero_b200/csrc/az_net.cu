@@ -267,15 +267,22 @@ __global__ void __launch_bounds__(256) k_head_convs(const __nv_bfloat16* __restr
     const float b0 = b[0], b1 = b[1], b2 = b[2];
     const long long warp = (long long)(blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = (long long)(gridDim.x * blockDim.x) >> 5;
-    for (long long base = 2 * warp; base < rows; base += 2 * n_warps) {  // two cells per warp and iteration
-        const long long row = base + sub;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        if (row < rows) {
-            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(x + row * 128) + l16);
-            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    constexpr int U = 4;  // cells in flight per half-warp: the kernel is latency bound with one
+    for (long long base = 2 * U * warp; base < rows; base += 2 * U * n_warps) {  // 2 * U cells per warp and iteration
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long row = base + 2 * u + sub;
+            v[u] = row < rows ? __ldcs(reinterpret_cast<const uint4*>(x + row * 128) + l16) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long row = base + 2 * u + sub;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float lo = __uint_as_float(u[j] << 16), hi = __uint_as_float(u[j] & 0xffff0000u);
+                const float lo = __uint_as_float(w4[j] << 16), hi = __uint_as_float(w4[j] & 0xffff0000u);
                 a0 = fmaf(lo, wr[0][2 * j], a0);
                 a0 = fmaf(hi, wr[0][2 * j + 1], a0);
                 a1 = fmaf(lo, wr[1][2 * j], a1);
@@ -283,20 +290,21 @@ __global__ void __launch_bounds__(256) k_head_convs(const __nv_bfloat16* __restr
                 a2 = fmaf(lo, wr[2][2 * j], a2);
                 a2 = fmaf(hi, wr[2][2 * j + 1], a2);
             }
-        }
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-        }
-        if (l16 == 0 && row < rows) {
-            out[row * 3 + 0] = fmaxf(a0 + b0, 0.f);
-            out[row * 3 + 1] = fmaxf(a1 + b1, 0.f);
-            out[row * 3 + 2] = fmaxf(a2 + b2, 0.f);
+            for (int o = 8; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            }
+            if (l16 == 0 && row < rows) {
+                out[row * 3 + 0] = fmaxf(a0 + b0, 0.f);
+                out[row * 3 + 1] = fmaxf(a1 + b1, 0.f);
+                out[row * 3 + 2] = fmaxf(a2 + b2, 0.f);
+            }
         }
     }
 }
+
 
 }  // namespace az
 
@@ -356,7 +364,7 @@ AZ_API int az_net_head_convs(const void* x, const float* conv_w, const float* co
     if (cudaGetDevice(&dev) != cudaSuccess) return fail_net(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback");
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long rows = (long long)n * cells;
-    long long grid = (rows + 15) / 16;  // 8 warps x 2 cells per block and iteration
+    long long grid = (rows + 63) / 64;  // 8 warps x 8 cells per block and iteration
     if (grid > (long long)sms * 8) grid = (long long)sms * 8;
     k_head_convs<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), conv_w,
                                                                                conv_b, rows, out);

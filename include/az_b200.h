@@ -299,10 +299,13 @@ int az_net_head_convs(const void *dev_x, const float *dev_conv_w, const float *d
  * the output of az_net_head_convs.
  *   hd: dev float [n][cells][3]; policy_w: dev bf16 [ceil(A / 128) * 128][2 * cells], rows >= A zero; policy_b: dev float [A];
  *   value1_w: dev bf16 [256][cells]; value1_b: dev float [256]; value2_w: dev float [256]; value2_b: dev float [1];
- *   priors_out: dev float [n][A]; values_out: dev float [n].  cells must be 64, A a multiple of 4. */
+ *   priors_out: dev float [n][A]; values_out: dev float [n]; scratch: dev float [n][AZ_DENSE_HEAD_SPLITS][2] (partial
+ *   softmax statistics between the two launches this call makes).  cells must be 64, A a multiple of 4. */
+#define AZ_DENSE_HEAD_SPLITS 4
 int az_net_dense_heads(const float *dev_hd, const void *dev_policy_w, const float *dev_policy_b, const void *dev_value1_w,
                        const float *dev_value1_b, const float *dev_value2_w, const float *dev_value2_b, int32_t n,
-                       int32_t cells, int32_t n_actions, float *dev_priors_out, float *dev_values_out, void *stream);
+                       int32_t cells, int32_t n_actions, float *dev_priors_out, float *dev_values_out, float *dev_scratch,
+                       void *stream);
 
 /* The three per-tree stages between two passes of the tower in ONE launch (one warp per tree):
  * az_net_heads on the tower output of each tree's pending leaf, az_step with those priors / value (kept in

@@ -305,8 +305,9 @@ def test_fused_dense_heads_against_float64():
         hd = torch.relu(torch.randn(n, 64, 3, device="cuda")).contiguous()
         priors = torch.full((n + 1, A), 7.0, device="cuda")
         values = torch.full((n + 1,), 7.0, device="cuda")
+        scratch = torch.empty((n, native.AZ_DENSE_HEAD_SPLITS, 2), device="cuda")
         native.check(lib.az_net_dense_heads(P(hd), P(wp_pad), P(bp), P(w1), P(b1), P(w2), P(b2), n, 64, A, P(priors), P(values),
-                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                            P(scratch), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         torch.cuda.synchronize()
         f = hd.to(torch.bfloat16).double()
         pf = f[:, :, :2].reshape(n, 128)            # Keras Flatten on [cells][2 planes]

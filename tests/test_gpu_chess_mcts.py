@@ -320,3 +320,42 @@ def test_fused_dense_heads_against_float64():
         assert dv <= 2e-5, (n, dv)
         assert bool((priors[n] == 7.0).all()) and float(values[n]) == 7.0  # nothing written past the last row
         assert float(ref_p.max()) > 50.0 / A  # sharp rows: the softmax statistics really matter
+
+
+def test_rings_and_pools_fail_loudly_and_recover():
+    """A full sample ring leaves trees READY until the host drains it; a full finished-game ring parks the game
+    (STALLED) and delivers it afterwards; an exhausted node pool sets the sticky flag instead of corrupting the tree."""
+    from az_b200 import native
+    from az_b200.chess_engine import ChessTreeEngine
+    from az_b200.native import NativeError
+
+    want = cr.mcts_game(sims=16, evaluator="hash", max_plies=6)
+    for sample_cap, fin_cap, expect in ((4, 8, native.AZ_PHASE_READY), (8, 2, native.AZ_PHASE_STALLED)):
+        eng = ChessTreeEngine(n_trees=6, sims_per_move=16, eval_mode="hash", prior_mode="f64", max_plies=6,
+                              sample_capacity=sample_cap, fin_capacity=fin_cap)
+        plies, fin = {}, {}
+        seen = False
+        for _ in range(200):
+            if bool((eng.phases() == native.AZ_PHASE_IDLE).all()):
+                break
+            eng.search()
+            eng.move()
+            seen |= bool((eng.phases() == expect).any())  # READY: no ring slot, the move waits; STALLED: game over, ring full
+            assert int(eng.view("smp_count")[0]) <= sample_cap and int(eng.view("fin_count")[0]) <= fin_cap
+            d = eng.drain()
+            for i in range(len(d["k"])):
+                plies.setdefault(int(d["game"][i]), []).append((int(d["ply"][i]), int(d["k"][i]), d["act"][i].copy(),
+                                                                d["n"][i].copy(), int(d["choice"][i])))
+            for g, ln, r in zip(d["fin_game"], d["fin_len"], d["fin_result"]):
+                fin[int(g)] = (int(ln), int(r))
+        eng.check_status()
+        assert seen and sorted(fin) == list(range(6)), (sample_cap, fin_cap)
+        for g in range(6):
+            _assert_game_equals(sorted(plies[g], key=lambda p: p[0]), fin[g], want)
+    # node pool too small for one search: flagged, never silent
+    small = ChessTreeEngine(n_trees=2, sims_per_move=64, eval_mode="uniform", prior_mode="f64", max_plies=4, node_capacity=256)
+    small.search()
+    torch.cuda.synchronize()
+    assert int(small.view("status")[0]) & native.AZ_FLAG_POOL_OVERFLOW
+    with pytest.raises(NativeError, match="node pool exhausted"):
+        small.check_status()

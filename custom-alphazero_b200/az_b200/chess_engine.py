@@ -128,9 +128,12 @@ class ChessTreeEngine:
             assert priors.is_contiguous() and values.is_contiguous() and priors.dtype == values.dtype
             assert priors.shape == (self.n_trees, N_ACTIONS)
             eval_dtype = {torch.float32: native.AZ_F32, torch.float64: native.AZ_F64}[priors.dtype]
-        assert states_out.dtype == torch.bfloat16 and states_out.is_contiguous() and leaf_valid_out.dtype == torch.int32
-        stride = states_out.shape[-1]  # >= 118: extra planes are written as zeros (channel padding for the stem)
-        assert states_out.shape == (self.n_trees, 8, 8, stride) and stride >= PLANES
+        assert leaf_valid_out.dtype == torch.int32
+        stride = PLANES
+        if states_out is not None:  # None: no planes, the caller runs az_chess_stem on view("leaf_pos")
+            assert states_out.dtype == torch.bfloat16 and states_out.is_contiguous()
+            stride = states_out.shape[-1]  # >= 118: extra planes are written as zeros (channel padding for the stem)
+            assert states_out.shape == (self.n_trees, 8, 8, stride) and stride >= PLANES
         check(lib().az_chess_step(self._h, _ptr(priors), _ptr(values), eval_dtype, _ptr(states_out), stride,
                                   _ptr(leaf_valid_out), _stream()))
 

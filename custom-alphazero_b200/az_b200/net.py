@@ -156,6 +156,22 @@ class InferenceNet(nn.Module):
             self.v1_w16 = nn.Parameter(net.value_fc1.weight.detach().to(device=device, dtype=torch.bfloat16).contiguous(),
                                        requires_grad=False)
         self.fused_dense_heads = True  # az_net_dense_heads where it applies (GPU, 64 cells, wide policy); else cuBLAS
+        if net.in_planes == 118 and net.height == 8 and net.width == 8 and net.filters == 128:
+            # az_chess_stem: the stem restricted to the planes that vary on the self-play path (current entry 98-111 and
+            # scalars 112-117, padded to 24) + the per-cell constant (bias + the initial position in history entry 6:
+            # planes 84-97), from the same bf16-rounded weights the cuDNN stem uses
+            w16 = self.stem_w.detach().float()  # [128, 118, 3, 3]
+            red = torch.zeros((net.filters, 24, 3, 3), dtype=torch.float32, device=w16.device)
+            red[:, :14] = w16[:, 98:112]
+            red[:, 14:20] = w16[:, 112:118]
+            self.chess_stem_w = nn.Parameter(red.reshape(net.filters, 24, 9).contiguous(), requires_grad=False)
+            from .chess import position_from_fen, unpack_position
+
+            arr = torch.as_tensor(unpack_position(position_from_fen())["array"].astype("int64"))
+            start = torch.zeros((1, 14, 8, 8), dtype=torch.float32, device=w16.device)
+            start[0, :13] = F.one_hot(arr % 13, 13).permute(2, 0, 1).float()  # np.eye(13)[array] with negative wrap
+            cmap = F.conv2d(start, w16[:, 84:98], self.stem_b.detach().float(), padding=1)  # [1, 128, 8, 8]
+            self.chess_stem_map = nn.Parameter(cmap[0].permute(1, 2, 0).reshape(64, net.filters).contiguous(), requires_grad=False)
         self.v1_w, self.v1_b = f32(net.value_fc1.weight), f32(net.value_fc1.bias)
         # az_net_heads wants the policy rows padded to an odd stride and the value weights transposed
         # (bank-conflict-free shared memory images that the kernel copies verbatim)
@@ -211,17 +227,7 @@ class InferenceNet(nn.Module):
             h0 = torch.cudnn_convolution_relu(x.contiguous(memory_format=torch.channels_last),
                                               self.stem_w_pad if self.in_pad else self.stem_w, self.stem_b,
                                               (1, 1), (1, 1), (1, 1), 1)
-            xm = self.tower(h0.permute(0, 2, 3, 1))
-            hd = torch.empty((B, self.height, self.width, 3), dtype=torch.float32, device=xm.device)
-            if self.filters == 128:  # hand-written: one pass over the tower output, float32 accumulation
-                from .engine import _ptr, _stream
-                from .native import check, lib
-
-                check(lib().az_net_head_convs(_ptr(xm), _ptr(self.head_w32), _ptr(self.head_b32), B,
-                                              self.height * self.width, self.filters, _ptr(hd), _stream()))
-            else:
-                hd = F.relu_(F.linear(xm.float(), self.head_w32, self.head_b32))
-            xf = None
+            return self.forward_from_stem(h0.permute(0, 2, 3, 1), priors_out, values_out)
         else:
             x = F.relu_(F.conv2d(x, self.stem_w, self.stem_b, padding=1))
             for i in range(self.depth):
@@ -231,27 +237,43 @@ class InferenceNet(nn.Module):
                 y += F.conv2d(x, wp)
                 x = F.relu_(y)
             xf = x.permute(0, 2, 3, 1).float()  # [B, H, W, C]
-        if xf is not None:
-            hd = F.relu_(F.linear(xf, self.head_w32, self.head_b32))  # 1x1 convs: [B, H, W, 3]
-        if (xf is None and self.n_actions > 128 and self.fused_dense_heads and self.filters == 128
+        hd = F.relu_(F.linear(xf, self.head_w32, self.head_b32))  # 1x1 convs: [B, H, W, 3]
+        return self._dense_heads_library(hd, False, priors_out, values_out)
+
+    @torch.no_grad()
+    def forward_from_stem(self, h0, priors_out=None, values_out=None):
+        """The net after its stem, GPU bf16 route for shapes the fused Connect-N kernels do not cover (chess): h0
+        [B, H, W, 128] bf16 NHWC (cuDNN stem or az_chess_stem) -> cuDNN fused-epilogue tower -> az_net_head_convs ->
+        az_net_dense_heads (or cuBLAS)."""
+        from .engine import _ptr, _stream
+        from .native import AZ_DENSE_HEAD_SPLITS, check, lib
+
+        B = h0.shape[0]
+        xm = self.tower(h0)
+        if self.filters == 128:  # hand-written: one pass over the tower output, float32 accumulation
+            hd = torch.empty((B, self.height, self.width, 3), dtype=torch.float32, device=xm.device)
+            check(lib().az_net_head_convs(_ptr(xm), _ptr(self.head_w32), _ptr(self.head_b32), B,
+                                          self.height * self.width, self.filters, _ptr(hd), _stream()))
+        else:
+            hd = F.relu_(F.linear(xm.float(), self.head_w32, self.head_b32))
+        if (self.n_actions > 128 and self.fused_dense_heads and self.filters == 128
                 and self.height * self.width == 64 and self.n_actions % 4 == 0 and self.v1_w.shape[0] == 256):
             # chess: both heads' dense layers, softmax and tanh in one tcgen05 kernel
-            from .engine import _ptr, _stream
-            from .native import check, lib
-
             if priors_out is None:
                 priors_out = torch.empty((B, self.n_actions), dtype=torch.float32, device=hd.device)
                 values_out = torch.empty(B, dtype=torch.float32, device=hd.device)
-            from .native import AZ_DENSE_HEAD_SPLITS
-
             scratch = torch.empty((B, AZ_DENSE_HEAD_SPLITS, 2), dtype=torch.float32, device=hd.device)
             check(lib().az_net_dense_heads(_ptr(hd), _ptr(self.pfc_w16), _ptr(self.pfc_b), _ptr(self.v1_w16), _ptr(self.v1_b),
                                            _ptr(self.v2_w), _ptr(self.v2_b), B, 64, self.n_actions, _ptr(priors_out),
                                            _ptr(values_out), _ptr(scratch), _stream()))
             return priors_out, values_out
+        return self._dense_heads_library(hd, True, priors_out, values_out)
+
+    def _dense_heads_library(self, hd, gpu_bf16, priors_out, values_out):
+        B = hd.shape[0]
         p = hd[..., :2].reshape(B, -1)
         v = hd[..., 2].reshape(B, -1)
-        if xf is None and self.n_actions > 128:
+        if gpu_bf16 and self.n_actions > 128:
             # wide policy layer without the fused kernel: bf16 operands on the tensor cores, float32 accumulation and softmax
             logits = F.linear(p.to(torch.bfloat16), self.pfc_w16[: self.n_actions]).float() + self.pfc_b
         else:
@@ -323,6 +345,17 @@ class InferenceNet(nn.Module):
         out = torch.empty_like(xn)
         check(lib().az_net_conv1x1(_ptr(xn), _ptr(wp), xn.numel() // self.filters, self.filters, _ptr(out), _stream()))
         return out.permute(0, 3, 1, 2)
+
+    @torch.no_grad()
+    def chess_stem(self, positions):
+        """positions int64 [B, 8] (az_chess_pos) on the GPU -> stem output [B, 8, 8, 128] bf16 (az_chess_stem)."""
+        from .engine import _ptr, _stream
+        from .native import check, lib
+
+        B = positions.shape[0]
+        out = torch.empty((B, 8, 8, self.filters), dtype=torch.bfloat16, device=positions.device)
+        check(lib().az_chess_stem(_ptr(positions), B, _ptr(self.chess_stem_w), _ptr(self.chess_stem_map), _ptr(out), _stream()))
+        return out
 
     def load_from(self, net: PolicyValueNet):
         """Refreshes the folded weights in place (after a training step / weight broadcast): the CUDA

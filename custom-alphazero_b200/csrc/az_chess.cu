@@ -17,6 +17,7 @@
 
 #include "../../include/az_b200.h"
 #include "az_chess.cuh"
+#include "az_mma.cuh"
 #include "az_tree.cuh"
 
 namespace az {
@@ -168,6 +169,108 @@ __global__ void __launch_bounds__(128) k_chess_encode(const Pos* pos, const Pos*
     const Pos cur = load_cpos(pos + i);
     stage_history(cur, hist ? hist + (size_t)i * 7 : nullptr, s_e[warp], lane);
     encode_planes<T>(s_e[warp], out + (size_t)i * 64 * kPlanes, lane);
+}
+
+// ------------------------------------------------------------------------------------------ stem from bitboards
+// Stem of the net (Conv3x3(118 -> 128) + BN + ReLU, model/tensorflow/model.py:36-46) for leaves of the self-play
+// path, computed straight from the 64-byte positions - the 15 kB plane tensor is never written or read.  On that path
+// Board.full_state is six all-zero history entries, the state of the initial position and the current state (see
+// oracle/chess_ref.py), so of the 118 input planes only the current entry's 14 and the 6 scalar planes vary: the
+// initial position's contribution and the bias are a per-cell constant map (host-computed from the weights), and the
+// convolution that remains has 20 input planes (24 with padding): K = 9 taps x 24 instead of 9 x 118.
+// Implicit GEMM per position on mma.sync (m16n8k16 for planes 0-15 of a tap, m16n8k8 for planes 16-23), A fragments
+// read from a zero-bordered 10 x 10 copy of the position in shared memory (12 words per cell: conflict free), the
+// warp's weights (32 output channels) in 108 registers; block = 4 warps = the 128 output channels of one position.
+__device__ __forceinline__ void mma_1688(float (&d)[4], const uint32_t (&a)[2], uint32_t b) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(b));
+}
+
+constexpr int kStemPlanes = 24;                 // 14 piece / repetition planes, 6 scalar planes, 4 zero planes
+constexpr int kStemWords = kStemPlanes / 2;     // 32-bit words per cell
+constexpr int kStemPad = 100;                   // 10 x 10 zero-bordered board
+
+__global__ void __launch_bounds__(128) k_chess_stem(const Pos* __restrict__ pos, int n, const float* __restrict__ w,
+                                                    const float* __restrict__ cmap, __nv_bfloat16* __restrict__ out) {
+    __shared__ uint32_t s_in[4][kStemPad * kStemWords];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    uint32_t* sw = s_in[warp];
+    for (int i = lane; i < kStemPad * kStemWords; i += 32) sw[i] = 0u;
+    // B fragments of this warp's 32 output channels: w [128][24 planes][9 taps] float32 (BN folded, reduced plane set)
+    uint32_t b16[9][4][2], b8[9][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const float* wc = w + (size_t)(warp * 32 + nt * 8 + g) * kStemPlanes * 9;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            b16[tap][nt][0] = az::pack_bf16(wc[(2 * t4) * 9 + tap], wc[(2 * t4 + 1) * 9 + tap]);
+            b16[tap][nt][1] = az::pack_bf16(wc[(2 * t4 + 8) * 9 + tap], wc[(2 * t4 + 9) * 9 + tap]);
+            b8[tap][nt] = az::pack_bf16(wc[(2 * t4 + 16) * 9 + tap], wc[(2 * t4 + 17) * 9 + tap]);
+        }
+    }
+    __syncwarp();
+    for (int t = blockIdx.x; t < n; t += gridDim.x) {
+        const Pos p = load_cpos(pos + t);
+        __syncwarp();
+        // the position's 20 planes into the padded board: lane = cell (two per lane)
+        const bool black = black_to_move(p);
+        const int own_k = black ? 4 : 1, own_q = black ? 8 : 2, opp_k = black ? 1 : 4, opp_q = black ? 2 : 8;
+        const uint32_t one = 0x3f80u;  // bf16 1.0
+        const uint32_t s01 = ((p.meta & own_q) ? one : 0u) | ((p.meta & own_k) ? one << 16 : 0u);          // planes 14, 15
+        const uint32_t s23 = ((p.meta & opp_q) ? one : 0u) | ((p.meta & opp_k) ? one << 16 : 0u);          // planes 16, 17
+        const uint32_t s45 = az::pack_bf16((float)fullmove(p), (float)halfmove(p));                           // planes 18, 19
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int cell = lane + 32 * half;
+            const int sq = ((7 - (cell >> 3)) << 3) | (cell & 7);
+            uint32_t* c = sw + (((cell >> 3) + 1) * 10 + (cell & 7) + 1) * kStemWords;
+            const int pl = piece_plane(piece_at(p, sq));  // 0 = empty ... 12; plane 13 (repetition) stays 0
+#pragma unroll
+            for (int wd = 0; wd < 7; ++wd) c[wd] = (pl >> 1) == wd ? (one << (16 * (pl & 1))) : 0u;
+            c[7] = s01;
+            c[8] = s23;
+            c[9] = s45;
+        }
+        __syncwarp();
+        __nv_bfloat16* o = out + (size_t)t * 64 * 128 + warp * 32 + t4 * 2;
+        const float* cm = cmap + warp * 32 + t4 * 2;
+#pragma unroll 1
+        for (int mt = 0; mt < 4; ++mt) {
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+            const uint32_t* a0p = sw + ((r0 >> 3) * 10 + (r0 & 7)) * kStemWords;
+            const uint32_t* a1p = sw + ((r1 >> 3) * 10 + (r1 & 7)) * kStemWords;
+            float acc[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int toff = ((tap / 3) * 10 + tap % 3) * kStemWords;
+                uint32_t a[4], a8[2];
+                a[0] = a0p[toff + t4];
+                a[1] = a1p[toff + t4];
+                a[2] = a0p[toff + t4 + 4];
+                a[3] = a1p[toff + t4 + 4];
+                a8[0] = a0p[toff + t4 + 8];
+                a8[1] = a1p[toff + t4 + 8];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    az::mma_16816(acc[nt], a, b16[tap][nt]);
+                    mma_1688(acc[nt], a8, b8[tap][nt]);
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float2 c0 = *reinterpret_cast<const float2*>(cm + (size_t)r0 * 128 + nt * 8);
+                const float2 c1 = *reinterpret_cast<const float2*>(cm + (size_t)r1 * 128 + nt * 8);
+                *reinterpret_cast<uint32_t*>(o + (size_t)r0 * 128 + nt * 8) =
+                    az::pack_bf16(fmaxf(acc[nt][0] + c0.x, 0.f), fmaxf(acc[nt][1] + c0.y, 0.f));
+                *reinterpret_cast<uint32_t*>(o + (size_t)r1 * 128 + nt * 8) =
+                    az::pack_bf16(fmaxf(acc[nt][2] + c1.x, 0.f), fmaxf(acc[nt][3] + c1.y, 0.f));
+            }
+        }
+    }
 }
 
 constexpr int kPerftMaxDepth = 8;
@@ -482,8 +585,9 @@ AZ_API int az_chess_search(az_chess_engine* e, void* stream) {
 
 AZ_API int az_chess_step(az_chess_engine* e, const void* priors, const void* values, int32_t eval_dtype, void* states_out,
                          int32_t plane_stride, int32_t* leaf_valid_out, void* stream) {
-    if (!e || !states_out || !leaf_valid_out) return az::fail_net(AZ_ERR_ARG, "az_chess_step: null argument");
-    if (plane_stride < kPlanes || plane_stride > 256) return az::fail_net(AZ_ERR_ARG, "az_chess_step: plane_stride must be in [118, 256]");
+    if (!e || !leaf_valid_out) return az::fail_net(AZ_ERR_ARG, "az_chess_step: null argument");
+    if (states_out && (plane_stride < kPlanes || plane_stride > 256))
+        return az::fail_net(AZ_ERR_ARG, "az_chess_step: plane_stride must be in [118, 256]");
     if ((priors == nullptr) != (values == nullptr)) return az::fail_net(AZ_ERR_ARG, "az_chess_step: priors and values go together");
     if (eval_dtype != AZ_F32 && eval_dtype != AZ_F64) return az::fail_net(AZ_ERR_ARG, "az_chess_step: eval_dtype must be AZ_F32 or AZ_F64");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -533,6 +637,20 @@ AZ_API int az_chess_decode_samples(const az_chess_pos* pos, const int32_t* k, co
     if (int rc = have_device()) return rc;
     k_chess_decode<<<flat_grid(n * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const Pos*>(pos), k, act, nv, choice, n, states_out, policies_out);
+    AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_chess_stem(const az_chess_pos* pos, int32_t n, const float* w_reduced, const float* cell_map, void* out, void* stream) {
+    if (n == 0) return AZ_OK;
+    if (!pos || !w_reduced || !cell_map || !out || n < 0) return az::fail_net(AZ_ERR_ARG, "az_chess_stem: bad argument");
+    if (int rc = have_device()) return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = n < sms * 3 ? n : sms * 3;
+    k_chess_stem<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const Pos*>(pos), n, w_reduced, cell_map,
+                                                                      static_cast<__nv_bfloat16*>(out));
     AZC_CUDA(cudaGetLastError());
     return AZ_OK;
 }

@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(kCWarps * 32, MINB) k_chess_step(CEng e, const
     const int mode = sizeof(PT) == 4 ? AZ_PRIOR_F32 : AZ_PRIOR_F64;
     const int want = c_step_tree<true>(e, t, ws, lane, have_eval != 0, v, mode, [&](int a) { return (double)pt[a]; }, leaf);
     if (lane == 0) leaf_valid[t] = want;
-    if (want) {
+    if (want && states_out) {  // states_out null: the caller computes the stem from leaf_pos (az_chess_stem)
         stage_history(leaf, nullptr, ws.e8, lane);
         encode_planes_strided<__nv_bfloat16>(ws.e8, states_out + (size_t)t * 64 * plane_stride, lane, plane_stride);
     }

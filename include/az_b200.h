@@ -463,6 +463,17 @@ int az_chess_search(az_chess_engine *e, void *stream);
  * tensor-core stem can read a channel count that is a multiple of 8 in place) and leaf_valid_out dev int32 [T]. */
 int az_chess_step(az_chess_engine *e, const void *dev_priors, const void *dev_values, int32_t eval_dtype,
                   void *dev_states_out, int32_t plane_stride, int32_t *dev_leaf_valid_out, void *stream);
+/* states_out may be NULL: then no planes are written and the caller evaluates the leaves from `leaf_pos` in the slab
+ * (az_chess_stem below). */
+
+/* Stem of the net (model/tensorflow/model.py:36-46: Conv3x3(118 -> 128) + BN + ReLU) for positions on the self-play
+ * path, straight from the 64-byte boards.  There Board.full_state (chess/board.py:58-73) is six empty history entries +
+ * the initial position + the current entry, so only 20 planes vary: w_reduced = dev float [128][24][9] holds the folded
+ * stem weights of the current entry's 14 planes (98-111), the 6 scalar planes (112-117) and 4 zero planes, [plane][tap]
+ * per output channel; cell_map = dev float [64][128] = folded bias + the initial position's contribution per cell (array
+ * order, row 0 = rank 8).  out: dev bf16 [n][8][8][128], the tower's input. */
+int az_chess_stem(const az_chess_pos *dev_pos, int32_t n, const float *dev_w_reduced, const float *dev_cell_map, void *dev_out,
+                  void *stream);
 /* MCTS.play for every tree whose budget is spent: sample-ring entry, move, re-root (in place, or compacted into the
  * other pool half), game end -> finished ring + next game.  greedy_override / move_mode_override: -1 = configured. */
 int az_chess_move(az_chess_engine *e, int32_t greedy_override, int32_t move_mode_override, void *stream);

@@ -359,3 +359,66 @@ def test_rings_and_pools_fail_loudly_and_recover():
     assert int(small.view("status")[0]) & native.AZ_FLAG_POOL_OVERFLOW
     with pytest.raises(NativeError, match="node pool exhausted"):
         small.check_status()
+
+
+def test_stem_from_boards_equals_the_convolution_on_planes():
+    """az_chess_stem (20 varying planes from the 64-byte board + per-cell constant) against cuDNN's stem convolution on
+    the full 118-plane tensor, for positions of the self-play path (clocks, castling rights, promotions, en passant)."""
+    from az_b200 import chess
+    from az_b200.chess_selfplay import chess_net
+    from az_b200.net import InferenceNet, randomise_bn
+
+    torch.manual_seed(4)
+    net = randomise_bn(chess_net()).eval()
+    inf = InferenceNet(net, dtype=torch.bfloat16, device="cuda")
+    acts = cr.all_possible_moves()
+    index = {m: i for i, m in enumerate(acts)}
+    samples = []
+    for game in range(12):
+        rng = _lcg_local(game)
+        s = cr.start_state()
+        for ply in range(120):
+            moves = [m for m in cr.legal(s) if m in index]
+            if cr.status(s) != 0 or not moves:
+                break
+            samples.append(s.copy())
+            s = cr.push(s, moves[next(rng) % len(moves)], keep_same_player=True)
+    pos = np.stack([cr.to_pos(x) for x in samples])
+    assert len(pos) > 800 and any(x.halfmove > 5 for x in samples) and any(x.castling != 15 for x in samples)
+    planes = chess.chess_encode(pos, dtype=torch.bfloat16)                       # [n, 8, 8, 118] bf16 on the GPU
+    x = torch.nn.functional.pad(planes, (0, inf.in_pad)).permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+    ref = torch.cudnn_convolution_relu(x, inf.stem_w_pad, inf.stem_b, (1, 1), (1, 1), (1, 1), 1).permute(0, 2, 3, 1).float()
+    got = inf.chess_stem(torch.from_numpy(pos.view(np.int64)).cuda()).float()
+    assert got.shape == ref.shape == (len(pos), 8, 8, 128)
+    err = (got - ref).abs().max().item()
+    assert err <= 2.0 ** -6 * max(1.0, ref.abs().max().item()), err   # one bf16 rounding of the output, different summation order
+    assert float(ref.max()) > 0.5 and float((ref > 0).float().mean()) > 0.2  # the probe is not all zeros after the ReLU
+    # end to end: priors / values through both routes
+    p1, v1 = inf.forward_from_stem(inf.chess_stem(torch.from_numpy(pos.view(np.int64)).cuda()))
+    p0, v0 = inf(planes)
+    assert (p1 - p0).abs().max().item() <= 2e-3 * max(p0.max().item(), 1e-3) + 1e-5 and (v1 - v0).abs().max().item() <= 2e-2
+
+
+def test_runner_with_stem_from_boards_plays_the_same_games():
+    """The two leaf routes (planes + cuDNN stem / boards + az_chess_stem) feed the same search: with argmax moves and a
+    short horizon the games coincide unless a near-tie in the bf16 net flips a visit; at least most plies must agree."""
+    from az_b200.chess_selfplay import ChessSelfPlayRunner, chess_net
+
+    outs = []
+    for flag in (False, True):
+        torch.manual_seed(0)
+        r = ChessSelfPlayRunner(n_trees=8, sims_per_move=16, net=chess_net(), games_target=8, max_plies=6, unroll=2,
+                                move_mode="argmax", auto_restart=False, stem_from_boards=flag)
+        assert r.stem_from_boards == flag
+        states, policies, values, known = r.run_until_done(poll_every=16, max_advances=4000)
+        assert states.shape == (48, 8, 8, 118) and known.all()
+        outs.append(policies)
+    agree = (np.abs(outs[0] - outs[1]).max(-1) < 0.13).mean()   # a flipped visit moves a target by 1/15
+    assert agree >= 0.8, agree
+
+
+def _lcg_local(seed):
+    s = (seed * 0x9E3779B97F4A7C15 + 1) % 2 ** 64
+    while True:
+        s = (s * 6364136223846793005 + 1442695040888963407) % 2 ** 64
+        yield s >> 33

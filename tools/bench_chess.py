@@ -160,7 +160,10 @@ def main(args, ClockSampler, load_peaks):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            runner.net(runner.states, runner.priors, runner.values)
+            if runner.stem_from_boards:
+                runner.net.forward_from_stem(runner.net.chess_stem(runner.engine.view("leaf_pos")), runner.priors, runner.values)
+            else:
+                runner.net(runner.states, runner.priors, runner.values)
         for _ in range(5):
             g.replay()
         a.record()
@@ -172,8 +175,9 @@ def main(args, ClockSampler, load_peaks):
         ach = T * runner.flops_per_eval / (net_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_sustained"], "traffic": None,
-                "kernel": "policy/value net forward timed alone (library kernels): pad 118->120 planes, cuDNN stem, 12 cuDNN "
-                          "tcgen05 implicit-GEMM convolutions with fused epilogues, cuBLAS heads (policy over 1 880 actions)",
+                "kernel": "policy/value net forward timed alone: az_chess_stem (from the 64-byte boards), 12 cuDNN tcgen05 implicit-GEMM "
+                          "convolutions with fused epilogues, az_net_head_convs, az_net_dense_heads (tcgen05: policy over 1 880 "
+                          "actions + softmax, value MLP)",
                 "flops_per_launch": T * runner.flops_per_eval, "positions_per_launch": T, "ms_per_launch": net_ms,
                 "peak_source": peaks["source"] + ", sustained"}
         # az_chess_step alone: algorithmic bytes per tree and launch from the measured mean depth / fan-out
@@ -184,10 +188,10 @@ def main(args, ClockSampler, load_peaks):
                    + 8 * d_bar + 2 * (64 + 256)          # stored path, leaf position and legal mask out and back
                    + k_bar * 26                          # expand: k children x (record + prior + action)
                    + d_bar * 32 + 64 + 64)               # backup RMW, root position, header words
-        bytes_per_tree = per_sim * sims_per_leaf + 4 * 1880 + 4 + 2 * 64 * 118  # + priors / value in, bf16 planes out
+        bytes_per_tree = per_sim * sims_per_leaf + 4 * k_bar + 4 + (0 if runner.stem_from_boards else 2 * 64 * 118)  # + legal priors / value in (+ bf16 planes out)
 
         def launch():
-            runner.engine.step(runner.priors, runner.values, runner.states, runner.valid)
+            runner.engine.step(runner.priors, runner.values, None if runner.stem_from_boards else runner.states, runner.valid)
         for _ in range(3):
             launch()
         a.record()

@@ -120,7 +120,7 @@ class ChessTreeEngine:
     def search(self):
         check(lib().az_chess_search(self._h, _stream()))
 
-    def step(self, priors, values, states_out, leaf_valid_out):
+    def step(self, priors, values, states_out, leaf_valid_out, plane_first=0):
         """One lock-step advance.  priors [T, 1880] / values [T] float32 or float64 (or None on the first call);
         states_out bf16 [T, 8, 8, 118 or more]; leaf_valid_out int32 [T]."""
         eval_dtype = native.AZ_F32
@@ -132,9 +132,9 @@ class ChessTreeEngine:
         stride = PLANES
         if states_out is not None:  # None: no planes, the caller runs az_chess_stem on view("leaf_pos")
             assert states_out.dtype == torch.bfloat16 and states_out.is_contiguous()
-            stride = states_out.shape[-1]  # >= 118: extra planes are written as zeros (channel padding for the stem)
-            assert states_out.shape == (self.n_trees, 8, 8, stride) and stride >= PLANES
-        check(lib().az_chess_step(self._h, _ptr(priors), _ptr(values), eval_dtype, _ptr(states_out), stride,
+            stride = states_out.shape[-1]  # extra channels are written as zeros (channel padding for the stem)
+            assert states_out.shape == (self.n_trees, 8, 8, stride) and stride >= PLANES - plane_first
+        check(lib().az_chess_step(self._h, _ptr(priors), _ptr(values), eval_dtype, _ptr(states_out), stride, int(plane_first),
                                   _ptr(leaf_valid_out), _stream()))
 
     def move(self, greedy=None, move_mode=None):

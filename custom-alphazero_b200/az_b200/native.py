@@ -140,7 +140,7 @@ SYMBOLS = {
     "az_chess_set_roots": (ctypes.c_int, [_P, _P, _P, _I, _P]),
     "az_chess_begin_search": (ctypes.c_int, [_P, _I, _P]),
     "az_chess_search": (ctypes.c_int, [_P, _P]),
-    "az_chess_step": (ctypes.c_int, [_P, _P, _P, _I, _P, _I, _P, _P]),
+    "az_chess_step": (ctypes.c_int, [_P, _P, _P, _I, _P, _I, _I, _P, _P]),
     "az_chess_stem": (ctypes.c_int, [_P, _I, _P, _P, _P, _P]),
     "az_chess_move": (ctypes.c_int, [_P, _I, _I, _P]),
     "az_chess_rings_clear": (ctypes.c_int, [_P, _P]),

@@ -165,6 +165,10 @@ class InferenceNet(nn.Module):
             red[:, :14] = w16[:, 98:112]
             red[:, 14:20] = w16[:, 112:118]
             self.chess_stem_w = nn.Parameter(red.reshape(net.filters, 24, 9).contiguous(), requires_grad=False)
+            # the stem restricted to planes 84-117 (initial-position entry, current entry, scalars; 34 planes padded to
+            # 40): on the self-play path the six older history entries are always empty (az_chess_step plane_first = 84)
+            tail = F.pad(self.stem_w.detach().contiguous()[:, 84:118], (0, 0, 0, 0, 0, 6)).contiguous(memory_format=cl)
+            self.stem_w_tail = nn.Parameter(tail, requires_grad=False)
             from .chess import position_from_fen, unpack_position
 
             arr = torch.as_tensor(unpack_position(position_from_fen())["array"].astype("int64"))
@@ -222,10 +226,12 @@ class InferenceNet(nn.Module):
         if x.is_cuda and self.dtype == torch.bfloat16:
             # other input planes / action spaces (chess: 118 planes, 1 880 actions): library stem, the same cuDNN
             # fused-epilogue tower as the fast path, heads through cuBLAS
-            if self.in_pad and x_nhwc.shape[-1] != self.stem_w_pad.shape[1]:  # not padded by the producer already
+            if self.in_pad and x_nhwc.shape[-1] == self.stem_w.shape[1]:  # not padded by the producer already
                 x = F.pad(x_nhwc.to(self.dtype), (0, self.in_pad)).permute(0, 3, 1, 2)
-            h0 = torch.cudnn_convolution_relu(x.contiguous(memory_format=torch.channels_last),
-                                              self.stem_w_pad if self.in_pad else self.stem_w, self.stem_b,
+            w_stem = self.stem_w_pad if self.in_pad else self.stem_w
+            if x.shape[1] == 40 and hasattr(self, "stem_w_tail"):  # chess leaf batch without the empty history entries
+                w_stem = self.stem_w_tail
+            h0 = torch.cudnn_convolution_relu(x.contiguous(memory_format=torch.channels_last), w_stem, self.stem_b,
                                               (1, 1), (1, 1), (1, 1), 1)
             return self.forward_from_stem(h0.permute(0, 2, 3, 1), priors_out, values_out)
         else:

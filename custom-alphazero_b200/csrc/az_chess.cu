@@ -121,7 +121,9 @@ __device__ __forceinline__ __nv_bfloat16 plane_cast<__nv_bfloat16>(float v) { re
 // plane and one repetition plane per deque entry plus the six scalar planes), so the warp first clears the block with
 // coalesced 128-bit stores and then each lane scatters the few non-zero values of its two cells.
 template <typename T>
-__device__ __forceinline__ void encode_planes_strided(const Pos* e8, T* out, int lane, int stride) {
+__device__ __forceinline__ void encode_planes_strided(const Pos* e8, T* out, int lane, int stride, int first = 0) {
+    // planes [first, 118) land at out[cell][plane - first]; `first` is a multiple of 14 (whole history entries are dropped:
+    // on the self-play path entries 0-5 are always empty, so first = 84 loses nothing)
     const int total = 64 * stride;  // elements; the block starts 16-byte aligned (n * 64 * stride * sizeof(T))
     constexpr int per16 = 16 / (int)sizeof(T);
     if ((total % per16) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
@@ -135,13 +137,15 @@ __device__ __forceinline__ void encode_planes_strided(const Pos* e8, T* out, int
     const bool black = black_to_move(cur);
     const int own_k = black ? 4 : 1, own_q = black ? 8 : 2, opp_k = black ? 1 : 4, opp_q = black ? 2 : 8;
     const T one = plane_cast<T>(1.0f);
+    const int h0 = first / 14;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int cell = lane + 32 * half;
         const int sq = ((7 - (cell >> 3)) << 3) | (cell & 7);  // array row 0 is rank 8 (chess/board.py:119-131)
-        T* row = out + (size_t)cell * stride;
+        T* row = out + (size_t)cell * stride - first;
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
+            if (h < h0) continue;
             const Pos& e = e8[h];
             if (!(e.meta & META_VALID)) continue;
             row[h * 14 + piece_plane(piece_at(e, sq))] = one;  // plane 0 = empty square
@@ -584,10 +588,11 @@ AZ_API int az_chess_search(az_chess_engine* e, void* stream) {
 }
 
 AZ_API int az_chess_step(az_chess_engine* e, const void* priors, const void* values, int32_t eval_dtype, void* states_out,
-                         int32_t plane_stride, int32_t* leaf_valid_out, void* stream) {
+                         int32_t plane_stride, int32_t plane_first, int32_t* leaf_valid_out, void* stream) {
     if (!e || !leaf_valid_out) return az::fail_net(AZ_ERR_ARG, "az_chess_step: null argument");
-    if (states_out && (plane_stride < kPlanes || plane_stride > 256))
-        return az::fail_net(AZ_ERR_ARG, "az_chess_step: plane_stride must be in [118, 256]");
+    if (states_out && (plane_first < 0 || plane_first > 98 || plane_first % 14 || plane_stride < kPlanes - plane_first ||
+                       plane_stride > 256))
+        return az::fail_net(AZ_ERR_ARG, "az_chess_step: plane_first must be a multiple of 14 <= 98, plane_stride in [118 - plane_first, 256]");
     if ((priors == nullptr) != (values == nullptr)) return az::fail_net(AZ_ERR_ARG, "az_chess_step: priors and values go together");
     if (eval_dtype != AZ_F32 && eval_dtype != AZ_F64) return az::fail_net(AZ_ERR_ARG, "az_chess_step: eval_dtype must be AZ_F32 or AZ_F64");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -602,7 +607,7 @@ AZ_API int az_chess_step(az_chess_engine* e, const void* priors, const void* val
     const dim3 grid = ctree_grid(e);
 #define AZC_STEP(PT, MINB)                                                                                              \
     k_chess_step<PT, MINB><<<grid, kCWarps * 32, 0, s>>>(e->eng, static_cast<const PT*>(priors), static_cast<const PT*>(values), \
-                                                         have, so, plane_stride, leaf_valid_out)
+                                                         have, so, plane_stride, plane_first, leaf_valid_out)
     if (eval_dtype == AZ_F32) {
         if (minb <= 4) AZC_STEP(float, 4); else AZC_STEP(float, 7);
     } else {

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kCWarps * 32) k_chess_search(CEng e) {
 // one wave (72 registers, some spills); 4 keeps everything in registers (112) but needs two waves.
 template <typename PT, int MINB>
 __global__ void __launch_bounds__(kCWarps * 32, MINB) k_chess_step(CEng e, const PT* priors, const PT* values, int have_eval,
-                                                             __nv_bfloat16* states_out, int plane_stride, int32_t* leaf_valid) {
+                                                             __nv_bfloat16* states_out, int plane_stride, int plane_first, int32_t* leaf_valid) {
     __shared__ CScratch s_ws[kCWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * kCWarps + warp;
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kCWarps * 32, MINB) k_chess_step(CEng e, const
     if (lane == 0) leaf_valid[t] = want;
     if (want && states_out) {  // states_out null: the caller computes the stem from leaf_pos (az_chess_stem)
         stage_history(leaf, nullptr, ws.e8, lane);
-        encode_planes_strided<__nv_bfloat16>(ws.e8, states_out + (size_t)t * 64 * plane_stride, lane, plane_stride);
+        encode_planes_strided<__nv_bfloat16>(ws.e8, states_out + (size_t)t * 64 * plane_stride, lane, plane_stride, plane_first);
     }
 }
 

@@ -459,10 +459,13 @@ int az_chess_begin_search(az_chess_engine *e, int32_t sims, void *stream);
 int az_chess_search(az_chess_engine *e, void *stream);
 /* one lock-step advance with an external evaluator, like az_step: consume priors dev [T][1880] / values dev [T]
  * (AZ_F32 or AZ_F64; ignored for trees without a pending leaf), simulate up to the next leaf, write its 118 planes
- * to states_out dev bf16 [T][8][8][plane_stride] (plane_stride >= 118; the planes beyond 118 are written as zeros so a
- * tensor-core stem can read a channel count that is a multiple of 8 in place) and leaf_valid_out dev int32 [T]. */
+ * to states_out dev bf16 [T][8][8][plane_stride] and leaf_valid_out dev int32 [T].  Only planes [plane_first, 118) are
+ * written, at channel index plane - plane_first (plane_first = 0: all of them; 84: the initial-position entry, the
+ * current entry and the scalars - on the self-play path the six older history entries are always empty, so nothing is
+ * lost and the stem multiplies 34 planes instead of 118); channels beyond 118 - plane_first are written as zeros so a
+ * tensor-core stem can read a channel count that is a multiple of 8 in place (plane_stride >= 118 - plane_first). */
 int az_chess_step(az_chess_engine *e, const void *dev_priors, const void *dev_values, int32_t eval_dtype,
-                  void *dev_states_out, int32_t plane_stride, int32_t *dev_leaf_valid_out, void *stream);
+                  void *dev_states_out, int32_t plane_stride, int32_t plane_first, int32_t *dev_leaf_valid_out, void *stream);
 /* states_out may be NULL: then no planes are written and the caller evaluates the leaves from `leaf_pos` in the slab
  * (az_chess_stem below). */
 

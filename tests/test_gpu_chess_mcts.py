@@ -417,6 +417,49 @@ def test_runner_with_stem_from_boards_plays_the_same_games():
     assert agree >= 0.8, agree
 
 
+def test_tail_planes_are_the_last_34_and_change_nothing():
+    """az_chess_step with plane_first = 84 writes planes 84-117 (+ 6 zero channels); the net gives the same priors and
+    values from them as from all 118 planes, because planes 0-83 are empty on the self-play path."""
+    from az_b200 import chess
+    from az_b200.chess_engine import ChessTreeEngine
+    from az_b200.chess_selfplay import chess_net
+    from az_b200.net import InferenceNet, randomise_bn
+
+    torch.manual_seed(6)
+    T = 64
+    eng = ChessTreeEngine(n_trees=T, sims_per_move=20, eval_mode="external", move_mode="philox", seed=3, index_move_greedy=99)
+    full = torch.full((T, 8, 8, 120), 7.0, dtype=torch.bfloat16, device="cuda")
+    tail = torch.full((T, 8, 8, 40), 7.0, dtype=torch.bfloat16, device="cuda")
+    valid = torch.zeros(T, dtype=torch.int32, device="cuda")
+    pri = torch.rand(T, 1880, device="cuda")
+    val = torch.zeros(T, device="cuda")
+    inf = InferenceNet(randomise_bn(chess_net()).eval(), dtype=torch.bfloat16, device="cuda")
+    checked = 0
+    for adv in range(120):
+        if adv % 2 == 0:
+            eng.step(pri if adv else None, val if adv else None, full, valid)
+        else:
+            eng.step(pri, val, tail, valid, plane_first=84)
+        if adv % 20 == 19:
+            eng.move()
+        ok = valid.bool()
+        if not bool(ok.any()):
+            continue
+        pos = eng.view("leaf_pos")[ok].cpu().numpy().view(np.uint64)
+        want = torch.from_numpy(chess.chess_encode(pos)).cuda()
+        if adv % 2 == 0:
+            assert torch.equal(full[ok][..., :118].float(), want) and not full[ok][..., 118:].any()
+            assert not want[..., :84].any()  # the empty history entries
+        else:
+            assert torch.equal(tail[ok][..., :34].float(), want[..., 84:]) and not tail[ok][..., 34:].any()
+            p_tail, v_tail = inf(tail[ok])
+            p_full, v_full = inf(torch.nn.functional.pad(want, (0, 2)).to(torch.bfloat16))
+            assert (p_tail - p_full).abs().max().item() <= 1e-3 * p_full.max().item() + 1e-6
+            assert (v_tail - v_full).abs().max().item() <= 1e-2
+            checked += int(ok.sum())
+    assert checked > 1000
+
+
 def _lcg_local(seed):
     s = (seed * 0x9E3779B97F4A7C15 + 1) % 2 ** 64
     while True:

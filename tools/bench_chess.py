@@ -172,13 +172,15 @@ def main(args, ClockSampler, load_peaks):
         b.record()
         torch.cuda.synchronize()
         net_ms = a.elapsed_time(b) / n_rep
-        ach = T * runner.flops_per_eval / (net_ms * 1e-3) / 1e12
+        ach = T * runner.flops_per_eval_executed / (net_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_sustained"], "traffic": None,
                 "kernel": "policy/value net forward timed alone: az_chess_stem (from the 64-byte boards), 12 cuDNN tcgen05 implicit-GEMM "
                           "convolutions with fused epilogues, az_net_head_convs, az_net_dense_heads (tcgen05: policy over 1 880 "
                           "actions + softmax, value MLP)",
-                "flops_per_launch": T * runner.flops_per_eval, "positions_per_launch": T, "ms_per_launch": net_ms,
+                "flops_per_launch": T * runner.flops_per_eval_executed, "flops_per_launch_reference_net": T * runner.flops_per_eval,
+                "flops_note": "executed FLOPs: with tail_planes the stem multiplies the 34 planes that can be non-zero on the self-play path instead of 118",
+                "positions_per_launch": T, "ms_per_launch": net_ms,
                 "peak_source": peaks["source"] + ", sustained"}
         # az_chess_step alone: algorithmic bytes per tree and launch from the measured mean depth / fan-out
         d_bar = depth_sum / max(sims, 1.0)
@@ -188,10 +190,11 @@ def main(args, ClockSampler, load_peaks):
                    + 8 * d_bar + 2 * (64 + 256)          # stored path, leaf position and legal mask out and back
                    + k_bar * 26                          # expand: k children x (record + prior + action)
                    + d_bar * 32 + 64 + 64)               # backup RMW, root position, header words
-        bytes_per_tree = per_sim * sims_per_leaf + 4 * k_bar + 4 + (0 if runner.stem_from_boards else 2 * 64 * 118)  # + legal priors / value in (+ bf16 planes out)
+        bytes_per_tree = per_sim * sims_per_leaf + 4 * k_bar + 4 + (0 if runner.stem_from_boards else 2 * 64 * runner.states.shape[-1])  # + legal priors / value in (+ bf16 planes out)
 
         def launch():
-            runner.engine.step(runner.priors, runner.values, None if runner.stem_from_boards else runner.states, runner.valid)
+            runner.engine.step(runner.priors, runner.values, None if runner.stem_from_boards else runner.states, runner.valid,
+                               runner.plane_first)
         for _ in range(3):
             launch()
         a.record()
@@ -232,7 +235,7 @@ def main(args, ClockSampler, load_peaks):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"C5: {T} concurrent chess self-play games per GPU x {S} simulations/move, bf16 net leaf evaluation",
                        "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "max_free_sims": args.max_free,
-                       "max_plies": args.max_plies,
+                       "max_plies": args.max_plies, "leaf_planes": int(runner.states.shape[-1]),
                        "net": f"4-block 128-filter projection-residual tower, 8x8x118 in, 1880 actions, {fp32.n_parameters()} params, random init",
                        "l2": "working set per advance (node pools ~GBs + 134 MB activations per conv at 8192 trees) exceeds the 126 MB L2"},
             "leaf_evals_per_sec": evals / ms * 1e3, "selfplay_moves_per_sec": moves / ms * 1e3, "games_finished": games,

@@ -87,13 +87,16 @@ __device__ __forceinline__ int c_select(const CEng& e, const NodeA* A, const dou
         const int base = (int)(link & 0xffffffu), k = (int)(link >> 24);
         NodeA rec[kKC];
         double pr[kKC];
+        uint16_t mvv[kKC];  // the children's actions ride along with their records: no dependent load after the argmax
         int ln = 0;
 #pragma unroll
         for (int c = 0; c < kKC; ++c) {
             const int j = lane + 32 * c;
+            mvv[c] = 0;
             if (j < k) {
                 rec[c] = load_node(A + base + j);
                 pr[c] = Pr[base + j];
+                mvv[c] = Mv[base + j];
                 ln += rec[c].n;
             } else {
                 rec[c].n = 0;
@@ -134,11 +137,15 @@ __device__ __forceinline__ int c_select(const CEng& e, const NodeA* A, const dou
             mx = ov > mx ? ov : mx;
         }
         bi = __reduce_min_sync(kFull, (bi != 0x7fffffff && best == mx) ? bi : 0x7fffffff);  // first maximum
-        uint32_t clink = 0;
+        uint32_t clink = 0, cact = 0;
 #pragma unroll
         for (int c = 0; c < kKC; ++c)
-            if ((bi >> 5) == c) clink = rec[c].link;
+            if ((bi >> 5) == c) {
+                clink = rec[c].link;
+                cact = mvv[c];
+            }
         clink = __shfl_sync(kFull, clink, bi & 31);
+        cact = __shfl_sync(kFull, cact, bi & 31);
         node = base + bi;
         if (depth >= kCDepth) {  // the stored path is full: the tree is deeper than AZ_MAX_DEPTH
             flags |= AZ_FLAG_ILLEGAL;
@@ -146,7 +153,7 @@ __device__ __forceinline__ int c_select(const CEng& e, const NodeA* A, const dou
         }
         if (lane == 0) ws.path[depth] = node;
         ++depth;
-        const int mv = act_move(Mv[node]);
+        const int mv = act_move((int)cact);
         pos = play(pos, mv & 63, (mv >> 6) & 63, mv >> 12, true);  // chess/board.py:162-173
         link = clink;
     }
@@ -322,6 +329,17 @@ __device__ __forceinline__ int c_step_tree(const CEng& e, int t, CScratch& ws, i
     int sims = e.sims_done[t];
     long long n_sims = 0, n_evals = 0, sum_depth = 0;
     int want = 0;
+    {
+        // the root's child block (records, priors, actions) is the first thing the next selection reads: ask L2 for it
+        // now, so that the HBM round trip runs underneath the expansion and backup of the pending leaf
+        const uint32_t rl = load_node(A + root).link;
+        const int rb = (int)(rl & 0xffffffu), rk = (int)(rl >> 24);
+        if (rl) {
+            if (lane * 8 < rk) az::prefetch_l2(A + rb + lane * 8);          // 8 records per 128-byte line
+            if (lane * 16 < rk) az::prefetch_l2(Pr + rb + lane * 16);       // 16 priors per line
+            if (lane * 64 < rk) az::prefetch_l2(Mv + rb + lane * 64);       // 64 actions per line
+        }
+    }
     if (EXTERNAL && e.pending[t] == 1) {
         if (!have_eval) return 0;  // first call after a reset without priors: nothing to consume yet
         const int depth = e.path_len[t];

@@ -105,3 +105,54 @@ def test_full_state_layout():
         assert mv in cr.legal(t), u
         t = cr.push(t, mv, keep_same_player=True)
     assert cr.status(t) == 1 and cr.result(t) == -1
+
+
+@pytest.mark.parametrize("fen,want", [
+    ("8/8/8/4k3/8/8/8/4K3 w - - 0 1", 2),                       # K v K: insufficient material
+    ("8/8/8/4k3/8/8/8/4KN2 w - - 0 1", 2),                      # K+N v K
+    ("8/8/8/4k3/8/8/8/4KB2 w - - 0 1", 2),                      # K+B v K
+    ("8/8/8/2b1k3/8/8/8/4KB2 w - - 0 1", 0),                    # bishops on opposite colours (c5 dark, f1 light): mate is possible
+    ("8/8/8/3bk3/8/8/8/4KB2 w - - 0 1", 2),                     # all bishops on the same colour (d5 and f1 are light)
+    ("8/8/8/4k3/8/8/8/3NKN2 w - - 0 1", 0),                     # K+N+N v K: python-chess does not call it insufficient
+    ("8/8/8/4k3/8/8/4P3/4K3 w - - 0 1", 0),                     # a pawn is enough
+    ("7k/5Q2/6K1/8/8/8/8/8 b - - 0 1", 2),                      # stalemate (black to move, no moves, not in check)
+    ("7k/6Q1/6K1/8/8/8/8/8 b - - 0 1", 1),                      # checkmate
+    ("4k3/8/8/8/8/8/4R3/4K3 w - - 149 80", 0),                  # halfmove clock 149: still running
+    ("4k3/8/8/8/8/8/4R3/4K3 w - - 150 80", 2),                  # 75-move rule
+    ("rnb1kbnr/pppp1ppp/8/4p3/6Pq/5P2/PPPPP2P/RNBQKBNR w KQkq - 1 3", 1),  # fool's mate
+])
+def test_game_end_rules_oracle_and_device_header_agree(fen, want):
+    s = cr.from_fen(fen)
+    assert cr.status(s) == want
+    assert cr.host_status(cr.to_pos(s)) == want
+
+
+def test_castling_and_en_passant_bookkeeping():
+    acts = cr.all_possible_moves()
+    code = lambda u: next((m[0] | m[1] << 6 | cr.PROMO_LETTERS.index(m[2]) << 12, m) for m in acts if cr.uci(m) == u)  # noqa: E731
+    # capturing the rook on h8 removes black's king-side right; moving the a1 rook removes white's queen-side right
+    s = cr.from_fen("r3k2r/8/8/8/8/8/6B1/R3K2R w KQkq - 0 1")
+    c, m = code("a1a2")
+    assert cr.push(s, m).castling == 1 | 4 | 8 and cr.from_pos(cr.host_play(cr.to_pos(s), c, False)).castling == 1 | 4 | 8
+    s2 = cr.from_fen("r3k2r/8/8/8/8/8/8/R3K2B w Qkq - 0 1")
+    c, m = code("h1a8")
+    after = cr.push(s2, m)
+    assert after.castling == 2 | 4 and cr.states_equal(cr.from_pos(cr.host_play(cr.to_pos(s2), c, False)), after)
+    # castling through an attacked square is illegal, castling out of check too; the rook may pass an attacked square
+    s3 = cr.from_fen("4k3/8/8/8/8/5r2/8/R3K2R w KQ - 0 1")  # f1 attacked: no O-O, O-O-O fine
+    legal = {cr.uci(m) for m in cr.legal(s3)}
+    assert "e1c1" in legal and "e1g1" not in legal
+    got, _, _ = cr.host_legal(cr.to_pos(s3))
+    assert {cr.uci(acts[a]) for a in got} == legal
+    s4 = cr.from_fen("4k3/8/8/8/8/1r6/8/R3K2R w KQ - 0 1")  # b1 attacked: the rook passes it, O-O-O is legal
+    assert "e1c1" in {cr.uci(m) for m in cr.legal(s4)}
+    assert "e1c1" in {cr.uci(acts[a]) for a in cr.host_legal(cr.to_pos(s4))[0]}
+    # en passant that would expose the king along the rank is illegal (the classic perft trap)
+    s5 = cr.from_fen("8/8/8/K2pP2r/8/8/8/4k3 w - d6 0 1")
+    assert "e5d6" not in {cr.uci(m) for m in cr.legal(s5)}
+    assert "e5d6" not in {cr.uci(acts[a]) for a in cr.host_legal(cr.to_pos(s5))[0]}
+    s6 = cr.from_fen("8/8/8/3pP3/8/8/8/K3k3 w - d6 0 1")
+    assert "e5d6" in {cr.uci(m) for m in cr.legal(s6)} and "e5d6" in {cr.uci(acts[a]) for a in cr.host_legal(cr.to_pos(s6))[0]}
+    c, m = code("e5d6")
+    after = cr.push(s6, m)
+    assert after.sq[35] == 0 and after.sq[43] == 1 and cr.states_equal(cr.from_pos(cr.host_play(cr.to_pos(s6), c, False)), after)

@@ -24,9 +24,8 @@ from custom_alphazero.mcts.utils import normalize_probabilities  # noqa: F401  (
 from custom_alphazero.serving.factory import infer_sample
 
 if ConfigGeneral.game == "chess":  # mcts.py:12-14 of the reference
-    # The module imports like the reference's; the search object below drives the Connect-N engine, chess searches run
-    # through az_b200.chess_engine.ChessTreeEngine / chess_selfplay (the reference's own MCTS cannot finish a chess
-    # simulation: mcts.py:179 passes keep_same_player to a Board.get_result that does not take it).
+    # The module imports like the reference's; MCTS is rebound at the bottom to the chess search object
+    # (custom_alphazero/mcts/chess_mcts.py), a batch-of-one view on az_b200.chess_engine.ChessTreeEngine.
     from custom_alphazero.chess.board import Board
     from custom_alphazero.chess.move import Move
 elif ConfigGeneral.game == "connect_n":
@@ -105,7 +104,7 @@ class MCTS:
         if use_solver:
             raise NotImplementedError("the exact solver back-end is outside the B200 hot path (SURVEY 2 #12)")
         if ConfigGeneral.game != "connect_n":
-            raise NotImplementedError("this search object drives the Connect-N engine; chess: az_b200.chess_engine")
+            raise NotImplementedError("this search object drives the Connect-N engine; chess: custom_alphazero.mcts.chess_mcts")
         # ConfigMCTS.enable_dirichlet_noise (mcts.py:114-115): root noise is drawn on the device (same distribution as
         # np.random.dirichlet, different stream: statistical parity only - SURVEY 8a row a5)
         self.board = deepcopy(board)
@@ -244,3 +243,8 @@ class MCTS:
         opp = sum(int(w) << (64 * i) for i, w in enumerate(words[1]))
         return [[1 if (cur >> (y * (W + 1) + x)) & 1 else (-1 if (opp >> (y * (W + 1) + x)) & 1 else 0) for x in range(W)]
                 for y in range(H)]
+
+
+if ConfigGeneral.game == "chess":  # same name, same constructor, same methods: the chess search object
+    ConnectNMCTS = MCTS
+    from custom_alphazero.mcts.chess_mcts import ChessMCTS as MCTS  # noqa: E402,F811

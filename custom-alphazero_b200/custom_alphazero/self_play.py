@@ -48,10 +48,6 @@ def play_game(process_id: int, all_possible_moves: List[Move], mcts_iterations: 
     """One game through the drop-in MCTS class; signature and return values of the reference's play_game
     (self_play.py:37-82): states [T, H, W, 4] float32 (positions BEFORE each move), policies [T, A] float64,
     rewards [T], and the search object with its model detached."""
-    if ConfigGeneral.game == "chess":
-        # the reference's own chess path cannot finish a game inside its MCTS (mcts.py:179 passes keep_same_player to a
-        # Board.get_result that does not take it); chess self-play goes through play() / az_b200.chess_selfplay
-        raise NotImplementedError("play_game drives the Connect-N search object; for chess use play()")
     np.random.seed(int((process_id + 1) * time.time()) % (2**32 - 1))  # every worker samples differently
     evaluator = None if ConfigGeneral.http_inference else HostModel(best_saved_model(run_id))
     search = MCTS(board=Board(), all_possible_moves=all_possible_moves, concurrency=ConfigGeneral.concurrency,

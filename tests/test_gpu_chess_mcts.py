@@ -265,7 +265,7 @@ def test_entry_point_plays_chess(tmp_path, monkeypatch):
     monkeypatch.setattr(config.ConfigB200, "chess_max_plies", 6)
     monkeypatch.setattr(config.ConfigB200, "graph_unroll", 2)
     monkeypatch.setattr(config.ConfigServing, "serving_address", "http://127.0.0.1:9")  # nothing listens: stand-alone
-    for name in ("custom_alphazero.self_play", "custom_alphazero.mcts.mcts"):
+    for name in ("custom_alphazero.self_play", "custom_alphazero.mcts.mcts", "custom_alphazero.mcts.chess_mcts"):
         sys.modules.pop(name, None)
     sp = importlib.import_module("custom_alphazero.self_play")
     try:
@@ -276,10 +276,22 @@ def test_entry_point_plays_chess(tmp_path, monkeypatch):
         data = np.load(files[0])
         assert set(data.files) == {"states", "policies", "values"}
         assert data["states"].shape == (72, 8, 8, 118) and data["policies"].shape == (72, 1880) and len(data["values"]) == 72
-        with pytest.raises(NotImplementedError):
-            sp.play_game(0, [], 8, "x")
+        # play_game: one game through the drop-in search object (a host round trip per simulation)
+        monkeypatch.setattr(config.ConfigB200, "chess_max_plies", 512)
+        cut = {"n": 0}
+        real_over = sp.Board.is_game_over
+
+        def over_after_four(self):  # stop the plumbing check after four plies
+            cut["n"] += 1
+            return cut["n"] > 4 or real_over(self)
+
+        monkeypatch.setattr(sp.Board, "is_game_over", over_after_four)
+        monkeypatch.setattr(sp.Board, "get_result", lambda self, keep_same_player=False: 0)
+        states, policies, rewards, search = sp.play_game(0, sp.get_all_possible_moves(), 8, "x")
+        assert states.shape == (4, 8, 8, 118) and policies.shape == (4, 1880) and len(rewards) == 4 and search.model is None
+        assert np.allclose(policies.sum(-1), 1.0)
     finally:
-        for name in ("custom_alphazero.self_play", "custom_alphazero.mcts.mcts"):
+        for name in ("custom_alphazero.self_play", "custom_alphazero.mcts.mcts", "custom_alphazero.mcts.chess_mcts"):
             sys.modules.pop(name, None)  # the next importer gets the Connect-N flavour again
 
 
@@ -458,6 +470,60 @@ def test_tail_planes_are_the_last_34_and_change_nothing():
             assert (v_tail - v_full).abs().max().item() <= 1e-2
             checked += int(ok.sum())
     assert checked > 1000
+
+
+def test_drop_in_mcts_class_for_chess(monkeypatch):
+    """custom_alphazero.mcts.mcts.MCTS with ConfigGeneral.game = "chess", driven like the reference drives it (search,
+    play(return_details=True, deterministic=True), evaluator through the module-level infer_sample hook), against the
+    C oracle's MCTS with the same fixed evaluator."""
+    import importlib
+    import sys
+
+    from custom_alphazero import config
+
+    monkeypatch.setattr(config.ConfigGeneral, "game", "chess")
+    monkeypatch.setattr(config.ConfigMCTS, "index_move_greedy", 3)
+    for name in ("custom_alphazero.mcts.mcts", "custom_alphazero.mcts.chess_mcts"):
+        sys.modules.pop(name, None)
+    mm = importlib.import_module("custom_alphazero.mcts.mcts")
+    try:
+        from custom_alphazero.chess.board import Board
+        from custom_alphazero.chess.utils import get_all_possible_moves
+
+        calls = []
+
+        def uniform(state, concurrency):
+            calls.append(state.shape)
+            return np.full(1880, 1 / 1880), 0.0
+
+        monkeypatch.setattr(mm, "infer_sample", uniform)
+        sims, plies = 40, 6
+        want = cr.mcts_game(sims=sims, evaluator="uniform", prior_mode="f64", max_plies=plies, greedy_idx=3)
+        moves = get_all_possible_moves()
+        search = mm.MCTS(board=Board(), all_possible_moves=moves, concurrency=False, plays_inferences={}, model=None)
+        assert type(search).__name__ == "ChessMCTS" and search.current_root.edges == []
+        for ply in range(plies):
+            search.search(sims)
+            k = int(want["k"][ply])
+            edges = search.current_root.edges
+            assert [e.visit_count for e in edges] == want["n"][ply][:k].tolist(), ply
+            assert [moves.index(e.action) for e in edges] == want["act"][ply][:k].tolist()
+            greedy = ply >= 3
+            parent, child, policy, move = search.play(greedy, return_details=True, deterministic=True)
+            assert moves.index(move) == int(want["choice"][ply]) & 0xFFFF
+            assert parent.shape == child.shape == (8, 8, 118) and policy.shape == (1880,)
+            n = want["n"][ply][:k].astype(np.float64)
+            ref = np.zeros(1880)
+            if greedy:
+                ref[want["act"][ply][int(np.argmax(n))]] = 1.0
+            else:
+                ref[want["act"][ply][:k].astype(np.int64)] = n / n.sum()
+            assert np.array_equal(policy, ref), ply
+        assert calls and set(calls) == {(8, 8, 118)}
+        assert search.board.turn is True and not search.board.is_game_over()
+    finally:
+        for name in ("custom_alphazero.mcts.mcts", "custom_alphazero.mcts.chess_mcts"):
+            sys.modules.pop(name, None)
 
 
 def _lcg_local(seed):

@@ -27,6 +27,11 @@ class ChessSelfPlayRunner:
                  move_mode="philox", auto_restart=True, unroll=8, use_graph=True, max_free_sims=8, node_capacity=None,
                  max_plies=512, sample_capacity=None, device=None, index_move_greedy=8, stem_from_boards=False, tail_planes=False):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        import os
+
+        route = os.environ.get("AZ_CHESS_STEM")  # experiment knob: boards | tail | planes
+        if route:
+            stem_from_boards, tail_planes = route == "boards", route == "tail"
         T = int(n_trees)
         if net is None:
             net = chess_net()

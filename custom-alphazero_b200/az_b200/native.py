@@ -142,6 +142,7 @@ SYMBOLS = {
     "az_chess_search": (ctypes.c_int, [_P, _P]),
     "az_chess_step": (ctypes.c_int, [_P, _P, _P, _I, _P, _I, _I, _P, _P]),
     "az_chess_stem": (ctypes.c_int, [_P, _I, _P, _P, _P, _P]),
+    "az_chess_stem_tc": (ctypes.c_int, [_P, _I, _P, _P, _P, _P]),
     "az_chess_move": (ctypes.c_int, [_P, _I, _I, _P]),
     "az_chess_rings_clear": (ctypes.c_int, [_P, _P]),
     "az_chess_decode_samples": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _P, _P, _P]),

@@ -165,6 +165,9 @@ class InferenceNet(nn.Module):
             red[:, :14] = w16[:, 98:112]
             red[:, 14:20] = w16[:, 112:118]
             self.chess_stem_w = nn.Parameter(red.reshape(net.filters, 24, 9).contiguous(), requires_grad=False)
+            # the same weights as a [128][256] bf16 GEMM operand, K = tap * 24 + plane (az_chess_stem_tc)
+            k_major = red.reshape(net.filters, 24, 9).permute(0, 2, 1).reshape(net.filters, 216)
+            self.chess_stem_w16 = nn.Parameter(F.pad(k_major, (0, 40)).to(torch.bfloat16).contiguous(), requires_grad=False)
             # the stem restricted to planes 84-117 (initial-position entry, current entry, scalars; 34 planes padded to
             # 40): on the self-play path the six older history entries are always empty (az_chess_step plane_first = 84)
             tail = F.pad(self.stem_w.detach().contiguous()[:, 84:118], (0, 0, 0, 0, 0, 6)).contiguous(memory_format=cl)
@@ -353,14 +356,19 @@ class InferenceNet(nn.Module):
         return out.permute(0, 3, 1, 2)
 
     @torch.no_grad()
-    def chess_stem(self, positions):
-        """positions int64 [B, 8] (az_chess_pos) on the GPU -> stem output [B, 8, 8, 128] bf16 (az_chess_stem)."""
+    def chess_stem(self, positions, tc=True):
+        """positions int64 [B, 8] (az_chess_pos) on the GPU -> stem output [B, 8, 8, 128] bf16: az_chess_stem_tc
+        (tcgen05) or az_chess_stem (mma.sync)."""
         from .engine import _ptr, _stream
         from .native import check, lib
 
         B = positions.shape[0]
         out = torch.empty((B, 8, 8, self.filters), dtype=torch.bfloat16, device=positions.device)
-        check(lib().az_chess_stem(_ptr(positions), B, _ptr(self.chess_stem_w), _ptr(self.chess_stem_map), _ptr(out), _stream()))
+        if tc:
+            check(lib().az_chess_stem_tc(_ptr(positions), B, _ptr(self.chess_stem_w16), _ptr(self.chess_stem_map), _ptr(out),
+                                         _stream()))
+        else:
+            check(lib().az_chess_stem(_ptr(positions), B, _ptr(self.chess_stem_w), _ptr(self.chess_stem_map), _ptr(out), _stream()))
         return out
 
     def load_from(self, net: PolicyValueNet):

@@ -455,6 +455,190 @@ __global__ void __launch_bounds__(128, 1) k_dense_heads(DenseHeadParams P) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kHeadsTmemCols) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Chess stem from the 64-byte boards on tcgen05 (the product-path version of az_chess.cu's k_chess_stem).  On the
+// self-play path only 20 of the 118 input planes vary (current entry + scalars; az_chess.cu explains why), so the stem is
+// out[cell][ch] = relu(cmap[cell][ch] + sum_{tap, plane < 24} x[cell + tap][plane] * w[ch][tap * 24 + plane]):
+// an implicit GEMM with K = 9 x 24 = 216 (padded to 256).  A tile is two positions = 128 cells = the 128 TMEM lanes.
+//   * the reduced weights [128][256] bf16 stay resident in shared memory (K-major SWIZZLE_128B, 64 KB);
+//   * per tile the CTA first writes each cell's 24 planes as three 16-byte chunks (from the bitboards: one-hot piece
+//     plane, castling flags, clocks), then builds the im2col tile: row = cell, chunks 3 * tap .. 3 * tap + 2 = the
+//     neighbour's three chunks (zeros off the board) - 128-bit shared-memory copies into the swizzled layout;
+//   * one thread issues 16 tcgen05.mma (128 x 128 x 16) into TMEM; the A tile is double buffered so the next tile is
+//     built while the tensor core runs; epilogue as in k_conv1x1 (+ the per-cell constant, ReLU), 8 warps.
+constexpr int kStemK = 256;
+constexpr int kStemATile = 4 * kKBlockBytes;        // [128 rows][256 K] bf16 = 64 KB
+constexpr int kStemSmem = 3 * kStemATile + 2 * 64 * 48 + 1024;  // weights + two A tiles + the two positions' cell chunks
+
+struct StemTcParams {
+    const uint64_t* pos;       // [n][8] az_chess_pos
+    const __nv_bfloat16* w;    // [128][256] reduced stem weights, K = tap * 24 + plane, zero beyond 216
+    const float* cmap;         // [64][128] bias + initial-position contribution per cell
+    __nv_bfloat16* out;        // [n][64][128]
+    int n;
+};
+
+__device__ __forceinline__ int stem_piece_plane(const uint64_t* p, int sq) {
+    const uint64_t s = 1ull << sq;
+    int v = 0;
+    if (p[0] & s) v = 1;
+    else if (p[1] & s) v = 2;
+    else if (p[2] & s) v = 3;
+    else if (p[3] & s) v = 4;
+    else if (p[4] & s) v = 5;
+    else if (p[5] & s) v = 6;
+    if (v && !(p[6] & s)) v = 13 - v;  // black pieces: np.eye(13)[negative] wraps (chess/board.py:50-56)
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 1) k_chess_stem_tc(StemTcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sW = base, sA0 = base + kStemATile;
+    uint4* cellchunks = reinterpret_cast<uint4*>(gen + 3 * kStemATile);  // [2 positions][64 cells][3 chunks]
+    const uint32_t bar = smem_u32(&s_bar);
+    const int n_tiles = (P.n + 1) / 2;
+
+    // weights: [128 rows][256 K] -> four K blocks of the UMMA layout; both A tiles start as zeros (their K padding stays)
+    for (int idx = tid; idx < 128 * 32; idx += 256) {
+        const int r = idx >> 5, c = idx & 31;  // 32 chunks of 8 K per row
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.w + r * kStemK) + c);
+        *reinterpret_cast<uint4*>(gen + (c >> 3) * kKBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + (((c & 7) ^ (r & 7)) << 4)) = v;
+    }
+    for (int idx = tid; idx < 2 * kStemATile / 16; idx += 256)
+        reinterpret_cast<uint4*>(gen + kStemATile)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    uint32_t phase = 0;
+
+    // the boards of a tile are fetched one tile ahead (registers), so their HBM latency is off the per-tile critical path
+    uint64_t q[8];
+    bool q_valid = false;
+    auto fetch = [&](int tile) {
+        q_valid = false;
+        if (tid < 128 && tile < n_tiles) {
+            const long long pidx = 2LL * tile + (tid >> 6);
+            if (pidx < P.n) {
+                q_valid = true;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) q[i] = __ldg(P.pos + pidx * 8 + i);
+            }
+        }
+    };
+    // builds the im2col tile of the fetched boards in A buffer `buf` (all 256 threads)
+    auto build = [&](int buf) {
+        // (1) the 24 planes of every cell of the two positions as three 16-byte chunks
+        if (tid < 128) {
+            const int which = tid >> 6, cell = tid & 63;
+            uint32_t w[12] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (q_valid) {
+                const int sq = ((7 - (cell >> 3)) << 3) | (cell & 7);  // array row 0 is rank 8
+                const int pl = stem_piece_plane(q, sq);
+                const uint64_t meta = q[7];
+                const bool black = (meta >> 11) & 1;
+                const int own_k = black ? 4 : 1, own_q = black ? 8 : 2, opp_k = black ? 1 : 4, opp_q = black ? 2 : 8;
+                const uint32_t one = 0x3f80u;
+#pragma unroll
+                for (int wd = 0; wd < 7; ++wd) w[wd] = (pl >> 1) == wd ? (one << (16 * (pl & 1))) : 0u;
+                w[7] = ((meta & own_q) ? one : 0u) | ((meta & own_k) ? one << 16 : 0u);
+                w[8] = ((meta & opp_q) ? one : 0u) | ((meta & opp_k) ? one << 16 : 0u);
+                w[9] = pack_bf16((float)((meta >> 32) & 0xffff), (float)((meta >> 16) & 0xffff));  // fullmove, halfmove
+            }
+            uint4* cc = cellchunks + (which * 64 + cell) * 3;
+            cc[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            cc[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            cc[2] = make_uint4(w[8], w[9], w[10], w[11]);
+        }
+        __syncthreads();
+        // (2) row r = (position, cell), chunk 3 * tap + j <- chunk j of the neighbour cell (zeros off the board)
+        uint8_t* A = gen + kStemATile + buf * kStemATile;
+        for (int idx = tid; idx < 128 * 27; idx += 256) {
+            const int r = idx / 27, gc = idx - r * 27, tap = gc / 3, j = gc - tap * 3;
+            const int which = r >> 6, cell = r & 63;
+            const int y = (cell >> 3) + tap / 3 - 1, x = (cell & 7) + tap % 3 - 1;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if ((unsigned)y < 8u && (unsigned)x < 8u) v = cellchunks[(which * 64 + y * 8 + x) * 3 + j];
+            *reinterpret_cast<uint4*>(A + (gc >> 3) * kKBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + (((gc & 7) ^ (r & 7)) << 4)) = v;
+        }
+    };
+
+    int tile = blockIdx.x, buf = 0;
+    fetch(tile);
+    if (tile < n_tiles) build(0);
+    fetch(tile + gridDim.x);
+    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();  // A[buf] complete; the previous epilogue is done with TMEM and its staging buffer
+        const uint32_t sA = sA0 + buf * kStemATile;
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < kStemK / 16; ++k) {
+                const uint32_t koff = (uint32_t)((k >> 2) * kKBlockBytes + (k & 3) * 32);
+                mma_bf16_i(tmem, umma_desc(sA + koff), umma_desc(sW + koff), idesc_bf16(128, 128), k > 0);
+            }
+            commit_to(bar);
+        }
+        const int next = tile + gridDim.x;
+        if (next < n_tiles) build(buf ^ 1);  // while the tensor core works on this tile (contains a __syncthreads)
+        fetch(next + gridDim.x);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        // epilogue: warp w reads TMEM lanes 32 * (w & 3), columns 64 * (w >> 2) .. + 63; row r = lane of the quarter
+        uint8_t* stage = gen + kStemATile + buf * kStemATile;  // this tile's A buffer: the MMA has finished reading it
+        const int r = (warp & 3) * 32 + lane, cell = r & 63, ch0 = (warp >> 2) * 64;
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(ch0 + cb * 32), v);
+            const float4* cm = reinterpret_cast<const float4*>(P.cmap + cell * 128 + ch0 + cb * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 c0 = __ldg(cm + 2 * q), c1 = __ldg(cm + 2 * q + 1);
+                uint4 o;
+                o.x = pack_bf16(fmaxf(__uint_as_float(v[8 * q + 0]) + c0.x, 0.f), fmaxf(__uint_as_float(v[8 * q + 1]) + c0.y, 0.f));
+                o.y = pack_bf16(fmaxf(__uint_as_float(v[8 * q + 2]) + c0.z, 0.f), fmaxf(__uint_as_float(v[8 * q + 3]) + c0.w, 0.f));
+                o.z = pack_bf16(fmaxf(__uint_as_float(v[8 * q + 4]) + c1.x, 0.f), fmaxf(__uint_as_float(v[8 * q + 5]) + c1.y, 0.f));
+                o.w = pack_bf16(fmaxf(__uint_as_float(v[8 * q + 6]) + c1.z, 0.f), fmaxf(__uint_as_float(v[8 * q + 7]) + c1.w, 0.f));
+                *reinterpret_cast<uint4*>(stage + stage_chunk_offset(r, (ch0 >> 3) + cb * 4 + q)) = o;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        const long long row0 = (long long)tile * 128, rows = (long long)P.n * 64;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + 256 * i, rr = idx >> 4, c = idx & 15;
+            if (row0 + rr < rows)
+                *(reinterpret_cast<uint4*>(P.out + (row0 + rr) * 128) + c) =
+                    *reinterpret_cast<const uint4*>(stage + stage_chunk_offset(rr, c));
+        }
+        // the staging area is the first 32 KB of this tile's A buffer (K blocks 0 and 1); the K padding lives in block 3
+        // and is never touched, and the next build into this buffer rewrites every real chunk
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kTmemCols) : "memory");
+}
+
 }  // namespace gemm
 }  // namespace az
 
@@ -518,5 +702,29 @@ extern "C" __attribute__((visibility("default"))) int az_net_dense_heads(const f
     k_dense_heads<0><<<grid, 128, kHeadsSmem, s>>>(P);
     k_dense_heads<1><<<grid, 128, kHeadsSmem, s>>>(P);
     if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_dense_heads: launch failed");
+    return AZ_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int az_chess_stem_tc(const void* pos, int32_t n, const void* w_reduced_bf16,
+                                                                        const float* cell_map, void* out, void* stream) {
+    using namespace az::gemm;
+    if (n == 0) return AZ_OK;
+    if (!pos || !w_reduced_bf16 || !cell_map || !out || n < 0) return az::fail_net(AZ_ERR_ARG, "az_chess_stem_tc: bad argument");
+    if ((reinterpret_cast<uintptr_t>(w_reduced_bf16) | reinterpret_cast<uintptr_t>(cell_map) | reinterpret_cast<uintptr_t>(out)) & 15)
+        return az::fail_net(AZ_ERR_ARG, "az_chess_stem_tc: pointers must be 16-byte aligned");
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return az::fail_net(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback");
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_chess_stem_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem) != cudaSuccess)
+            return az::fail_net(AZ_ERR_CUDA, "az_chess_stem_tc: shared memory request refused");
+        configured = true;
+    }
+    const int n_tiles = (n + 1) / 2;
+    StemTcParams P{static_cast<const uint64_t*>(pos), static_cast<const __nv_bfloat16*>(w_reduced_bf16), cell_map,
+                   static_cast<__nv_bfloat16*>(out), n};
+    k_chess_stem_tc<<<n_tiles < sms ? n_tiles : sms, 256, kStemSmem, static_cast<cudaStream_t>(stream)>>>(P);
+    if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_chess_stem_tc: launch failed");
     return AZ_OK;
 }

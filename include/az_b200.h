@@ -477,6 +477,10 @@ int az_chess_step(az_chess_engine *e, const void *dev_priors, const void *dev_va
  * order, row 0 = rank 8).  out: dev bf16 [n][8][8][128], the tower's input. */
 int az_chess_stem(const az_chess_pos *dev_pos, int32_t n, const float *dev_w_reduced, const float *dev_cell_map, void *dev_out,
                   void *stream);
+/* The same on tcgen05 (csrc/az_gemm.cu): w_reduced_bf16 = dev bf16 [128][256], K index = tap * 24 + plane (zero beyond
+ * 216); two positions per 128-row tile, im2col tile built in shared memory from the boards. */
+int az_chess_stem_tc(const void *dev_pos, int32_t n, const void *dev_w_reduced_bf16, const float *dev_cell_map, void *dev_out,
+                     void *stream);
 /* MCTS.play for every tree whose budget is spent: sample-ring entry, move, re-root (in place, or compacted into the
  * other pool half), game end -> finished ring + next game.  greedy_override / move_mode_override: -1 = configured. */
 int az_chess_move(az_chess_engine *e, int32_t greedy_override, int32_t move_mode_override, void *stream);

@@ -400,10 +400,13 @@ def test_stem_from_boards_equals_the_convolution_on_planes():
     planes = chess.chess_encode(pos, dtype=torch.bfloat16)                       # [n, 8, 8, 118] bf16 on the GPU
     x = torch.nn.functional.pad(planes, (0, inf.in_pad)).permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
     ref = torch.cudnn_convolution_relu(x, inf.stem_w_pad, inf.stem_b, (1, 1), (1, 1), (1, 1), 1).permute(0, 2, 3, 1).float()
-    got = inf.chess_stem(torch.from_numpy(pos.view(np.int64)).cuda()).float()
-    assert got.shape == ref.shape == (len(pos), 8, 8, 128)
-    err = (got - ref).abs().max().item()
-    assert err <= 2.0 ** -6 * max(1.0, ref.abs().max().item()), err   # one bf16 rounding of the output, different summation order
+    dev_pos = torch.from_numpy(pos.view(np.int64)).cuda()
+    for tc in (True, False):  # tcgen05 and mma.sync versions
+        for n in (len(pos), 1, 7):  # odd counts: the last tcgen05 tile holds one position
+            got = inf.chess_stem(dev_pos[:n], tc=tc).float()
+            assert got.shape == (n, 8, 8, 128)
+            err = (got - ref[:n]).abs().max().item()
+            assert err <= 2.0 ** -6 * max(1.0, ref.abs().max().item()), (tc, n, err)   # one bf16 rounding, other summation order
     assert float(ref.max()) > 0.5 and float((ref > 0).float().mean()) > 0.2  # the probe is not all zeros after the ReLU
     # end to end: priors / values through both routes
     p1, v1 = inf.forward_from_stem(inf.chess_stem(torch.from_numpy(pos.view(np.int64)).cuda()))

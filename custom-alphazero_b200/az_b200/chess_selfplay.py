@@ -25,7 +25,7 @@ def chess_net(filters=128, depth=4):
 class ChessSelfPlayRunner:
     def __init__(self, n_trees=1024, sims_per_move=200, net=None, *, games_target=None, game_id_base=0, seed=0,
                  move_mode="philox", auto_restart=True, unroll=8, use_graph=True, max_free_sims=8, node_capacity=None,
-                 max_plies=512, sample_capacity=None, device=None, index_move_greedy=8, stem_from_boards=False, tail_planes=False):
+                 max_plies=512, sample_capacity=None, device=None, index_move_greedy=8, stem_from_boards=True, tail_planes=False):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         import os
 
@@ -56,15 +56,15 @@ class ChessSelfPlayRunner:
         self.valid = torch.zeros(T, dtype=torch.int32, device=self.device)
         self.priors = torch.zeros((T, N_ACTIONS), dtype=torch.float32, device=self.device)
         self.values = torch.zeros(T, dtype=torch.float32, device=self.device)
-        # stem_from_boards: az_chess_stem computes the stem from the 64-byte leaf boards and no plane tensor exists
-        # (63 MB less traffic per advance at 4096 trees); its mma.sync implicit GEMM takes ~97 us against 69 us for
-        # cuDNN's tcgen05 stem on the planes, which cancels the saving (4.76 vs 4.77 M simulations/s): opt-in
+        # stem_from_boards (default): az_chess_stem_tc computes the stem from the 64-byte leaf boards on tcgen05 (50 us at
+        # 4096 positions against 64.5 us for cuDNN on the 120-plane tensor) and no plane tensor exists at all (63 MB less
+        # traffic per advance): 4.89 vs 4.69 M simulations/s on the same box
         self.stem_from_boards = bool(stem_from_boards) and hasattr(self.net, "chess_stem_w")
         self.unroll, self.use_graph, self.graph = int(unroll), use_graph, None
         self.advances = 0
         self.flops_per_eval = flops_per_eval(8, 8, N_ACTIONS, in_planes=PLANES)  # of the reference's net
         # FLOPs the GPU route really executes per evaluation: the structurally zero planes are not multiplied
-        self.flops_per_eval_executed = flops_per_eval(8, 8, N_ACTIONS, in_planes=34 if self.tail_planes else PLANES)
+        self.flops_per_eval_executed = flops_per_eval(8, 8, N_ACTIONS, in_planes=24 if self.stem_from_boards else (34 if self.tail_planes else PLANES))
         self.launches_per_advance = 2  # az_chess_step + az_chess_move (ours); the net's kernels are library calls
         self._games = {}  # game id -> (length, result) of games whose samples may still sit in a later drain
 

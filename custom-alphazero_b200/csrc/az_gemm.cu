@@ -492,6 +492,21 @@ __device__ __forceinline__ int stem_piece_plane(const uint64_t* p, int sq) {
     return v;
 }
 
+template <int H>
+__device__ __forceinline__ void im2col_half(uint8_t* A, const uint4* cellchunks, int r) {
+    const int which = r >> 6, cell = r & 63, cy = cell >> 3, cx = cell & 7, r7 = r & 7;
+    uint8_t* row = A + (r >> 3) * 1024 + r7 * 128;
+    const uint4* cc = cellchunks + which * 64 * 3;
+#pragma unroll
+    for (int g = 0; g < (H ? 13 : 14); ++g) {
+        const int gc = H * 14 + g, tap = gc / 3, j = gc - tap * 3, dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int y = cy + dy, x = cx + dx;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if ((unsigned)y < 8u && (unsigned)x < 8u) v = cc[(y * 8 + x) * 3 + j];
+        *reinterpret_cast<uint4*>(row + (gc >> 3) * kKBlockBytes + (((gc & 7) ^ r7) << 4)) = v;
+    }
+}
+
 __global__ void __launch_bounds__(256, 1) k_chess_stem_tc(StemTcParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -505,11 +520,12 @@ __global__ void __launch_bounds__(256, 1) k_chess_stem_tc(StemTcParams P) {
     const int n_tiles = (P.n + 1) / 2;
 
     // weights: [128 rows][256 K] -> four K blocks of the UMMA layout; both A tiles start as zeros (their K padding stays)
-    for (int idx = tid; idx < 128 * 32; idx += 256) {
-        const int r = idx >> 5, c = idx & 31;  // 32 chunks of 8 K per row
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.w + r * kStemK) + c);
-        *reinterpret_cast<uint4*>(gen + (c >> 3) * kKBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + (((c & 7) ^ (r & 7)) << 4)) = v;
+    for (int idx = tid; idx < 128 * 32; idx += 256) {  // cp.async: in flight underneath the first tile's build
+        const int r = idx >> 5, c = idx & 31;          // 32 chunks of 8 K per row
+        const uint32_t dst = sW + (uint32_t)((c >> 3) * kKBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + (((c & 7) ^ (r & 7)) << 4));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(P.w + r * kStemK + c * 8) : "memory");
     }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
     for (int idx = tid; idx < 2 * kStemATile / 16; idx += 256)
         reinterpret_cast<uint4*>(gen + kStemATile)[idx] = make_uint4(0u, 0u, 0u, 0u);
     if (warp == 0) {
@@ -566,22 +582,19 @@ __global__ void __launch_bounds__(256, 1) k_chess_stem_tc(StemTcParams P) {
             cc[2] = make_uint4(w[8], w[9], w[10], w[11]);
         }
         __syncthreads();
-        // (2) row r = (position, cell), chunk 3 * tap + j <- chunk j of the neighbour cell (zeros off the board)
+        // (2) row r = (position, cell), chunk 3 * tap + j <- chunk j of the neighbour cell (zeros off the board).  Warps 0-3
+        // copy chunks 0-13 of rows 0-127, warps 4-7 chunks 14-26: every index below is a compile-time constant after
+        // unrolling (the first version spent two thirds of the kernel's instructions on idx / 27, gc / 3, tap / 3 ...)
         uint8_t* A = gen + kStemATile + buf * kStemATile;
-        for (int idx = tid; idx < 128 * 27; idx += 256) {
-            const int r = idx / 27, gc = idx - r * 27, tap = gc / 3, j = gc - tap * 3;
-            const int which = r >> 6, cell = r & 63;
-            const int y = (cell >> 3) + tap / 3 - 1, x = (cell & 7) + tap % 3 - 1;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if ((unsigned)y < 8u && (unsigned)x < 8u) v = cellchunks[(which * 64 + y * 8 + x) * 3 + j];
-            *reinterpret_cast<uint4*>(A + (gc >> 3) * kKBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + (((gc & 7) ^ (r & 7)) << 4)) = v;
-        }
+        if (tid < 128) im2col_half<0>(A, cellchunks, tid);
+        else im2col_half<1>(A, cellchunks, tid - 128);
     };
 
     int tile = blockIdx.x, buf = 0;
     fetch(tile);
     if (tile < n_tiles) build(0);
     fetch(tile + gridDim.x);
+    asm volatile("cp.async.wait_all;\n" ::: "memory");  // the weights
     for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -602,37 +615,48 @@ __global__ void __launch_bounds__(256, 1) k_chess_stem_tc(StemTcParams P) {
         mbar_wait(bar, phase);
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        // epilogue: warp w reads TMEM lanes 32 * (w & 3), columns 64 * (w >> 2) .. + 63; row r = lane of the quarter
-        uint8_t* stage = gen + kStemATile + buf * kStemATile;  // this tile's A buffer: the MMA has finished reading it
-        const int r = (warp & 3) * 32 + lane, cell = r & 63, ch0 = (warp >> 2) * 64;
+        // epilogue: warp w reads TMEM lanes 32 * (w & 3), columns 64 * (w >> 2) .. + 63 and parks the raw float32
+        // accumulators in this tile's A buffer (the MMA has finished reading it; 128 rows x 512 B, chunks XOR-ed with the
+        // row: conflict free).  The per-cell constant is added in the coalesced pass below - read per row it would cost
+        // 32 cache lines per load instruction.
+        uint8_t* stage = gen + kStemATile + buf * kStemATile;
+        const int r = (warp & 3) * 32 + lane, ch0 = (warp >> 2) * 64;
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
             uint32_t v[32];
             tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(ch0 + cb * 32), v);
-            const float4* cm = reinterpret_cast<const float4*>(P.cmap + cell * 128 + ch0 + cb * 32);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 c0 = __ldg(cm + 2 * q), c1 = __ldg(cm + 2 * q + 1);
-                uint4 o;
-                o.x = pack_bf16(fmaxf(__uint_as_float(v[8 * q + 0]) + c0.x, 0.f), fmaxf(__uint_as_float(v[8 * q + 1]) + c0.y, 0.f));
-                o.y = pack_bf16(fmaxf(__uint_as_float(v[8 * q + 2]) + c0.z, 0.f), fmaxf(__uint_as_float(v[8 * q + 3]) + c0.w, 0.f));
-                o.z = pack_bf16(fmaxf(__uint_as_float(v[8 * q + 4]) + c1.x, 0.f), fmaxf(__uint_as_float(v[8 * q + 5]) + c1.y, 0.f));
-                o.w = pack_bf16(fmaxf(__uint_as_float(v[8 * q + 6]) + c1.z, 0.f), fmaxf(__uint_as_float(v[8 * q + 7]) + c1.w, 0.f));
-                *reinterpret_cast<uint4*>(stage + stage_chunk_offset(r, (ch0 >> 3) + cb * 4 + q)) = o;
+            for (int q = 0; q < 8; ++q) {
+                const int ch4 = (ch0 >> 2) + cb * 8 + q;  // 16-byte chunk of four float32
+                *reinterpret_cast<uint4*>(stage + r * 512 + ((ch4 ^ (r & 31)) << 4)) =
+                    make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncthreads();
         const long long row0 = (long long)tile * 128, rows = (long long)P.n * 64;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8; ++i) {  // 16 lanes = one output row of 256 B: coalesced stores, coalesced constant loads
             const int idx = tid + 256 * i, rr = idx >> 4, c = idx & 15;
-            if (row0 + rr < rows)
-                *(reinterpret_cast<uint4*>(P.out + (row0 + rr) * 128) + c) =
-                    *reinterpret_cast<const uint4*>(stage + stage_chunk_offset(rr, c));
+            const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * 512 + (((2 * c) ^ (rr & 31)) << 4));
+            const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * 512 + (((2 * c + 1) ^ (rr & 31)) << 4));
+            const float4* cm = reinterpret_cast<const float4*>(P.cmap + (rr & 63) * 128 + c * 8);
+            const float4 c0 = __ldg(cm), c1 = __ldg(cm + 1);
+            uint4 o;
+            o.x = pack_bf16(fmaxf(a0.x + c0.x, 0.f), fmaxf(a0.y + c0.y, 0.f));
+            o.y = pack_bf16(fmaxf(a0.z + c0.z, 0.f), fmaxf(a0.w + c0.w, 0.f));
+            o.z = pack_bf16(fmaxf(a1.x + c1.x, 0.f), fmaxf(a1.y + c1.y, 0.f));
+            o.w = pack_bf16(fmaxf(a1.z + c1.z, 0.f), fmaxf(a1.w + c1.w, 0.f));
+            if (row0 + rr < rows) *(reinterpret_cast<uint4*>(P.out + (row0 + rr) * 128) + c) = o;
         }
-        // the staging area is the first 32 KB of this tile's A buffer (K blocks 0 and 1); the K padding lives in block 3
-        // and is never touched, and the next build into this buffer rewrites every real chunk
+        __syncthreads();
+        // the float32 staging covered the whole A buffer: its K padding (chunks 27-31 of every row) must be zero again
+        // before the buffer is an operand the next time; the 27 real chunks per row are rewritten by the next build
+        if (tid < 128) {
+            uint8_t* prow = stage + 3 * kKBlockBytes + (tid >> 3) * 1024 + (tid & 7) * 128;
+#pragma unroll
+            for (int gc = 27; gc < 32; ++gc) *reinterpret_cast<uint4*>(prow + (((gc & 7) ^ (tid & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();

@@ -142,6 +142,15 @@ class InferenceNet(nn.Module):
         # float32 copies for the hand-written stem / heads kernels (az_net_stem, az_net_heads)
         sw, sb = net.stem.folded()
         self.stem_w32, self.stem_b32 = f32(sw), f32(sb)
+        if net.in_planes == 4:
+            # the stem as a [128][64] bf16 GEMM operand, K = tap * 4 + plane, for az_net_stem_tc (tcgen05)
+            k_major = sw.detach().permute(0, 2, 3, 1).reshape(sw.shape[0], 36)
+            self.stem_w16_k = nn.Parameter(F.pad(k_major, (0, 28)).to(device=device, dtype=torch.bfloat16).contiguous(),
+                                           requires_grad=False)
+        import os as _os
+
+        self.tc_stem = (net.in_planes == 4 and net.filters == 128 and net.height * net.width <= 128
+                        and _os.environ.get("AZ_TC_STEM", "1") != "0")
         # both 1x1 head convolutions as one [3, C] matrix (2 policy planes + 1 value plane)
         pw, pb = net.policy_conv.folded()
         vw, vb = net.value_conv.folded()
@@ -304,8 +313,12 @@ class InferenceNet(nn.Module):
         B, H, W = x_nhwc.shape[0], self.height, self.width
         x_nhwc = x_nhwc.to(torch.bfloat16).contiguous()
         h0 = torch.empty((B, H, W, self.filters), dtype=torch.bfloat16, device=x_nhwc.device)
-        check(lib().az_net_stem(_ptr(x_nhwc), _ptr(self.stem_w32), _ptr(self.stem_b32), B, H, W, self.filters,
-                                _ptr(h0), _stream()))
+        if self.tc_stem:
+            check(lib().az_net_stem_tc(_ptr(x_nhwc), _ptr(self.stem_w16_k), _ptr(self.stem_b32), B, H, W, self.filters,
+                                       _ptr(h0), _stream()))
+        else:
+            check(lib().az_net_stem(_ptr(x_nhwc), _ptr(self.stem_w32), _ptr(self.stem_b32), B, H, W, self.filters,
+                                    _ptr(h0), _stream()))
         xm = self.tower(h0)
         if priors_out is None:
             priors_out = torch.empty((B, self.n_actions), dtype=torch.float32, device=xm.device)

@@ -663,6 +663,153 @@ __global__ void __launch_bounds__(256, 1) k_chess_stem_tc(StemTcParams P) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kTmemCols) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Connect-N stem on tcgen05: Conv3x3(4 -> 128) + BN + ReLU (model/tensorflow/model.py:36-46) on the [n][H][W][4] bf16 leaf
+// batch az_step writes - the tensor-core replacement of az_net_stem's mma.sync kernel.  K = 9 taps x 4 planes = 36
+// (one 64-wide K block); a 128-row tile holds floor(128 / cells) whole positions (3 at 6x7); a cell's four planes are one
+// 8-byte word, so an im2col chunk (two taps) is two neighbour words (zeros off the board).
+constexpr int kC4StemSmem = 16384 + 2 * 16384 + 32768 + 2 * 1024 + 1024;
+
+struct C4StemParams {
+    const uint2* in;           // [n][cells] four bf16 planes per cell
+    const __nv_bfloat16* w;    // [128][64], K index = tap * 4 + plane, zero beyond 36
+    const float* bias;         // [128]
+    __nv_bfloat16* out;        // [n][cells][128]
+    int n, H, W, cells, ppt;   // ppt = positions per tile
+};
+
+__global__ void __launch_bounds__(256, 2) k_stem_tc(C4StemParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_bias[128];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sW = base, sA0 = base + 16384;
+    uint8_t* stage = gen + 3 * 16384;
+    uint2* cellbuf = reinterpret_cast<uint2*>(gen + 3 * 16384 + 32768);  // [2 buffers][128 cells]
+    const uint32_t bar = smem_u32(&s_bar);
+    const int rows_used = P.ppt * P.cells;
+    const int n_tiles = (P.n + P.ppt - 1) / P.ppt;
+
+    for (int idx = tid; idx < 128 * 8; idx += 256) {  // weights: one K block
+        const int r = idx >> 3, c = idx & 7;
+        const uint32_t dst = sW + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(P.w + r * 64 + c * 8) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    if (tid < 128) s_bias[tid] = P.bias[tid];
+    for (int idx = tid; idx < 2 * 16384 / 16; idx += 256) reinterpret_cast<uint4*>(gen + 16384)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    uint32_t phase = 0;
+
+    // this thread's im2col row is the same in every tile: row r = tid & 127, chunks 0-2 (taps 0-5) for warps 0-3,
+    // chunks 3-4 (taps 6-8) for warps 4-7
+    const int r = tid & 127, half = tid >> 7, r7 = r & 7;
+    const int lp = r / P.cells, cell = r - lp * P.cells, cy = cell / P.W, cx = cell - cy * P.W;
+    const bool row_live = r < rows_used;
+    int nb[6];  // neighbour indices into cellbuf for this thread's taps (-1 = off the board / dead row)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int tap = half * 6 + i, y = cy + tap / 3 - 1, x = cx + tap % 3 - 1;
+        nb[i] = (row_live && tap < 9 && (unsigned)y < (unsigned)P.H && (unsigned)x < (unsigned)P.W) ? lp * P.cells + y * P.W + x : -1;
+    }
+    uint2 pre = make_uint2(0u, 0u);  // this thread's cell of the next tile, fetched one tile ahead
+    auto fetch = [&](int tile) {
+        pre = make_uint2(0u, 0u);
+        if (tid < rows_used && tile < n_tiles) {
+            const long long g = (long long)tile * rows_used + tid;
+            if (g < (long long)P.n * P.cells) pre = __ldg(P.in + g);
+        }
+    };
+    auto build = [&](int buf) {
+        uint2* cb = cellbuf + buf * 128;
+        if (tid < 128) cb[tid] = pre;
+        __syncthreads();
+        uint8_t* row = gen + 16384 + buf * 16384 + (r >> 3) * 1024 + r7 * 128;
+        const uint2 z = make_uint2(0u, 0u);
+        if (half == 0) {
+#pragma unroll
+            for (int gc = 0; gc < 3; ++gc) {
+                const uint2 a = nb[2 * gc] >= 0 ? cb[nb[2 * gc]] : z, b = nb[2 * gc + 1] >= 0 ? cb[nb[2 * gc + 1]] : z;
+                *reinterpret_cast<uint4*>(row + ((gc ^ r7) << 4)) = make_uint4(a.x, a.y, b.x, b.y);
+            }
+        } else {
+#pragma unroll
+            for (int gc = 3; gc < 5; ++gc) {
+                const uint2 a = nb[2 * (gc - 3)] >= 0 ? cb[nb[2 * (gc - 3)]] : z, b = nb[2 * (gc - 3) + 1] >= 0 ? cb[nb[2 * (gc - 3) + 1]] : z;
+                *reinterpret_cast<uint4*>(row + ((gc ^ r7) << 4)) = make_uint4(a.x, a.y, b.x, b.y);
+            }
+        }
+    };
+
+    int tile = blockIdx.x, buf = 0;
+    fetch(tile);
+    if (tile < n_tiles) build(0);
+    fetch(tile + gridDim.x);
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        const uint32_t sA = sA0 + buf * 16384;
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_bf16_i(tmem, umma_desc(sA + k * 32), umma_desc(sW + k * 32), idesc_bf16(128, 128), k > 0);
+            commit_to(bar);
+        }
+        const int next = tile + gridDim.x;
+        if (next < n_tiles) build(buf ^ 1);
+        fetch(next + gridDim.x);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const int er = (warp & 3) * 32 + lane, ch0 = (warp >> 2) * 64;
+#pragma unroll
+        for (int cb2 = 0; cb2 < 2; ++cb2) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(ch0 + cb2 * 32), v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float* bb = s_bias + ch0 + cb2 * 32 + 8 * q;
+                uint4 o;
+                o.x = pack_bf16(fmaxf(__uint_as_float(v[8 * q + 0]) + bb[0], 0.f), fmaxf(__uint_as_float(v[8 * q + 1]) + bb[1], 0.f));
+                o.y = pack_bf16(fmaxf(__uint_as_float(v[8 * q + 2]) + bb[2], 0.f), fmaxf(__uint_as_float(v[8 * q + 3]) + bb[3], 0.f));
+                o.z = pack_bf16(fmaxf(__uint_as_float(v[8 * q + 4]) + bb[4], 0.f), fmaxf(__uint_as_float(v[8 * q + 5]) + bb[5], 0.f));
+                o.w = pack_bf16(fmaxf(__uint_as_float(v[8 * q + 6]) + bb[6], 0.f), fmaxf(__uint_as_float(v[8 * q + 7]) + bb[7], 0.f));
+                *reinterpret_cast<uint4*>(stage + stage_chunk_offset(er, (ch0 >> 3) + cb2 * 4 + q)) = o;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        const long long row0 = (long long)tile * rows_used, rows = (long long)P.n * P.cells;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + 256 * i, rr = idx >> 4, c = idx & 15;
+            if (rr < rows_used && row0 + rr < rows)
+                *(reinterpret_cast<uint4*>(P.out + (row0 + rr) * 128) + c) = *reinterpret_cast<const uint4*>(stage + stage_chunk_offset(rr, c));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kTmemCols) : "memory");
+}
+
 }  // namespace gemm
 }  // namespace az
 
@@ -750,5 +897,31 @@ extern "C" __attribute__((visibility("default"))) int az_chess_stem_tc(const voi
                    static_cast<__nv_bfloat16*>(out), n};
     k_chess_stem_tc<<<n_tiles < sms ? n_tiles : sms, 256, kStemSmem, static_cast<cudaStream_t>(stream)>>>(P);
     if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_chess_stem_tc: launch failed");
+    return AZ_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int az_net_stem_tc(const void* states, const void* w_bf16, const float* bias, int32_t n,
+                                                                      int32_t H, int32_t W, int32_t channels, void* out, void* stream) {
+    using namespace az::gemm;
+    if (n == 0) return AZ_OK;
+    if (!states || !w_bf16 || !bias || !out || n < 0 || H < 1 || W < 1) return az::fail_net(AZ_ERR_ARG, "az_net_stem_tc: bad argument");
+    if (channels != kC) return az::fail_net(AZ_ERR_ARG, "az_net_stem_tc: built for 128 filters (config.py:71)");
+    if (H * W > 128) return az::fail_net(AZ_ERR_ARG, "az_net_stem_tc: a position must fit one 128-row tile (H * W <= 128)");
+    if ((reinterpret_cast<uintptr_t>(states) & 7) || ((reinterpret_cast<uintptr_t>(w_bf16) | reinterpret_cast<uintptr_t>(out)) & 15))
+        return az::fail_net(AZ_ERR_ARG, "az_net_stem_tc: misaligned pointer");
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return az::fail_net(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback");
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_stem_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kC4StemSmem) != cudaSuccess)
+            return az::fail_net(AZ_ERR_CUDA, "az_net_stem_tc: shared memory request refused");
+        configured = true;
+    }
+    const int cells = H * W, ppt = 128 / cells, n_tiles = (n + ppt - 1) / ppt;
+    C4StemParams P{static_cast<const uint2*>(states), static_cast<const __nv_bfloat16*>(w_bf16), bias,
+                   static_cast<__nv_bfloat16*>(out), n, H, W, cells, ppt};
+    k_stem_tc<<<n_tiles < 2 * sms ? n_tiles : 2 * sms, 256, kC4StemSmem, static_cast<cudaStream_t>(stream)>>>(P);
+    if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_stem_tc: launch failed");
     return AZ_OK;
 }

@@ -275,6 +275,11 @@ typedef struct az_head_weights {
 int az_net_stem(const void *dev_states, const float *dev_w, const float *dev_b, int32_t n, int32_t height,
                 int32_t width, int32_t channels, void *dev_out, void *stream);
 
+/* The same stem on tcgen05 (csrc/az_gemm.cu): states as above; w_bf16: dev bf16 [128][64] with K index = tap * 4 + plane
+ * (tap = ky * 3 + kx), zero beyond 36; bias: dev float [128]; H * W <= 128. */
+int az_net_stem_tc(const void *dev_states, const void *dev_w_bf16, const float *dev_bias, int32_t n, int32_t height, int32_t width,
+                   int32_t channels, void *dev_out, void *stream);
+
 /* PolicyHead + ValueHead (model/tensorflow/model.py:68-149) on the tower output x: dev bf16 [n][H*W][C].
  * priors_out: dev float [n][A] (softmax), values_out: dev float [n] (tanh) - the buffers az_step reads. */
 int az_net_heads(const void *dev_x, const az_head_weights *weights, int32_t n, int32_t cells, int32_t channels,

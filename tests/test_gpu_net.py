@@ -257,3 +257,40 @@ def test_tower_with_tcgen05_shortcut_equals_cudnn_tower():
     b = inf.tower(h0).float()
     scale = b.abs().max().item()
     assert (a - b).abs().max().item() <= 0.02 * scale  # two bf16 roundings of the shortcut per block, different order
+
+
+def test_tcgen05_stem_equals_the_float32_convolution():
+    """az_net_stem_tc against conv3x3 in float32 on the bf16-rounded weights, for 6x7, 9x9 and 3x3 boards and batch sizes
+    that leave the last tile partly empty."""
+    import ctypes
+
+    from az_b200 import native
+    from az_b200.net import InferenceNet, PolicyValueNet, randomise_bn
+
+    lib = native.lib()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    for (H, W, A) in ((6, 7, 7), (9, 9, 81), (3, 3, 9)):
+        torch.manual_seed(H)
+        inf = InferenceNet(randomise_bn(PolicyValueNet(H, W, A)).eval(), dtype=torch.bfloat16, device="cuda")
+        assert inf.tc_stem
+        for n in (4096, 1, 2, 3, 4, 1001):
+            code = torch.randint(0, 3, (n, H, W), device="cuda")
+            x = torch.cat([torch.nn.functional.one_hot(code, 3).float(), torch.ones(n, H, W, 1, device="cuda")], -1).to(torch.bfloat16)
+            out = torch.full((n + 1, H, W, 128), 7.0, dtype=torch.bfloat16, device="cuda")
+            native.check(lib.az_net_stem_tc(P(x), P(inf.stem_w16_k), P(inf.stem_b32), n, H, W, 128, P(out),
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            torch.cuda.synchronize()
+            w = inf.stem_w.detach().float()  # the same bf16-rounded weights
+            ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w, inf.stem_b32, padding=1)).permute(0, 2, 3, 1)
+            err = (out[:n].float() - ref).abs().max().item()
+            assert err <= 2.0 ** -7 * max(1.0, ref.abs().max().item()), (H, W, n, err)
+            assert bool((out[n] == 7.0).all())
+        # and the mma.sync kernel it replaces gives the same tensor up to the output rounding
+        x = torch.zeros(64, H, W, 4, device="cuda", dtype=torch.bfloat16)
+        x[..., 0] = 1
+        x[..., 3] = 1
+        inf.tc_stem = True
+        a = inf(x)[0].clone()
+        inf.tc_stem = False
+        b = inf(x)[0]
+        assert (a - b).abs().max().item() <= 2e-3

@@ -293,35 +293,31 @@ __global__ void __launch_bounds__(128, 1) k_dense_heads(DenseHeadParams P) {
         s_bias[i] = col < P.n_actions ? __ldg(P.bp + col) : 0.0f;
     }
     // features: hd [row][cell][plane] float32 -> bf16 operands (policy K index = cell * 2 + plane, the NHWC flatten
-    // order of the Dense layer; value K index = cell).  The tile's 128 x 192 floats are contiguous: 128-bit loads, twelve
-    // in flight per thread, then scattered 2-byte shared-memory stores.
+    // order of the Dense layer; value K index = cell).  Thread = row: twelve floats (four cells) make exactly one 16-byte
+    // policy chunk and half a value chunk, so every shared-memory store is a 128-bit store at a compile-time position of
+    // the row (the first version scattered 2-byte stores with idx / 192, rem / 3 arithmetic per element: half the kernel).
     {
-        const float4* src = reinterpret_cast<const float4*>(P.hd + row0 * 192);
-        const long long valid4 = (min((long long)P.n, row0 + 128) - row0) * 48;  // float4s of the tile that exist
-#pragma unroll 1
-        for (int it0 = 0; it0 < 48; it0 += 12) {
+        const long long grow = row0 + tid;
+        const bool live = grow < P.n;
+        const float4* src = reinterpret_cast<const float4*>(P.hd + (live ? grow : 0) * 192);
+        uint8_t* prow = gen + kHA_P + (tid >> 3) * 1024 + (tid & 7) * 128;
+        uint8_t* vrow = gen + kHA_V + (tid >> 3) * 1024 + (tid & 7) * 128;
+        const int r7 = tid & 7;
+#pragma unroll
+        for (int g0 = 0; g0 < 16; g0 += 4) {
             float4 f[12];
 #pragma unroll
-            for (int u = 0; u < 12; ++u) {
-                const int i4 = tid + 128 * (it0 + u);
-                f[u] = i4 < valid4 ? __ldg(src + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int u = 0; u < 12; ++u) f[u] = live ? __ldg(src + 3 * g0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int u = 0; u < 12; ++u) {
-                const int i4 = tid + 128 * (it0 + u);
-                const float vals[4] = {f[u].x, f[u].y, f[u].z, f[u].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int li = i4 * 4 + e, r = li / 192, rem = li - r * 192, cell = rem / 3, plane = rem - cell * 3;
-                    uint32_t off;
-                    if (plane < 2) {
-                        const int k = cell * 2 + plane;
-                        off = kHA_P + umma_chunk_offset(r, k >> 3) + (uint32_t)((k & 7) * 2);
-                    } else {
-                        if (!do_value) continue;
-                        off = kHA_V + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((cell >> 3) ^ (r & 7)) << 4) + (cell & 7) * 2);
-                    }
-                    *reinterpret_cast<__nv_bfloat16*>(gen + off) = __float2bfloat16(vals[e]);
+            for (int gg = 0; gg < 4; ++gg) {
+                const int g = g0 + gg;  // cells 4g .. 4g + 3
+                const float4 a = f[3 * gg], b = f[3 * gg + 1], c = f[3 * gg + 2];
+                // a = (c0p0, c0p1, c0v, c1p0)  b = (c1p1, c1v, c2p0, c2p1)  c = (c2v, c3p0, c3p1, c3v)
+                const uint4 pc = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.w, b.x), pack_bf16(b.z, b.w), pack_bf16(c.y, c.z));
+                *reinterpret_cast<uint4*>(prow + (g >> 3) * kKBlockBytes + (((g & 7) ^ r7) << 4)) = pc;
+                if (do_value) {
+                    const uint2 vh = make_uint2(pack_bf16(a.z, b.y), pack_bf16(c.x, c.w));
+                    *reinterpret_cast<uint2*>(vrow + ((((g >> 1) & 7) ^ r7) << 4) + (g & 1) * 8) = vh;
                 }
             }
         }

@@ -149,6 +149,7 @@ class InferenceNet(nn.Module):
                                            requires_grad=False)
         import os as _os
 
+        self.split_heads = _os.environ.get("AZ_SPLIT_HEADS", "0") == "1"
         self.tc_stem = (net.in_planes == 4 and net.filters == 128 and net.height * net.width <= 128
                         and _os.environ.get("AZ_TC_STEM", "1") != "0")
         # both 1x1 head convolutions as one [3, C] matrix (2 policy planes + 1 value plane)
@@ -324,8 +325,15 @@ class InferenceNet(nn.Module):
             priors_out = torch.empty((B, self.n_actions), dtype=torch.float32, device=xm.device)
             values_out = torch.empty(B, dtype=torch.float32, device=xm.device)
         hw = self._heads_arg()
-        check(lib().az_net_heads(_ptr(xm), ctypes.byref(hw), B, H * W, self.filters, self.n_actions, _ptr(priors_out),
-                                 _ptr(values_out), _stream()))
+        if self.split_heads:  # 128-bit-load head convolutions, then the dense layers
+            hd = torch.empty((B, H * W, 3), dtype=torch.float32, device=xm.device)
+            check(lib().az_net_head_convs(_ptr(xm), _ptr(self.head_w32), _ptr(self.head_b32), B, H * W, self.filters, _ptr(hd),
+                                          _stream()))
+            check(lib().az_net_heads_dense(_ptr(hd), ctypes.byref(hw), B, H * W, self.n_actions, _ptr(priors_out),
+                                           _ptr(values_out), _stream()))
+        else:
+            check(lib().az_net_heads(_ptr(xm), ctypes.byref(hw), B, H * W, self.filters, self.n_actions, _ptr(priors_out),
+                                     _ptr(values_out), _stream()))
         return priors_out, values_out
 
     @torch.no_grad()

@@ -125,7 +125,9 @@ constexpr int kHeadWarps = 16;
 // 1x1 convolutions: D[pixel][3] = X[pixel][128] * Wc[128][3] with mma.sync, the A fragments loaded straight
 // from global memory (every byte of the position is requested exactly once, 96 independent loads per lane).
 // Shared layout (floats): policy_w [A][2*cells | 1 pad] | value1_w transposed [cells][256] | per-warp h [3*cells]
-template <int C>
+// FROM_HD: the 1x1 convolutions were already done by k_head_convs (128-bit loads, float32 accumulation) and `x` is their
+// output hd [n][cells][3] float32; the kernel then only runs the dense layers.
+template <int C, bool FROM_HD = false>
 __global__ void __launch_bounds__(kHeadWarps * 32) k_heads(const __nv_bfloat16* __restrict__ x, HeadParams hp,
                                                            float* __restrict__ priors, float* __restrict__ values) {
     static_assert(C == 128, "8 k-steps of 16 channels");
@@ -161,7 +163,14 @@ __global__ void __launch_bounds__(kHeadWarps * 32) k_heads(const __nv_bfloat16* 
     const int mtiles = (cells + 15) >> 4;
     for (int t = blockIdx.x * kHeadWarps + warp; t < hp.n; t += gridDim.x * kHeadWarps) {
         const uint32_t* xb = reinterpret_cast<const uint32_t*>(x + (size_t)t * cells * C);
-        for (int mt = 0; mt < mtiles; ++mt) {
+        if (FROM_HD) {
+            const float* hd = reinterpret_cast<const float*>(x) + (size_t)t * cells * 3;
+            for (int i = lane; i < 3 * cells; i += 32) {
+                const int r = i / 3, pl = i - r * 3;
+                h[pl < 2 ? r * 2 + pl : 2 * cells + r] = __ldg(hd + i);
+            }
+        }
+        for (int mt = 0; !FROM_HD && mt < mtiles; ++mt) {
             const int r0 = mt * 16 + g, r1 = r0 + 8;
             const int q0 = r0 < cells ? r0 : cells - 1, q1 = r1 < cells ? r1 : cells - 1;
             uint32_t a[C / 16][4];
@@ -327,8 +336,21 @@ AZ_API int az_net_stem(const void* states, const float* w, const float* b, int32
     return AZ_OK;
 }
 
+static int launch_heads(const void* x, const az_head_weights* hw, int32_t n, int32_t cells, int32_t C, int32_t A, float* priors,
+                        float* values, void* stream, bool from_hd);
+
 AZ_API int az_net_heads(const void* x, const az_head_weights* hw, int32_t n, int32_t cells, int32_t C, int32_t A,
                         float* priors, float* values, void* stream) {
+    return launch_heads(x, hw, n, cells, C, A, priors, values, stream, false);
+}
+
+AZ_API int az_net_heads_dense(const float* hd, const az_head_weights* hw, int32_t n, int32_t cells, int32_t A, float* priors,
+                              float* values, void* stream) {
+    return launch_heads(hd, hw, n, cells, 128, A, priors, values, stream, true);
+}
+
+static int launch_heads(const void* x, const az_head_weights* hw, int32_t n, int32_t cells, int32_t C, int32_t A, float* priors,
+                        float* values, void* stream, bool from_hd) {
     if (n == 0) return AZ_OK;
     if (!x || !hw || !priors || !values || n < 0 || cells < 1 || A < 1 || A > AZ_MAX_ACTIONS)
         return fail_net(AZ_ERR_ARG, "az_net_heads: bad argument");
@@ -339,7 +361,8 @@ AZ_API int az_net_heads(const void* x, const az_head_weights* hw, int32_t n, int
                                          (size_t)kHeadWarps * 3 * cells);
     static size_t configured = 0;
     if (smem > configured) {
-        if (cudaFuncSetAttribute(k_heads<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_heads<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_heads<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail_net(AZ_ERR_CUDA, "az_net_heads: shared memory request refused");
         configured = smem;
     }
@@ -349,8 +372,12 @@ AZ_API int az_net_heads(const void* x, const az_head_weights* hw, int32_t n, int
     int grid = (n + kHeadWarps - 1) / kHeadWarps;
     const int per_sm = smem > 100 * 1024 ? 1 : 2;
     if (grid > sms * per_sm) grid = sms * per_sm;
-    k_heads<128><<<grid, kHeadWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), hp, priors, values);
+    if (from_hd)
+        k_heads<128, true><<<grid, kHeadWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(x), hp, priors, values);
+    else
+        k_heads<128, false><<<grid, kHeadWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(x), hp, priors, values);
     if (cudaGetLastError() != cudaSuccess) return fail_net(AZ_ERR_CUDA, "az_net_heads: launch failed");
     return AZ_OK;
 }

@@ -292,6 +292,12 @@ int az_net_heads(const void *dev_x, const az_head_weights *weights, int32_t n, i
  * all 16-byte aligned; channels must be 128. */
 int az_net_conv1x1(const void *dev_x, const void *dev_w, int64_t rows, int32_t channels, void *dev_y, void *stream);
 
+/* The dense layers of az_net_heads alone, on the output of az_net_head_convs: hd dev float [n][cells][3] -> priors / values
+ * as above (same weights struct; conv_w / conv_b unused).  az_net_head_convs + az_net_heads_dense = az_net_heads with the
+ * convolutions read in 128-bit loads and accumulated in float32. */
+int az_net_heads_dense(const float *dev_hd, const az_head_weights *weights, int32_t n, int32_t cells, int32_t n_actions,
+                       float *dev_priors_out, float *dev_values_out, void *stream);
+
 /* Only the two 1x1 head convolutions + BN + ReLU (model.py:76-80, :114-118) of az_net_heads, for shapes whose dense
  * layers do not fit its shared memory (chess: 64 cells x 1 880 actions; they then run through cuBLAS).
  * x: dev bf16 [n][cells][C]; conv_w: dev float [3][C] (rows 0-1 policy, row 2 value); conv_b: dev float [3];

@@ -294,3 +294,23 @@ def test_tcgen05_stem_equals_the_float32_convolution():
         inf.tc_stem = False
         b = inf(x)[0]
         assert (a - b).abs().max().item() <= 2e-3
+
+
+def test_split_heads_equal_the_single_kernel():
+    """az_net_head_convs + az_net_heads_dense against az_net_heads on the same tower output."""
+    from az_b200.net import InferenceNet, PolicyValueNet, randomise_bn
+
+    for (H, W, A) in ((6, 7, 7), (9, 9, 81)):
+        torch.manual_seed(H + 1)
+        inf = InferenceNet(randomise_bn(PolicyValueNet(H, W, A)).eval(), dtype=torch.bfloat16, device="cuda")
+        code = torch.randint(0, 3, (777, H, W), device="cuda")
+        x = torch.cat([torch.nn.functional.one_hot(code, 3).float(), torch.ones(777, H, W, 1, device="cuda")], -1).to(torch.bfloat16)
+        inf.split_heads = False
+        p0, v0 = inf(x)
+        p0, v0 = p0.clone(), v0.clone()
+        inf.split_heads = True
+        p1, v1 = inf(x)
+        # az_net_heads rounds the 1x1 convolution weights to bf16 for mma.sync; az_net_head_convs keeps them in float32
+        dp, dv = (p1 - p0).abs().max().item(), (v1 - v0).abs().max().item()
+        assert dp <= 4e-3 and dv <= 4e-3, (H, W, dp, dv)
+

@@ -114,6 +114,17 @@ class ChessSelfPlayRunner:
     def ring_fill(self):
         return int(self.engine.view("smp_count")[0]) / self.engine.cfg.sample_capacity
 
+    def collect_all_ranks(self):
+        """collect() with the rings of every rank gathered first (torch.distributed; the trainer rank uses the result)."""
+        from . import dist as azdist
+
+        d = azdist.all_gather_chess_rings(self.engine.drain(), self.device)
+        for g, ln, r in zip(d["fin_game"], d["fin_len"], d["fin_result"]):
+            self._games[int(g)] = (int(ln), int(r))
+        states, policies = decode_samples(d, self.device)
+        values, known = sample_values(d, self._games)
+        return states.cpu().numpy(), policies.cpu().numpy(), values, known, d
+
     def collect(self):
         """Drains the rings: (states f32 [n, 8, 8, 118], policies f64 [n, 1880], values int32 [n], known bool [n]) as
         host arrays.  `known` is False for samples whose game has not finished yet (their value comes with a later

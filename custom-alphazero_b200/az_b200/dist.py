@@ -56,3 +56,35 @@ def all_gather_records(records):
         dist.all_gather(parts, pad)
         out[key] = torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
     return out
+
+
+CHESS_SAMPLE_KEYS = ("game", "ply", "pos", "k", "act", "n", "choice")
+CHESS_FIN_KEYS = ("fin_game", "fin_len", "fin_result")
+
+
+def all_gather_chess_rings(drained, device=None):
+    """The chess runner's drained rings (numpy arrays: one entry per finished ply under CHESS_SAMPLE_KEYS, one per finished
+    game under CHESS_FIN_KEYS) from every rank, concatenated in rank order - the replay-buffer gather for chess.  Game ids
+    are global (game_id_base per rank), so the host join by game id (chess_engine.sample_values) works on the result."""
+    import numpy as np
+
+    rank, ws = world()
+    if ws == 1:
+        return drained
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    out = {}
+    for keys in (CHESS_SAMPLE_KEYS, CHESS_FIN_KEYS):
+        group = {}
+        for k in keys:
+            a = np.ascontiguousarray(drained[k])
+            if a.dtype == np.uint64:
+                a = a.view(np.int64)      # same bits: the collectives have no unsigned 64-bit type
+            elif a.dtype == np.uint16:
+                a = a.astype(np.int32)    # ... and gloo no 16-bit one: widened for the wire
+            group[k] = torch.from_numpy(a).to(device)
+        gathered = all_gather_records(group)
+        for k in keys:
+            g = gathered[k].cpu().numpy()
+            out[k] = g.view(np.uint64) if drained[k].dtype == np.uint64 else g.astype(drained[k].dtype)
+    return out

@@ -43,6 +43,19 @@ assert allrec["game_id"].tolist() == list(range(11)), allrec["game_id"]
 assert allrec["visits"].shape == (11, 4, 7)
 assert allrec["len"].tolist() == [3] * 6 + [4] * 5
 assert allrec["visits"][:6].eq(0).all() and allrec["visits"][6:].eq(1).all()
+# chess: the two rings (finished plies, finished games) gathered separately, unsigned dtypes preserved
+import numpy as np
+n, f = 3 + rank, 1 + rank
+d = {"game": np.full(n, 100 * rank, dtype=np.int64), "ply": np.arange(n, dtype=np.int32),
+     "pos": np.full((n, 8), 2**63 + rank, dtype=np.uint64), "k": np.full(n, 20, dtype=np.int32),
+     "act": np.full((n, 224), 0xffff - rank, dtype=np.uint16), "n": np.full((n, 224), rank, dtype=np.int32),
+     "choice": np.full(n, 7, dtype=np.int32), "fin_game": np.full(f, 100 * rank, dtype=np.int64),
+     "fin_len": np.full(f, n, dtype=np.int32), "fin_result": np.full(f, rank, dtype=np.int32)}
+g = azdist.all_gather_chess_rings(d)
+assert g["game"].tolist() == [0] * 3 + [100] * 4 and g["fin_game"].tolist() == [0, 100, 100]
+assert g["pos"].dtype == np.uint64 and g["pos"][0, 0] == 2**63 and g["pos"][3, 0] == 2**63 + 1
+assert g["act"].dtype == np.uint16 and g["act"][0, 0] == 0xffff and g["act"][6, 223] == 0xfffe
+assert g["ply"].tolist() == [0, 1, 2, 0, 1, 2, 3] and g["fin_len"].tolist() == [3, 4, 4]
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''

@@ -114,11 +114,14 @@ class ChessSelfPlayRunner:
     def ring_fill(self):
         return int(self.engine.view("smp_count")[0]) / self.engine.cfg.sample_capacity
 
-    def collect_all_ranks(self):
-        """collect() with the rings of every rank gathered first (torch.distributed; the trainer rank uses the result)."""
+    def collect_all_ranks(self, trainer_rank=0):
+        """collect() with the rings of every rank gathered first (torch.distributed).  Only the trainer rank decodes the
+        samples; the other ranks take part in the gather and return None."""
         from . import dist as azdist
 
         d = azdist.all_gather_chess_rings(self.engine.drain(), self.device)
+        if azdist.world()[0] != trainer_rank:
+            return None
         for g, ln, r in zip(d["fin_game"], d["fin_len"], d["fin_result"]):
             self._games[int(g)] = (int(ln), int(r))
         states, policies = decode_samples(d, self.device)

@@ -147,12 +147,12 @@ def main(args, ClockSampler, load_peaks):
                 p_.copy_(flat_dev[off: off + p_.numel()].view_as(p_))
                 off += p_.numel()
         runner.run(ADV)
-        if world > 1:  # the replay-buffer gather: every rank's finished plies reach the trainer rank
-            st, po, va, known, _ = runner.collect_all_ranks()
+        if world > 1:  # the replay-buffer gather: every rank's finished plies reach the trainer rank, which decodes them
+            got = runner.collect_all_ranks()
         else:
-            st, po, va, known, _ = runner.collect()
-        if rank == 0:
-            d2h += st.nbytes + po.nbytes + va.nbytes
+            got = runner.collect()
+        if got is not None:
+            d2h += got[0].nbytes + got[1].nbytes + got[2].nbytes
     t1.record()
     barrier()
     e1 = runner.totals()

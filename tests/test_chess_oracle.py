@@ -156,3 +156,52 @@ def test_castling_and_en_passant_bookkeeping():
     c, m = code("e5d6")
     after = cr.push(s6, m)
     assert after.sq[35] == 0 and after.sq[43] == 1 and cr.states_equal(cr.from_pos(cr.host_play(cr.to_pos(s6), c, False)), after)
+
+
+def _golden(name):
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".json")) as fp:
+        return json.load(fp)
+
+
+def test_oracle_reproduces_the_committed_chess_fixtures():
+    """tests/golden/chess_*.json (tests/golden/make_chess_golden.py) freeze the oracle's behaviour: playout fingerprint
+    and whole MCTS games."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "make_chess_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_chess_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    want = _golden("chess_playouts")
+    got = mk.playouts(want["games"], want["max_plies"])
+    assert got == want
+    for name in ("chess_mcts_hash_f64_100", "chess_mcts_uniform_f32_64", "chess_mcts_hash_f32_200"):
+        w = _golden(name)
+        assert mk.mcts(w["evaluator"], w["prior_mode"], w["sims"], w["max_plies"], w["greedy_idx"]) == w
+
+
+def test_device_header_reproduces_the_playout_fixture():
+    """The same 300 playouts through the DEVICE rules header compiled for the host: same moves, same final positions."""
+    import hashlib
+
+    want = _golden("chess_playouts")
+    acts = cr.all_possible_moves()
+    lines = []
+    for g in range(want["games"]):
+        rng = _lcg(g)
+        pos = cr.to_pos(cr.start_state())
+        picked = []
+        for _ in range(want["max_plies"]):
+            if cr.host_status(pos):
+                break
+            legal, _, _ = cr.host_legal(pos)
+            a = legal[next(rng) % len(legal)]
+            picked.append(a)
+            m = acts[a]
+            pos = cr.host_play(pos, m[0] | m[1] << 6 | cr.PROMO_LETTERS.index(m[2]) << 12, True)
+        lines.append("{}|{}|{}\n".format(",".join(map(str, picked)), cr.host_status(pos), pos.tolist()))
+    assert hashlib.sha256("".join(lines).encode()).hexdigest()[:16] == want["sha"]

@@ -534,3 +534,23 @@ def _lcg_local(seed):
     while True:
         s = (s * 6364136223846793005 + 1442695040888963407) % 2 ** 64
         yield s >> 33
+
+
+@pytest.mark.parametrize("name", ["chess_mcts_hash_f64_100", "chess_mcts_uniform_f32_64", "chess_mcts_hash_f32_200"])
+def test_engine_reproduces_the_committed_fixtures(name):
+    """tests/golden/chess_mcts_*.json (frozen oracle games, tests/golden/make_chess_golden.py) on the GPU."""
+    import json
+    import os
+
+    from az_b200.chess_engine import ChessTreeEngine
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".json")) as fp:
+        w = json.load(fp)
+    eng = ChessTreeEngine(n_trees=3, sims_per_move=w["sims"], eval_mode=w["evaluator"], prior_mode=w["prior_mode"],
+                          max_plies=w["max_plies"], index_move_greedy=w["greedy_idx"])
+    per_game, fin = _play_games(eng, w["max_plies"] + 2)
+    for g in range(3):
+        assert fin[g] == (w["plies"], w["result"])
+        for ply, k, act, n, choice in per_game[g]:
+            assert k == w["k"][ply] and choice == w["choice"][ply]
+            assert act[:k].tolist() == w["act"][ply] and n[:k].tolist() == w["n"][ply]

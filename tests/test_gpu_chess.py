@@ -190,3 +190,42 @@ def test_drop_in_board_follows_the_reference_flow():
     assert d is not c and c.array[5, 5] == 0 and d.array[5, 5] == 2
     with pytest.raises(ValueError):
         c.play(Move(uci="e1e3"))
+
+
+def test_integration_md_chess_stub_runs():
+    """The ctypes stub printed in INTEGRATION.md for chess is executed as written (only the library path is made
+    absolute) on an object with python-chess's Board attributes."""
+    import os
+    import re
+    import types
+
+    chess = _chess()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    stub = next(b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "def pack(board)" in b)
+    stub = stub.replace('ctypes.CDLL("libaz_b200.so")', 'ctypes.CDLL("{}")'.format(os.path.join(root, "custom-alphazero_b200", "libaz_b200.so")))
+    ns = {}
+    exec(stub, ns)
+
+    def fake_board(fen):  # what python-chess exposes: piece bitboards, occupied_co, castling_rights as a rook-square mask
+        w = [int(x) for x in chess.position_from_fen(fen)]
+        f = chess.unpack_position(np.array(w, dtype=np.uint64))
+        occ = w[0] | w[1] | w[2] | w[3] | w[4] | w[5]
+        rights = sum(1 << sq for bit, sq in ((1, 7), (2, 0), (4, 63), (8, 56)) if f["castling"] & bit)
+        return types.SimpleNamespace(pawns=w[0], knights=w[1], bishops=w[2], rooks=w[3], queens=w[4], kings=w[5],
+                                     occupied_co={True: w[6], False: occ & ~w[6]}, castling_rights=rights,
+                                     ep_square=f["ep_square"], turn=bool(f["turn"]), halfmove_clock=f["halfmove_clock"],
+                                     fullmove_number=f["fullmove_number"])
+
+    fens = [chess.START_FEN, "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1",
+            "rnb1kbnr/pppp1ppp/8/4p3/6Pq/5P2/PPPPP2P/RNBQKBNR w KQkq - 1 3"]
+    boards = [fake_board(f) for f in fens]
+    for b, f in zip(boards, fens):
+        want = chess.position_from_fen(f)
+        want[7] &= np.uint64(~(3 << 48) & (2 ** 64 - 1))  # the valid / repetition flags only matter for history entries
+        assert np.array_equal(ns["pack"](b), want)
+    mask, count, status = ns["legal_moves_mask"](boards)
+    torch.cuda.synchronize()
+    assert count.tolist() == [20, 48, 0] and [s & 3 for s in status.tolist()] == [0, 0, 1]
+    planes = ns["full_state"](boards)
+    assert np.array_equal(planes.cpu().numpy(), chess.chess_encode(np.stack([chess.position_from_fen(f) for f in fens])))

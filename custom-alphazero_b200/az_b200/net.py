@@ -32,6 +32,22 @@ def flops_per_eval(height, width, n_actions, filters=128, depth=4, in_planes=4):
     return 2 * macs
 
 
+def pack_tower_weights(blocks):
+    """[(w1, b1, w2, wp, b2p)] per block (BN folded; w [128, 128, k, k], any float dtype) -> (w_img bf16 [depth * 38 * 8192],
+    bias float32 [depth, 2, 128]) in the layout az_net_tower streams (include/az_b200.h): a 16 KB stage is one filter tap
+    x 64 input channels as the K-major, unswizzled UMMA B operand [8 chunks][128 cout][8 cin]; stages come in
+    consumption order: conv1 taps (ky, kx) row-major x 2 channel halves, the 1x1 shortcut x 2, conv2 taps x 2."""
+    imgs, biases = [], []
+    for w1, b1, w2, wp, b2p in blocks:
+        for w in (w1, wp, w2):
+            cout, cin, kh, kw = w.shape
+            assert cout == 128 and cin == 128, "az_net_tower is built for 128 filters"
+            t = w.detach().float().permute(2, 3, 1, 0).reshape(kh * kw, 2, 8, 8, cout)  # tap, half, chunk, e, cout
+            imgs.append(t.permute(0, 1, 2, 4, 3).reshape(-1))                             # tap, half, chunk, cout, e
+        biases.append(torch.stack([b1.detach().float(), b2p.detach().float()]))
+    return torch.cat(imgs).to(torch.bfloat16).contiguous(), torch.stack(biases).contiguous()
+
+
 class ConvBN(nn.Module):
     def __init__(self, cin, cout, k, relu):
         super().__init__()
@@ -138,6 +154,18 @@ class InferenceNet(nn.Module):
             b2p = nn.Parameter((b2.float() + bp.float()).to(dtype), requires_grad=False)
             self.block_params.extend([w1, b1, w2, wp, b2p])
         self.depth = len(net.blocks)
+        # the whole tower as one persistent tcgen05 kernel (az_net_tower, csrc/az_tower.cu) where its tiling fits:
+        # 128 filters, whole positions in a 128-row tile with (positions * W + 1) <= 22 padding rows (6x7, 8x8, ...)
+        import os as _os0
+
+        cells_ = net.height * net.width
+        self.fused_tower = (torch.device(device).type == "cuda" and dtype == torch.bfloat16 and net.filters == 128
+                            and 1 <= self.depth <= 6 and cells_ <= 128 and (128 // cells_) * net.width + 1 <= 22
+                            and (128 // cells_) * cells_ >= 96 and _os0.environ.get("AZ_FUSED_TOWER", "1") != "0")
+        if self.fused_tower:
+            img, tb = pack_tower_weights([tuple(self.block_params[5 * i: 5 * i + 5]) for i in range(self.depth)])
+            self.tower_img = nn.Parameter(img.to(device), requires_grad=False)
+            self.tower_bias = nn.Parameter(tb.to(device), requires_grad=False)
         f32 = lambda t: nn.Parameter(t.detach().to(device=device, dtype=torch.float32).contiguous(), requires_grad=False)  # noqa: E731
         # float32 copies for the hand-written stem / heads kernels (az_net_stem, az_net_heads)
         sw, sb = net.stem.folded()
@@ -338,8 +366,24 @@ class InferenceNet(nn.Module):
 
     @torch.no_grad()
     def tower(self, h0):
-        """The residual tower on the stem output h0 [B, H, W, 128] bf16 (NHWC): 4 x (cuDNN conv+bias+ReLU,
-        cuDNN 1x1 shortcut, cuDNN conv+shortcut+bias+ReLU) -> [B, H, W, 128] bf16, NHWC-contiguous."""
+        """The residual tower on the stem output h0 [B, H, W, 128] bf16 (NHWC) -> [B, H, W, 128] bf16, NHWC-contiguous:
+        az_net_tower (one hand-written tcgen05 kernel, activations resident on chip) or, where that does not apply,
+        4 x (cuDNN conv+bias+ReLU, cuDNN 1x1 shortcut, cuDNN conv+shortcut+bias+ReLU)."""
+        if self.fused_tower and h0.is_cuda:
+            from .engine import _ptr, _stream
+            from .native import check, lib
+
+            h0 = h0 if h0.is_contiguous() else h0.contiguous()
+            out = torch.empty_like(h0)
+            check(lib().az_net_tower(_ptr(h0), _ptr(self.tower_img), _ptr(self.tower_bias), h0.shape[0], self.height,
+                                     self.width, self.filters, self.depth, _ptr(out), _stream()))
+            return out
+        return self.tower_library(h0)
+
+    @torch.no_grad()
+    def tower_library(self, h0):
+        """The same tower through cuDNN (12 launches): the comparison arm of az_net_tower and the route for boards
+        its tiling does not fit (9x9)."""
         x = h0.permute(0, 3, 1, 2)  # logical NCHW over NHWC memory (channels_last)
         one = (1, 1)
         cur = torch.cuda.current_stream()

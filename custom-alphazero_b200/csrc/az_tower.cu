@@ -1,0 +1,356 @@
+// az_tower.cu - the whole residual tower of the policy/value net (base_layers.py:85-125 of the reference, four times:
+// model/tensorflow/model.py:48-66) as ONE persistent tcgen05 kernel for sm_100a.
+//
+//   per block:   h = relu(conv3x3(x, w1) + b1)        y = relu(conv3x3(h, w2) + conv1x1(x, wp) + b2p)
+//
+// cuDNN runs this as 12 kernels that stream 817 MB through DRAM per 4096-position forward (profiles/
+// advance_traffic_r1.json).  Here a CTA takes a tile of whole positions (3 boards of 6x7 = 126 of the 128 rows of a UMMA
+// tile, 2 boards of 8x8 = 128) through all blocks: activations never leave shared memory / TMEM, the only DRAM traffic
+// is the tile in (bf16 [cells][128]) and out, and the 2.4 MB of weights stream from L2 through a bulk-copy ring.
+//
+// Implicit GEMM without an im2col buffer.  Activations live in shared memory in the canonical K-major *no-swizzle*
+// UMMA layout with the rows linear: 16-byte chunk kc (8 channels) of row r at  kc * LBO + r * 16.  With the rows of a
+// tile ordered (y, position, x) a filter tap (dy, dx) of a 3x3 convolution is the SAME buffer read through a descriptor
+// whose start address is moved by  (dy * positions * W + dx) * 16  bytes:
+//   * rows above / below the board fall into zero padding rows before / after the tile (22 each);
+//   * a tap that leaves the board sideways lands on the neighbouring cell in row order, which is always an x = W-1
+//     cell (dx = -1) or an x = 0 cell (dx = +1): the dx = -1 taps read a copy of the activations whose x = W-1 rows
+//     are zero, the dx = +1 taps a copy whose x = 0 rows are zero.  The epilogue that produces a layer's output writes
+//     the three copies (plain, left-masked, right-masked), so no tap ever needs its own im2col tile.
+// Four activation buffers (x, x-left, x-right, h) of 128 + 22 rows share one row space: 159 KB.
+//
+// Roles (320 threads, 1 CTA per SM, persistent over tiles):
+//   warp 0   producer: one lane streams the weight stages (16 KB = one tap x 64 input channels x 128 output channels,
+//            pre-packed by the host in the UMMA layout, in the order they are consumed) from global memory with
+//            cp.async.bulk into a 4-deep ring, full / empty mbarriers;
+//   warp 1   MMA issuer: one lane issues 4 tcgen05.mma (128 x 128 x 16) per stage; conv1 -> TMEM columns 0-127, the
+//            1x1 shortcut (needs only x) and then conv2 -> columns 128-255, so the shortcut runs under epilogue 1;
+//   warps 2-9  epilogue: tcgen05.ld (32 lanes x 32 columns), + bias, ReLU, bf16, three masked 16-byte stores per chunk
+//            (conflict free: a warp writes 512 contiguous bytes), fence.proxy.async, arrive on the "activations ready"
+//            barrier.  The same warps load a tile from global memory at its start and store it after the last block.
+// SASS: UTCHMMA (tcgen05.mma), UBLKCP (cp.async.bulk), LDTM (tcgen05.ld).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/az_b200.h"
+
+namespace az {
+int fail_net(int code, const char* msg);
+
+namespace tower {
+
+constexpr int kC = 128;                           // filters (config.py:71)
+constexpr int kPad = 22;                          // zero rows either side of a tile: >= positions * W + 1
+constexpr int kTileRows = 128;                    // UMMA M
+constexpr int kBufRows = kTileRows + kPad;        // a buffer = its tile rows + the pad that follows them
+constexpr int kNBuf = 4;                          // x, x-left-masked, x-right-masked, h
+constexpr int kRows = kPad + kNBuf * kBufRows;    // 622 rows of 16 bytes per chunk column
+constexpr int kLboA = kRows * 16;                 // byte distance between adjacent 8-channel chunk columns
+constexpr int kActBytes = 16 * kLboA;             // 159 232
+constexpr int kStageBytes = 16384;                // [8 chunks][128 output channels][8 input channels] bf16
+constexpr int kLboB = 2048;                       // 128 rows x 16 bytes
+constexpr int kStages = 4;
+constexpr int kMaxDepth = 6;
+constexpr int kBiasBytes = kMaxDepth * 2 * kC * 4;
+constexpr int kSmemBytes = kActBytes + kStages * kStageBytes + kBiasBytes;
+constexpr int kStagesPerBlock = 38;               // conv1: 9 taps x 2, shortcut: 2, conv2: 9 taps x 2
+constexpr int kThreads = 320;
+constexpr uint32_t kTmemCols = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start >> 4 in
+// bits 0-13, leading byte offset (between the two 8-element core matrices of one K = 16 step) bits 16-29, stride byte
+// offset (between 8-row groups; 128 = rows linear at 16 bytes) bits 32-45, version 1 bits 46-47, layout type 0.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr & 0x3ffff) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+// D = F32 (bit 4), A = B = BF16 (bits 7, 10), both K-major, N >> 3 in bits 17-22, M >> 4 in bits 24-28
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void commit_to(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 24)) __trap();  // a lost arrival must fail loudly, never hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+          "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(fmaxf(lo, 0.0f), fmaxf(hi, 0.0f));
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct TowerParams {
+    const __nv_bfloat16* x;    // [n][cells][128] stem output
+    const uint8_t* w_img;      // [depth][38] stages of 16 KB in consumption order (az_b200/net.py: pack_tower_weights)
+    const float* bias;         // [depth][2][128]: conv1 bias, conv2 bias + shortcut bias
+    __nv_bfloat16* y;          // [n][cells][128]
+    int n, W, cells, ppt, depth, n_tiles;
+};
+
+// byte offset of (buffer, row 0, chunk 0) inside the activation area
+__device__ __forceinline__ uint32_t buf_row0(int buf) { return (uint32_t)(kPad + buf * kBufRows) * 16u; }
+
+__global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_acc, s_act;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t act = smem_u32(smem), stages = act + kActBytes;
+    float* s_bias = reinterpret_cast<float*>(smem + kActBytes + kStages * kStageBytes);
+    const uint32_t bar_acc = smem_u32(&s_acc), bar_act = smem_u32(&s_act);
+    const int rowstride = P.ppt * P.W, rows_used = P.ppt * P.cells;
+    const int stages_per_tile = kStagesPerBlock * P.depth;
+
+    // one-time: zero the activation area (pads and dead rows stay zero for ever), biases, barriers, TMEM
+    for (int i = tid; i < kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < P.depth * 2 * kC; i += kThreads) s_bias[i] = P.bias[i];
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(&s_full[s]), 1);
+            mbar_init(smem_u32(&s_empty[s]), 1);
+        }
+        mbar_init(bar_acc, 1);
+        mbar_init(bar_act, kThreads - 64);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- producer
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                const uint8_t* src = P.w_img;
+                for (int s = 0; s < stages_per_tile; ++s, ++cnt, src += kStageBytes) {
+                    const uint32_t slot = cnt % kStages, k = cnt / kStages;
+                    mbar_wait(smem_u32(&s_empty[slot]), (k & 1) ^ 1);
+                    const uint32_t full = smem_u32(&s_full[slot]);
+                    mbar_expect_tx(full, kStageBytes);
+                    bulk_g2s(stages + slot * kStageBytes, src, kStageBytes, full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            uint32_t cnt = 0, act_phase = 0;
+            // one weight stage = 64 input channels (chunk columns 8 * kb ..) of one tap: four K = 16 steps
+            auto stage_mmas = [&](uint32_t d_tmem, uint32_t a_base, int kb, bool fresh) {
+                const uint32_t slot = cnt % kStages, k = cnt / kStages;
+                mbar_wait(smem_u32(&s_full[slot]), k & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint32_t b_base = stages + slot * kStageBytes;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    mma_bf16(d_tmem, desc_kmajor(a_base + (uint32_t)(kb * 8 + 2 * j) * kLboA, kLboA),
+                             desc_kmajor(b_base + (uint32_t)(2 * j) * kLboB, kLboB), (fresh && j == 0) ? 0u : 1u);
+                commit_to(smem_u32(&s_empty[slot]));  // frees the slot when these MMAs have read it
+                ++cnt;
+            };
+            auto conv3x3 = [&](uint32_t d_tmem, int centre_buf, bool fresh) {
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    const int buf = dx < 0 ? 1 : (dx > 0 ? 2 : centre_buf);
+                    const uint32_t a_base = act + buf_row0(buf) + (uint32_t)((dy * rowstride + dx) * 16);
+                    stage_mmas(d_tmem, a_base, 0, fresh && tap == 0);
+                    stage_mmas(d_tmem, a_base, 1, false);
+                }
+            };
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                for (int b = 0; b < P.depth; ++b) {
+                    mbar_wait(bar_act, act_phase);  // x (and its masked copies) in place
+                    act_phase ^= 1;
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    conv3x3(tmem, 0, true);
+                    commit_to(bar_acc);
+                    // the shortcut needs only x: it runs while the epilogue turns accumulator 0 into h
+                    stage_mmas(tmem + 128, act + buf_row0(0), 0, true);
+                    stage_mmas(tmem + 128, act + buf_row0(0), 1, false);
+                    mbar_wait(bar_act, act_phase);  // h in place
+                    act_phase ^= 1;
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    conv3x3(tmem + 128, 3, false);
+                    commit_to(bar_acc);
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue / tile load / tile store
+        const int e = tid - 64;                       // 0..255
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int hf = (warp - 2) >> 2;               // which 64 of the 128 output channels
+        const int r = q * 32 + lane;                  // accumulator row = tile row
+        // tile row -> (y, position, x): r = y * rowstride + p * W + x
+        const int ry = r / rowstride, rrem = r - ry * rowstride, rp = rrem / P.W, rx = rrem - rp * P.W;
+        const bool row_live = r < rows_used;
+        const bool zero_l = rx == P.W - 1, zero_r = rx == 0;
+        const long long row_in_tile = (long long)rp * P.cells + ry * P.W + rx;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 64);
+        // the loader's view: row lr = e & 127, chunk half lh = e >> 7 (a warp = 32 consecutive rows: conflict-free stores)
+        const int lr = e & 127, lh = e >> 7;
+        const int ly = lr / rowstride, lrem = lr - ly * rowstride, lp = lrem / P.W, lx = lrem - lp * P.W;
+        const bool l_live = lr < rows_used;
+        const long long l_row_in_tile = (long long)lp * P.cells + ly * P.W + lx;
+        uint32_t acc_phase = 0;
+        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            const long long pos0 = (long long)tile * P.ppt;
+            // ---- tile in: x, x-left-masked, x-right-masked
+            if (l_live) {
+                uint4 v[8];
+                const bool have = pos0 + lp < P.n;
+                const uint4* src = reinterpret_cast<const uint4*>(P.x + (pos0 * P.cells + l_row_in_tile) * kC) + lh * 8;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = have ? __ldg(src + c) : zero4;
+                const bool zl = lx == P.W - 1, zr = lx == 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t off = (uint32_t)(lh * 8 + c) * kLboA + (uint32_t)lr * 16u;
+                    *reinterpret_cast<uint4*>(smem + buf_row0(0) + off) = v[c];
+                    *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = zl ? zero4 : v[c];
+                    *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = zr ? zero4 : v[c];
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            mbar_arrive(bar_act);
+
+            for (int b = 0; b < P.depth; ++b) {
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {  // 0: accumulator 0 -> h, 1: accumulator 1 -> block output
+                    const float* bias = s_bias + (b * 2 + half) * kC + hf * 64;
+                    const bool last = half == 1 && b == P.depth - 1;
+                    mbar_wait(bar_acc, acc_phase);
+                    acc_phase ^= 1;
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const int centre = half == 0 ? 3 : 0;
+                    __nv_bfloat16* grow = P.y + (pos0 * P.cells + row_in_tile) * kC + hf * 64;
+                    const bool store_global = last && row_live && pos0 + rp < P.n;
+#pragma unroll
+                    for (int cb = 0; cb < 2; ++cb) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + (uint32_t)(half * 128 + cb * 32), v);
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias + cb * 32 + c4 * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias + cb * 32 + c4 * 8 + 4);
+                            uint4 o;
+                            o.x = pack_relu_bf16(__uint_as_float(v[8 * c4 + 0]) + b0.x, __uint_as_float(v[8 * c4 + 1]) + b0.y);
+                            o.y = pack_relu_bf16(__uint_as_float(v[8 * c4 + 2]) + b0.z, __uint_as_float(v[8 * c4 + 3]) + b0.w);
+                            o.z = pack_relu_bf16(__uint_as_float(v[8 * c4 + 4]) + b1.x, __uint_as_float(v[8 * c4 + 5]) + b1.y);
+                            o.w = pack_relu_bf16(__uint_as_float(v[8 * c4 + 6]) + b1.z, __uint_as_float(v[8 * c4 + 7]) + b1.w);
+                            const int kc = hf * 8 + cb * 4 + c4;
+                            if (last) {
+                                if (store_global) *(reinterpret_cast<uint4*>(grow) + cb * 4 + c4) = o;
+                            } else if (row_live) {
+                                const uint32_t off = (uint32_t)kc * kLboA + (uint32_t)r * 16u;
+                                *reinterpret_cast<uint4*>(smem + buf_row0(centre) + off) = o;
+                                *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = zero_l ? zero4 : o;
+                                *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = zero_r ? zero4 : o;
+                            }
+                        }
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                    if (!last) {
+                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                        mbar_arrive(bar_act);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kTmemCols) : "memory");
+}
+
+}  // namespace tower
+}  // namespace az
+
+extern "C" __attribute__((visibility("default"))) int az_net_tower(const void* x, const void* w_img, const float* bias, int32_t n,
+                                                                    int32_t H, int32_t W, int32_t channels, int32_t depth, void* y,
+                                                                    void* stream) {
+    using namespace az::tower;
+    if (n == 0) return AZ_OK;
+    if (!x || !w_img || !bias || !y || n < 0 || H < 1 || W < 1) return az::fail_net(AZ_ERR_ARG, "az_net_tower: bad argument");
+    if (channels != kC) return az::fail_net(AZ_ERR_ARG, "az_net_tower: built for 128 filters (config.py:71)");
+    if (depth < 1 || depth > kMaxDepth) return az::fail_net(AZ_ERR_ARG, "az_net_tower: depth must be 1..6 (config.py:63 uses 4)");
+    const int cells = H * W;
+    if (cells > kTileRows) return az::fail_net(AZ_ERR_ARG, "az_net_tower: a position must fit one 128-row tile (H * W <= 128)");
+    const int ppt = kTileRows / cells;
+    if (ppt * W + 1 > kPad) return az::fail_net(AZ_ERR_ARG, "az_net_tower: positions-per-tile * W + 1 must be <= 22 (padding rows)");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_img) | reinterpret_cast<uintptr_t>(y)) & 15)
+        return az::fail_net(AZ_ERR_ARG, "az_net_tower: pointers must be 16-byte aligned");
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return az::fail_net(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback");
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_tower, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+            return az::fail_net(AZ_ERR_CUDA, "az_net_tower: shared memory request refused");
+        configured = true;
+    }
+    const int n_tiles = (n + ppt - 1) / ppt;
+    TowerParams P{static_cast<const __nv_bfloat16*>(x), static_cast<const uint8_t*>(w_img), bias,
+                  static_cast<__nv_bfloat16*>(y), n, W, cells, ppt, depth, n_tiles};
+    k_tower<<<n_tiles < sms ? n_tiles : sms, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(P);
+    if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_tower: launch failed");
+    return AZ_OK;
+}

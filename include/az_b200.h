@@ -292,6 +292,18 @@ int az_net_heads(const void *dev_x, const az_head_weights *weights, int32_t n, i
  * all 16-byte aligned; channels must be 128. */
 int az_net_conv1x1(const void *dev_x, const void *dev_w, int64_t rows, int32_t channels, void *dev_y, void *stream);
 
+/* The whole residual tower (model/tensorflow/model.py:48-66: `depth` x ResidualBlock with projection shortcut,
+ * base_layers.py:85-125, BN folded) in ONE persistent tcgen05 kernel (csrc/az_tower.cu):
+ *   per block  h = relu(conv3x3(x, w1) + b1);  x' = relu(conv3x3(h, w2) + conv1x1(x, wp) + b2p)
+ * Activations stay in shared memory / TMEM from the first block to the last; replaces the 12 library convolutions.
+ * x, y: dev bf16 [n][H*W][128] (NHWC; y may not alias x).  w_img: dev bf16, depth x 38 stages of 16 KB, each
+ * [8 chunks][128 output channels][8 input channels] in consumption order - per block: conv1 taps (ky, kx) row-major x
+ * 2 halves of the input channels, the shortcut x 2 halves, conv2 taps x 2 halves (az_b200/net.py pack_tower_weights).
+ * bias: dev float [depth][2][128] (b1; b2 + shortcut bias).  channels must be 128, H * W <= 128,
+ * (128 / (H * W)) * W + 1 <= 22 (6x7, 8x8, ...), depth 1..6.  All pointers 16-byte aligned. */
+int az_net_tower(const void *dev_x, const void *dev_w_img, const float *dev_bias, int32_t n, int32_t H, int32_t W,
+                 int32_t channels, int32_t depth, void *dev_y, void *stream);
+
 /* The dense layers of az_net_heads alone, on the output of az_net_head_convs: hd dev float [n][cells][3] -> priors / values
  * as above (same weights struct; conv_w / conv_b unused).  az_net_head_convs + az_net_heads_dense = az_net_heads with the
  * convolutions read in 128-bit loads and accumulated in float32. */

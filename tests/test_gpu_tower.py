@@ -1,0 +1,125 @@
+"""GPU tests of az_net_tower (csrc/az_tower.cu): the whole residual tower (model/tensorflow/base_layers.py:85-125 x
+depth, model.py:48-66) as one tcgen05 kernel, through the C ABI, against float32 convolutions on the same bf16-rounded
+operands and against the cuDNN route it replaces.  Floating point: tolerances stated per test."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+F = torch.nn.functional
+
+
+def _mods():
+    from az_b200 import engine, native, net
+
+    return engine, native, net
+
+
+def _blocks(depth, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(depth):
+        w1 = (torch.randn(128, 128, 3, 3, generator=g) * 0.03 * scale).to(torch.bfloat16).float()
+        w2 = (torch.randn(128, 128, 3, 3, generator=g) * 0.03 * scale).to(torch.bfloat16).float()
+        wp = (torch.randn(128, 128, 1, 1, generator=g) * 0.08 * scale).to(torch.bfloat16).float()
+        out.append((w1, torch.randn(128, generator=g) * 0.1, w2, wp, torch.randn(128, generator=g) * 0.1))
+    return out
+
+
+def _reference(x, blocks):
+    """float32 convolutions, activations rounded to bf16 where the kernel rounds them (h and every block output)."""
+    t = x.float().permute(0, 3, 1, 2)
+    for w1, b1, w2, wp, b2p in blocks:
+        h = F.relu(F.conv2d(t, w1, b1, padding=1)).to(torch.bfloat16).float()
+        t = F.relu(F.conv2d(h, w2, b2p, padding=1) + F.conv2d(t, wp)).to(torch.bfloat16).float()
+    return t.permute(0, 2, 3, 1)
+
+
+def _run(x, blocks, H, W):
+    engine, native, net = _mods()
+    img, bias = net.pack_tower_weights(blocks)
+    img, bias = img.cuda(), bias.cuda()
+    xd = x.to("cuda", torch.bfloat16).contiguous()
+    out = torch.full_like(xd, float("nan"))
+    native.check(native.lib().az_net_tower(engine._ptr(xd), engine._ptr(img), engine._ptr(bias), xd.shape[0], H, W, 128,
+                                           len(blocks), engine._ptr(out), engine._stream()))
+    torch.cuda.synchronize()
+    return out.float().cpu()
+
+
+@pytest.mark.parametrize("H,W,n,depth", [(6, 7, 3, 1), (6, 7, 1, 1), (6, 7, 500, 4), (8, 8, 131, 4), (7, 7, 9, 2), (9, 9, 5, 1)])
+def test_fused_tower_equals_the_float32_convolutions(H, W, n, depth):
+    blocks = _blocks(depth, seed=H * 10 + depth)
+    g = torch.Generator().manual_seed(n)
+    x = torch.rand(n, H, W, 128, generator=g).to(torch.bfloat16)
+    got = _run(x, blocks, H, W)
+    want = _reference(x, blocks)
+    assert torch.isfinite(got).all()
+    # same operands, float32 accumulation in another order; an activation that lands on a bf16 rounding boundary may
+    # differ by one ulp (2^-8 relative) per layer and is then carried through the later layers
+    err = (got - want).abs()
+    assert float(err.max()) <= 2 ** -5 * max(1.0, float(want.abs().max())), float(err.max())
+    assert float((err > 2 ** -7 * want.abs().clamp(min=1.0)).float().mean()) < 0.01
+
+
+def test_every_tap_lands_on_the_right_cell_and_edges_are_zero_padded():
+    """One-hot probes: input 1 at one cell / channel, conv1 = a single tap copying channel 0 -> 0, conv2 = centre-tap
+    identity, no shortcut: the output must be the input shifted by the tap, and nothing may wrap around a board edge or
+    leak into a neighbouring position of the same tile."""
+    H, W, n = 6, 7, 4
+    eye = torch.zeros(128, 128, 3, 3)
+    eye[:, :, 1, 1] = torch.eye(128)
+    zero_p, zero_b = torch.zeros(128, 128, 1, 1), torch.zeros(128)
+    x = torch.zeros(n, H, W, 128)
+    cells = [(0, 0), (0, 6), (5, 0), (5, 6), (2, 3), (0, 3), (3, 0), (3, 6)]
+    for i, (y, xx) in enumerate(cells):
+        x[i % n, y, xx, i] = 1.0 + i  # a different channel per probe so they can share a launch
+    for ky in range(3):
+        for kx in range(3):
+            w1 = torch.zeros(128, 128, 3, 3)
+            w1[:, :, ky, kx] = torch.eye(128)
+            got = _run(x, [(w1, zero_b, eye, zero_p, zero_b)], H, W)
+            want = torch.zeros_like(x)
+            for i, (y, xx) in enumerate(cells):
+                oy, ox = y - (ky - 1), xx - (kx - 1)  # out[oy, ox] = in[oy + ky - 1, ox + kx - 1]
+                if 0 <= oy < H and 0 <= ox < W:
+                    want[i % n, oy, ox, i] = 1.0 + i
+            assert torch.equal(got, want), (ky, kx, (got - want).abs().nonzero()[:8].tolist())
+
+
+def test_shortcut_and_biases_reach_the_output():
+    H, W, n = 6, 7, 5
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(n, H, W, 128, generator=g).to(torch.bfloat16)
+    wp = (torch.randn(128, 128, 1, 1, generator=g) * 0.1).to(torch.bfloat16).float()
+    z3 = torch.zeros(128, 128, 3, 3)
+    b1, b2 = torch.randn(128, generator=g), torch.randn(128, generator=g)
+    got = _run(x, [(z3, b1, z3, wp, b2)], H, W)
+    want = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wp) + b2[None, :, None, None]).permute(0, 2, 3, 1)
+    assert torch.allclose(got, want.to(torch.bfloat16).float(), rtol=2 ** -7, atol=1e-6)
+
+
+def test_inference_net_routes_through_the_fused_tower_and_matches_the_library_route():
+    engine, native, net = _mods()
+    torch.manual_seed(5)
+    fp32 = net.randomise_bn(net.PolicyValueNet(6, 7, 7))
+    inf = net.InferenceNet(fp32)
+    assert inf.fused_tower
+    h0 = torch.rand(1000, 6, 7, 128, device="cuda").to(torch.bfloat16)
+    a = inf.tower(h0).float()
+    b = inf.tower_library(h0).float()
+    # both are bf16 pipelines with float32 accumulation; the library rounds the shortcut to bf16 before the add
+    assert float((a - b).abs().max()) <= 2 ** -5 * max(1.0, float(b.abs().max()))
+    assert float(((a - b).abs() > 2 ** -6 * b.abs().clamp(min=1.0)).float().mean()) < 0.01
+
+
+def test_fused_tower_is_deterministic_and_independent_of_the_batch_split():
+    """A position's output may not depend on which tile / CTA it lands in."""
+    blocks = _blocks(2, seed=11)
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(1000, 6, 7, 128, generator=g).to(torch.bfloat16)
+    full = _run(x, blocks, 6, 7)
+    again = _run(x, blocks, 6, 7)
+    assert torch.equal(full, again)
+    part = _run(x[301:555], blocks, 6, 7)
+    assert torch.equal(full[301:555], part)

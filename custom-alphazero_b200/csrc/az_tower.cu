@@ -33,6 +33,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/az_b200.h"
 
@@ -64,19 +65,27 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start >> 4 in
 // bits 0-13, leading byte offset (between the two 8-element core matrices of one K = 16 step) bits 16-29, stride byte
 // offset (between 8-row groups; 128 = rows linear at 16 bytes) bits 32-45, version 1 bits 46-47, layout type 0.
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t lbo_bytes) {
-    return (uint64_t)((saddr & 0x3ffff) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
-           ((uint64_t)1 << 46);
+// The issuing thread keeps only the low word per operand (address + LBO) and steps it by constants: ncu showed the
+// first version issue-bound on 64-bit descriptor arithmetic (93 cycles of instructions per 64-cycle MMA).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr & 0x3ffff) >> 4) | ((lbo_bytes >> 4) << 16);
 }
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
 // D = F32 (bit 4), A = B = BF16 (bits 7, 10), both K-major, N >> 3 in bits 17-22, M >> 4 in bits 24-28
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(kIdesc), "r"(accumulate), "r"(kDescHi)
         : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t is_leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(is_leader));
+    return is_leader != 0;
 }
 __device__ __forceinline__ void commit_to(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
@@ -131,6 +140,8 @@ struct TowerParams {
     const float* bias;         // [depth][2][128]: conv1 bias, conv2 bias + shortcut bias
     __nv_bfloat16* y;          // [n][cells][128]
     int n, W, cells, ppt, depth, n_tiles;
+    int debug;                 // timing experiments only (AZ_TOWER_DEBUG): bit 0 = do not refill weight stages after the first ring pass,
+                               // bit 1 = epilogue skips its shared-memory stores, bit 2 = every tap reads the unshifted centre buffer
 };
 
 // byte offset of (buffer, row 0, chunk 0) inside the activation area
@@ -180,6 +191,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                     const uint32_t slot = cnt % kStages, k = cnt / kStages;
                     mbar_wait(smem_u32(&s_empty[slot]), (k & 1) ^ 1);
                     const uint32_t full = smem_u32(&s_full[slot]);
+                    if ((P.debug & 1) && cnt >= kStages) {
+                        mbar_arrive(full);
+                        continue;
+                    }
                     mbar_expect_tx(full, kStageBytes);
                     bulk_g2s(stages + slot * kStageBytes, src, kStageBytes, full);
                 }
@@ -187,46 +202,54 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            uint32_t cnt = 0, act_phase = 0;
-            // one weight stage = 64 input channels (chunk columns 8 * kb ..) of one tap: four K = 16 steps
-            auto stage_mmas = [&](uint32_t d_tmem, uint32_t a_base, int kb, bool fresh) {
-                const uint32_t slot = cnt % kStages, k = cnt / kStages;
-                mbar_wait(smem_u32(&s_full[slot]), k & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint32_t b_base = stages + slot * kStageBytes;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    mma_bf16(d_tmem, desc_kmajor(a_base + (uint32_t)(kb * 8 + 2 * j) * kLboA, kLboA),
-                             desc_kmajor(b_base + (uint32_t)(2 * j) * kLboB, kLboB), (fresh && j == 0) ? 0u : 1u);
+        // The whole warp runs the control flow (waits included) so that everything stays warp-uniform; one elected
+        // lane issues.  Taps, channel halves and K steps are fully unrolled: every descriptor is base + constant.
+        uint32_t cnt = 0, act_phase = 0;
+        const bool leader = elect_one();
+        const uint32_t a_step = 2u * (kLboA >> 4), a_half = 8u * (kLboA >> 4), b_step = 2u * (kLboB >> 4);
+        const uint32_t a_buf = (uint32_t)kBufRows;  // descriptor units (16 B) between buffers = rows
+        const uint32_t a0 = desc_lo(act + buf_row0(0), kLboA), b0 = desc_lo(stages, kLboB);
+        // one weight stage = 64 input channels of one tap: four K = 16 steps
+        auto stage_mmas = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t first_accumulate) {
+            const uint32_t slot = cnt % kStages, k = cnt / kStages;
+            mbar_wait(smem_u32(&s_full[slot]), k & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (leader) {
+                const uint32_t b_lo = b0 + slot * (kStageBytes >> 4);
+                mma_bf16(d_tmem, a_lo, b_lo, first_accumulate);
+                mma_bf16(d_tmem, a_lo + a_step, b_lo + b_step, 1u);
+                mma_bf16(d_tmem, a_lo + 2 * a_step, b_lo + 2 * b_step, 1u);
+                mma_bf16(d_tmem, a_lo + 3 * a_step, b_lo + 3 * b_step, 1u);
                 commit_to(smem_u32(&s_empty[slot]));  // frees the slot when these MMAs have read it
-                ++cnt;
-            };
-            auto conv3x3 = [&](uint32_t d_tmem, int centre_buf, bool fresh) {
+            }
+            __syncwarp();
+            ++cnt;
+        };
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            for (int b = 0; b < P.depth; ++b) {
 #pragma unroll 1
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                    const int buf = dx < 0 ? 1 : (dx > 0 ? 2 : centre_buf);
-                    const uint32_t a_base = act + buf_row0(buf) + (uint32_t)((dy * rowstride + dx) * 16);
-                    stage_mmas(d_tmem, a_base, 0, fresh && tap == 0);
-                    stage_mmas(d_tmem, a_base, 1, false);
-                }
-            };
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-                for (int b = 0; b < P.depth; ++b) {
-                    mbar_wait(bar_act, act_phase);  // x (and its masked copies) in place
+                for (uint32_t half = 0; half < 2; ++half) {  // 0: conv1 on x -> accumulator 0, 1: conv2 on h -> accumulator 1
+                    mbar_wait(bar_act, act_phase);  // x (and its masked copies) / h in place
                     act_phase ^= 1;
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    conv3x3(tmem, 0, true);
-                    commit_to(bar_acc);
-                    // the shortcut needs only x: it runs while the epilogue turns accumulator 0 into h
-                    stage_mmas(tmem + 128, act + buf_row0(0), 0, true);
-                    stage_mmas(tmem + 128, act + buf_row0(0), 1, false);
-                    mbar_wait(bar_act, act_phase);  // h in place
-                    act_phase ^= 1;
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    conv3x3(tmem + 128, 3, false);
-                    commit_to(bar_acc);
+                    const uint32_t d_tmem = tmem + half * 128u;
+                    const uint32_t centre = a0 + half * 3u * a_buf;  // buffer 0 (x) or 3 (h)
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        const uint32_t a_lo = (P.debug & 4) ? centre
+                                                            : (dx < 0 ? a0 + a_buf : (dx > 0 ? a0 + 2u * a_buf : centre)) +
+                                                                  (uint32_t)(dy * rowstride + dx);
+                        stage_mmas(d_tmem, a_lo, tap == 0 ? half : 1u);  // conv2 accumulates on top of the shortcut
+                        stage_mmas(d_tmem, a_lo + a_half, 1u);
+                    }
+                    if (leader) commit_to(bar_acc);
+                    __syncwarp();
+                    if (half == 0) {
+                        // the shortcut needs only x: it runs while the epilogue turns accumulator 0 into h
+                        stage_mmas(tmem + 128u, a0, 0u);
+                        stage_mmas(tmem + 128u, a0 + a_half, 1u);
+                    }
                 }
             }
         }
@@ -299,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                             const int kc = hf * 8 + cb * 4 + c4;
                             if (last) {
                                 if (store_global) *(reinterpret_cast<uint4*>(grow) + cb * 4 + c4) = o;
-                            } else if (row_live) {
+                            } else if (row_live && !(P.debug & 2)) {
                                 const uint32_t off = (uint32_t)kc * kLboA + (uint32_t)r * 16u;
                                 *reinterpret_cast<uint4*>(smem + buf_row0(centre) + off) = o;
                                 *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = zero_l ? zero4 : o;
@@ -349,7 +372,8 @@ extern "C" __attribute__((visibility("default"))) int az_net_tower(const void* x
     }
     const int n_tiles = (n + ppt - 1) / ppt;
     TowerParams P{static_cast<const __nv_bfloat16*>(x), static_cast<const uint8_t*>(w_img), bias,
-                  static_cast<__nv_bfloat16*>(y), n, W, cells, ppt, depth, n_tiles};
+                  static_cast<__nv_bfloat16*>(y), n, W, cells, ppt, depth, n_tiles, 0};
+    if (const char* dbg = getenv("AZ_TOWER_DEBUG")) P.debug = atoi(dbg);
     k_tower<<<n_tiles < sms ? n_tiles : sms, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(P);
     if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_tower: launch failed");
     return AZ_OK;

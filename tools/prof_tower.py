@@ -1,0 +1,21 @@
+#!/usr/bin/env python3
+"""A few launches of az_net_tower at the headline batch, for ncu (tools/prof_tower.py [n] [route])."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "custom-alphazero_b200")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+from az_b200 import net  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+route = sys.argv[2] if len(sys.argv) > 2 else "fused"
+torch.manual_seed(1)
+inf = net.InferenceNet(net.randomise_bn(net.PolicyValueNet(6, 7, 7)))
+x = torch.rand(n, 6, 7, 128, device="cuda").to(torch.bfloat16)
+for _ in range(4):
+    y = inf.tower(x) if route == "fused" else inf.tower_library(x)
+torch.cuda.synchronize()
+print("ok", float(y.float().abs().mean()))

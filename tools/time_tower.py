@@ -1,0 +1,70 @@
+#!/usr/bin/env python3
+"""Sustained timing of az_net_tower variants (AZ_TOWER_DEBUG experiments) and the cuDNN tower with the SM clock sampled
+through NVML during each timed loop.  python tools/time_tower.py [n] [debug flags ...]"""
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "custom-alphazero_b200")):
+    sys.path.insert(0, p)
+import pynvml  # noqa: E402
+import torch  # noqa: E402
+
+from az_b200 import net  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+flags = [int(v) for v in sys.argv[2:]] or [0]
+torch.manual_seed(1)
+inf = net.InferenceNet(net.randomise_bn(net.PolicyValueNet(6, 7, 7)))
+xs = [torch.rand(n, 6, 7, 128, device="cuda").to(torch.bfloat16) for _ in range(4)]
+torch.backends.cudnn.benchmark = True
+pynvml.nvmlInit()
+h = pynvml.nvmlDeviceGetHandleByIndex(0)
+
+
+def timed(fn, seconds=1.2):
+    for i in range(10):
+        fn(i % 4)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(20):
+        fn(i % 4)
+    torch.cuda.synchronize()
+    reps = max(50, int(seconds / ((time.time() - t0) / 20)))
+    clocks, power, stop = [], [], False
+
+    def sample():
+        while not stop:
+            clocks.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            time.sleep(0.05)
+
+    th = threading.Thread(target=sample)
+    th.start()
+    a.record()
+    for i in range(reps):
+        fn(i % 4)
+    b.record()
+    torch.cuda.synchronize()
+    stop = True
+    th.join()
+    clocks.sort()
+    return {"ms": a.elapsed_time(b) / reps, "reps": reps, "sm_mhz_median": clocks[len(clocks) // 2], "sm_mhz_min": clocks[0],
+            "power_w_max": max(power)}
+
+
+out = {}
+for f in flags:
+    os.environ["AZ_TOWER_DEBUG"] = str(f)
+    out[f"fused_debug{f}"] = timed(lambda i: inf.tower(xs[i]))
+    print(f, json.dumps(out[f"fused_debug{f}"]), flush=True)
+os.environ["AZ_TOWER_DEBUG"] = "0"
+out["cudnn"] = timed(lambda i: inf.tower_library(xs[i]))
+print("cudnn", json.dumps(out["cudnn"]), flush=True)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+with open(os.path.join(ROOT, "gpurun_out", "time_tower.json"), "w") as fp:
+    json.dump(out, fp, indent=1)

@@ -36,14 +36,15 @@ def pack_tower_weights(blocks):
     """[(w1, b1, w2, wp, b2p)] per block (BN folded; w [128, 128, k, k], any float dtype) -> (w_img bf16 [depth * 38 * 8192],
     bias float32 [depth, 2, 128]) in the layout az_net_tower streams (include/az_b200.h): a 16 KB stage is one filter tap
     x 64 input channels as the K-major, unswizzled UMMA B operand [8 chunks][128 cout][8 cin]; stages come in
-    consumption order: conv1 taps (ky, kx) row-major x 2 channel halves, the 1x1 shortcut x 2, conv2 taps x 2."""
+    consumption order: conv1 = 2 input-channel halves x taps (ky, kx) row-major, the 1x1 shortcut x 2 halves, conv2 like
+    conv1 (channel-half major, so the MMAs on channels 0-63 can start while the epilogue still writes 64-127)."""
     imgs, biases = [], []
     for w1, b1, w2, wp, b2p in blocks:
         for w in (w1, wp, w2):
             cout, cin, kh, kw = w.shape
             assert cout == 128 and cin == 128, "az_net_tower is built for 128 filters"
             t = w.detach().float().permute(2, 3, 1, 0).reshape(kh * kw, 2, 8, 8, cout)  # tap, half, chunk, e, cout
-            imgs.append(t.permute(0, 1, 2, 4, 3).reshape(-1))                             # tap, half, chunk, cout, e
+            imgs.append(t.permute(1, 0, 2, 4, 3).reshape(-1))                             # half, tap, chunk, cout, e
         biases.append(torch.stack([b1.detach().float(), b2p.detach().float()]))
     return torch.cat(imgs).to(torch.bfloat16).contiguous(), torch.stack(biases).contiguous()
 

@@ -21,7 +21,8 @@
 //
 // Roles (320 threads, 1 CTA per SM, persistent over tiles):
 //   warp 0   producer: one lane streams the weight stages (16 KB = one tap x 64 input channels x 128 output channels,
-//            pre-packed by the host in the UMMA layout, in the order they are consumed) from global memory with
+//            pre-packed by the host in the UMMA layout, in the order they are consumed: per convolution the
+//            input-channel half is the outer loop, the tap the inner one) from global memory with
 //            cp.async.bulk into a 4-deep ring, full / empty mbarriers;
 //   warp 1   MMA issuer: one lane issues 4 tcgen05.mma (128 x 128 x 16) per stage; conv1 -> TMEM columns 0-127, the
 //            1x1 shortcut (needs only x) and then conv2 -> columns 128-255, so the shortcut runs under epilogue 1;
@@ -129,6 +130,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+          "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(fmaxf(lo, 0.0f), fmaxf(hi, 0.0f));
     return *reinterpret_cast<uint32_t*>(&v);
@@ -149,12 +162,12 @@ __device__ __forceinline__ uint32_t buf_row0(int buf) { return (uint32_t)(kPad +
 
 __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_acc, s_act;
+    __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_acc, s_act[2];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t act = smem_u32(smem), stages = act + kActBytes;
     float* s_bias = reinterpret_cast<float*>(smem + kActBytes + kStages * kStageBytes);
-    const uint32_t bar_acc = smem_u32(&s_acc), bar_act = smem_u32(&s_act);
+    const uint32_t bar_acc = smem_u32(&s_acc), bar_act0 = smem_u32(&s_act[0]), bar_act1 = smem_u32(&s_act[1]);
     const int rowstride = P.ppt * P.W, rows_used = P.ppt * P.cells;
     const int stages_per_tile = kStagesPerBlock * P.depth;
 
@@ -167,7 +180,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
             mbar_init(smem_u32(&s_empty[s]), 1);
         }
         mbar_init(bar_acc, 1);
-        mbar_init(bar_act, kThreads - 64);
+        mbar_init(bar_act0, (kThreads - 64) / 32);  // one arrival per epilogue warp
+        mbar_init(bar_act1, (kThreads - 64) / 32);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
@@ -229,20 +243,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
             for (int b = 0; b < P.depth; ++b) {
 #pragma unroll 1
                 for (uint32_t half = 0; half < 2; ++half) {  // 0: conv1 on x -> accumulator 0, 1: conv2 on h -> accumulator 1
-                    mbar_wait(bar_act, act_phase);  // x (and its masked copies) / h in place
-                    act_phase ^= 1;
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const uint32_t d_tmem = tmem + half * 128u;
                     const uint32_t centre = a0 + half * 3u * a_buf;  // buffer 0 (x) or 3 (h)
+                    // channel-half major: the MMAs on input channels 0-63 start as soon as the epilogue (or the tile
+                    // load) has written that half of the three copies; it writes channels 64-127 underneath them
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                        const uint32_t a_lo = (P.debug & 4) ? centre
-                                                            : (dx < 0 ? a0 + a_buf : (dx > 0 ? a0 + 2u * a_buf : centre)) +
-                                                                  (uint32_t)(dy * rowstride + dx);
-                        stage_mmas(d_tmem, a_lo, tap == 0 ? half : 1u);  // conv2 accumulates on top of the shortcut
-                        stage_mmas(d_tmem, a_lo + a_half, 1u);
+                    for (int kb = 0; kb < 2; ++kb) {
+                        mbar_wait(kb == 0 ? bar_act0 : bar_act1, act_phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                            const uint32_t a_lo = (P.debug & 4) ? centre
+                                                                : (dx < 0 ? a0 + a_buf : (dx > 0 ? a0 + 2u * a_buf : centre)) +
+                                                                      (uint32_t)(dy * rowstride + dx);
+                            // conv2 accumulates on top of the shortcut
+                            stage_mmas(d_tmem, a_lo + (uint32_t)kb * a_half, (tap == 0 && kb == 0) ? half : 1u);
+                        }
                     }
+                    act_phase ^= 1;
                     if (leader) commit_to(bar_acc);
                     __syncwarp();
                     if (half == 0) {
@@ -257,71 +276,86 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
         // ---------------------------------------------------------------- epilogue / tile load / tile store
         const int e = tid - 64;                       // 0..255
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
-        const int hf = (warp - 2) >> 2;               // which 64 of the 128 output channels
+        const int sub = (warp - 2) >> 2;              // which 32 columns of each 64-channel half
         const int r = q * 32 + lane;                  // accumulator row = tile row
         // tile row -> (y, position, x): r = y * rowstride + p * W + x
         const int ry = r / rowstride, rrem = r - ry * rowstride, rp = rrem / P.W, rx = rrem - rp * P.W;
         const bool row_live = r < rows_used;
         const bool zero_l = rx == P.W - 1, zero_r = rx == 0;
         const long long row_in_tile = (long long)rp * P.cells + ry * P.W + rx;
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 64);
-        // the loader's view: row lr = e & 127, chunk half lh = e >> 7 (a warp = 32 consecutive rows: conflict-free stores)
-        const int lr = e & 127, lh = e >> 7;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 32);
+        // the loader's view: row lr = e & 127, chunks sub * 4 .. + 3 of each half (a warp = 32 consecutive rows:
+        // conflict-free 512-byte stores)
+        const int lr = e & 127, lsub = e >> 7;
         const int ly = lr / rowstride, lrem = lr - ly * rowstride, lp = lrem / P.W, lx = lrem - lp * P.W;
         const bool l_live = lr < rows_used;
         const long long l_row_in_tile = (long long)lp * P.cells + ly * P.W + lx;
         uint32_t acc_phase = 0;
         const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+        // this half of the three copies is complete: every thread orders its stores for the tensor core's proxy, one
+        // lane per warp arrives
+        auto publish = [&](uint32_t bar) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        };
 
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
             const long long pos0 = (long long)tile * P.ppt;
-            // ---- tile in: x, x-left-masked, x-right-masked
-            if (l_live) {
+            // ---- tile in: x, x-left-masked, x-right-masked; channels 0-63 first
+            {
                 uint4 v[8];
-                const bool have = pos0 + lp < P.n;
-                const uint4* src = reinterpret_cast<const uint4*>(P.x + (pos0 * P.cells + l_row_in_tile) * kC) + lh * 8;
+                const bool have = l_live && pos0 + lp < P.n;
+                const uint4* src = reinterpret_cast<const uint4*>(P.x + (pos0 * P.cells + l_row_in_tile) * kC) + lsub * 4;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = have ? __ldg(src + c) : zero4;
+                for (int c = 0; c < 8; ++c) v[c] = have ? __ldg(src + (c >> 2) * 8 + (c & 3)) : zero4;
                 const bool zl = lx == P.W - 1, zr = lx == 0;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t off = (uint32_t)(lh * 8 + c) * kLboA + (uint32_t)lr * 16u;
-                    *reinterpret_cast<uint4*>(smem + buf_row0(0) + off) = v[c];
-                    *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = zl ? zero4 : v[c];
-                    *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = zr ? zero4 : v[c];
+                for (int ch = 0; ch < 2; ++ch) {
+                    if (l_live) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const uint32_t off = (uint32_t)(ch * 8 + lsub * 4 + c) * kLboA + (uint32_t)lr * 16u;
+                            *reinterpret_cast<uint4*>(smem + buf_row0(0) + off) = v[ch * 4 + c];
+                            *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = zl ? zero4 : v[ch * 4 + c];
+                            *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = zr ? zero4 : v[ch * 4 + c];
+                        }
+                    }
+                    publish(ch == 0 ? bar_act0 : bar_act1);
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            mbar_arrive(bar_act);
 
             for (int b = 0; b < P.depth; ++b) {
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {  // 0: accumulator 0 -> h, 1: accumulator 1 -> block output
-                    const float* bias = s_bias + (b * 2 + half) * kC + hf * 64;
+                    const float* bias = s_bias + (b * 2 + half) * kC + sub * 32;
                     const bool last = half == 1 && b == P.depth - 1;
                     mbar_wait(bar_acc, acc_phase);
                     acc_phase ^= 1;
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const int centre = half == 0 ? 3 : 0;
-                    __nv_bfloat16* grow = P.y + (pos0 * P.cells + row_in_tile) * kC + hf * 64;
+                    __nv_bfloat16* grow = P.y + (pos0 * P.cells + row_in_tile) * kC + sub * 32;
                     const bool store_global = last && row_live && pos0 + rp < P.n;
+                    uint32_t v[2][32];  // both channel halves in flight before the first is used
+                    tmem_ld32_nowait(taddr + (uint32_t)(half * 128), v[0]);
+                    tmem_ld32_nowait(taddr + (uint32_t)(half * 128 + 64), v[1]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-                    for (int cb = 0; cb < 2; ++cb) {
-                        uint32_t v[32];
-                        tmem_ld32(taddr + (uint32_t)(half * 128 + cb * 32), v);
+                    for (int ch = 0; ch < 2; ++ch) {
 #pragma unroll
                         for (int c4 = 0; c4 < 4; ++c4) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(bias + cb * 32 + c4 * 8);
-                            const float4 b1 = *reinterpret_cast<const float4*>(bias + cb * 32 + c4 * 8 + 4);
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias + ch * 64 + c4 * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias + ch * 64 + c4 * 8 + 4);
+                            const uint32_t* w = &v[ch][8 * c4];
                             uint4 o;
-                            o.x = pack_relu_bf16(__uint_as_float(v[8 * c4 + 0]) + b0.x, __uint_as_float(v[8 * c4 + 1]) + b0.y);
-                            o.y = pack_relu_bf16(__uint_as_float(v[8 * c4 + 2]) + b0.z, __uint_as_float(v[8 * c4 + 3]) + b0.w);
-                            o.z = pack_relu_bf16(__uint_as_float(v[8 * c4 + 4]) + b1.x, __uint_as_float(v[8 * c4 + 5]) + b1.y);
-                            o.w = pack_relu_bf16(__uint_as_float(v[8 * c4 + 6]) + b1.z, __uint_as_float(v[8 * c4 + 7]) + b1.w);
-                            const int kc = hf * 8 + cb * 4 + c4;
+                            o.x = pack_relu_bf16(__uint_as_float(w[0]) + b0.x, __uint_as_float(w[1]) + b0.y);
+                            o.y = pack_relu_bf16(__uint_as_float(w[2]) + b0.z, __uint_as_float(w[3]) + b0.w);
+                            o.z = pack_relu_bf16(__uint_as_float(w[4]) + b1.x, __uint_as_float(w[5]) + b1.y);
+                            o.w = pack_relu_bf16(__uint_as_float(w[6]) + b1.z, __uint_as_float(w[7]) + b1.w);
+                            const int kc = ch * 8 + sub * 4 + c4;
                             if (last) {
-                                if (store_global) *(reinterpret_cast<uint4*>(grow) + cb * 4 + c4) = o;
+                                if (store_global) *(reinterpret_cast<uint4*>(grow + ch * 64) + c4) = o;
                             } else if (row_live && !(P.debug & 2)) {
                                 const uint32_t off = (uint32_t)kc * kLboA + (uint32_t)r * 16u;
                                 *reinterpret_cast<uint4*>(smem + buf_row0(centre) + off) = o;
@@ -329,12 +363,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                                 *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = zero_r ? zero4 : o;
                             }
                         }
+                        if (!last) publish(ch == 0 ? bar_act0 : bar_act1);
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                    if (!last) {
-                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                        mbar_arrive(bar_act);
-                    }
                 }
             }
         }

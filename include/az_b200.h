@@ -297,8 +297,8 @@ int az_net_conv1x1(const void *dev_x, const void *dev_w, int64_t rows, int32_t c
  *   per block  h = relu(conv3x3(x, w1) + b1);  x' = relu(conv3x3(h, w2) + conv1x1(x, wp) + b2p)
  * Activations stay in shared memory / TMEM from the first block to the last; replaces the 12 library convolutions.
  * x, y: dev bf16 [n][H*W][128] (NHWC; y may not alias x).  w_img: dev bf16, depth x 38 stages of 16 KB, each
- * [8 chunks][128 output channels][8 input channels] in consumption order - per block: conv1 taps (ky, kx) row-major x
- * 2 halves of the input channels, the shortcut x 2 halves, conv2 taps x 2 halves (az_b200/net.py pack_tower_weights).
+ * [8 chunks][128 output channels][8 input channels] in consumption order - per block: conv1 = 2 halves of the input
+ * channels x taps (ky, kx) row-major, the shortcut x 2 halves, conv2 like conv1 (az_b200/net.py pack_tower_weights).
  * bias: dev float [depth][2][128] (b1; b2 + shortcut bias).  channels must be 128, H * W <= 128,
  * (128 / (H * W)) * W + 1 <= 22 (6x7, 8x8, ...), depth 1..6.  All pointers 16-byte aligned. */
 int az_net_tower(const void *dev_x, const void *dev_w_img, const float *dev_bias, int32_t n, int32_t H, int32_t W,

@@ -54,7 +54,7 @@ def emulate_tower(x, img, bias, H, W, depth):
                     start = row0[buf] + dy * rowstride + dx
                     a = space[start:start + TILE]
                     for kb in range(2):
-                        acc += a[:, kb * 64:(kb + 1) * 64] @ b_operand(b, s0 + tap * 2 + kb).T
+                        acc += a[:, kb * 64:(kb + 1) * 64] @ b_operand(b, s0 + kb * 9 + tap).T
                 return acc
             h = np.maximum(conv3(0, 0) + bias[b, 0], 0)
             a0 = space[row0[0]:row0[0] + TILE]

@@ -8,14 +8,19 @@ Workload (config C2 of BASELINE.json, per GPU): 4096 concurrent 6x7 Connect-4 ga
 per move, every leaf evaluated by the bf16 policy/value net (random-init weights of the reference
 architecture: synthetic), finished games refilled so the batch stays full.  One "step" = 800 lock-step
 advances of all trees = one move's worth of simulations for every game (~3.3 M simulations per GPU).
-N > 1: weak scaling - every rank owns 4096 games and a net replica (32768 games at N = 8 = config C3);
-the only collectives are the per-step weight broadcast and, in the e2e leg, the game-record gather.
+N > 1: weak scaling by default - every rank owns 4096 games and a net replica (32768 games at N = 8); --scaling strong
+--total-games 32768 is config C3 as BASELINE.json words it (32768 games sharded across the GPUs).  The only collectives
+are the weight broadcast (side stream, never on the simulation path) and, in the e2e leg, the game-record gather to the
+trainer rank.  At N > 1 rank 0 first replays games of other ranks and checks them bit for bit ("multi_rank_parity").
+The timed steps follow an untimed pre-roll of more than one game generation (steady state), and the device-resident and
+end-to-end steps alternate so that both see the same mix of plies.
 
 Prints ONE JSON line (rank 0).  `value` = whole-job simulations/s, device-timed with everything
 resident in HBM; `e2e` = the same metric through the public API with host buffers: every step uploads
 the weights from pinned host memory and downloads the decoded training samples of the games that
-finished.  `roofline` is the net forward (tensor bound, the dominant kernels); `roofline_tree` the
-az_step kernel (HBM bound).  `cpu_baseline` = the oracle's Python port of the reference run the way the
+finished.  `roofline` is the residual tower (tensor bound, the dominant kernel: az_net_tower), timed alone
+against the measured BURST peak plus `in_loop_frac` against the sustained one; `roofline_tree` the per-tree kernel
+(HBM bound).  `cpu_baseline` = the oracle's Python port of the reference run the way the
 reference runs self-play (os.cpu_count()-1 processes, batch-1 fp32 CPU net), on a bounded sample.
 """
 import argparse
@@ -134,13 +139,55 @@ def run_reference(args):
     }))
 
 
+def multi_rank_parity(dist, azdist, selfplay, rules, fp32, sims, rank, world, n_games=64):
+    """SURVEY 4 test 5 on hardware: every rank plays games [rank << 40, +n_games) with its own net replica, the records
+    are gathered over NCCL to rank 0, and rank 0 replays the ids of rank 1 and of the last rank locally: moves, visit
+    counts, lengths and results must be identical (a game depends on its id, the seed and the weights - not on the rank
+    or on what else is in the batch).  Returns the status string printed in the JSON line."""
+    import torch
+
+    def play(base):
+        r = selfplay.SelfPlayRunner(rules, n_trees=n_games, sims_per_move=sims, net=fp32, games_target=n_games,
+                                    game_id_base=base, seed=1234, move_mode="philox", auto_restart=True, unroll=8,
+                                    fin_capacity=n_games)
+        r.run_until_done(poll_every=512)
+        fin = {k: v.clone() for k, v in r.finished_device().items()}
+        r.check_status()
+        return fin
+
+    mine = play(rank << 40)
+    gathered = azdist.gather_records({k: v.contiguous() for k, v in mine.items()}, dst=0)
+    status = None
+    if rank == 0:
+        checked = 0
+        for peer in sorted({1, world - 1}):
+            want = play(peer << 40)
+            sel = (gathered["game_id"] >> 40) == peer
+            got = {k: v[sel] for k, v in gathered.items()}
+            assert int(sel.sum()) == n_games, "rank %d sent %d games" % (peer, int(sel.sum()))
+            og, ow = torch.argsort(got["game_id"]), torch.argsort(want["game_id"])
+            for k in ("game_id", "len", "result", "action", "visits", "board"):
+                assert torch.equal(got[k][og], want[k][ow]), "multi-rank parity: %s of rank %d differs" % (k, peer)
+            checked += n_games
+        status = "ok: %d games of ranks %s (%d simulations/move) gathered over NCCL equal their replay on rank 0 (moves, visit counts, results)" % (
+            checked, sorted({1, world - 1}), sims)
+    return status
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--trees", type=int, default=4096, help="concurrent games per GPU")
+    ap.add_argument("--trees", type=int, default=4096, help="concurrent games per GPU (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong = BASELINE config C3 as written: --total-games sharded across the GPUs")
+    ap.add_argument("--total-games", type=int, default=32768, help="concurrent games of the whole job under --scaling strong")
+    ap.add_argument("--preroll", type=int, default=48,
+                    help="untimed steps before the warm-up: > one game generation (42 plies), so that finished games have "
+                         "been refilled and the timed steps see the steady-state mix of plies")
+    ap.add_argument("--parity-games", type=int, default=64, help="N > 1: games per rank of the multi-rank parity check (0 = skip)")
     ap.add_argument("--sims", type=int, default=800, help="simulations per move")
     ap.add_argument("--advances", type=int, default=800, help="lock-step advances per step")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bounded CPU baseline sample (0 = skip)")
@@ -188,7 +235,7 @@ def main():
 
     from az_b200 import dist as azdist
     from az_b200 import engine, selfplay
-    from az_b200.net import PolicyValueNet
+    from az_b200.net import PolicyValueNet, flops_per_eval
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -197,8 +244,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.benchmark = True
     peaks = load_peaks()
-    # cuDNN's autotuner times each candidate once, at the first convolution: bring the clocks to their loaded state first
-    # so that it does not pick its algorithms on an idle, boosting GPU (run-to-run spread of the net forward: 0.43-0.48 ms)
+    # bring the clocks to their loaded state before anything is autotuned or timed
     burn = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
     for _ in range(200):
         burn @ burn
@@ -206,144 +252,183 @@ def main():
     del burn
 
     rules = engine.Rules(*RULES)
-    T, S, ADV = args.trees, args.sims, args.advances
+    S, ADV = args.sims, args.advances
+    if args.scaling == "strong":
+        assert args.total_games % world == 0, "--total-games must divide by the number of GPUs"
+        T = args.total_games // world
+    else:
+        T = args.trees
     torch.manual_seed(0)
     fp32 = PolicyValueNet(rules.height, rules.width, rules.n_actions)
+
+    parity = None
+    if world > 1 and args.parity_games > 0:
+        parity = multi_rank_parity(dist, azdist, selfplay, rules, fp32, S, rank, world, args.parity_games)
+        torch.cuda.empty_cache()
+
     runner = selfplay.SelfPlayRunner(rules, n_trees=T, sims_per_move=S, net=fp32, games_target=1 << 40,
                                      game_id_base=rank << 40, seed=1234, move_mode="philox", auto_restart=True,
                                      unroll=args.unroll, fin_capacity=4 * T, groups=args.groups, max_free_sims=args.max_free, fused=not args.no_fused,
                                      eval_cache_log2=args.memo_log2)
-    flat_dev = runner.net.flat_weights()  # what the trainer rank would broadcast after a training step
+    params = list(runner.net.parameters())
+    flat_dev = runner.net.flat_weights()            # the live weights as one vector
+    flat_trainer = flat_dev.clone()                 # what the trainer rank holds after a training step
+    flat_host = flat_dev.cpu().pin_memory()         # ... and on the host (e2e leg)
     n_w = flat_dev.numel()
+    bcast = azdist.WeightBroadcaster(n_w, dev)
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
-    def step_device():
-        if world > 1:
-            azdist.broadcast_weights(flat_dev, src=0)
-        runner.run(ADV)
-
-    for _ in range(args.warmup):
-        step_device()
-    runner.fin_clear()
-    barrier()
-    c0 = runner.totals()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for k in range(args.steps):
-        step_device()
-        if (k + 1) % 2 == 0:
-            runner.fin_clear()  # ring bookkeeping only; samples are consumed in the e2e leg
-    ev1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    c1 = runner.totals()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    delta = torch.tensor([c1[k] - c0[k] for k in ("sims", "evals", "moves", "games", "depth_sum", "children")],
-                         dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(delta, op=dist.ReduceOp.SUM)
-    ms = float(ms)
-    sims, evals, moves, games, depth_sum, children = [float(x) for x in delta]
-    runner.check_status()
-
-    # ---- e2e: public API with host buffers (weights up from pinned memory, decoded samples down)
-    flat_host = flat_dev.cpu().pin_memory()
-    params = list(runner.net.parameters())
-    # one untimed pass over the sample path (first use loads the decode kernel and torch's index ops)
-    runner.run(args.unroll)
-    _warm = runner.finished_device()
-    if world > 1:
-        _warm = azdist.all_gather_records({k_: v.contiguous() for k_, v in _warm.items()})
-    selfplay.decode_samples(rules, _warm)
-    runner.fin_clear()
-    barrier()
-    e0 = runner.totals()
-    h2d = d2h = 0
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    dbg = []
-    for _ in range(args.steps):
-        dbg.append(time.perf_counter())
-        flat_dev.copy_(flat_host, non_blocking=True)
-        h2d += n_w * 4
-        if world > 1:
-            azdist.broadcast_weights(flat_dev, src=0)
+    def install_weights():
+        """flat_dev -> the parameters the captured graphs read (device-to-device, on the compute stream)."""
         off = 0
         with torch.no_grad():
             for p_ in params:
                 p_.copy_(flat_dev[off: off + p_.numel()].view_as(p_))
                 off += p_.numel()
+
+    def step_device():
+        """One step with everything resident: pick up the weights the last broadcast staged, start the next broadcast
+        on the side stream (NCCL, N > 1), 800 advances.  The compute stream never waits inside a collective."""
+        if world > 1:
+            if bcast.take(flat_dev):
+                install_weights()
+            bcast.start(flat_trainer if rank == 0 else None)
+        runner.run(ADV)
+
+    h2d = d2h = 0
+
+    def step_e2e():
+        """The same step through the public API with host buffers: weights from pinned host memory (+ broadcast),
+        800 advances, the games that finished gathered to the trainer rank, decoded to (states f32, policies f64,
+        values) and copied to the host."""
+        nonlocal h2d, d2h
+        if rank == 0:
+            flat_trainer.copy_(flat_host, non_blocking=True)
+            h2d += n_w * 4
+        if world > 1:
+            if bcast.pending:
+                bcast.take(flat_dev)  # drop the one the device leg left in flight
+            bcast.start(flat_trainer if rank == 0 else None)
+            bcast.take(flat_dev)
+        else:
+            flat_dev.copy_(flat_trainer, non_blocking=True)
+        install_weights()
         runner.run(ADV)
         fin = runner.finished_device()
         if world > 1:
-            fin = azdist.all_gather_records({k_: v.contiguous() for k_, v in fin.items()})
-        if rank == 0 or world == 1:
+            fin = azdist.gather_records({k_: v.contiguous() for k_, v in fin.items()}, dst=0)
+        if rank == 0:
             st, po, va = selfplay.decode_samples(rules, fin)
             d2h += st.nbytes + po.nbytes + va.nbytes // 2
         runner.fin_clear()
-        dbg.append(time.perf_counter())
-    t1.record()
-    barrier()
-    e1 = runner.totals()
-    e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
-    e2e_sims = torch.tensor([e1["sims"] - e0["sims"]], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_sims, op=dist.ReduceOp.SUM)
-    e2e_value = float(e2e_sims) / float(e2e_ms) * 1e3
-    if rank == 0 and os.environ.get("AZ_BENCH_DEBUG"):
-        print("e2e host wall per step (ms):", [round((dbg[i + 1] - dbg[i]) * 1e3, 1) for i in range(0, len(dbg), 2)],
-              "device ms:", float(e2e_ms), file=sys.stderr)
 
-    # ---- roofline of the dominant kernels: the net forward (tensor bound), timed alone with CUDA events
+    # ---- untimed: pre-roll (more than a game generation), then W warm-up steps of both legs
+    for k in range(args.preroll):
+        step_device()
+        if (k + 1) % 2 == 0:
+            runner.fin_clear()
+    for _ in range(args.warmup):
+        step_device()
+        step_e2e()
+    runner.fin_clear()
+    h2d = d2h = 0
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    mk = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    dev_ev = [(mk(), mk()) for _ in range(args.steps)]
+    e2e_ev = [(mk(), mk()) for _ in range(args.steps)]
+    dev_tot = {k_: 0.0 for k_ in ("sims", "evals", "moves", "games", "depth_sum", "children", "memo_hits")}
+    e2e_sims = 0.0
+    barrier()
+    # ---- timed: K device-resident steps and K end-to-end steps, interleaved step by step so that both legs see the
+    # same phase of the games; each step is bracketed by CUDA events on the compute stream
+    for k in range(args.steps):
+        c0 = runner.totals()
+        dev_ev[k][0].record()
+        step_device()
+        dev_ev[k][1].record()
+        c1 = runner.totals()   # reads device counters: synchronises the host with the end of the step
+        for k_ in dev_tot:
+            dev_tot[k_] += c1.get(k_, 0) - c0.get(k_, 0)
+        runner.fin_clear()
+        e2e_ev[k][0].record()
+        step_e2e()
+        e2e_ev[k][1].record()
+        c2 = runner.totals()
+        e2e_sims += c2["sims"] - c1["sims"]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    runner.check_status()
+    my_ms = sum(a.elapsed_time(b) for a, b in dev_ev)
+    my_e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_ev)
+    ms_max = torch.tensor([my_ms, my_e2e_ms, -my_ms], dtype=torch.float64, device=dev)
+    delta = torch.tensor([dev_tot[k_] for k_ in ("sims", "evals", "moves", "games", "depth_sum", "children", "memo_hits")] + [e2e_sims],
+                         dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(delta, op=dist.ReduceOp.SUM)
+    ms, e2e_ms, ms_min = float(ms_max[0]), float(ms_max[1]), -float(ms_max[2])
+    sims, evals, moves, games, depth_sum, children, memo_hits, e2e_sims = [float(x) for x in delta]
+    e2e_value = e2e_sims / e2e_ms * 1e3
+
+    # ---- roofline of the dominant kernel, timed alone with CUDA events on the launching stream
     roof = roof_tree = None
     if rank == 0:
         x = runner.states  # the batch one net call really sees: T / groups positions
         Tg = x.shape[0]
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            runner.net(x)
-        for _ in range(5):
-            g.replay()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
         n_rep = 50
-        for _ in range(n_rep):
-            g.replay()
+        cells = rules.height * rules.width
+        tower_flops = 4 * (2 * 2 * cells * 9 * 128 * 128 + 2 * cells * 128 * 128)  # per position: 8 conv3x3 + 4 conv1x1
+        g0 = runner.groups[0]
+        h_in = [torch.rand((Tg, rules.height, rules.width, 128), device=dev).to(torch.bfloat16) for _ in range(4)]
+        for i in range(8):
+            runner.net.tower(h_in[i % 4])
+        a.record()
+        for i in range(n_rep):
+            runner.net.tower(h_in[i % 4])  # inputs rotate through 4 x 44 MB: more than the L2 holds
         b.record()
         torch.cuda.synchronize()
-        net_ms = a.elapsed_time(b) / n_rep
-        ach = Tg * runner.flops_per_eval / (net_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_sustained"],
-                "traffic": 817.0e6 if (Tg == 4096 and RULES == (7, 6, 4, True)) else None,
-                "traffic_note": "DRAM bytes of the 12 tower convolutions per forward at 4096 positions (ncu, steady state, profiles/advance_traffic_r1.json); algorithmic in+out bytes are 1232 MB - the 126 MB L2 keeps part of every activation tensor on chip",
-                "kernel": "policy/value net forward timed alone: az_net_stem + 12 cuDNN tcgen05 implicit-GEMM convolutions (cutlass3x_sm100_tensorop, fused bias/ReLU/residual epilogues) + az_net_heads",
-                "flops_per_launch": Tg * runner.flops_per_eval, "positions_per_launch": Tg, "ms_per_launch": net_ms, "peak_source": peaks["source"] + ", sustained"}
+        tower_ms = a.elapsed_time(b) / n_rep
+        del h_in
+        ach = Tg * tower_flops / (tower_ms * 1e-3) / 1e12
+        evals_per_s = evals / ms * 1e3
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "tower_traffic_r2.json")
+        if os.path.exists(tpath) and Tg == 4096 and RULES == (7, 6, 4, True) and runner.net.fused_tower:
+            with open(tpath) as fp:
+                tj = json.load(fp)
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/tower_traffic_r2.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one k_tower launch at 4096 positions)"
+        fused_tower = bool(getattr(runner.net, "fused_tower", False))
+        roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_burst"],
+                "in_loop_frac": evals_per_s / world * tower_flops / 1e12 / peaks["bf16_sustained"],
+                "in_loop_note": "leaf evaluations/s per GPU inside the timed steps x tower FLOPs per position / the measured SUSTAINED bf16 peak (the step also contains the per-tree kernel, which runs serially with the tower)",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": ("az::tower::k_tower (az_net_tower): the whole 4-block residual tower, one persistent tcgen05 kernel, activations resident in shared memory / TMEM" if fused_tower
+                           else "12 cuDNN tcgen05 implicit-GEMM convolutions (cutlass3x_sm100_tensorop) of the residual tower"),
+                "flops_per_launch": Tg * tower_flops, "positions_per_launch": Tg, "ms_per_launch": tower_ms,
+                "share_of_net_flops": tower_flops / flops_per_eval(rules.height, rules.width, rules.n_actions),
+                "peak_source": peaks["source"] + ", burst (kernel timed alone)"}
         # the per-tree kernel alone (HBM bound): algorithmic bytes per tree and launch with the measured mean
         # depth / fan-out.  Fused route: az_advance_fused = heads + tree step + stem (reads the tower output of the
         # tree's leaf, writes the stem output of the next one); else az_step.
         d_bar = depth_sum / max(sims, 1.0)
         k_bar = children / max(evals, 1.0)
         sims_per_tree = sims / max(evals, 1.0)  # simulations finished per evaluated leaf
-        A, cells = rules.n_actions, rules.height * rules.width
+        A = rules.n_actions
         tree_bytes = (16 + d_bar * k_bar * 24      # select: root record + per level k children x (16 B record + 8 B prior)
                       + 4 * d_bar + 16 + 4         # path + leaf position + path length written
                       + 4 * d_bar + 16             # path + leaf position re-read at expansion
                       + k_bar * 24                 # expand: k children x 24 B
                       + d_bar * 32                 # backup: 16 B read + 16 B write per path node
                       + 64)                        # per-tree header words
-        g0 = runner.groups[0]
         if runner.fused:
             import ctypes
 
@@ -373,28 +458,34 @@ def main():
         step_ms = a.elapsed_time(b) / n_rep
         ach_gbs = Tg * bytes_per_tree / (step_ms * 1e-3) / 1e9
         roof_tree = {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach_gbs / peaks["hbm_gbs"], "traffic": 89.7e6 if runner.fused else None,
-                     "traffic_source": "profiles/advance_traffic_r1.json (DRAM bytes of k_advance per launch, ncu, steady state)",
+                     "frac": ach_gbs / peaks["hbm_gbs"], "traffic": None,
                      "kernel": kname, "bytes_per_tree": bytes_per_tree, "tree_bytes_per_sim": tree_bytes,
                      "mean_depth": d_bar, "mean_children": k_bar, "sims_per_evaluated_leaf": sims_per_tree,
                      "trees_per_launch": Tg, "ms_per_launch": step_ms, "peak_source": peaks["source"]}
 
     if rank == 0:
         per_adv = args.steps * ADV
+        games_job = T * world
+        cfg_name = "C3" if args.scaling == "strong" else ("C2" if RULES == (7, 6, 4, True) else "C4")
         out = {
             "metric": METRIC, "value": sims / ms * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{'C2' if RULES == (7, 6, 4, True) else 'C4'}: {T} concurrent {rules.height}x{rules.width} Connect-{rules.n} self-play games per GPU x {S} simulations/move, bf16 net leaf evaluation",
-                       "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "fused_advance": bool(runner.fused), "evaluation_memo_log2": args.memo_log2, "board": f"{rules.height}x{rules.width}", "n_connect": rules.n, "gravity": rules.gravity,
+            "config": {"workload": f"{cfg_name}: {games_job} concurrent {rules.height}x{rules.width} Connect-{rules.n} self-play games ({T} per GPU) x {S} simulations/move, bf16 net leaf evaluation",
+                       "games_per_gpu": T, "games_total": games_job, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "fused_advance": bool(runner.fused),
+                       "fused_tower": bool(getattr(runner.net, "fused_tower", False)), "evaluation_memo_log2": args.memo_log2, "board": f"{rules.height}x{rules.width}", "n_connect": rules.n, "gravity": rules.gravity,
                        "net": f"4-block 128-filter projection-residual tower, {fp32.n_parameters()} params, random init",
-                       "l2": "working set per advance (node pools ~GBs + 177 MB activations per conv) exceeds the 126 MB L2; no flush needed"},
-            "leaf_evals_per_sec": evals / ms * 1e3, "memo_hits_per_sec": (c1.get("memo_hits", 0) - c0.get("memo_hits", 0)) / ms * 1e3, "selfplay_moves_per_sec": moves / ms * 1e3,
+                       "preroll_steps": args.preroll,
+                       "phase": "steady state: the timed steps follow an untimed pre-roll of more than one game generation; the device-resident and the end-to-end steps alternate, so both see the same mix of plies",
+                       "l2": "working set per advance (node pools ~GBs + 88 MB of activations in and out of the tower) exceeds the 126 MB L2; no flush needed"},
+            "leaf_evals_per_sec": evals / ms * 1e3, "memo_hits_per_sec": memo_hits / ms * 1e3, "selfplay_moves_per_sec": moves / ms * 1e3,
             "games_finished": games,
+            "rank_ms_per_step": {"min": ms_min / args.steps, "max": ms / args.steps},
+            "multi_rank_parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(args.steps, 1),
                     "d2h_bytes_per_step": d2h // max(args.steps, 1),
-                    "what": "per step: weights from pinned host memory -> device (+ NCCL broadcast), 800 advances, finished games decoded to (states f32, policies f64, values) and copied to the host"},
-            "gpu_launches": int((runner.launches_per_advance * per_adv + per_adv // args.unroll + args.steps // 2) * world),
+                    "what": "per step: weights from pinned host memory -> device (+ NCCL broadcast on a side stream), 800 advances, finished games gathered to the trainer rank, decoded to (states f32, policies f64, values) and copied to the host"},
+            "gpu_launches": int((2 * runner.launches_per_advance * per_adv + args.steps) * world),
             "roofline": roof, "roofline_tree": roof_tree, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(out))

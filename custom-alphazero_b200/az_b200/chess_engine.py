@@ -102,7 +102,10 @@ class ChessTreeEngine:
         return w, ints[..., 2], ints[..., 3]
 
     # ------------------------------------------------------------------ C ABI calls
-    def reset(self):
+    def reset(self, game_id_base=None):
+        if game_id_base is not None:  # see TreeEngine.reset
+            check(lib().az_chess_set_game_id_base(self._h, int(game_id_base)))
+            self.cfg.game_id_base = int(game_id_base)
         check(lib().az_chess_reset_games(self._h, _stream()))
 
     def set_roots(self, tree_ids, positions):

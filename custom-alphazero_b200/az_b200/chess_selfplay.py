@@ -176,8 +176,12 @@ def chess_training_loop(runner: ChessSelfPlayRunner, trainer, window, iterations
     (reference train.py:16-84, self_play.py:122-188) with the chess runner's sample ring in place of the finished-game
     records.  Drawn games contribute no samples when exclude_null_games (self_play.py:155-162)."""
     history = []
+    base0, stride = int(runner.engine.cfg.game_id_base), int(runner.engine.cfg.games_target)
     for it in range(iterations):
-        runner.engine.reset()  # the runner's games_target games, every iteration
+        # the runner's games_target games, every iteration, under NEW game ids (they key the move-sampling counters:
+        # reusing them would replay identical games until the weights change)
+        runner.engine.reset(game_id_base=base0 + it * stride)
+        runner.graph = None  # the captured launches hold the old id range
         runner.valid.zero_()
         runner._games.clear()
         states, policies, values, known = runner.run_until_done(max_advances=max_advances)

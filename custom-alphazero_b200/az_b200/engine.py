@@ -145,7 +145,12 @@ class TreeEngine:
         return w, ints[..., 2], ints[..., 3]
 
     # ------------------------------------------------------------------ C ABI calls
-    def reset(self):
+    def reset(self, game_id_base=None):
+        """Fresh games in every tree.  game_id_base moves the id range first (a new iteration of a self-play loop must
+        not reuse ids: they key the sampling counters); graphs captured before are stale then."""
+        if game_id_base is not None:
+            check(lib().az_set_game_id_base(self._h, int(game_id_base)))
+            self.cfg.game_id_base = int(game_id_base)
         check(lib().az_reset_games(self._h, _stream()))
 
     def set_roots(self, tree_ids, cells, plies):

@@ -106,6 +106,7 @@ SYMBOLS = {
     "az_engine_create": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _S, _P, _P, ctypes.POINTER(_P)]),
     "az_engine_destroy": (None, [_P]),
     "az_reset_games": (ctypes.c_int, [_P, _P]),
+    "az_set_game_id_base": (ctypes.c_int, [_P, ctypes.c_int64]),
     "az_set_roots": (ctypes.c_int, [_P, _P, _P, _P, _I, _P]),
     "az_begin_search": (ctypes.c_int, [_P, _I, _P]),
     "az_step": (ctypes.c_int, [_P, _P, _P, _I, _P, _I, _P, _P]),
@@ -140,6 +141,7 @@ SYMBOLS = {
     "az_chess_engine_create": (ctypes.c_int, [ctypes.POINTER(AzChessConfig), _P, _S, _P, _P, ctypes.POINTER(_P)]),
     "az_chess_engine_destroy": (None, [_P]),
     "az_chess_reset_games": (ctypes.c_int, [_P, _P]),
+    "az_chess_set_game_id_base": (ctypes.c_int, [_P, ctypes.c_int64]),
     "az_chess_set_roots": (ctypes.c_int, [_P, _P, _P, _I, _P]),
     "az_chess_begin_search": (ctypes.c_int, [_P, _I, _P]),
     "az_chess_search": (ctypes.c_int, [_P, _P]),

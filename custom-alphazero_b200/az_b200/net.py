@@ -217,7 +217,11 @@ class InferenceNet(nn.Module):
             start = torch.zeros((1, 14, 8, 8), dtype=torch.float32, device=w16.device)
             start[0, :13] = F.one_hot(arr % 13, 13).permute(2, 0, 1).float()  # np.eye(13)[array] with negative wrap
             cmap = F.conv2d(start, w16[:, 84:98], self.stem_b.detach().float(), padding=1)  # [1, 128, 8, 8]
-            self.chess_stem_map = nn.Parameter(cmap[0].permute(1, 2, 0).reshape(64, net.filters).contiguous(), requires_grad=False)
+            # [2][64][128]: map 0 for boards that went through play() + mirror() (initial position in history entry 6), map 1
+            # = the bias alone for the un-mirrored ply-0 root, whose deque is seven empty entries (chess/board.py:37-40)
+            fresh = self.stem_b.detach().float()[None, :].expand(64, net.filters)
+            self.chess_stem_map = nn.Parameter(torch.stack([cmap[0].permute(1, 2, 0).reshape(64, net.filters), fresh]).contiguous(),
+                                               requires_grad=False)
         self.v1_w, self.v1_b = f32(net.value_fc1.weight), f32(net.value_fc1.bias)
         # az_net_heads wants the policy rows padded to an odd stride and the value weights transposed
         # (bank-conflict-free shared memory images that the kernel copies verbatim)

@@ -21,13 +21,16 @@ from .native import check, lib
 from .net import InferenceNet, PolicyValueNet, flops_per_eval
 
 
-def decode_samples(rules: Rules, fin_dev, exclude_null_games=False):
+def decode_samples(rules: Rules, fin_dev, exclude_null_games=False, with_distance=False):
     """Finished-game records (device tensors, ring layout) -> (states f32 [S,H,W,4], policies f64 [S,A],
-    values int64 [S]) on the host, via the az_decode_samples kernel.  Games are emitted in game-id order."""
+    values int64 [S]) on the host, via the az_decode_samples kernel.  Games are emitted in game-id order.
+    with_distance: a fourth array, plies from each sample to the end of its game (the exponent of
+    ConfigSelfPlay.discounting_factor, self_play.py:77-78 of the reference)."""
     n = fin_dev["len"].numel()
     A = rules.n_actions
     if n == 0:
-        return (np.zeros((0, rules.height, rules.width, 4), np.float32), np.zeros((0, A)), np.zeros(0, np.int64))
+        out = (np.zeros((0, rules.height, rules.width, 4), np.float32), np.zeros((0, A)), np.zeros(0, np.int64))
+        return out + (np.zeros(0, np.int64),) if with_distance else out
     order = torch.argsort(fin_dev["game_id"])
     lens = fin_dev["len"][order].contiguous()
     results = fin_dev["result"][order].contiguous()
@@ -46,7 +49,12 @@ def decode_samples(rules: Rules, fin_dev, exclude_null_games=False):
     check(lib().az_decode_samples(ctypes.byref(cfg), _ptr(boards), _ptr(visits), _ptr(actions), _ptr(lens),
                                   _ptr(results), _ptr(offsets), n, _ptr(states), _ptr(policies), _ptr(values),
                                   _stream()))
-    return states.cpu().numpy(), policies.cpu().numpy(), values.cpu().numpy().astype(np.int64)
+    out = (states.cpu().numpy(), policies.cpu().numpy(), values.cpu().numpy().astype(np.int64))
+    if with_distance:
+        host_lens = lens.cpu().numpy()
+        dist_to_end = np.concatenate([np.arange(int(ln))[::-1] for ln in host_lens]) if S else np.zeros(0, np.int64)
+        out = out + (dist_to_end.astype(np.int64),)
+    return out
 
 
 class _Group:
@@ -118,8 +126,9 @@ class SelfPlayRunner:
         self.advances = 0
         self.flops_per_eval = flops_per_eval(rules.height, rules.width, A)
         # kernels of libaz_b200 launched per advance and group: az_advance_fused, or az_step + az_net_stem +
-        # az_net_heads (+ az_play sweeps)
-        self.launches_per_advance = ((1 if self.fused else 3) + (1 if extra_sims and self.fused else 0)) * groups
+        # az_net_heads (+ az_play sweeps); + az_net_tower when the tower is the hand-written kernel
+        self.launches_per_advance = ((1 if self.fused else 3) + (1 if extra_sims and self.fused else 0)
+                                     + (1 if getattr(self.net, "fused_tower", False) else 0)) * groups
         self._side = [torch.cuda.Stream(device=self.device) for _ in range(groups - 1)]
 
     # single-group conveniences (tests, compat code)
@@ -223,17 +232,25 @@ class SelfPlayRunner:
         self.advances += advances
         return advances
 
-    def reset(self):
+    def reset(self, game_id_base=None):
+        """Fresh games in every tree.  With game_id_base the groups' id ranges move to [base, base + games_target) and
+        the captured graph (which holds the old range in its kernel arguments) is dropped."""
+        off = 0
         for g in self.groups:
-            g.engine.reset()
+            g.engine.reset(None if game_id_base is None else int(game_id_base) + off)
+            off += int(g.engine.cfg.games_target)
             g.valid.zero_()
             g.tower_out = None
+        if game_id_base is not None:
+            self.graph = None
 
     def active_trees(self):
         return sum(int((g.engine.phases() != native.AZ_PHASE_IDLE).sum()) for g in self.groups)
 
     def run_until_done(self, poll_every=64, max_advances=None):
-        """Runs until every tree is idle (all games_target games finished); returns advances executed."""
+        """Runs until every tree is idle (all games_target games finished); returns advances executed.  A finished-game
+        ring smaller than games_target would stall the trees for ever (they wait for a free slot): that is an error
+        here, not a silent spin - size fin_capacity >= games_target or drain with collect() between run() calls."""
         done = 0
         while True:
             done += self.run(poll_every)
@@ -241,6 +258,13 @@ class SelfPlayRunner:
                 break
             if max_advances is not None and done >= max_advances:
                 break
+            for g in self.groups:
+                stalled = int((g.engine.phases() == native.AZ_PHASE_STALLED).sum())
+                full = int(g.engine.view("fin_count")[0]) >= int(g.engine.cfg.fin_capacity)
+                if stalled and full:
+                    raise RuntimeError("finished-game ring full (%d slots) with %d trees waiting for a slot: "
+                                       "fin_capacity must cover games_target, or drain it with collect()" %
+                                       (int(g.engine.cfg.fin_capacity), stalled))
         self.check_status()
         return done
 
@@ -271,11 +295,22 @@ class SelfPlayRunner:
             return parts[0]
         return {k: torch.cat([p[k] for p in parts], dim=0) for k in parts[0]}
 
-    def collect(self, exclude_null_games=False):
-        """Decodes and drains the finished-game rings: (states, policies, values) host arrays."""
-        out = decode_samples(self.rules, self.finished_device(), exclude_null_games)
+    def collect(self, exclude_null_games=False, with_distance=False):
+        """Decodes and drains the finished-game rings: (states, policies, values[, plies to the end]) host arrays."""
+        out = decode_samples(self.rules, self.finished_device(), exclude_null_games, with_distance)
         self.fin_clear()
         return out
+
+    def load_flat_weights(self, flat):
+        """The inference copy's parameters from one flat float32 vector (what the trainer rank broadcasts,
+        InferenceNet.flat_weights), and the memoised evaluations forgotten - they belong to the old weights."""
+        off = 0
+        with torch.no_grad():
+            for q in self.net.parameters():
+                q.copy_(flat[off: off + q.numel()].view_as(q))
+                off += q.numel()
+        for g in self.groups:
+            g.engine.cache_clear()
 
     def load_weights(self, net: PolicyValueNet):
         """New weights: refresh the folded inference copy and forget the memoised evaluations (the reference

@@ -117,12 +117,17 @@ def selfplay_training_loop(runner, trainer: Trainer, window: ReplayWindow, itera
     from . import dist as azdist
     from .selfplay import decode_samples
 
-    rank, _ = azdist.world()
+    rank, ws = azdist.world()
     history = []
+    base0 = sum(int(g.engine.cfg.game_id_base) for g in runner.groups[:1])
+    mine = sum(int(g.engine.cfg.games_target) for g in runner.groups)
+    stride = mine * ws  # every rank plays `mine` games per iteration: ids never repeat across iterations or ranks
     for it in range(iterations):
-        runner.reset()
+        # a new id range every iteration: the ids key the move-sampling counters, so reusing them would replay the
+        # same games until the weights change (the reference draws fresh random numbers every iteration)
+        runner.reset(game_id_base=base0 + it * stride)
         runner.run_until_done()
-        fin = azdist.all_gather_records({k: v.contiguous() for k, v in runner.finished_device().items()})
+        fin = azdist.gather_records({k: v.contiguous() for k, v in runner.finished_device().items()}, dst=0)
         runner.fin_clear()
         if rank == 0:
             s, p, v = decode_samples(runner.rules, fin, exclude_null_games=exclude_null_games)
@@ -134,11 +139,7 @@ def selfplay_training_loop(runner, trainer: Trainer, window: ReplayWindow, itera
         flat = runner.net.flat_weights()
         azdist.broadcast_weights(flat, src=0)
         if rank != 0:
-            off = 0
-            with torch.no_grad():
-                for q in runner.net.parameters():
-                    q.copy_(flat[off: off + q.numel()].view_as(q))
-                    off += q.numel()
+            runner.load_flat_weights(flat)  # also forgets the evaluations memoised under the old weights
         if log is not None and rank == 0:
             log(it, len(window), history[-1] if history else None)
     return history

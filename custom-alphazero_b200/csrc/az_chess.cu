@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) k_chess_play(const Pos* pos_in, const int
 
 // The 8 deque entries of Board.full_state for `cur` (oldest first; entry 7 is the current state) into e8.
 // hist: 7 older entries or null for the self-play path's deque (six empty entries, then the state of the initial
-// position - see oracle/chess_ref.py on python-chess's mirror()).
+// position - see oracle/chess_ref.py on python-chess's mirror(); seven empty entries for the un-mirrored ply-0 root).
 __device__ __forceinline__ void stage_history(const Pos& cur, const Pos* hist, Pos* e8, int lane) {
     if (lane < 8) {
         Pos e;
@@ -102,7 +102,7 @@ __device__ __forceinline__ void stage_history(const Pos& cur, const Pos* hist, P
             e = load_cpos(hist + lane);
         } else {
             e = start_position();
-            e.meta = lane == 6 ? (e.meta | META_VALID) : 0;
+            e.meta = (lane == 6 && !fresh_root(cur)) ? (e.meta | META_VALID) : 0;  // Board() itself: 7 empty entries
         }
         e8[lane] = e;
     }
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(128) k_chess_stem(const Pos* __restrict__ pos,
         }
         __syncwarp();
         __nv_bfloat16* o = out + (size_t)t * 64 * 128 + warp * 32 + t4 * 2;
-        const float* cm = cmap + warp * 32 + t4 * 2;
+        const float* cm = cmap + (fresh_root(p) ? 64 * 128 : 0) + warp * 32 + t4 * 2;  // map 1: no initial-position entry
 #pragma unroll 1
         for (int mt = 0; mt < 4; ++mt) {
             const int r0 = mt * 16 + g, r1 = r0 + 8;
@@ -475,6 +475,12 @@ AZ_API int az_chess_reset_games(az_chess_engine* e, void* stream) {
     if (!e) return az::fail_net(AZ_ERR_ARG, "null engine");
     k_chess_reset<<<flat_grid(e->eng.T * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(e->eng);
     AZC_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+AZ_API int az_chess_set_game_id_base(az_chess_engine* e, int64_t game_id_base) {
+    if (!e || game_id_base < 0) return az::fail_net(AZ_ERR_ARG, "az_chess_set_game_id_base: bad argument");
+    e->eng.game_base = game_id_base;
     return AZ_OK;
 }
 

@@ -174,6 +174,16 @@ AZC_HD Pos start_position() {
     return p;
 }
 
+// A root straight out of the constructor, before any play(): the reference's deque then holds seven empty entries and
+// the state (chess/board.py:37-40); only boards that went through play() + mirror() carry the initial position in entry
+// 6 (oracle/chess_ref.py).  On the self-play path that is exactly the start position with a zero halfmove clock: any
+// later recurrence of the start position has a non-zero clock (pawn moves and captures are irreversible).
+AZC_HD bool fresh_root(const Pos& p) {
+    const Pos s = start_position();
+    return p.pawns == s.pawns && p.knights == s.knights && p.bishops == s.bishops && p.rooks == s.rooks && p.queens == s.queens &&
+           p.kings == s.kings && p.white == s.white && halfmove(p) == 0 && !black_to_move(p);
+}
+
 // python-chess Board.mirror(): vertical flip, colours swapped, castling rights and en-passant square follow,
 // side to move flips; the clocks are kept (the mirrored board is a stack-less copy).
 AZC_HD Pos mirror(const Pos& p) {

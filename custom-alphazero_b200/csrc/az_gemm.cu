@@ -470,7 +470,7 @@ constexpr int kStemSmem = 3 * kStemATile + 2 * 64 * 48 + 1024;  // weights + two
 struct StemTcParams {
     const uint64_t* pos;       // [n][8] az_chess_pos
     const __nv_bfloat16* w;    // [128][256] reduced stem weights, K = tap * 24 + plane, zero beyond 216
-    const float* cmap;         // [64][128] bias + initial-position contribution per cell
+    const float* cmap;         // [2][64][128]: bias + initial-position contribution per cell; [1] = bias only (fresh ply-0 root)
     __nv_bfloat16* out;        // [n][64][128]
     int n;
 };
@@ -512,6 +512,7 @@ __global__ void __launch_bounds__(256, 1) k_chess_stem_tc(StemTcParams P) {
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sW = base, sA0 = base + kStemATile;
     uint4* cellchunks = reinterpret_cast<uint4*>(gen + 3 * kStemATile);  // [2 positions][64 cells][3 chunks]
+    __shared__ int s_fresh[2][2];  // [A buffer][position of the tile]: un-mirrored ply-0 root (seven empty history entries)
     const uint32_t bar = smem_u32(&s_bar);
     const int n_tiles = (P.n + 1) / 2;
 
@@ -559,6 +560,11 @@ __global__ void __launch_bounds__(256, 1) k_chess_stem_tc(StemTcParams P) {
         if (tid < 128) {
             const int which = tid >> 6, cell = tid & 63;
             uint32_t w[12] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (cell == 0)  // the start position (white set = ranks 1-2, ...) with a zero halfmove clock, white to move
+                s_fresh[buf][which] = q_valid && q[0] == 0x00ff00000000ff00ull && q[1] == 0x4200000000000042ull &&
+                                      q[2] == 0x2400000000000024ull && q[3] == 0x8100000000000081ull && q[4] == 0x0800000000000008ull &&
+                                      q[5] == 0x1000000000000010ull && q[6] == 0xffffull && ((q[7] >> 16) & 0xffff) == 0 &&
+                                      !((q[7] >> 11) & 1);
             if (q_valid) {
                 const int sq = ((7 - (cell >> 3)) << 3) | (cell & 7);  // array row 0 is rank 8
                 const int pl = stem_piece_plane(q, sq);
@@ -636,7 +642,7 @@ __global__ void __launch_bounds__(256, 1) k_chess_stem_tc(StemTcParams P) {
             const int idx = tid + 256 * i, rr = idx >> 4, c = idx & 15;
             const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * 512 + (((2 * c) ^ (rr & 31)) << 4));
             const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * 512 + (((2 * c + 1) ^ (rr & 31)) << 4));
-            const float4* cm = reinterpret_cast<const float4*>(P.cmap + (rr & 63) * 128 + c * 8);
+            const float4* cm = reinterpret_cast<const float4*>(P.cmap + (s_fresh[buf][rr >> 6] ? 64 * 128 : 0) + (rr & 63) * 128 + c * 8);
             const float4 c0 = __ldg(cm), c1 = __ldg(cm + 1);
             uint4 o;
             o.x = pack_bf16(fmaxf(a0.x + c0.x, 0.f), fmaxf(a0.y + c0.y, 0.f));

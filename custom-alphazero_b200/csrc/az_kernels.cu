@@ -1188,6 +1188,13 @@ AZ_API int az_reset_games(az_engine* e, void* stream) {
     return AZ_OK;
 }
 
+AZ_API int az_set_game_id_base(az_engine* e, int64_t game_id_base) {
+    if (!e || game_id_base < 0) return fail(AZ_ERR_ARG, "az_set_game_id_base: bad argument%s");
+    e->cfg.game_id_base = game_id_base;
+    e->eng.game_base = game_id_base;
+    return AZ_OK;
+}
+
 AZ_API int az_set_roots(az_engine* e, const int32_t* ids, const int8_t* cells, const int32_t* plies, int32_t n,
                             void* stream) {
     if (!e || n < 0) return fail(AZ_ERR_ARG, "az_set_roots: bad argument%s");

@@ -82,4 +82,5 @@ class ConfigB200:
     graph_unroll = 8  # lock-step advances captured per CUDA graph
     max_free_sims = 8  # terminal-leaf simulations one advance may finish per tree
     seed = 0  # Philox key of the move sampler
+    eval_cache_log2 = 20  # device memo of leaf evaluations with 2^n entries (the reference's plays_inferences); 0 = off
     chess_max_plies = 512  # chess: a game still running after this many plies is recorded as a draw

@@ -177,6 +177,12 @@ void az_engine_destroy(az_engine *e);
 /* Starts a fresh game from the empty board in every tree (Board(), board.py:13-42); game ids are
  * game_id_base + tree.  Also clears the finished-game ring and the counters. */
 int az_reset_games(az_engine *e, void *stream);
+/* Moves the engine's game-id range to [base, base + games_target): the next az_reset_games starts games base + tree.
+ * Game ids key the move-sampling / root-noise counters (Philox over seed, game id, ply), so a self-play loop that
+ * resets the engine every iteration must move the base or it replays the same games (the reference draws fresh
+ * np.random numbers every iteration, self_play.py:37-40).  Host-side only; kernel launches captured in a CUDA graph
+ * before the call keep the old base - re-capture. */
+int az_set_game_id_base(az_engine *e, int64_t game_id_base);
 
 /* Roots given trees at arbitrary positions: what MCTS(board=...) does with a caller-supplied Board
  * (mcts/mcts.py:98,108-109).  cells: dev int8 [n][H][W] in the reference's convention (+1 = side to
@@ -473,6 +479,8 @@ int az_chess_engine_create(const az_chess_config *cfg, void *dev_slab, size_t sl
 void az_chess_engine_destroy(az_chess_engine *e);
 /* every tree starts game `game_id_base + tree` from the initial position (MCTS.__init__ / initialize_root) */
 int az_chess_reset_games(az_chess_engine *e, void *stream);
+/* as az_set_game_id_base */
+int az_chess_set_game_id_base(az_chess_engine *e, int64_t game_id_base);
 /* trees tree_ids[i] get the root position positions[i] (white to move) and a fresh tree */
 int az_chess_set_roots(az_chess_engine *e, const int32_t *dev_tree_ids, const az_chess_pos *dev_positions, int32_t n,
                        void *stream);
@@ -496,8 +504,10 @@ int az_chess_step(az_chess_engine *e, const void *dev_priors, const void *dev_va
  * path, straight from the 64-byte boards.  There Board.full_state (chess/board.py:58-73) is six empty history entries +
  * the initial position + the current entry, so only 20 planes vary: w_reduced = dev float [128][24][9] holds the folded
  * stem weights of the current entry's 14 planes (98-111), the 6 scalar planes (112-117) and 4 zero planes, [plane][tap]
- * per output channel; cell_map = dev float [64][128] = folded bias + the initial position's contribution per cell (array
- * order, row 0 = rank 8).  out: dev bf16 [n][8][8][128], the tower's input. */
+ * per output channel; cell_map = dev float [2][64][128]: map 0 = folded bias + the initial position's contribution per
+ * cell (array order, row 0 = rank 8); map 1 = the folded bias alone, used for the un-mirrored ply-0 root (the start
+ * position with a zero halfmove clock), whose deque is seven empty entries + the state (chess/board.py:37-40).
+ * out: dev bf16 [n][8][8][128], the tower's input. */
 int az_chess_stem(const az_chess_pos *dev_pos, int32_t n, const float *dev_w_reduced, const float *dev_cell_map, void *dev_out,
                   void *stream);
 /* The same on tcgen05 (csrc/az_gemm.cu): w_reduced_bf16 = dev bf16 [128][256], K index = tap * 24 + plane (zero beyond

@@ -243,6 +243,15 @@ def selfplay_history():
     return [None] * 6 + [state_planes(start_state())]
 
 
+def history_of(state):
+    """The deque a self-play position is evaluated with: a Board() that has not moved yet still has the constructor's
+    seven empty entries (chess/board.py:37-40); after play() + mirror() it is selfplay_history().  On that path the
+    un-moved board is the start position with a zero halfmove clock (its recurrences have a non-zero clock)."""
+    s0 = start_state()
+    fresh = list(state.sq) == list(s0.sq) and state.halfmove == 0 and bool(state.turn) and state.castling == s0.castling
+    return [None] * 7 if fresh else selfplay_history()
+
+
 # ---------------------------------------------------------------- bridge to the engine's bitboard position
 def to_pos(state, repetition=False, valid=True):
     """co_state -> the engine's Pos as 8 uint64 (pawns, knights, bishops, rooks, queens, kings, white, meta)."""

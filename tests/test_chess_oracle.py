@@ -95,7 +95,12 @@ def test_full_state_layout():
     assert cur[2:6, :, 0].sum() == 32 and cur[:, :, 13].sum() == 0
     assert fs[:, :, :84].sum() == 0 and np.array_equal(fs[:, :, 84:98], cur)
     assert [fs[0, 0, 112 + i] for i in range(6)] == [1, 1, 1, 1, 1, 0]
+    # Board() before any move: the constructor's deque, seven empty entries + the state (chess/board.py:37-40)
+    assert cr.history_of(s) == [None] * 7
+    fresh = cr.full_state(s, cr.history_of(s))
+    assert fresh[:, :, :98].sum() == 0 and np.array_equal(fresh[:, :, 98:], fs[:, :, 98:])
     s2 = cr.push(s, (12, 28, ""), keep_same_player=True)  # e2e4 then mirror
+    assert len(cr.history_of(s2)) == 7 and cr.history_of(s2)[6] is not None and cr.history_of(s2)[5] is None
     assert s2.ep == (20 ^ 56) and s2.halfmove == 0 and cr.array_of(s2)[3, 4] == -1
     assert cr.result(s2) is None
     # fool's mate on the mirrored path: the side to move (always "white") is mated -> -1 (chess/board.py:183-187)

@@ -131,8 +131,9 @@ def test_encoder_matches_full_state():
     got = chess.chess_encode(pos)
     assert got.shape == (len(samples), 8, 8, 118) and got.dtype == np.float32
     for i, x in enumerate(samples):
-        want = cr.full_state(x, cr.selfplay_history())
+        want = cr.full_state(x, cr.history_of(x))  # ply 0 = Board() itself: seven empty entries
         assert np.array_equal(got[i].astype(np.float64), want), i
+    assert not got[0][:, :, :98].any() and got[1][:, :, 84:98].any() and not got[1][:, :, :84].any()
     # (ii) an explicit 7-entry history: sliding window over the same game, with a repetition flag and padding
     hist = np.zeros((len(samples), 7, 8), dtype=np.uint64)
     wants = []

@@ -201,9 +201,14 @@ def test_chess_selfplay_runner_with_the_net():
     assert tot["games"] == 24 and tot["moves"] == 240 and states.shape == (240, 8, 8, 118) and policies.shape == (240, 1880)
     assert known.all() and np.allclose(policies.sum(-1), 1.0) and set(np.unique(values)).issubset({-1, 0, 1})
     assert tot["sims"] >= 240 * 12
-    # planes of a first ply: the start position in the last history slot and in the "initial position" slot
-    first = states[np.nonzero(np.abs(states[:, :, :, 84:98] - states[:, :, :, 98:112]).sum((1, 2, 3)) == 0)[0]]
-    assert len(first) == 24
+    # planes of a first ply: Board() itself, seven empty history entries (chess/board.py:37-40); every later ply carries the
+    # initial position in entry 6 (planes 84-97)
+    empty6 = np.abs(states[:, :, :, 84:98]).sum((1, 2, 3)) == 0
+    assert int(empty6.sum()) == 24
+    start = cr.full_state(cr.start_state(), [None] * 7)
+    assert all(np.array_equal(x.astype(np.float64), start) for x in states[empty6])
+    later = states[~empty6]
+    assert all(np.array_equal(x[:, :, 84:98].astype(np.float64), start[:, :, 98:112]) for x in later[:50])
 
 
 def test_sharding_invariance():

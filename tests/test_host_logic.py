@@ -43,6 +43,26 @@ assert allrec["game_id"].tolist() == list(range(11)), allrec["game_id"]
 assert allrec["visits"].shape == (11, 4, 7)
 assert allrec["len"].tolist() == [3] * 6 + [4] * 5
 assert allrec["visits"][:6].eq(0).all() and allrec["visits"][6:].eq(1).all()
+# the trainer-only gather: rank 0 gets everything, the others nothing
+one = azdist.gather_records(rec, dst=0)
+if rank == 0:
+    assert one["game_id"].tolist() == list(range(11)) and one["visits"].shape == (11, 4, 7)
+    assert one["len"].dtype == torch.int32 and one["len"].tolist() == [3] * 6 + [4] * 5
+    assert one["visits"][:6].eq(0).all() and one["visits"][6:].eq(1).all()
+else:
+    assert one is None
+empty = {"game_id": torch.arange(0, 3 if rank == 1 else 0), "board": torch.ones((3 if rank == 1 else 0, 2, 5), dtype=torch.int8)}
+one = azdist.gather_records(empty, dst=0)
+if rank == 0:
+    assert one["game_id"].tolist() == [0, 1, 2] and one["board"].shape == (3, 2, 5) and one["board"].eq(1).all()
+# weight broadcast through the staging buffer: nothing lands in the live weights before take()
+wb = azdist.WeightBroadcaster(10, "cpu")
+live = torch.zeros(10)
+assert not wb.take(live)
+wb.start(torch.arange(10, dtype=torch.float32) + 5 if rank == 0 else None)
+assert live.eq(0).all()
+assert wb.take(live) and torch.equal(live, torch.arange(10, dtype=torch.float32) + 5)
+assert not wb.take(live)
 # chess: the two rings (finished plies, finished games) gathered separately, unsigned dtypes preserved
 import numpy as np
 n, f = 3 + rank, 1 + rank
@@ -144,3 +164,75 @@ def test_pow_half_table_is_cpython_pow():
     t = pow_half_table(3000)
     assert t[2921] == 2921**0.5 and t[2921] != float(np.sqrt(np.float64(2921)))
     assert t[0] == 0.0 and t[1] == 1.0 and t[4] == 2.0
+
+
+_ENTRY_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.path.join(sys.argv[1], "custom-alphazero_b200"))
+os.chdir(sys.argv[2])
+os.environ["AZ_DIST_BACKEND"] = "gloo"
+import numpy as np, torch
+from az_b200.engine import Rules
+from custom_alphazero import self_play
+from custom_alphazero.config import ConfigB200, ConfigSelfPlay
+import az_b200.selfplay as sp
+
+ConfigB200.games_per_iteration = 11
+seen = {}
+
+class FakeRunner:  # stands in for the CUDA engine: every game of the shard "finishes" with 2 + id % 3 plies
+    def __init__(self, games, base):
+        self.rules, self.games, self.base = Rules(7, 6, 4, True), games, base
+        seen["shard"] = (base, games)
+    def run_until_done(self):
+        pass
+    def finished_device(self):
+        ids = torch.arange(self.base, self.base + self.games)
+        return {"game_id": ids, "len": (2 + ids % 3).to(torch.int32), "result": (ids % 2).to(torch.int32) * 2 - 1}
+    def fin_clear(self):
+        pass
+
+def fake_decode(rules, fin, exclude_null_games=False, with_distance=False):
+    order = torch.argsort(fin["game_id"])
+    lens, res, ids = fin["len"][order].numpy(), fin["result"][order].numpy(), fin["game_id"][order].numpy()
+    S = int(lens.sum())
+    values = np.concatenate([np.full(l, r) for l, r in zip(lens, res)]).astype(np.int64)
+    states = np.concatenate([np.full((l, 6, 7, 4), g, np.float32) for l, g in zip(lens, ids)])
+    out = (states, np.full((S, 7), 1 / 7), values)
+    return out + (np.concatenate([np.arange(l)[::-1] for l in lens]),) if with_distance else out
+
+self_play._runner = lambda net, games, game_id_base: FakeRunner(games, game_id_base)
+self_play.best_saved_model = lambda run_id: None
+sp.decode_samples = fake_decode
+self_play.main(max_iterations=2)
+import torch.distributed as dist
+rank = dist.get_rank()
+base, count = seen["shard"]
+assert (base, count) == ((11, 6) if rank == 0 else (17, 5)), (rank, base, count)   # iteration 1: ids 11..21 sharded 6 + 5
+root = os.path.join("results", "connect_n")
+runs = os.listdir(root)
+assert len(runs) == 1
+if rank == 0:
+    for it in (0, 1):
+        d = np.load(os.path.join(root, runs[0], "self_play", "iteration_%d" % it, "samples.npz"))
+        ids = np.unique(d["states"][:, 0, 0, 0]).astype(int).tolist()
+        assert ids == list(range(11 * it, 11 * it + 11)), ids        # every rank's games reached rank 0, none twice
+        assert len(d["values"]) == sum(2 + g % 3 for g in ids)
+print("rank", rank, "ok")
+'''
+
+
+def test_self_play_entry_point_world_size_2_gloo(tmp_path):
+    """torchrun --nproc-per-node 2 -m custom_alphazero.self_play, host logic only (the CUDA engine and the decode kernel
+    are stubbed): games sharded by id, records gathered to rank 0, which alone writes samples.npz; the run id is
+    broadcast so that both ranks work in the same run directory.  Replaces the reference's joblib fan-out
+    (self_play.py:98-110) and checkpoint polling (:142-150)."""
+    script = tmp_path / "entry.py"
+    script.write_text(_ENTRY_WORKER)
+    work = tmp_path / "work"
+    work.mkdir()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", str(script), ROOT, str(work)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--groups", type=int, default=1, help="tree slices advanced on parallel graph branches")
     ap.add_argument("--max-free", type=int, default=8)
     ap.add_argument("--no-fused", action="store_true", help="three-kernel route instead of az_advance_fused")
+    ap.add_argument("--no-whole-net", action="store_true",
+                    help="az_advance_fused + az_net_tower instead of az_step + az_net_forward (the whole net in one kernel)")
     ap.add_argument("--memo-log2", type=int, default=0,
                     help="evaluation memo (the reference's plays_inferences) with 2^n entries; 0 = off (headline)")
     ap.add_argument("--board", default="7x6", help="WxH (headline: 7x6); other boards are extra configurations (C4)")
@@ -269,7 +271,7 @@ def main():
     runner = selfplay.SelfPlayRunner(rules, n_trees=T, sims_per_move=S, net=fp32, games_target=1 << 40,
                                      game_id_base=rank << 40, seed=1234, move_mode="philox", auto_restart=True,
                                      unroll=args.unroll, fin_capacity=4 * T, groups=args.groups, max_free_sims=args.max_free, fused=not args.no_fused,
-                                     eval_cache_log2=args.memo_log2)
+                                     eval_cache_log2=args.memo_log2, whole_net=False if args.no_whole_net else None)
     params = list(runner.net.parameters())
     flat_dev = runner.net.flat_weights()            # the live weights as one vector
     flat_trainer = flat_dev.clone()                 # what the trainer rank holds after a training step
@@ -387,16 +389,25 @@ def main():
         cells = rules.height * rules.width
         tower_flops = 4 * (2 * 2 * cells * 9 * 128 * 128 + 2 * cells * 128 * 128)  # per position: 8 conv3x3 + 4 conv1x1
         g0 = runner.groups[0]
-        h_in = [torch.rand((Tg, rules.height, rules.width, 128), device=dev).to(torch.bfloat16) for _ in range(4)]
+        whole = bool(runner.whole_net)
+        if whole:
+            # the dominant kernel is the whole net (az_net_forward): leaf planes in, priors / values out
+            tower_flops = flops_per_eval(rules.height, rules.width, rules.n_actions)
+            pr = torch.empty((Tg, rules.n_actions), dtype=torch.float32, device=dev)
+            va = torch.empty(Tg, dtype=torch.float32, device=dev)
+            s_in = [torch.randint(0, 2, (Tg, rules.height, rules.width, 4), device=dev).to(torch.bfloat16) for _ in range(4)]
+            run_it = lambda i: runner.net(s_in[i % 4], pr, va)  # noqa: E731
+        else:
+            h_in = [torch.rand((Tg, rules.height, rules.width, 128), device=dev).to(torch.bfloat16) for _ in range(4)]
+            run_it = lambda i: runner.net.tower(h_in[i % 4])  # noqa: E731  (inputs rotate through 4 x 44 MB: more than the L2 holds)
         for i in range(8):
-            runner.net.tower(h_in[i % 4])
+            run_it(i)
         a.record()
         for i in range(n_rep):
-            runner.net.tower(h_in[i % 4])  # inputs rotate through 4 x 44 MB: more than the L2 holds
+            run_it(i)
         b.record()
         torch.cuda.synchronize()
         tower_ms = a.elapsed_time(b) / n_rep
-        del h_in
         ach = Tg * tower_flops / (tower_ms * 1e-3) / 1e12
         evals_per_s = evals / ms * 1e3
         traffic, traffic_src = None, None
@@ -411,7 +422,8 @@ def main():
                 "in_loop_frac": evals_per_s / world * tower_flops / 1e12 / peaks["bf16_sustained"],
                 "in_loop_note": "leaf evaluations/s per GPU inside the timed steps x tower FLOPs per position / the measured SUSTAINED bf16 peak (the step also contains the per-tree kernel, which runs serially with the tower)",
                 "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": ("az::tower::k_tower (az_net_tower): the whole 4-block residual tower, one persistent tcgen05 kernel, activations resident in shared memory / TMEM" if fused_tower
+                "kernel": ("az::tower::k_tower<true> (az_net_forward): the whole policy/value net - stem, 4-block residual tower, both heads - in one persistent tcgen05 kernel, activations resident in shared memory / TMEM" if whole
+                           else "az::tower::k_tower<false> (az_net_tower): the whole 4-block residual tower, one persistent tcgen05 kernel, activations resident in shared memory / TMEM" if fused_tower
                            else "12 cuDNN tcgen05 implicit-GEMM convolutions (cutlass3x_sm100_tensorop) of the residual tower"),
                 "flops_per_launch": Tg * tower_flops, "positions_per_launch": Tg, "ms_per_launch": tower_ms,
                 "share_of_net_flops": tower_flops / flops_per_eval(rules.height, rules.width, rules.n_actions),
@@ -472,7 +484,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{cfg_name}: {games_job} concurrent {rules.height}x{rules.width} Connect-{rules.n} self-play games ({T} per GPU) x {S} simulations/move, bf16 net leaf evaluation",
-                       "games_per_gpu": T, "games_total": games_job, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "fused_advance": bool(runner.fused),
+                       "games_per_gpu": T, "games_total": games_job, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "fused_advance": bool(runner.fused), "whole_net_kernel": bool(runner.whole_net),
                        "fused_tower": bool(getattr(runner.net, "fused_tower", False)), "evaluation_memo_log2": args.memo_log2, "board": f"{rules.height}x{rules.width}", "n_connect": rules.n, "gravity": rules.gravity,
                        "net": f"4-block 128-filter projection-residual tower, {fp32.n_parameters()} params, random init",
                        "preroll_steps": args.preroll,

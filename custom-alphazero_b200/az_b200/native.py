@@ -91,6 +91,13 @@ class AzChessLayout(ctypes.Structure):
     _fields_ = [("total_bytes", ctypes.c_size_t)] + [(n, ctypes.c_size_t) for n in CHESS_LAYOUT_ARRAYS]
 
 
+class AzNetHeadParams(ctypes.Structure):
+    """az_net_head_params (include/az_b200.h): plain row-major float32 head weights of az_net_forward."""
+
+    _fields_ = [(n, ctypes.c_void_p) for n in ("conv_w", "conv_b", "policy_w", "policy_b", "value1_w", "value1_b",
+                                               "value2_w", "value2_b")]
+
+
 class AzHeadWeights(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("conv_w", "conv_b", "policy_w", "policy_b", "value1_w", "value1_b",
                                                 "value2_w", "value2_b")]
@@ -124,6 +131,7 @@ SYMBOLS = {
     "az_net_heads_dense": (ctypes.c_int, [_P, ctypes.POINTER(AzHeadWeights), _I, _I, _I, _P, _P, _P]),
     "az_net_conv1x1": (ctypes.c_int, [_P, _P, ctypes.c_int64, _I, _P, _P]),
     "az_net_tower": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "az_net_forward": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(AzNetHeadParams), _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "az_net_dense_heads": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "az_net_head_convs": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "az_advance_fused": (ctypes.c_int, [_P, _P, ctypes.POINTER(AzHeadWeights), _P, _P, _P, _P, _P]),

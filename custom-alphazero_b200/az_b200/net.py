@@ -49,6 +49,19 @@ def pack_tower_weights(blocks):
     return torch.cat(imgs).to(torch.bfloat16).contiguous(), torch.stack(biases).contiguous()
 
 
+def pack_stem_weights(w):
+    """Folded stem weights [128, 4, 3, 3] -> the 3 stages (bf16, 3 * 8192 elements) az_net_forward reads before the tower
+    image: tap t = (ky, kx) row-major sits in stage t // 4 at chunk columns 2 * (t % 4) (planes in K 0-3, zeros in K 4-7)
+    and 2 * (t % 4) + 1 (zeros): each tap is one K = 16 MMA against chunk columns 0-1 of the activation buffers."""
+    cout, cin, kh, kw = w.shape
+    assert cout == 128 and cin == 4 and kh == 3 and kw == 3
+    img = torch.zeros((3, 8, cout, 8), dtype=torch.float32)
+    wt = w.detach().float().cpu().permute(2, 3, 0, 1).reshape(9, cout, cin)  # tap, cout, plane
+    for t in range(9):
+        img[t // 4, 2 * (t % 4), :, :4] = wt[t]
+    return img.reshape(-1).to(torch.bfloat16).contiguous()
+
+
 class ConvBN(nn.Module):
     def __init__(self, cin, cout, k, relu):
         super().__init__()
@@ -167,6 +180,14 @@ class InferenceNet(nn.Module):
             img, tb = pack_tower_weights([tuple(self.block_params[5 * i: 5 * i + 5]) for i in range(self.depth)])
             self.tower_img = nn.Parameter(img.to(device), requires_grad=False)
             self.tower_bias = nn.Parameter(tb.to(device), requires_grad=False)
+        # ... and the whole net as one kernel (az_net_forward: stem + tower + both heads) for 4-plane boards of up to
+        # 48 cells with a narrow action space (Connect-N)
+        ppt_ = 128 // cells_
+        self.fused_net = (self.fused_tower and net.in_planes == 4 and cells_ <= 48 and ppt_ * net.n_actions <= 32
+                          and net.value_fc1.out_features == 256 and _os0.environ.get("AZ_FUSED_NET", "1") != "0")
+        if self.fused_net:
+            self.net_img = nn.Parameter(torch.cat([pack_stem_weights(self.stem_w.float()).to(device), self.tower_img.data]),
+                                        requires_grad=False)
         f32 = lambda t: nn.Parameter(t.detach().to(device=device, dtype=torch.float32).contiguous(), requires_grad=False)  # noqa: E731
         # float32 copies for the hand-written stem / heads kernels (az_net_stem, az_net_heads)
         sw, sb = net.stem.folded()
@@ -230,6 +251,7 @@ class InferenceNet(nn.Module):
         self.v1_w_pad = f32(net.value_fc1.weight.detach().t())  # transposed [cells][256] for 128-bit smem loads
         self.v2_w, self.v2_b = f32(net.value_fc2.weight), f32(net.value_fc2.bias)
         self.filters = net.filters
+        self._net_heads = None
         dev = torch.device(device)
         # fast path: custom stem/heads kernels + cuDNN fused-epilogue tower (GPU, bf16, 128 filters)
         self.fast = (dev.type == "cuda" and dtype == torch.bfloat16 and net.filters == 128 and net.value_fc1.out_features == 256
@@ -338,6 +360,16 @@ class InferenceNet(nn.Module):
             return priors_out, values_out
         return policy, value
 
+    def _net_heads_arg(self):
+        from . import native
+
+        if self._net_heads is None:
+            self._net_heads = native.AzNetHeadParams(
+                conv_w=self.head_w32.data_ptr(), conv_b=self.head_b32.data_ptr(), policy_w=self.pfc_w.data_ptr(),
+                policy_b=self.pfc_b.data_ptr(), value1_w=self.v1_w.data_ptr(), value1_b=self.v1_b.data_ptr(),
+                value2_w=self.v2_w.data_ptr(), value2_b=self.v2_b.data_ptr())
+        return self._net_heads
+
     def _forward_fast(self, x_nhwc, priors_out, values_out):
         import ctypes
 
@@ -346,6 +378,15 @@ class InferenceNet(nn.Module):
 
         B, H, W = x_nhwc.shape[0], self.height, self.width
         x_nhwc = x_nhwc.to(torch.bfloat16).contiguous()
+        if self.fused_net:
+            # the whole forward pass in one kernel: planes in, priors and values out
+            if priors_out is None:
+                priors_out = torch.empty((B, self.n_actions), dtype=torch.float32, device=x_nhwc.device)
+                values_out = torch.empty(B, dtype=torch.float32, device=x_nhwc.device)
+            check(lib().az_net_forward(_ptr(x_nhwc), _ptr(self.net_img), _ptr(self.stem_b32), _ptr(self.tower_bias),
+                                       ctypes.byref(self._net_heads_arg()), B, H, W, self.filters, self.depth, self.n_actions,
+                                       _ptr(priors_out), _ptr(values_out), _stream()))
+            return priors_out, values_out
         h0 = torch.empty((B, H, W, self.filters), dtype=torch.bfloat16, device=x_nhwc.device)
         if self.tc_stem:
             check(lib().az_net_stem_tc(_ptr(x_nhwc), _ptr(self.stem_w16_k), _ptr(self.stem_b32), B, H, W, self.filters,

@@ -82,7 +82,7 @@ class SelfPlayRunner:
                  game_id_base=0, seed=0, move_mode="philox", auto_restart=True, dtype=torch.bfloat16, unroll=8,
                  use_graph=True, max_free_sims=8, node_capacity=None, fin_capacity=None, device=None,
                  index_move_greedy=8, groups=1, fused=True, extra_sims=0, dirichlet_noise=False, dirichlet_alpha=0.03,
-                 dirichlet_ratio=0.25, eval_cache_log2=0):
+                 dirichlet_ratio=0.25, eval_cache_log2=0, whole_net=None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.rules = rules
         T, A = int(n_trees), rules.n_actions
@@ -109,8 +109,13 @@ class SelfPlayRunner:
             t0 += ti
             g0 += gi
         self.n_trees = T
-        # fused route: heads + tree step + stem in one launch (az_advance_fused) around the cuDNN tower
-        self.fused = bool(fused) and getattr(self.net, "fast", False)
+        # Routes of one advance.  whole_net (default where the net has it): az_step (the tree step alone) + az_net_forward
+        # (stem, tower and heads in ONE tcgen05 kernel: planes in, priors / values out, no activation in HBM).  Else
+        # fused: heads + tree step + stem in one per-tree launch (az_advance_fused) around the tower kernel; else the
+        # three-kernel route az_step + stem + tower + heads.
+        has_net = bool(getattr(self.net, "fused_net", False))
+        self.whole_net = has_net if whole_net is None else (bool(whole_net) and has_net)
+        self.fused = bool(fused) and getattr(self.net, "fast", False) and not self.whole_net
         if self.fused:
             for g in self.groups:
                 shape = (g.engine.n_trees, rules.height, rules.width, self.net.filters)
@@ -127,8 +132,11 @@ class SelfPlayRunner:
         self.flops_per_eval = flops_per_eval(rules.height, rules.width, A)
         # kernels of libaz_b200 launched per advance and group: az_advance_fused, or az_step + az_net_stem +
         # az_net_heads (+ az_play sweeps); + az_net_tower when the tower is the hand-written kernel
-        self.launches_per_advance = ((1 if self.fused else 3) + (1 if extra_sims and self.fused else 0)
-                                     + (1 if getattr(self.net, "fused_tower", False) else 0)) * groups
+        if self.whole_net:
+            self.launches_per_advance = 2 * groups
+        else:
+            self.launches_per_advance = ((1 if self.fused else 3) + (1 if extra_sims and self.fused else 0)
+                                         + (1 if getattr(self.net, "fused_tower", False) else 0)) * groups
         self._side = [torch.cuda.Stream(device=self.device) for _ in range(groups - 1)]
 
     # single-group conveniences (tests, compat code)

@@ -54,8 +54,8 @@ constexpr int kActBytes = 16 * kLboA;             // 159 232
 constexpr int kStageBytes = 16384;                // [8 chunks][128 output channels][8 input channels] bf16
 constexpr int kLboB = 2048;                       // 128 rows x 16 bytes
 constexpr int kStages = 4;
-constexpr int kMaxDepth = 6;
-constexpr int kBiasBytes = kMaxDepth * 2 * kC * 4;
+constexpr int kMaxDepth = 4;                      // config.py:63
+constexpr int kBiasBytes = ((1 + 2 * kMaxDepth) * kC + 3 * kC) * 4;  // stem + tower biases, the 1x1 head convolutions
 constexpr int kSmemBytes = kActBytes + kStages * kStageBytes + kBiasBytes;
 constexpr int kStagesPerBlock = 38;               // conv1: 9 taps x 2, shortcut: 2, conv2: 9 taps x 2
 constexpr int kThreads = 320;
@@ -147,33 +147,69 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+struct HeadParams {
+    const float* conv_w;    // [3][128] 1x1 head convolutions (rows 0-1 policy, row 2 value), BN folded
+    const float* conv_b;    // [3]
+    const float* policy_w;  // [A][2 * cells] Dense(A) on the NHWC-flattened policy planes
+    const float* policy_b;  // [A]
+    const float* value1_w;  // [256][cells] Dense(256)
+    const float* value1_b;  // [256]
+    const float* value2_w;  // [256] Dense(1)
+    const float* value2_b;  // [1]
+    float* priors;          // [n][A] softmax
+    float* values;          // [n] tanh
+    int A;
+};
+
 struct TowerParams {
-    const __nv_bfloat16* x;    // [n][cells][128] stem output
-    const uint8_t* w_img;      // [depth][38] stages of 16 KB in consumption order (az_b200/net.py: pack_tower_weights)
+    const __nv_bfloat16* x;    // tower mode: [n][cells][128] stem output; net mode: [n][cells][4] leaf planes (az_step)
+    const uint8_t* w_img;      // stages of 16 KB in consumption order (az_b200/net.py: pack_tower_weights / pack_stem_weights):
+                               // net mode 3 stem stages first, then [depth][38]
     const float* bias;         // [depth][2][128]: conv1 bias, conv2 bias + shortcut bias
-    __nv_bfloat16* y;          // [n][cells][128]
+    const float* stem_bias;    // net mode: [128]
+    __nv_bfloat16* y;          // tower mode: [n][cells][128]
+    HeadParams heads;          // net mode
     int n, W, cells, ppt, depth, n_tiles;
     int debug;                 // timing experiments only (AZ_TOWER_DEBUG): bit 0 = do not refill weight stages after the first ring pass,
                                // bit 1 = epilogue skips its shared-memory stores, bit 2 = every tap reads the unshifted centre buffer
 };
 
+constexpr int kStemStages = 3;     // 9 taps x [128 output channels][16 K: 4 planes + zeros] = 4 taps per 16 KB stage
+constexpr int kHeadMaxCells = 48;  // the value layer keeps one weight row per thread in registers
+constexpr int kHidden = 256;       // Dense(256) of the value head (model.py:129-139) = the 256 epilogue threads
+static_assert(kThreads - 64 == kHidden, "one hidden unit of the value head per epilogue thread");
+
 // byte offset of (buffer, row 0, chunk 0) inside the activation area
 __device__ __forceinline__ uint32_t buf_row0(int buf) { return (uint32_t)(kPad + buf * kBufRows) * 16u; }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }  // the 8 epilogue warps
 
+// NET = false: the residual tower alone (x -> y, both [cells][128] bf16).
+// NET = true : the whole policy/value net of the reference (model/tensorflow/model.py:21-188) for boards whose leaf
+//              planes are [cells][4]: stem Conv3x3(4 -> 128) as nine K = 16 MMAs on the same shifted-window scheme,
+//              tower, then both heads in the last epilogue (1x1 convolutions from the registers that hold the tower's
+//              output, dense layers with one hidden unit per epilogue thread).  Nothing but 8 bytes per cell goes in
+//              and A + 1 floats per position come out.
+template <bool NET>
 __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_acc, s_act[2];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t act = smem_u32(smem), stages = act + kActBytes;
-    float* s_bias = reinterpret_cast<float*>(smem + kActBytes + kStages * kStageBytes);
+    float* s_bias = reinterpret_cast<float*>(smem + kActBytes + kStages * kStageBytes);  // [stem][depth][2][128]
+    float* s_headw = s_bias + (1 + 2 * kMaxDepth) * kC;                                   // [3][128] head convolutions
     const uint32_t bar_acc = smem_u32(&s_acc), bar_act0 = smem_u32(&s_act[0]), bar_act1 = smem_u32(&s_act[1]);
     const int rowstride = P.ppt * P.W, rows_used = P.ppt * P.cells;
-    const int stages_per_tile = kStagesPerBlock * P.depth;
+    const int stages_per_tile = kStagesPerBlock * P.depth + (NET ? kStemStages : 0);
 
     // one-time: zero the activation area (pads and dead rows stay zero for ever), biases, barriers, TMEM
     for (int i = tid; i < kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < P.depth * 2 * kC; i += kThreads) s_bias[i] = P.bias[i];
+    for (int i = tid; i < P.depth * 2 * kC; i += kThreads) s_bias[kC + i] = P.bias[i];
+    if (NET) {
+        for (int i = tid; i < kC; i += kThreads) s_bias[i] = P.stem_bias[i];
+        // the existing heads kernel feeds the 1x1 convolutions to the tensor cores as bf16: same rounding here
+        for (int i = tid; i < 3 * kC; i += kThreads) s_headw[i] = __bfloat162float(__float2bfloat16(P.heads.conv_w[i]));
+    }
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(smem_u32(&s_full[s]), 1);
@@ -223,6 +259,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
         const uint32_t a_step = 2u * (kLboA >> 4), a_half = 8u * (kLboA >> 4), b_step = 2u * (kLboB >> 4);
         const uint32_t a_buf = (uint32_t)kBufRows;  // descriptor units (16 B) between buffers = rows
         const uint32_t a0 = desc_lo(act + buf_row0(0), kLboA), b0 = desc_lo(stages, kLboB);
+        // descriptor of the window a tap reads: left / right masked copy for dx = -1 / +1, shifted by the tap
+        auto tap_window = [&](int tap, uint32_t centre) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            return (P.debug & 4) ? centre
+                                 : (dx < 0 ? a0 + a_buf : (dx > 0 ? a0 + 2u * a_buf : centre)) + (uint32_t)(dy * rowstride + dx);
+        };
         // one weight stage = 64 input channels of one tap: four K = 16 steps
         auto stage_mmas = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t first_accumulate) {
             const uint32_t slot = cnt % kStages, k = cnt / kStages;
@@ -240,6 +282,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
             ++cnt;
         };
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            if (NET) {
+                // stem: the four planes of a cell sit in chunk column 0 (column 1 is zero), one K = 16 MMA per tap; a
+                // stage carries the [128][16] weights of four taps
+                mbar_wait(bar_act0, act_phase);
+                mbar_wait(bar_act1, act_phase);
+                act_phase ^= 1;
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+                for (int s = 0; s < kStemStages; ++s) {
+                    const uint32_t slot = cnt % kStages, k = cnt / kStages;
+                    mbar_wait(smem_u32(&s_full[slot]), k & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    if (leader) {
+                        const uint32_t b_lo = b0 + slot * (kStageBytes >> 4);
+#pragma unroll
+                        for (int tt = 0; tt < 4; ++tt)
+                            if (4 * s + tt < 9) mma_bf16(tmem, tap_window(4 * s + tt, a0), b_lo + (uint32_t)tt * b_step, (s | tt) ? 1u : 0u);
+                        commit_to(smem_u32(&s_empty[slot]));
+                    }
+                    __syncwarp();
+                    ++cnt;
+                }
+                if (leader) commit_to(bar_acc);
+                __syncwarp();
+            }
             for (int b = 0; b < P.depth; ++b) {
 #pragma unroll 1
                 for (uint32_t half = 0; half < 2; ++half) {  // 0: conv1 on x -> accumulator 0, 1: conv2 on h -> accumulator 1
@@ -252,14 +319,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                         mbar_wait(kb == 0 ? bar_act0 : bar_act1, act_phase);
                         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                            const uint32_t a_lo = (P.debug & 4) ? centre
-                                                                : (dx < 0 ? a0 + a_buf : (dx > 0 ? a0 + 2u * a_buf : centre)) +
-                                                                      (uint32_t)(dy * rowstride + dx);
-                            // conv2 accumulates on top of the shortcut
-                            stage_mmas(d_tmem, a_lo + (uint32_t)kb * a_half, (tap == 0 && kb == 0) ? half : 1u);
-                        }
+                        for (int tap = 0; tap < 9; ++tap)  // conv2 accumulates on top of the shortcut
+                            stage_mmas(d_tmem, tap_window(tap, centre) + (uint32_t)kb * a_half, (tap == 0 && kb == 0) ? half : 1u);
                     }
                     act_phase ^= 1;
                     if (leader) commit_to(bar_acc);
@@ -273,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
             }
         }
     } else {
-        // ---------------------------------------------------------------- epilogue / tile load / tile store
+        // ---------------------------------------------------------------- epilogue / tile load / tile store / heads
         const int e = tid - 64;                       // 0..255
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
         const int sub = (warp - 2) >> 2;              // which 32 columns of each 64-channel half
@@ -300,11 +361,152 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar);
         };
+        // net mode: this thread's row of the value head's Dense(256) (hidden unit e) lives in registers for the whole kernel
+        float w1row[NET ? kHeadMaxCells : 1], b1u = 0.f, w2u = 0.f;
+        if (NET) {
+#pragma unroll
+            for (int c = 0; c < kHeadMaxCells; ++c) w1row[c] = c < P.cells ? __ldg(P.heads.value1_w + (size_t)e * P.cells + c) : 0.f;
+            b1u = __ldg(P.heads.value1_b + e);
+            w2u = __ldg(P.heads.value2_w + e);
+        }
+        // scratch of the heads: the live rows of buffer 3 (dead between the last convolution of a tile and epilogue 1 of the
+        // next tile's first block, which rewrites them); one 2016-byte run per chunk column, rows 126-127 and pads untouched
+        auto scratch = [&](int col) { return reinterpret_cast<float*>(smem + (uint32_t)col * kLboA + buf_row0(3)); };
+
+        // accumulator `acc` (0 / 1) + bias, ReLU, bf16 -> the three copies (centre buffer `centre`), channel half by
+        // channel half; or (last layer) -> global memory / the heads
+        auto epilogue = [&](int acc, const float* bias, int centre, bool last, long long pos0) {
+            mbar_wait(bar_acc, acc_phase);
+            acc_phase ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            __nv_bfloat16* grow = NET ? nullptr : P.y + (pos0 * P.cells + row_in_tile) * kC + sub * 32;
+            const bool store_global = !NET && last && row_live && pos0 + rp < P.n;
+            uint32_t v[2][32];  // both channel halves in flight before the first is used
+            tmem_ld32_nowait(taddr + (uint32_t)(acc * 128), v[0]);
+            tmem_ld32_nowait(taddr + (uint32_t)(acc * 128 + 64), v[1]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            float hsum0 = 0.f, hsum1 = 0.f, hsum2 = 0.f;  // net mode, last layer: this thread's share of the 1x1 head convolutions
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float* bb = bias + ch * 64 + sub * 32 + c4 * 8;
+                    const float4 b0 = *reinterpret_cast<const float4*>(bb);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bb + 4);
+                    const uint32_t* w = &v[ch][8 * c4];
+                    uint4 o;
+                    o.x = pack_relu_bf16(__uint_as_float(w[0]) + b0.x, __uint_as_float(w[1]) + b0.y);
+                    o.y = pack_relu_bf16(__uint_as_float(w[2]) + b0.z, __uint_as_float(w[3]) + b0.w);
+                    o.z = pack_relu_bf16(__uint_as_float(w[4]) + b1.x, __uint_as_float(w[5]) + b1.y);
+                    o.w = pack_relu_bf16(__uint_as_float(w[6]) + b1.z, __uint_as_float(w[7]) + b1.w);
+                    const int kc = ch * 8 + sub * 4 + c4;
+                    if (last) {
+                        if (NET) {
+                            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+                            const float* cw = s_headw + kc * 8;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {  // the bf16-rounded activations, as the stand-alone heads kernel reads them
+                                const float lo = __uint_as_float(ow[j] << 16), hi = __uint_as_float(ow[j] & 0xffff0000u);
+                                hsum0 = fmaf(lo, cw[2 * j], fmaf(hi, cw[2 * j + 1], hsum0));
+                                hsum1 = fmaf(lo, cw[kC + 2 * j], fmaf(hi, cw[kC + 2 * j + 1], hsum1));
+                                hsum2 = fmaf(lo, cw[2 * kC + 2 * j], fmaf(hi, cw[2 * kC + 2 * j + 1], hsum2));
+                            }
+                        } else if (store_global) {
+                            *(reinterpret_cast<uint4*>(grow + ch * 64) + c4) = o;
+                        }
+                    } else if (row_live && !(P.debug & 2)) {
+                        const uint32_t off = (uint32_t)kc * kLboA + (uint32_t)r * 16u;
+                        *reinterpret_cast<uint4*>(smem + buf_row0(centre) + off) = o;
+                        *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = zero_l ? zero4 : o;
+                        *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = zero_r ? zero4 : o;
+                    }
+                }
+                if (!last) publish(ch == 0 ? bar_act0 : bar_act1);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            if (NET && last) {
+                // ---- heads (model.py:68-149) for the tile's positions.  (1) the two column groups of a row meet in scratch
+                const int cells = P.cells, A = P.heads.A;
+                if (row_live) {
+                    float* part = scratch(sub) + r * 3;
+                    part[0] = hsum0;
+                    part[1] = hsum1;
+                    part[2] = hsum2;
+                }
+                epi_barrier();
+                // (2) + bias, ReLU: policy planes NHWC-flattened [position][cell][2], value plane [position][cell]
+                float* hp_s = scratch(2);
+                float* hv_s = scratch(3);
+                if (sub == 0 && row_live) {
+                    const float* p0 = scratch(0) + r * 3;
+                    const float* p1 = scratch(1) + r * 3;
+                    const int cell = ry * P.W + rx;
+                    hp_s[(rp * cells + cell) * 2] = fmaxf(p0[0] + p1[0] + __ldg(P.heads.conv_b), 0.f);
+                    hp_s[(rp * cells + cell) * 2 + 1] = fmaxf(p0[1] + p1[1] + __ldg(P.heads.conv_b + 1), 0.f);
+                    hv_s[rp * cells + cell] = fmaxf(p0[2] + p1[2] + __ldg(P.heads.conv_b + 2), 0.f);
+                }
+                epi_barrier();
+                // (3) value: hidden unit e of every position of the tile, then the Dense(1) contribution, reduced per warp
+                float* red = scratch(4);  // [8 warps][ppt]
+                for (int p = 0; p < P.ppt; ++p) {
+                    float h = b1u;
+#pragma unroll
+                    for (int c = 0; c < kHeadMaxCells; ++c)
+                        if (c < cells) h = fmaf(hv_s[p * cells + c], w1row[c], h);
+                    float contrib = fmaxf(h, 0.f) * w2u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                    if (lane == 0) red[(warp - 2) * P.ppt + p] = contrib;
+                }
+                // (4) policy: 8 lanes per (position, action) share the 2 * cells products, softmax by the group's first lane
+                float* logit_s = scratch(5);  // [ppt][A]
+                const int grp = e >> 3, part8 = e & 7;
+                {
+                    const bool on = grp < P.ppt * A;  // no divergence around the shuffles: idle groups carry zeros
+                    const int p = on ? grp / A : 0, a = on ? grp - p * A : 0;
+                    float acc2 = 0.f;
+                    if (on)
+                        for (int i = part8; i < 2 * cells; i += 8)
+                            acc2 = fmaf(hp_s[p * 2 * cells + i], __ldg(P.heads.policy_w + (size_t)a * 2 * cells + i), acc2);
+                    acc2 += __shfl_xor_sync(0xffffffffu, acc2, 4);
+                    acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
+                    acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1);
+                    if (on && part8 == 0) logit_s[p * A + a] = acc2 + __ldg(P.heads.policy_b + a);
+                }
+                epi_barrier();
+                if (e < P.ppt && pos0 + e < P.n) {
+                    float vsum = __ldg(P.heads.value2_b);
+                    for (int w8 = 0; w8 < 8; ++w8) vsum += red[w8 * P.ppt + e];
+                    P.heads.values[pos0 + e] = tanhf(vsum);
+                    float mx = -INFINITY, ssum = 0.f;
+                    for (int a = 0; a < A; ++a) mx = fmaxf(mx, logit_s[e * A + a]);
+                    for (int a = 0; a < A; ++a) ssum += expf(logit_s[e * A + a] - mx);
+                    for (int a = 0; a < A; ++a) P.heads.priors[(pos0 + e) * A + a] = expf(logit_s[e * A + a] - mx) / ssum;
+                }
+                epi_barrier();  // scratch (and through it buffer 3) is free again before anybody runs ahead
+            }
+        };
 
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
             const long long pos0 = (long long)tile * P.ppt;
-            // ---- tile in: x, x-left-masked, x-right-masked; channels 0-63 first
-            {
+            if (NET) {
+                // ---- tile in: the four planes of a cell -> chunk column 0 of the three copies, chunk column 1 cleared
+                if (l_live) {
+                    uint4 v4 = zero4;
+                    if (lsub == 0 && pos0 + lp < P.n) {
+                        const uint2 pl = __ldg(reinterpret_cast<const uint2*>(P.x) + pos0 * P.cells + l_row_in_tile);
+                        v4 = make_uint4(pl.x, pl.y, 0u, 0u);
+                    }
+                    const uint32_t off = (uint32_t)lsub * kLboA + (uint32_t)lr * 16u;
+                    *reinterpret_cast<uint4*>(smem + buf_row0(0) + off) = v4;
+                    *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = lx == P.W - 1 ? zero4 : v4;
+                    *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = lx == 0 ? zero4 : v4;
+                }
+                publish(bar_act0);
+                publish(bar_act1);
+                epilogue(0, s_bias, 0, false, pos0);  // stem: accumulator 0 + bias, ReLU -> x and its masked copies
+            } else {
+                // ---- tile in: x, x-left-masked, x-right-masked; channels 0-63 first
                 uint4 v[8];
                 const bool have = l_live && pos0 + lp < P.n;
                 const uint4* src = reinterpret_cast<const uint4*>(P.x + (pos0 * P.cells + l_row_in_tile) * kC) + lsub * 4;
@@ -325,54 +527,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                     publish(ch == 0 ? bar_act0 : bar_act1);
                 }
             }
-
             for (int b = 0; b < P.depth; ++b) {
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {  // 0: accumulator 0 -> h, 1: accumulator 1 -> block output
-                    const float* bias = s_bias + (b * 2 + half) * kC + sub * 32;
-                    const bool last = half == 1 && b == P.depth - 1;
-                    mbar_wait(bar_acc, acc_phase);
-                    acc_phase ^= 1;
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    const int centre = half == 0 ? 3 : 0;
-                    __nv_bfloat16* grow = P.y + (pos0 * P.cells + row_in_tile) * kC + sub * 32;
-                    const bool store_global = last && row_live && pos0 + rp < P.n;
-                    uint32_t v[2][32];  // both channel halves in flight before the first is used
-                    tmem_ld32_nowait(taddr + (uint32_t)(half * 128), v[0]);
-                    tmem_ld32_nowait(taddr + (uint32_t)(half * 128 + 64), v[1]);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-#pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(bias + ch * 64 + c4 * 8);
-                            const float4 b1 = *reinterpret_cast<const float4*>(bias + ch * 64 + c4 * 8 + 4);
-                            const uint32_t* w = &v[ch][8 * c4];
-                            uint4 o;
-                            o.x = pack_relu_bf16(__uint_as_float(w[0]) + b0.x, __uint_as_float(w[1]) + b0.y);
-                            o.y = pack_relu_bf16(__uint_as_float(w[2]) + b0.z, __uint_as_float(w[3]) + b0.w);
-                            o.z = pack_relu_bf16(__uint_as_float(w[4]) + b1.x, __uint_as_float(w[5]) + b1.y);
-                            o.w = pack_relu_bf16(__uint_as_float(w[6]) + b1.z, __uint_as_float(w[7]) + b1.w);
-                            const int kc = ch * 8 + sub * 4 + c4;
-                            if (last) {
-                                if (store_global) *(reinterpret_cast<uint4*>(grow + ch * 64) + c4) = o;
-                            } else if (row_live && !(P.debug & 2)) {
-                                const uint32_t off = (uint32_t)kc * kLboA + (uint32_t)r * 16u;
-                                *reinterpret_cast<uint4*>(smem + buf_row0(centre) + off) = o;
-                                *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = zero_l ? zero4 : o;
-                                *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = zero_r ? zero4 : o;
-                            }
-                        }
-                        if (!last) publish(ch == 0 ? bar_act0 : bar_act1);
-                    }
-                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                }
+                epilogue(0, s_bias + kC + (b * 2) * kC, 3, false, pos0);                          // accumulator 0 -> h
+                epilogue(1, s_bias + kC + (b * 2 + 1) * kC, 0, b == P.depth - 1, pos0);           // accumulator 1 -> block output
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kTmemCols) : "memory");
+}
+
+static int tower_launch_checks(const char* who, int n, int H, int W, int channels, int depth, int* ppt_out) {
+    if (n < 0 || H < 1 || W < 1) return az::fail_net(AZ_ERR_ARG, who);
+    if (channels != kC) return az::fail_net(AZ_ERR_ARG, "az_net_tower / az_net_forward: built for 128 filters (config.py:71)");
+    if (depth < 1 || depth > kMaxDepth) return az::fail_net(AZ_ERR_ARG, "az_net_tower / az_net_forward: depth must be 1..4 (config.py:63 uses 4)");
+    const int cells = H * W;
+    if (cells > kTileRows) return az::fail_net(AZ_ERR_ARG, "az_net_tower / az_net_forward: a position must fit one 128-row tile (H * W <= 128)");
+    const int ppt = kTileRows / cells;
+    if (ppt * W + 1 > kPad) return az::fail_net(AZ_ERR_ARG, "az_net_tower / az_net_forward: positions-per-tile * W + 1 must be <= 22 (padding rows)");
+    *ppt_out = ppt;
+    return AZ_OK;
 }
 
 }  // namespace tower
@@ -383,13 +558,9 @@ extern "C" __attribute__((visibility("default"))) int az_net_tower(const void* x
                                                                     void* stream) {
     using namespace az::tower;
     if (n == 0) return AZ_OK;
-    if (!x || !w_img || !bias || !y || n < 0 || H < 1 || W < 1) return az::fail_net(AZ_ERR_ARG, "az_net_tower: bad argument");
-    if (channels != kC) return az::fail_net(AZ_ERR_ARG, "az_net_tower: built for 128 filters (config.py:71)");
-    if (depth < 1 || depth > kMaxDepth) return az::fail_net(AZ_ERR_ARG, "az_net_tower: depth must be 1..6 (config.py:63 uses 4)");
-    const int cells = H * W;
-    if (cells > kTileRows) return az::fail_net(AZ_ERR_ARG, "az_net_tower: a position must fit one 128-row tile (H * W <= 128)");
-    const int ppt = kTileRows / cells;
-    if (ppt * W + 1 > kPad) return az::fail_net(AZ_ERR_ARG, "az_net_tower: positions-per-tile * W + 1 must be <= 22 (padding rows)");
+    if (!x || !w_img || !bias || !y) return az::fail_net(AZ_ERR_ARG, "az_net_tower: bad argument");
+    int ppt = 0;
+    if (int rc = tower_launch_checks("az_net_tower: bad argument", n, H, W, channels, depth, &ppt)) return rc;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_img) | reinterpret_cast<uintptr_t>(y)) & 15)
         return az::fail_net(AZ_ERR_ARG, "az_net_tower: pointers must be 16-byte aligned");
     int dev = 0, sms = 148;
@@ -397,15 +568,61 @@ extern "C" __attribute__((visibility("default"))) int az_net_tower(const void* x
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_tower, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_tower<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
             return az::fail_net(AZ_ERR_CUDA, "az_net_tower: shared memory request refused");
         configured = true;
     }
     const int n_tiles = (n + ppt - 1) / ppt;
-    TowerParams P{static_cast<const __nv_bfloat16*>(x), static_cast<const uint8_t*>(w_img), bias,
-                  static_cast<__nv_bfloat16*>(y), n, W, cells, ppt, depth, n_tiles, 0};
+    TowerParams P{};
+    P.x = static_cast<const __nv_bfloat16*>(x);
+    P.w_img = static_cast<const uint8_t*>(w_img);
+    P.bias = bias;
+    P.y = static_cast<__nv_bfloat16*>(y);
+    P.n = n, P.W = W, P.cells = H * W, P.ppt = ppt, P.depth = depth, P.n_tiles = n_tiles;
     if (const char* dbg = getenv("AZ_TOWER_DEBUG")) P.debug = atoi(dbg);
-    k_tower<<<n_tiles < sms ? n_tiles : sms, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(P);
+    k_tower<false><<<n_tiles < sms ? n_tiles : sms, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(P);
     if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_tower: launch failed");
+    return AZ_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int az_net_forward(const void* states, const void* w_img, const float* stem_bias,
+                                                                      const float* tower_bias, const az_net_head_params* heads,
+                                                                      int32_t n, int32_t H, int32_t W, int32_t channels, int32_t depth,
+                                                                      int32_t n_actions, float* priors, float* values, void* stream) {
+    using namespace az::tower;
+    if (n == 0) return AZ_OK;
+    if (!states || !w_img || !stem_bias || !tower_bias || !heads || !priors || !values) return az::fail_net(AZ_ERR_ARG, "az_net_forward: bad argument");
+    if (!heads->conv_w || !heads->conv_b || !heads->policy_w || !heads->policy_b || !heads->value1_w || !heads->value1_b ||
+        !heads->value2_w || !heads->value2_b)
+        return az::fail_net(AZ_ERR_ARG, "az_net_forward: null head weights");
+    int ppt = 0;
+    if (int rc = tower_launch_checks("az_net_forward: bad argument", n, H, W, channels, depth, &ppt)) return rc;
+    const int cells = H * W;
+    if (cells > kHeadMaxCells) return az::fail_net(AZ_ERR_ARG, "az_net_forward: the fused heads are built for boards of up to 48 cells");
+    if (n_actions < 1 || ppt * n_actions * 8 > 256 || ppt * n_actions > 126)
+        return az::fail_net(AZ_ERR_ARG, "az_net_forward: positions-per-tile * actions must be <= 32");
+    if ((reinterpret_cast<uintptr_t>(states) & 7) || (reinterpret_cast<uintptr_t>(w_img) & 15))
+        return az::fail_net(AZ_ERR_ARG, "az_net_forward: misaligned pointer");
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return az::fail_net(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback");
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_tower<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+            return az::fail_net(AZ_ERR_CUDA, "az_net_forward: shared memory request refused");
+        configured = true;
+    }
+    const int n_tiles = (n + ppt - 1) / ppt;
+    TowerParams P{};
+    P.x = static_cast<const __nv_bfloat16*>(states);
+    P.w_img = static_cast<const uint8_t*>(w_img);
+    P.bias = tower_bias;
+    P.stem_bias = stem_bias;
+    P.heads = HeadParams{heads->conv_w, heads->conv_b, heads->policy_w, heads->policy_b, heads->value1_w, heads->value1_b,
+                         heads->value2_w, heads->value2_b, priors, values, n_actions};
+    P.n = n, P.W = W, P.cells = cells, P.ppt = ppt, P.depth = depth, P.n_tiles = n_tiles;
+    if (const char* dbg = getenv("AZ_TOWER_DEBUG")) P.debug = atoi(dbg);
+    k_tower<true><<<n_tiles < sms ? n_tiles : sms, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(P);
+    if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_forward: launch failed");
     return AZ_OK;
 }

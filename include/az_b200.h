@@ -306,9 +306,33 @@ int az_net_conv1x1(const void *dev_x, const void *dev_w, int64_t rows, int32_t c
  * [8 chunks][128 output channels][8 input channels] in consumption order - per block: conv1 = 2 halves of the input
  * channels x taps (ky, kx) row-major, the shortcut x 2 halves, conv2 like conv1 (az_b200/net.py pack_tower_weights).
  * bias: dev float [depth][2][128] (b1; b2 + shortcut bias).  channels must be 128, H * W <= 128,
- * (128 / (H * W)) * W + 1 <= 22 (6x7, 8x8, ...), depth 1..6.  All pointers 16-byte aligned. */
+ * (128 / (H * W)) * W + 1 <= 22 (6x7, 8x8, ...), depth 1..4.  All pointers 16-byte aligned. */
 int az_net_tower(const void *dev_x, const void *dev_w_img, const float *dev_bias, int32_t n, int32_t H, int32_t W,
                  int32_t channels, int32_t depth, void *dev_y, void *stream);
+
+/* Head weights of az_net_forward: plain row-major float32, BN folded (no padding or transposition). */
+typedef struct az_net_head_params {
+    const float *conv_w;   /* dev [3][128]: rows 0-1 policy 1x1 conv (model.py:68-85), row 2 value 1x1 conv (:106-123) */
+    const float *conv_b;   /* dev [3] */
+    const float *policy_w; /* dev [A][2*H*W]: Dense(A) on the NHWC-flattened policy planes (model.py:86-103) */
+    const float *policy_b; /* dev [A] */
+    const float *value1_w; /* dev [256][H*W]: Dense(256) (model.py:129-139) */
+    const float *value1_b; /* dev [256] */
+    const float *value2_w; /* dev [256]: Dense(1) (model.py:140-149) */
+    const float *value2_b; /* dev [1] */
+} az_net_head_params;
+
+/* The whole policy/value net - PolicyValueModel.call (model/tensorflow/model.py:182-188): stem Conv3x3(4 -> 128) + BN +
+ * ReLU, `depth` residual blocks, PolicyHead softmax and ValueHead tanh - in ONE persistent tcgen05 kernel (the net mode
+ * of csrc/az_tower.cu): 8 bytes per cell in, A + 1 floats per position out, no activation ever written to HBM.
+ * states: dev bf16 [n][H*W][4] (Board.full_state, what az_step writes); w_img: dev bf16 = 3 stem stages (9 taps x
+ * [128][16 K], planes in K 0-3) followed by the az_net_tower image (az_b200/net.py pack_stem_weights /
+ * pack_tower_weights); stem_bias: dev float [128]; tower_bias: dev float [depth][2][128];
+ * priors: dev float [n][A]; values: dev float [n] - the buffers az_step consumes.
+ * H * W <= 48, (128 / (H*W)) * A <= 32, channels 128, depth 1..4; states 8-byte, w_img 16-byte aligned. */
+int az_net_forward(const void *dev_states, const void *dev_w_img, const float *dev_stem_bias, const float *dev_tower_bias,
+                   const az_net_head_params *heads, int32_t n, int32_t H, int32_t W, int32_t channels, int32_t depth,
+                   int32_t n_actions, float *dev_priors, float *dev_values, void *stream);
 
 /* The dense layers of az_net_heads alone, on the output of az_net_head_convs: hd dev float [n][cells][3] -> priors / values
  * as above (same weights struct; conv_w / conv_b unused).  az_net_head_convs + az_net_heads_dense = az_net_heads with the

@@ -123,3 +123,54 @@ def test_fused_tower_is_deterministic_and_independent_of_the_batch_split():
     assert torch.equal(full, again)
     part = _run(x[301:555], blocks, 6, 7)
     assert torch.equal(full[301:555], part)
+
+
+def _states(n, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    code = torch.randint(0, 3, (n, H, W), generator=g)
+    x = torch.zeros(n, H, W, 4)
+    x.scatter_(3, code[..., None], 1.0)
+    x[..., 3] = torch.where(torch.rand(n, generator=g) < 0.5, 1.0, -1.0)[:, None, None]  # side to move (board.py:83-98)
+    return x
+
+
+@pytest.mark.parametrize("n", [1, 3, 500, 4097])
+def test_whole_net_kernel_equals_the_float32_module(n):
+    """az_net_forward (stem + tower + heads in one kernel) against the fp32 PolicyValueNet and against the
+    multi-kernel bf16 route it replaces."""
+    import os
+
+    engine, native, net = _mods()
+    torch.manual_seed(7)
+    fp32 = net.randomise_bn(net.PolicyValueNet(6, 7, 7)).eval()
+    inf = net.InferenceNet(fp32)
+    assert inf.fused_net
+    x = _states(n, 6, 7, seed=n)
+    p, v = inf(x.cuda())
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        p32, v32 = fp32(x)
+    p, v = p.cpu(), v.cpu()
+    assert torch.isfinite(p).all() and torch.allclose(p.sum(-1), torch.ones(n), atol=1e-5)
+    # bf16 activations through 13 layers against float32: same bounds as the multi-kernel route (tests/test_gpu_net.py)
+    assert float((p - p32).abs().max()) <= 2e-2 and float((v - v32.reshape(-1)).abs().max()) <= 5e-2
+    os.environ["AZ_FUSED_NET"] = "0"
+    try:
+        old = net.InferenceNet(fp32)
+    finally:
+        del os.environ["AZ_FUSED_NET"]
+    assert not old.fused_net and old.fused_tower
+    p2, v2 = old(x.cuda())
+    # identical bf16 pipeline up to summation order inside the heads
+    assert float((p - p2.cpu()).abs().max()) <= 1e-3 and float((v - v2.cpu()).abs().max()) <= 2e-3
+
+
+def test_whole_net_kernel_is_batch_independent():
+    engine, native, net = _mods()
+    torch.manual_seed(8)
+    inf = net.InferenceNet(net.randomise_bn(net.PolicyValueNet(6, 7, 7)))
+    x = _states(700, 6, 7, seed=1).cuda()
+    p, v = inf(x)
+    p, v = p.clone(), v.clone()
+    p2, v2 = inf(x[100:461])
+    assert torch.equal(p[100:461], p2) and torch.equal(v[100:461], v2)

@@ -99,3 +99,41 @@ def test_layout_model_equals_the_convolutions(H, W, n, depth):
     # identical operands, float32 accumulation in a different order, bf16 rounding of the activations at the same places
     assert np.abs(got - want).max() <= 2 ** -6 * max(1.0, np.abs(want).max())
     assert np.mean(np.abs(got - want) > 1e-4) < 0.02
+
+
+def test_stem_stage_layout():
+    """pack_stem_weights: tap t of the 4-plane stem is one K = 16 slice (planes in K 0-3) of stage t // 4 at chunk columns
+    2 * (t % 4), 2 * (t % 4) + 1; read back through the same window arithmetic it must give the stem convolution."""
+    from az_b200.net import pack_stem_weights
+
+    g = torch.Generator().manual_seed(3)
+    H, W, n = 6, 7, 5
+    w = (torch.randn(128, 4, 3, 3, generator=g) * 0.3).to(torch.bfloat16).float()
+    b = torch.randn(128, generator=g) * 0.1
+    x = torch.randint(0, 2, (n, H, W, 4), generator=g).float()
+    img = pack_stem_weights(w).float().numpy().reshape(3, 8, 128, 8)  # stage, chunk column, cout, e
+    cells, ppt = H * W, TILE // (H * W)
+    rowstride = ppt * W
+    want = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=1)).permute(0, 2, 3, 1).numpy()
+    for tile in range((n + ppt - 1) // ppt):
+        space = np.zeros((ROWS, 16), np.float32)  # chunk columns 0-1 of the row space: K = 16
+        row0 = [PAD + i * BUF for i in range(3)]
+        for r in range(ppt * cells):
+            y, rem = divmod(r, rowstride)
+            p, xc = divmod(rem, W)
+            v = x[tile * ppt + p, y, xc].numpy() if tile * ppt + p < n else np.zeros(4, np.float32)
+            space[row0[0] + r, :4] = v
+            space[row0[1] + r, :4] = 0 if xc == W - 1 else v
+            space[row0[2] + r, :4] = 0 if xc == 0 else v
+        acc = np.zeros((TILE, 128), np.float32)
+        for tap in range(9):
+            dy, dx = tap // 3 - 1, tap % 3 - 1
+            start = row0[1 if dx < 0 else (2 if dx > 0 else 0)] + dy * rowstride + dx
+            bmat = np.concatenate([img[tap // 4, 2 * (tap % 4)], img[tap // 4, 2 * (tap % 4) + 1]], axis=1)  # [cout][16]
+            acc += space[start:start + TILE] @ bmat.T
+        out = np.maximum(acc + b.numpy(), 0)
+        for r in range(ppt * cells):
+            y, rem = divmod(r, rowstride)
+            p, xc = divmod(rem, W)
+            if tile * ppt + p < n:
+                assert np.allclose(out[r], want[tile * ppt + p, y, xc], atol=1e-5)

@@ -164,14 +164,21 @@ class TreeEngine:
         self.sims_per_move = int(sims)
         check(lib().az_begin_search(self._h, int(sims), _stream()))
 
-    def step(self, priors, values, states_out, leaf_valid_out):
-        """One lock-step advance (az_step).  priors [T, A] / values [T] float32 or float64 (or None)."""
+    def step(self, priors, values, states_out, leaf_valid_out, leaf_list_out=None, leaf_count_out=None):
+        """One lock-step advance (az_step).  priors [T, A] / values [T] float32 or float64 (or None).  With leaf_list_out
+        (int32 [T]) and leaf_count_out (int32 [1]) the trees whose leaf awaits evaluation are also listed
+        (az_step_gather), for InferenceNet.forward(..., index=, count=)."""
         eval_dtype = native.AZ_F32
         if priors is not None:
             assert priors.is_contiguous() and values.is_contiguous() and priors.dtype == values.dtype
             eval_dtype = {torch.float32: native.AZ_F32, torch.float64: native.AZ_F64}[priors.dtype]
         state_dtype = {torch.bfloat16: native.AZ_BF16, torch.float32: native.AZ_F32}[states_out.dtype]
         assert states_out.is_contiguous() and leaf_valid_out.dtype == torch.int32
+        if leaf_list_out is not None:
+            assert leaf_list_out.dtype == torch.int32 and leaf_count_out.dtype == torch.int32
+            check(lib().az_step_gather(self._h, _ptr(priors), _ptr(values), eval_dtype, _ptr(states_out), state_dtype,
+                                       _ptr(leaf_valid_out), _ptr(leaf_list_out), _ptr(leaf_count_out), _stream()))
+            return
         check(lib().az_step(self._h, _ptr(priors), _ptr(values), eval_dtype, _ptr(states_out), state_dtype,
                             _ptr(leaf_valid_out), _stream()))
 

@@ -117,6 +117,7 @@ SYMBOLS = {
     "az_set_roots": (ctypes.c_int, [_P, _P, _P, _P, _I, _P]),
     "az_begin_search": (ctypes.c_int, [_P, _I, _P]),
     "az_step": (ctypes.c_int, [_P, _P, _P, _I, _P, _I, _P, _P]),
+    "az_step_gather": (ctypes.c_int, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
     "az_extra_sims": (ctypes.c_int, [_P, _I, _P]),
     "az_search": (ctypes.c_int, [_P, _P]),
     "az_play": (ctypes.c_int, [_P, _I, _I, _P]),
@@ -132,6 +133,8 @@ SYMBOLS = {
     "az_net_conv1x1": (ctypes.c_int, [_P, _P, ctypes.c_int64, _I, _P, _P]),
     "az_net_tower": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "az_net_forward": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(AzNetHeadParams), _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "az_net_forward_gathered": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(AzNetHeadParams), _P, _P, _I, _I, _I, _I, _I,
+                                               _I, _P, _P, _P]),
     "az_net_dense_heads": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "az_net_head_convs": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "az_advance_fused": (ctypes.c_int, [_P, _P, ctypes.POINTER(AzHeadWeights), _P, _P, _P, _P, _P]),

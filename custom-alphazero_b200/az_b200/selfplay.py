@@ -71,6 +71,9 @@ class _Group:
         self.stem_out = None
         self.tower_out = None
         self.tower_carry = None
+        # whole-net route: the trees whose leaf awaits evaluation (az_step_gather) and their number
+        self.leaf_list = torch.zeros(T, dtype=torch.int32, device=device)
+        self.leaf_count = torch.zeros(1, dtype=torch.int32, device=device)
 
 
 class SelfPlayRunner:
@@ -181,6 +184,10 @@ class SelfPlayRunner:
                 cur.wait_stream(side)
             else:
                 g.tower_out = self.net.tower(g.stem_out)
+        elif self.whole_net:
+            # the tree step alone, then the whole net in one kernel on exactly the trees that have a leaf pending
+            g.engine.step(g.priors, g.values, g.states, g.valid, g.leaf_list, g.leaf_count)
+            self.net(g.states, g.priors, g.values, index=g.leaf_list, count=g.leaf_count)
         else:
             g.engine.step(g.priors, g.values, g.states, g.valid)
             self.net(g.states, g.priors, g.values)

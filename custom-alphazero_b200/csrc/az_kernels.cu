@@ -508,7 +508,7 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
 template <int NW, int KC, class R, bool NOISE = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     k_step(Eng e, Aux aux, const void* __restrict__ priors, const void* __restrict__ values, int eval_dtype, void* states,
-           int state_dtype, int32_t* leaf_valid) {
+           int state_dtype, int32_t* leaf_valid, int32_t* leaf_list = nullptr, int32_t* leaf_count = nullptr) {
     __shared__ WarpScratch s_ws[kWarpsPerBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * kWarpsPerBlock + warp;
@@ -537,7 +537,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         else
             encode_state_f32<NW>(r, leaf, static_cast<float*>(states) + (size_t)t * r.cells * 4, lane);
     }
-    if (lane == 0) leaf_valid[t] = pend;
+    if (lane == 0) {
+        leaf_valid[t] = pend;
+        // the leaf batch as a dense list of tree indices (az_step_gather): the net then runs on the trees that really
+        // have a leaf pending - 3 900 of 4 096 in steady state, which is 9 instead of 10 rounds of the net kernel's tiles
+        if (pend && leaf_list) leaf_list[atomicAdd(leaf_count, 1)] = t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ k_advance
@@ -1239,6 +1244,17 @@ AZ_API int az_step(az_engine* e, const void* priors, const void* values, int32_t
     if ((eval_dtype != AZ_F32 && eval_dtype != AZ_F64) || (state_dtype != AZ_BF16 && state_dtype != AZ_F32))
         return fail(AZ_ERR_ARG, "az_step: unsupported dtype%s");
     AZ_DISPATCH(k_step, e->eng, e->aux, priors, values, eval_dtype, states, state_dtype, leaf_valid);
+    return AZ_OK;
+}
+
+AZ_API int az_step_gather(az_engine* e, const void* priors, const void* values, int32_t eval_dtype, void* states,
+                          int32_t state_dtype, int32_t* leaf_valid, int32_t* leaf_list, int32_t* leaf_count, void* stream) {
+    if (!e || !states || !leaf_valid || !leaf_list || !leaf_count) return fail(AZ_ERR_ARG, "az_step_gather: null pointer%s");
+    if ((priors == nullptr) != (values == nullptr)) return fail(AZ_ERR_ARG, "az_step_gather: priors and values go together%s");
+    if ((eval_dtype != AZ_F32 && eval_dtype != AZ_F64) || (state_dtype != AZ_BF16 && state_dtype != AZ_F32))
+        return fail(AZ_ERR_ARG, "az_step_gather: unsupported dtype%s");
+    AZ_CUDA(cudaMemsetAsync(leaf_count, 0, sizeof(int32_t), static_cast<cudaStream_t>(stream)));
+    AZ_DISPATCH(k_step, e->eng, e->aux, priors, values, eval_dtype, states, state_dtype, leaf_valid, leaf_list, leaf_count);
     return AZ_OK;
 }
 

@@ -169,6 +169,8 @@ struct TowerParams {
     const float* stem_bias;    // net mode: [128]
     __nv_bfloat16* y;          // tower mode: [n][cells][128]
     HeadParams heads;          // net mode
+    const int32_t* index;      // net mode, optional: position i of the batch is tree index[i] (az_step_gather) ...
+    const int32_t* count;      // ... and the batch holds *count positions (read on the device)
     int n, W, cells, ppt, depth, n_tiles;
     int debug;                 // timing experiments only (AZ_TOWER_DEBUG): bit 0 = do not refill weight stages after the first ring pass,
                                // bit 1 = epilogue skips its shared-memory stores, bit 2 = every tap reads the unshifted centre buffer
@@ -201,6 +203,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
     const uint32_t bar_acc = smem_u32(&s_acc), bar_act0 = smem_u32(&s_act[0]), bar_act1 = smem_u32(&s_act[1]);
     const int rowstride = P.ppt * P.W, rows_used = P.ppt * P.cells;
     const int stages_per_tile = kStagesPerBlock * P.depth + (NET ? kStemStages : 0);
+    if (NET && P.count) {  // gathered batch: every thread reads the same device-side count before anything else
+        const int n = min(max(__ldg(P.count), 0), P.n);
+        P.n = n;
+        P.n_tiles = (n + P.ppt - 1) / P.ppt;
+    }
 
     // one-time: zero the activation area (pads and dead rows stay zero for ever), biases, barriers, TMEM
     for (int i = tid; i < kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -475,13 +482,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                 }
                 epi_barrier();
                 if (e < P.ppt && pos0 + e < P.n) {
+                    const long long tree = P.index ? (long long)__ldg(P.index + pos0 + e) : pos0 + e;
                     float vsum = __ldg(P.heads.value2_b);
                     for (int w8 = 0; w8 < 8; ++w8) vsum += red[w8 * P.ppt + e];
-                    P.heads.values[pos0 + e] = tanhf(vsum);
+                    P.heads.values[tree] = tanhf(vsum);
                     float mx = -INFINITY, ssum = 0.f;
                     for (int a = 0; a < A; ++a) mx = fmaxf(mx, logit_s[e * A + a]);
                     for (int a = 0; a < A; ++a) ssum += expf(logit_s[e * A + a] - mx);
-                    for (int a = 0; a < A; ++a) P.heads.priors[(pos0 + e) * A + a] = expf(logit_s[e * A + a] - mx) / ssum;
+                    for (int a = 0; a < A; ++a) P.heads.priors[tree * A + a] = expf(logit_s[e * A + a] - mx) / ssum;
                 }
                 epi_barrier();  // scratch (and through it buffer 3) is free again before anybody runs ahead
             }
@@ -494,7 +502,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                 if (l_live) {
                     uint4 v4 = zero4;
                     if (lsub == 0 && pos0 + lp < P.n) {
-                        const uint2 pl = __ldg(reinterpret_cast<const uint2*>(P.x) + pos0 * P.cells + l_row_in_tile);
+                        const long long tree = P.index ? (long long)__ldg(P.index + pos0 + lp) : pos0 + lp;
+                        const uint2 pl = __ldg(reinterpret_cast<const uint2*>(P.x) + tree * P.cells + (ly * P.W + lx));
                         v4 = make_uint4(pl.x, pl.y, 0u, 0u);
                     }
                     const uint32_t off = (uint32_t)lsub * kLboA + (uint32_t)lr * 16u;
@@ -585,10 +594,10 @@ extern "C" __attribute__((visibility("default"))) int az_net_tower(const void* x
     return AZ_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int az_net_forward(const void* states, const void* w_img, const float* stem_bias,
-                                                                      const float* tower_bias, const az_net_head_params* heads,
-                                                                      int32_t n, int32_t H, int32_t W, int32_t channels, int32_t depth,
-                                                                      int32_t n_actions, float* priors, float* values, void* stream) {
+static int net_forward_impl(const void* states, const void* w_img, const float* stem_bias, const float* tower_bias,
+                            const az_net_head_params* heads, const int32_t* index, const int32_t* count, int32_t n, int32_t H,
+                            int32_t W, int32_t channels, int32_t depth, int32_t n_actions, float* priors, float* values,
+                            void* stream) {
     using namespace az::tower;
     if (n == 0) return AZ_OK;
     if (!states || !w_img || !stem_bias || !tower_bias || !heads || !priors || !values) return az::fail_net(AZ_ERR_ARG, "az_net_forward: bad argument");
@@ -620,9 +629,28 @@ extern "C" __attribute__((visibility("default"))) int az_net_forward(const void*
     P.stem_bias = stem_bias;
     P.heads = HeadParams{heads->conv_w, heads->conv_b, heads->policy_w, heads->policy_b, heads->value1_w, heads->value1_b,
                          heads->value2_w, heads->value2_b, priors, values, n_actions};
+    P.index = index;
+    P.count = count;
     P.n = n, P.W = W, P.cells = cells, P.ppt = ppt, P.depth = depth, P.n_tiles = n_tiles;
     if (const char* dbg = getenv("AZ_TOWER_DEBUG")) P.debug = atoi(dbg);
     k_tower<true><<<n_tiles < sms ? n_tiles : sms, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(P);
     if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_forward: launch failed");
     return AZ_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int az_net_forward(const void* states, const void* w_img, const float* stem_bias,
+                                                                      const float* tower_bias, const az_net_head_params* heads,
+                                                                      int32_t n, int32_t H, int32_t W, int32_t channels, int32_t depth,
+                                                                      int32_t n_actions, float* priors, float* values, void* stream) {
+    return net_forward_impl(states, w_img, stem_bias, tower_bias, heads, nullptr, nullptr, n, H, W, channels, depth, n_actions,
+                            priors, values, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int az_net_forward_gathered(
+    const void* states, const void* w_img, const float* stem_bias, const float* tower_bias, const az_net_head_params* heads,
+    const int32_t* index, const int32_t* count, int32_t n_max, int32_t H, int32_t W, int32_t channels, int32_t depth,
+    int32_t n_actions, float* priors, float* values, void* stream) {
+    if (!index || !count) return az::fail_net(AZ_ERR_ARG, "az_net_forward_gathered: null index / count");
+    return net_forward_impl(states, w_img, stem_bias, tower_bias, heads, index, count, n_max, H, W, channels, depth, n_actions,
+                            priors, values, stream);
 }

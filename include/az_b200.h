@@ -208,6 +208,13 @@ int az_begin_search(az_engine *e, int32_t sims, void *stream);
  * states_out: dev [T][H][W][4] (AZ_BF16 or AZ_F32); leaf_valid_out: dev int32 [T]. */
 int az_step(az_engine *e, const void *dev_priors, const void *dev_values, int32_t eval_dtype, void *dev_states_out,
             int32_t state_dtype, int32_t *dev_leaf_valid_out, void *stream);
+/* az_step that also gathers the leaf batch: leaf_list (dev int32 [n_trees]) receives the indices of the trees whose
+ * leaf awaits evaluation (in no particular order), leaf_count (dev int32 [1]) their number.  az_net_forward_gathered
+ * evaluates exactly those positions, so a tree without a pending leaf (terminal leaf, game over) costs no net work -
+ * the reference evaluates only real leaves too (mcts/mcts.py:122-143). */
+int az_step_gather(az_engine *e, const void *dev_priors, const void *dev_values, int32_t eval_dtype, void *dev_states_out,
+                   int32_t state_dtype, int32_t *dev_leaf_valid_out, int32_t *dev_leaf_list_out, int32_t *dev_leaf_count_out,
+                   void *stream);
 
 /* Simulations that need no evaluator, for trees WITHOUT a leaf in flight (their last simulation ended in a
  * terminal leaf, mcts/mcts.py:179, or spent the move budget): up to max_sims more terminal-leaf simulations /
@@ -333,6 +340,13 @@ typedef struct az_net_head_params {
 int az_net_forward(const void *dev_states, const void *dev_w_img, const float *dev_stem_bias, const float *dev_tower_bias,
                    const az_net_head_params *heads, int32_t n, int32_t H, int32_t W, int32_t channels, int32_t depth,
                    int32_t n_actions, float *dev_priors, float *dev_values, void *stream);
+/* az_net_forward on a gathered batch (az_step_gather): position i of the batch is tree dev_index[i], i < *dev_count
+ * (read on the device: no host round trip); states / priors / values stay indexed by tree, n_max = their first
+ * dimension.  Trees that are not listed keep their old priors / values. */
+int az_net_forward_gathered(const void *dev_states, const void *dev_w_img, const float *dev_stem_bias,
+                            const float *dev_tower_bias, const az_net_head_params *heads, const int32_t *dev_index,
+                            const int32_t *dev_count, int32_t n_max, int32_t H, int32_t W, int32_t channels, int32_t depth,
+                            int32_t n_actions, float *dev_priors, float *dev_values, void *stream);
 
 /* The dense layers of az_net_heads alone, on the output of az_net_head_convs: hd dev float [n][cells][3] -> priors / values
  * as above (same weights struct; conv_w / conv_b unused).  az_net_head_convs + az_net_heads_dense = az_net_heads with the

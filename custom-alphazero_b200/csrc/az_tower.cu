@@ -380,9 +380,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
         // next tile's first block, which rewrites them); one 2016-byte run per chunk column, rows 126-127 and pads untouched
         auto scratch = [&](int col) { return reinterpret_cast<float*>(smem + (uint32_t)col * kLboA + buf_row0(3)); };
 
+        // net mode, tile in: the four planes of a cell -> chunk column 0 of the three copies, chunk column 1 cleared
+        auto load_planes = [&](long long pos0) {
+            if (l_live) {
+                uint4 v4 = zero4;
+                if (lsub == 0 && pos0 + lp < P.n) {
+                    const long long tree = P.index ? (long long)__ldg(P.index + pos0 + lp) : pos0 + lp;
+                    const uint2 pl = __ldg(reinterpret_cast<const uint2*>(P.x) + tree * P.cells + (ly * P.W + lx));
+                    v4 = make_uint4(pl.x, pl.y, 0u, 0u);
+                }
+                const uint32_t off = (uint32_t)lsub * kLboA + (uint32_t)lr * 16u;
+                *reinterpret_cast<uint4*>(smem + buf_row0(0) + off) = v4;
+                *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = lx == P.W - 1 ? zero4 : v4;
+                *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = lx == 0 ? zero4 : v4;
+            }
+            publish(bar_act0);
+            publish(bar_act1);
+        };
+
         // accumulator `acc` (0 / 1) + bias, ReLU, bf16 -> the three copies (centre buffer `centre`), channel half by
-        // channel half; or (last layer) -> global memory / the heads
-        auto epilogue = [&](int acc, const float* bias, int centre, bool last, long long pos0) {
+        // channel half; or (last layer) -> global memory / the heads.  next_pos0 >= 0 (net mode, last layer): the next
+        // tile's planes are loaded as soon as the accumulator has been read, so that its stem runs under the heads.
+        auto epilogue = [&](int acc, const float* bias, int centre, bool last, long long pos0, long long next_pos0) {
             mbar_wait(bar_acc, acc_phase);
             acc_phase ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -432,6 +451,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             if (NET && last) {
+                // buffers 0-2 are dead now: hand the next tile to the tensor core before the heads arithmetic
+                if (next_pos0 >= 0) load_planes(next_pos0);
                 // ---- heads (model.py:68-149) for the tile's positions.  (1) the two column groups of a row meet in scratch
                 const int cells = P.cells, A = P.heads.A;
                 if (row_live) {
@@ -495,25 +516,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
             }
         };
 
+        if (NET && (int)blockIdx.x < P.n_tiles) load_planes((long long)blockIdx.x * P.ppt);  // later tiles: inside the last epilogue
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
             const long long pos0 = (long long)tile * P.ppt;
+            const long long next_pos0 = tile + (int)gridDim.x < P.n_tiles ? (long long)(tile + gridDim.x) * P.ppt : -1;
             if (NET) {
-                // ---- tile in: the four planes of a cell -> chunk column 0 of the three copies, chunk column 1 cleared
-                if (l_live) {
-                    uint4 v4 = zero4;
-                    if (lsub == 0 && pos0 + lp < P.n) {
-                        const long long tree = P.index ? (long long)__ldg(P.index + pos0 + lp) : pos0 + lp;
-                        const uint2 pl = __ldg(reinterpret_cast<const uint2*>(P.x) + tree * P.cells + (ly * P.W + lx));
-                        v4 = make_uint4(pl.x, pl.y, 0u, 0u);
-                    }
-                    const uint32_t off = (uint32_t)lsub * kLboA + (uint32_t)lr * 16u;
-                    *reinterpret_cast<uint4*>(smem + buf_row0(0) + off) = v4;
-                    *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = lx == P.W - 1 ? zero4 : v4;
-                    *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = lx == 0 ? zero4 : v4;
-                }
-                publish(bar_act0);
-                publish(bar_act1);
-                epilogue(0, s_bias, 0, false, pos0);  // stem: accumulator 0 + bias, ReLU -> x and its masked copies
+                epilogue(0, s_bias, 0, false, pos0, -1);  // stem: accumulator 0 + bias, ReLU -> x and its masked copies
             } else {
                 // ---- tile in: x, x-left-masked, x-right-masked; channels 0-63 first
                 uint4 v[8];
@@ -537,8 +545,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                 }
             }
             for (int b = 0; b < P.depth; ++b) {
-                epilogue(0, s_bias + kC + (b * 2) * kC, 3, false, pos0);                          // accumulator 0 -> h
-                epilogue(1, s_bias + kC + (b * 2 + 1) * kC, 0, b == P.depth - 1, pos0);           // accumulator 1 -> block output
+                epilogue(0, s_bias + kC + (b * 2) * kC, 3, false, pos0, -1);                      // accumulator 0 -> h
+                epilogue(1, s_bias + kC + (b * 2 + 1) * kC, 0, b == P.depth - 1, pos0, next_pos0);  // accumulator 1 -> block output
             }
         }
     }

@@ -134,8 +134,8 @@ def test_fused_advance_equals_the_three_kernel_route():
         torch.manual_seed(0)
         fp32 = net.randomise_bn(net.PolicyValueNet())
         r = selfplay.SelfPlayRunner(rules, n_trees=96, sims_per_move=40, net=fp32, games_target=160, unroll=4, seed=11,
-                                    fused=fused, extra_sims=extra, max_free_sims=mf)
-        assert r.fused == fused
+                                    fused=fused, extra_sims=extra, max_free_sims=mf, whole_net=False)
+        assert r.fused == fused and not r.whole_net
         r.run_until_done(poll_every=64, max_advances=400000)
         fin = {k: v.cpu().numpy() for k, v in r.finished_device().items()}
         order = np.argsort(fin["game_id"])
@@ -190,11 +190,14 @@ def test_evaluation_memo_changes_nothing_but_the_number_of_evaluations():
     engine, native, net = _mods()
     rules = engine.Rules(7, 6, 4, True)
     out = []
-    for log2, fused in ((0, True), (18, True), (18, False), (10, True)):
+    # the whole-net route (az_step_gather + az_net_forward_gathered, the default) with and without the memo, then the two
+    # older routes against their own memo-free run
+    for log2, fused, whole in ((0, True, True), (18, True, True), (10, True, True)):
         torch.manual_seed(0)
         fp32 = net.randomise_bn(net.PolicyValueNet())
         r = selfplay.SelfPlayRunner(rules, n_trees=128, sims_per_move=64, net=fp32, games_target=256, unroll=4, seed=5,
-                                    fused=fused, eval_cache_log2=log2)
+                                    fused=fused, eval_cache_log2=log2, whole_net=whole)
+        assert r.whole_net == whole
         r.run_until_done(poll_every=64, max_advances=400000)
         fin = {k: v.cpu().numpy() for k, v in r.finished_device().items()}
         order = np.argsort(fin["game_id"])
@@ -211,8 +214,24 @@ def test_evaluation_memo_changes_nothing_but_the_number_of_evaluations():
             np.testing.assert_array_equal(a["visits"][g][:n], b["visits"][g][:n])
             np.testing.assert_array_equal(a["action"][g][:n], b["action"][g][:n])
     # a big table hits more often than a tiny, collision-ridden one
-    assert out[1][1]["memo_hits"] > out[3][1]["memo_hits"] > 0
+    assert out[1][1]["memo_hits"] > out[2][1]["memo_hits"] > 0
     assert out[1][1]["memo_hits"] > 0.15 * ta["evals"]
+    # az_advance_fused and the three-kernel route: same property
+    for fused in (True, False):
+        pair = []
+        for log2 in (0, 18):
+            torch.manual_seed(0)
+            fp32 = net.randomise_bn(net.PolicyValueNet())
+            r = selfplay.SelfPlayRunner(rules, n_trees=128, sims_per_move=64, net=fp32, games_target=256, unroll=4, seed=5,
+                                        fused=fused, eval_cache_log2=log2, whole_net=False)
+            r.run_until_done(poll_every=64, max_advances=400000)
+            fin = {k: v.cpu().numpy() for k, v in r.finished_device().items()}
+            order = np.argsort(fin["game_id"])
+            pair.append(({k: v[order] for k, v in fin.items()}, r.totals()))
+        (a2, t2), (b2, u2) = pair
+        assert u2["memo_hits"] > 0 and u2["evals"] + u2["memo_hits"] == t2["evals"] and u2["sims"] == t2["sims"]
+        for k in ("game_id", "len", "result", "action", "visits"):
+            np.testing.assert_array_equal(a2[k], b2[k])
 
 
 def test_tcgen05_shortcut_gemm_matches_the_library():

@@ -32,7 +32,13 @@ def flops_per_eval(height, width, n_actions, filters=128, depth=4, in_planes=4):
     return 2 * macs
 
 
-def pack_tower_weights(blocks):
+def _split_stage_halves(img):
+    """Stage images [.., 8 chunks, 128 cout, 8] -> the CTA-pair layout [.., 2 halves, 8 chunks, 64 cout, 8] (flat)."""
+    t = img.reshape(-1, 8, 2, 64, 8)                 # stage, chunk, half, cout, e
+    return t.permute(0, 2, 1, 3, 4).reshape(-1)      # stage, half, chunk, cout, e
+
+
+def pack_tower_weights(blocks, pair=False):
     """[(w1, b1, w2, wp, b2p)] per block (BN folded; w [128, 128, k, k], any float dtype) -> (w_img bf16 [depth * 38 * 8192],
     bias float32 [depth, 2, 128]) in the layout az_net_tower streams (include/az_b200.h): a 16 KB stage is one filter tap
     x 64 input channels as the K-major, unswizzled UMMA B operand [8 chunks][128 cout][8 cin]; stages come in
@@ -46,10 +52,13 @@ def pack_tower_weights(blocks):
             t = w.detach().float().permute(2, 3, 1, 0).reshape(kh * kw, 2, 8, 8, cout)  # tap, half, chunk, e, cout
             imgs.append(t.permute(1, 0, 2, 4, 3).reshape(-1))                             # half, tap, chunk, cout, e
         biases.append(torch.stack([b1.detach().float(), b2p.detach().float()]))
-    return torch.cat(imgs).to(torch.bfloat16).contiguous(), torch.stack(biases).contiguous()
+    img = torch.cat(imgs)
+    if pair:  # layout 1 of az_net_tower: CTA r of a pair streams output channels 64 r .. 64 r + 63 of every stage
+        img = _split_stage_halves(img)
+    return img.to(torch.bfloat16).contiguous(), torch.stack(biases).contiguous()
 
 
-def pack_stem_weights(w):
+def pack_stem_weights(w, pair=False):
     """Folded stem weights [128, 4, 3, 3] -> the 3 stages (bf16, 3 * 8192 elements) az_net_forward reads before the tower
     image: tap t = (ky, kx) row-major sits in stage t // 4 at chunk columns 2 * (t % 4) (planes in K 0-3, zeros in K 4-7)
     and 2 * (t % 4) + 1 (zeros): each tap is one K = 16 MMA against chunk columns 0-1 of the activation buffers."""
@@ -59,7 +68,10 @@ def pack_stem_weights(w):
     wt = w.detach().float().cpu().permute(2, 3, 0, 1).reshape(9, cout, cin)  # tap, cout, plane
     for t in range(9):
         img[t // 4, 2 * (t % 4), :, :4] = wt[t]
-    return img.reshape(-1).to(torch.bfloat16).contiguous()
+    flat = img.reshape(-1)
+    if pair:
+        flat = _split_stage_halves(flat)
+    return flat.to(torch.bfloat16).contiguous()
 
 
 class ConvBN(nn.Module):
@@ -176,8 +188,11 @@ class InferenceNet(nn.Module):
         self.fused_tower = (torch.device(device).type == "cuda" and dtype == torch.bfloat16 and net.filters == 128
                             and 1 <= self.depth <= 6 and cells_ <= 128 and (128 // cells_) * net.width + 1 <= 22
                             and (128 // cells_) * cells_ >= 96 and _os0.environ.get("AZ_FUSED_TOWER", "1") != "0")
+        # CTA pairs (cta_group::2) halve the weight traffic through each SM's shared memory; AZ_TOWER_PAIR=0 = one CTA per tile
+        self.tower_layout = 1 if _os0.environ.get("AZ_TOWER_PAIR", "1") != "0" else 0
         if self.fused_tower:
-            img, tb = pack_tower_weights([tuple(self.block_params[5 * i: 5 * i + 5]) for i in range(self.depth)])
+            img, tb = pack_tower_weights([tuple(self.block_params[5 * i: 5 * i + 5]) for i in range(self.depth)],
+                                         pair=bool(self.tower_layout))
             self.tower_img = nn.Parameter(img.to(device), requires_grad=False)
             self.tower_bias = nn.Parameter(tb.to(device), requires_grad=False)
         # ... and the whole net as one kernel (az_net_forward: stem + tower + both heads) for 4-plane boards of up to
@@ -186,8 +201,10 @@ class InferenceNet(nn.Module):
         self.fused_net = (self.fused_tower and net.in_planes == 4 and cells_ <= 48 and ppt_ * net.n_actions <= 32
                           and net.value_fc1.out_features == 256 and _os0.environ.get("AZ_FUSED_NET", "1") != "0")
         if self.fused_net:
-            self.net_img = nn.Parameter(torch.cat([pack_stem_weights(self.stem_w.float()).to(device), self.tower_img.data]),
+            self.net_img = nn.Parameter(torch.cat([pack_stem_weights(self.stem_w.float(), pair=bool(self.tower_layout)).to(device), self.tower_img.data]),
                                         requires_grad=False)
+            del self.tower_img  # one copy: the tower image is the tail of the net image (a view, not a second parameter)
+            self.tower_img = self.net_img.data[3 * 8192:]
         f32 = lambda t: nn.Parameter(t.detach().to(device=device, dtype=torch.float32).contiguous(), requires_grad=False)  # noqa: E731
         # float32 copies for the hand-written stem / heads kernels (az_net_stem, az_net_heads)
         sw, sb = net.stem.folded()
@@ -391,12 +408,12 @@ class InferenceNet(nn.Module):
             if index is not None:
                 check(lib().az_net_forward_gathered(_ptr(x_nhwc), _ptr(self.net_img), _ptr(self.stem_b32), _ptr(self.tower_bias),
                                                     ctypes.byref(self._net_heads_arg()), _ptr(index), _ptr(count), B, H, W,
-                                                    self.filters, self.depth, self.n_actions, _ptr(priors_out),
-                                                    _ptr(values_out), _stream()))
+                                                    self.filters, self.depth, self.n_actions, self.tower_layout,
+                                                    _ptr(priors_out), _ptr(values_out), _stream()))
                 return priors_out, values_out
             check(lib().az_net_forward(_ptr(x_nhwc), _ptr(self.net_img), _ptr(self.stem_b32), _ptr(self.tower_bias),
                                        ctypes.byref(self._net_heads_arg()), B, H, W, self.filters, self.depth, self.n_actions,
-                                       _ptr(priors_out), _ptr(values_out), _stream()))
+                                       self.tower_layout, _ptr(priors_out), _ptr(values_out), _stream()))
             return priors_out, values_out
         h0 = torch.empty((B, H, W, self.filters), dtype=torch.bfloat16, device=x_nhwc.device)
         if self.tc_stem:
@@ -433,7 +450,7 @@ class InferenceNet(nn.Module):
             h0 = h0 if h0.is_contiguous() else h0.contiguous()
             out = torch.empty_like(h0)
             check(lib().az_net_tower(_ptr(h0), _ptr(self.tower_img), _ptr(self.tower_bias), h0.shape[0], self.height,
-                                     self.width, self.filters, self.depth, _ptr(out), _stream()))
+                                     self.width, self.filters, self.depth, self.tower_layout, _ptr(out), _stream()))
             return out
         return self.tower_library(h0)
 

@@ -83,6 +83,52 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32_
         "r"(a_lo), "r"(b_lo), "r"(kIdesc), "r"(accumulate), "r"(kDescHi)
         : "memory");
 }
+// The same MMA across a CTA pair (cta_group::2, M = 256): each CTA contributes its own 128 rows of A and 64 of the 128 rows
+// of B from the same shared-memory offsets, and receives its 128 rows of D in its own TMEM.  Per SM that is 4 + 2 KB of
+// operand reads and 2 KB of weight refill per MMA instead of 4 + 4 + 4: ncu showed the single-CTA kernel bound by
+// shared-memory bandwidth at 88 cycles per 64-cycle MMA.
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(kIdesc2), "r"(accumulate), "r"(kDescHi)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair when the MMAs issued so far have finished
+__device__ __forceinline__ void commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// arrive (release at cluster scope) on the barrier at offset `bar` in the shared memory of CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 24)) __trap();
+    }
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t is_leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(is_leader));
@@ -191,12 +237,22 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;\n
 //              tower, then both heads in the last epilogue (1x1 convolutions from the registers that hold the tower's
 //              output, dense layers with one hidden unit per epilogue thread).  Nothing but 8 bytes per cell goes in
 //              and A + 1 floats per position come out.
-template <bool NET>
+// PAIR = true : two CTAs of a cluster (one SM pair) run as one: cta_group::2 MMAs issued by rank 0 over both CTAs' tiles,
+//              each CTA streams half of every weight stage (8 KB, 8-deep ring), the peer's warp 1 forwards "my half has
+//              landed" to rank 0, epilogue warps of both CTAs arrive on rank 0's barriers, commits are multicast.
+template <bool NET, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_acc, s_act[2];
+    constexpr int kRing = PAIR ? 2 * kStages : kStages;             // ring slots
+    constexpr uint32_t kSlotBytes = PAIR ? kStageBytes / 2 : kStageBytes;  // bytes of a weight stage this CTA holds
+    constexpr uint32_t kLboW = PAIR ? kLboB / 2 : kLboB;            // 64 or 128 rows x 16 bytes per chunk column
+    __shared__ __align__(8) uint64_t s_full[2 * kStages], s_empty[2 * kStages], s_pfull[2 * kStages], s_acc, s_act[2];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    // work units: a tile per CTA, or a pair of tiles per CTA pair (rank r takes the r-th tile of the unit)
+    const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int kTpu = PAIR ? 2 : 1;
     const uint32_t act = smem_u32(smem), stages = act + kActBytes;
     float* s_bias = reinterpret_cast<float*>(smem + kActBytes + kStages * kStageBytes);  // [stem][depth][2][128]
     float* s_headw = s_bias + (1 + 2 * kMaxDepth) * kC;                                   // [3][128] head convolutions
@@ -218,23 +274,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
         for (int i = tid; i < 3 * kC; i += kThreads) s_headw[i] = __bfloat162float(__float2bfloat16(P.heads.conv_w[i]));
     }
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kRing; ++s) {
             mbar_init(smem_u32(&s_full[s]), 1);
             mbar_init(smem_u32(&s_empty[s]), 1);
+            mbar_init(smem_u32(&s_pfull[s]), 1);
         }
         mbar_init(bar_acc, 1);
-        mbar_init(bar_act0, (kThreads - 64) / 32);  // one arrival per epilogue warp
-        mbar_init(bar_act1, (kThreads - 64) / 32);
+        mbar_init(bar_act0, kTpu * (kThreads - 64) / 32);  // one arrival per epilogue warp (of both CTAs of a pair)
+        mbar_init(bar_act1, kTpu * (kThreads - 64) / 32);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "n"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "n"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "n"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+        }
     }
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("fence.proxy.async;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync();  // the peer's barriers exist and its buffers are zeroed before anything reaches across
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = s_tmem;
 
@@ -242,30 +306,57 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
         // ---------------------------------------------------------------- producer
         if (lane == 0) {
             uint32_t cnt = 0;
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-                const uint8_t* src = P.w_img;
+            for (int unit = unit0; unit * kTpu < P.n_tiles; unit += n_units) {
+                const uint8_t* src = P.w_img + rank * kSlotBytes;  // pair: rank r streams output channels 64 r .. 64 r + 63
                 for (int s = 0; s < stages_per_tile; ++s, ++cnt, src += kStageBytes) {
-                    const uint32_t slot = cnt % kStages, k = cnt / kStages;
+                    const uint32_t slot = cnt % kRing, k = cnt / kRing;
                     mbar_wait(smem_u32(&s_empty[slot]), (k & 1) ^ 1);
                     const uint32_t full = smem_u32(&s_full[slot]);
-                    if ((P.debug & 1) && cnt >= kStages) {
+                    if ((P.debug & 1) && cnt >= (uint32_t)kRing) {
                         mbar_arrive(full);
                         continue;
                     }
-                    mbar_expect_tx(full, kStageBytes);
-                    bulk_g2s(stages + slot * kStageBytes, src, kStageBytes, full);
+                    mbar_expect_tx(full, kSlotBytes);
+                    bulk_g2s(stages + slot * kSlotBytes, src, kSlotBytes, full);
                 }
             }
         }
+    } else if (warp == 1 && PAIR && rank != 0) {
+        // ---------------------------------------------------------------- peer CTA: tell rank 0 that my half of a stage is here
+        uint32_t cnt = 0;
+        for (int unit = unit0; unit * kTpu < P.n_tiles; unit += n_units)
+            for (int s = 0; s < stages_per_tile; ++s, ++cnt) {
+                const uint32_t slot = cnt % kRing, k = cnt / kRing;
+                mbar_wait(smem_u32(&s_full[slot]), k & 1);
+                if (lane == 0) mbar_arrive_remote(smem_u32(&s_pfull[slot]), 0u);
+                __syncwarp();
+            }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
         // The whole warp runs the control flow (waits included) so that everything stays warp-uniform; one elected
         // lane issues.  Taps, channel halves and K steps are fully unrolled: every descriptor is base + constant.
         uint32_t cnt = 0, act_phase = 0;
         const bool leader = elect_one();
-        const uint32_t a_step = 2u * (kLboA >> 4), a_half = 8u * (kLboA >> 4), b_step = 2u * (kLboB >> 4);
+        const uint32_t a_step = 2u * (kLboA >> 4), a_half = 8u * (kLboA >> 4), b_step = 2u * (kLboW >> 4);
         const uint32_t a_buf = (uint32_t)kBufRows;  // descriptor units (16 B) between buffers = rows
-        const uint32_t a0 = desc_lo(act + buf_row0(0), kLboA), b0 = desc_lo(stages, kLboB);
+        const uint32_t a0 = desc_lo(act + buf_row0(0), kLboA), b0 = desc_lo(stages, kLboW);
+        auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
+            if (PAIR) mma_bf16_pair(d, a_lo, b_lo, accumulate);
+            else mma_bf16(d, a_lo, b_lo, accumulate);
+        };
+        auto commit = [&](uint32_t bar) {
+            if (PAIR) commit_pair(bar);
+            else commit_to(bar);
+        };
+        auto wait_stage = [&](uint32_t slot, uint32_t k) {
+            mbar_wait(smem_u32(&s_full[slot]), k & 1);
+            if (PAIR) mbar_wait_cluster(smem_u32(&s_pfull[slot]), k & 1);  // ... and the peer's half
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        };
+        auto wait_act = [&](uint32_t bar, uint32_t parity) {
+            if (PAIR) mbar_wait_cluster(bar, parity);
+            else mbar_wait(bar, parity);
+        };
         // descriptor of the window a tap reads: left / right masked copy for dx = -1 / +1, shifted by the tap
         auto tap_window = [&](int tap, uint32_t centre) {
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -274,44 +365,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
         };
         // one weight stage = 64 input channels of one tap: four K = 16 steps
         auto stage_mmas = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t first_accumulate) {
-            const uint32_t slot = cnt % kStages, k = cnt / kStages;
-            mbar_wait(smem_u32(&s_full[slot]), k & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t slot = cnt % kRing, k = cnt / kRing;
+            wait_stage(slot, k);
             if (leader) {
-                const uint32_t b_lo = b0 + slot * (kStageBytes >> 4);
-                mma_bf16(d_tmem, a_lo, b_lo, first_accumulate);
-                mma_bf16(d_tmem, a_lo + a_step, b_lo + b_step, 1u);
-                mma_bf16(d_tmem, a_lo + 2 * a_step, b_lo + 2 * b_step, 1u);
-                mma_bf16(d_tmem, a_lo + 3 * a_step, b_lo + 3 * b_step, 1u);
-                commit_to(smem_u32(&s_empty[slot]));  // frees the slot when these MMAs have read it
+                const uint32_t b_lo = b0 + slot * (kSlotBytes >> 4);
+                mma(d_tmem, a_lo, b_lo, first_accumulate);
+                mma(d_tmem, a_lo + a_step, b_lo + b_step, 1u);
+                mma(d_tmem, a_lo + 2 * a_step, b_lo + 2 * b_step, 1u);
+                mma(d_tmem, a_lo + 3 * a_step, b_lo + 3 * b_step, 1u);
+                commit(smem_u32(&s_empty[slot]));  // frees the slot (in both CTAs of a pair) when these MMAs have read it
             }
             __syncwarp();
             ++cnt;
         };
-        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int unit = unit0; unit * kTpu < P.n_tiles; unit += n_units) {
             if (NET) {
                 // stem: the four planes of a cell sit in chunk column 0 (column 1 is zero), one K = 16 MMA per tap; a
                 // stage carries the [128][16] weights of four taps
-                mbar_wait(bar_act0, act_phase);
-                mbar_wait(bar_act1, act_phase);
+                wait_act(bar_act0, act_phase);
+                wait_act(bar_act1, act_phase);
                 act_phase ^= 1;
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
                 for (int s = 0; s < kStemStages; ++s) {
-                    const uint32_t slot = cnt % kStages, k = cnt / kStages;
-                    mbar_wait(smem_u32(&s_full[slot]), k & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint32_t slot = cnt % kRing, k = cnt / kRing;
+                    wait_stage(slot, k);
                     if (leader) {
-                        const uint32_t b_lo = b0 + slot * (kStageBytes >> 4);
+                        const uint32_t b_lo = b0 + slot * (kSlotBytes >> 4);
 #pragma unroll
                         for (int tt = 0; tt < 4; ++tt)
-                            if (4 * s + tt < 9) mma_bf16(tmem, tap_window(4 * s + tt, a0), b_lo + (uint32_t)tt * b_step, (s | tt) ? 1u : 0u);
-                        commit_to(smem_u32(&s_empty[slot]));
+                            if (4 * s + tt < 9) mma(tmem, tap_window(4 * s + tt, a0), b_lo + (uint32_t)tt * b_step, (s | tt) ? 1u : 0u);
+                        commit(smem_u32(&s_empty[slot]));
                     }
                     __syncwarp();
                     ++cnt;
                 }
-                if (leader) commit_to(bar_acc);
+                if (leader) commit(bar_acc);
                 __syncwarp();
             }
             for (int b = 0; b < P.depth; ++b) {
@@ -323,14 +412,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                     // load) has written that half of the three copies; it writes channels 64-127 underneath them
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
-                        mbar_wait(kb == 0 ? bar_act0 : bar_act1, act_phase);
+                        wait_act(kb == 0 ? bar_act0 : bar_act1, act_phase);
                         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap)  // conv2 accumulates on top of the shortcut
                             stage_mmas(d_tmem, tap_window(tap, centre) + (uint32_t)kb * a_half, (tap == 0 && kb == 0) ? half : 1u);
                     }
                     act_phase ^= 1;
-                    if (leader) commit_to(bar_acc);
+                    if (leader) commit(bar_acc);
                     __syncwarp();
                     if (half == 0) {
                         // the shortcut needs only x: it runs while the epilogue turns accumulator 0 into h
@@ -363,10 +452,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
         // this half of the three copies is complete: every thread orders its stores for the tensor core's proxy, one
         // lane per warp arrives
         auto publish = [&](uint32_t bar) {
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            if (PAIR) asm volatile("fence.proxy.async;\n" ::: "memory");  // the MMA that reads these rows is issued by rank 0
+            else asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar);
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_remote(bar, 0u);
+                else mbar_arrive(bar);
+            }
         };
         // net mode: this thread's row of the value head's Dense(256) (hidden unit e) lives in registers for the whole kernel
         float w1row[NET ? kHeadMaxCells : 1], b1u = 0.f, w2u = 0.f;
@@ -516,10 +609,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
             }
         };
 
-        if (NET && (int)blockIdx.x < P.n_tiles) load_planes((long long)blockIdx.x * P.ppt);  // later tiles: inside the last epilogue
-        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-            const long long pos0 = (long long)tile * P.ppt;
-            const long long next_pos0 = tile + (int)gridDim.x < P.n_tiles ? (long long)(tile + gridDim.x) * P.ppt : -1;
+        // a CTA of a pair whose tile lies beyond the batch still takes part in every barrier: it computes on zeros and
+        // stores nothing (pos0 >= n)
+        if (NET && unit0 * kTpu < P.n_tiles) load_planes((long long)(unit0 * kTpu + (int)rank) * P.ppt);  // later tiles: inside the last epilogue
+        for (int unit = unit0; unit * kTpu < P.n_tiles; unit += n_units) {
+            const long long pos0 = (long long)(unit * kTpu + (int)rank) * P.ppt;
+            const long long next_pos0 = (unit + n_units) * kTpu < P.n_tiles ? (long long)((unit + n_units) * kTpu + (int)rank) * P.ppt : -1;
             if (NET) {
                 epilogue(0, s_bias, 0, false, pos0, -1);  // stem: accumulator 0 + bias, ReLU -> x and its masked copies
             } else {
@@ -552,7 +647,44 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    if (PAIR) cluster_sync();  // nobody frees TMEM or exits while the pair's MMAs / remote arrivals may still be in flight
+    if (warp == 0) {
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    }
+}
+
+// launches k_tower<NET, PAIR>: a plain grid of one CTA per SM, or clusters of two CTAs
+template <bool NET, bool PAIR>
+static int launch_tower(const TowerParams& P, int sms, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_tower<NET, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+            return az::fail_net(AZ_ERR_CUDA, "az_net_tower / az_net_forward: shared memory request refused");
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    if (PAIR) {
+        const int units = (P.n_tiles + 1) / 2, max_units = sms / 2;
+        cfg.gridDim = dim3(2u * (unsigned)(units < max_units ? units : max_units));
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    } else {
+        cfg.gridDim = dim3((unsigned)(P.n_tiles < sms ? P.n_tiles : sms));
+    }
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    if (cudaLaunchKernelEx(&cfg, k_tower<NET, PAIR>, P) != cudaSuccess) {
+        cudaGetLastError();
+        return az::fail_net(AZ_ERR_CUDA, "az_net_tower / az_net_forward: launch failed");
+    }
+    return AZ_OK;
 }
 
 static int tower_launch_checks(const char* who, int n, int H, int W, int channels, int depth, int* ppt_out) {
@@ -571,11 +703,11 @@ static int tower_launch_checks(const char* who, int n, int H, int W, int channel
 }  // namespace az
 
 extern "C" __attribute__((visibility("default"))) int az_net_tower(const void* x, const void* w_img, const float* bias, int32_t n,
-                                                                    int32_t H, int32_t W, int32_t channels, int32_t depth, void* y,
-                                                                    void* stream) {
+                                                                    int32_t H, int32_t W, int32_t channels, int32_t depth,
+                                                                    int32_t layout, void* y, void* stream) {
     using namespace az::tower;
     if (n == 0) return AZ_OK;
-    if (!x || !w_img || !bias || !y) return az::fail_net(AZ_ERR_ARG, "az_net_tower: bad argument");
+    if (!x || !w_img || !bias || !y || (layout != 0 && layout != 1)) return az::fail_net(AZ_ERR_ARG, "az_net_tower: bad argument");
     int ppt = 0;
     if (int rc = tower_launch_checks("az_net_tower: bad argument", n, H, W, channels, depth, &ppt)) return rc;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_img) | reinterpret_cast<uintptr_t>(y)) & 15)
@@ -583,32 +715,25 @@ extern "C" __attribute__((visibility("default"))) int az_net_tower(const void* x
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess) return az::fail_net(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback");
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_tower<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
-            return az::fail_net(AZ_ERR_CUDA, "az_net_tower: shared memory request refused");
-        configured = true;
-    }
-    const int n_tiles = (n + ppt - 1) / ppt;
     TowerParams P{};
     P.x = static_cast<const __nv_bfloat16*>(x);
     P.w_img = static_cast<const uint8_t*>(w_img);
     P.bias = bias;
     P.y = static_cast<__nv_bfloat16*>(y);
-    P.n = n, P.W = W, P.cells = H * W, P.ppt = ppt, P.depth = depth, P.n_tiles = n_tiles;
+    P.n = n, P.W = W, P.cells = H * W, P.ppt = ppt, P.depth = depth, P.n_tiles = (n + ppt - 1) / ppt;
     if (const char* dbg = getenv("AZ_TOWER_DEBUG")) P.debug = atoi(dbg);
-    k_tower<false><<<n_tiles < sms ? n_tiles : sms, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(P);
-    if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_tower: launch failed");
-    return AZ_OK;
+    return layout ? launch_tower<false, true>(P, sms, static_cast<cudaStream_t>(stream))
+                  : launch_tower<false, false>(P, sms, static_cast<cudaStream_t>(stream));
 }
 
 static int net_forward_impl(const void* states, const void* w_img, const float* stem_bias, const float* tower_bias,
                             const az_net_head_params* heads, const int32_t* index, const int32_t* count, int32_t n, int32_t H,
-                            int32_t W, int32_t channels, int32_t depth, int32_t n_actions, float* priors, float* values,
-                            void* stream) {
+                            int32_t W, int32_t channels, int32_t depth, int32_t n_actions, int32_t layout, float* priors,
+                            float* values, void* stream) {
     using namespace az::tower;
     if (n == 0) return AZ_OK;
-    if (!states || !w_img || !stem_bias || !tower_bias || !heads || !priors || !values) return az::fail_net(AZ_ERR_ARG, "az_net_forward: bad argument");
+    if (!states || !w_img || !stem_bias || !tower_bias || !heads || !priors || !values || (layout != 0 && layout != 1))
+        return az::fail_net(AZ_ERR_ARG, "az_net_forward: bad argument");
     if (!heads->conv_w || !heads->conv_b || !heads->policy_w || !heads->policy_b || !heads->value1_w || !heads->value1_b ||
         !heads->value2_w || !heads->value2_b)
         return az::fail_net(AZ_ERR_ARG, "az_net_forward: null head weights");
@@ -623,13 +748,6 @@ static int net_forward_impl(const void* states, const void* w_img, const float* 
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess) return az::fail_net(AZ_ERR_NO_DEVICE, "no CUDA device: libaz_b200 has no CPU fallback");
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_tower<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
-            return az::fail_net(AZ_ERR_CUDA, "az_net_forward: shared memory request refused");
-        configured = true;
-    }
-    const int n_tiles = (n + ppt - 1) / ppt;
     TowerParams P{};
     P.x = static_cast<const __nv_bfloat16*>(states);
     P.w_img = static_cast<const uint8_t*>(w_img);
@@ -639,26 +757,26 @@ static int net_forward_impl(const void* states, const void* w_img, const float* 
                          heads->value2_w, heads->value2_b, priors, values, n_actions};
     P.index = index;
     P.count = count;
-    P.n = n, P.W = W, P.cells = cells, P.ppt = ppt, P.depth = depth, P.n_tiles = n_tiles;
+    P.n = n, P.W = W, P.cells = cells, P.ppt = ppt, P.depth = depth, P.n_tiles = (n + ppt - 1) / ppt;
     if (const char* dbg = getenv("AZ_TOWER_DEBUG")) P.debug = atoi(dbg);
-    k_tower<true><<<n_tiles < sms ? n_tiles : sms, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(P);
-    if (cudaGetLastError() != cudaSuccess) return az::fail_net(AZ_ERR_CUDA, "az_net_forward: launch failed");
-    return AZ_OK;
+    return layout ? launch_tower<true, true>(P, sms, static_cast<cudaStream_t>(stream))
+                  : launch_tower<true, false>(P, sms, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" __attribute__((visibility("default"))) int az_net_forward(const void* states, const void* w_img, const float* stem_bias,
                                                                       const float* tower_bias, const az_net_head_params* heads,
                                                                       int32_t n, int32_t H, int32_t W, int32_t channels, int32_t depth,
-                                                                      int32_t n_actions, float* priors, float* values, void* stream) {
+                                                                      int32_t n_actions, int32_t layout, float* priors, float* values,
+                                                                      void* stream) {
     return net_forward_impl(states, w_img, stem_bias, tower_bias, heads, nullptr, nullptr, n, H, W, channels, depth, n_actions,
-                            priors, values, stream);
+                            layout, priors, values, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int az_net_forward_gathered(
     const void* states, const void* w_img, const float* stem_bias, const float* tower_bias, const az_net_head_params* heads,
     const int32_t* index, const int32_t* count, int32_t n_max, int32_t H, int32_t W, int32_t channels, int32_t depth,
-    int32_t n_actions, float* priors, float* values, void* stream) {
+    int32_t n_actions, int32_t layout, float* priors, float* values, void* stream) {
     if (!index || !count) return az::fail_net(AZ_ERR_ARG, "az_net_forward_gathered: null index / count");
     return net_forward_impl(states, w_img, stem_bias, tower_bias, heads, index, count, n_max, H, W, channels, depth, n_actions,
-                            priors, values, stream);
+                            layout, priors, values, stream);
 }

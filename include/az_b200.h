@@ -312,10 +312,13 @@ int az_net_conv1x1(const void *dev_x, const void *dev_w, int64_t rows, int32_t c
  * x, y: dev bf16 [n][H*W][128] (NHWC; y may not alias x).  w_img: dev bf16, depth x 38 stages of 16 KB, each
  * [8 chunks][128 output channels][8 input channels] in consumption order - per block: conv1 = 2 halves of the input
  * channels x taps (ky, kx) row-major, the shortcut x 2 halves, conv2 like conv1 (az_b200/net.py pack_tower_weights).
+ * layout 0: one CTA per tile (the stage layout above).  layout 1: CTA pairs (cta_group::2, M = 256 over two tiles): every
+ * 16 KB stage is split by output channel, [2 halves][8 chunks][64 output channels][8 input channels], and CTA r of a
+ * pair streams half r - per SM half the weight traffic through shared memory (pack_tower_weights(pair=True)).
  * bias: dev float [depth][2][128] (b1; b2 + shortcut bias).  channels must be 128, H * W <= 128,
  * (128 / (H * W)) * W + 1 <= 22 (6x7, 8x8, ...), depth 1..4.  All pointers 16-byte aligned. */
 int az_net_tower(const void *dev_x, const void *dev_w_img, const float *dev_bias, int32_t n, int32_t H, int32_t W,
-                 int32_t channels, int32_t depth, void *dev_y, void *stream);
+                 int32_t channels, int32_t depth, int32_t layout, void *dev_y, void *stream);
 
 /* Head weights of az_net_forward: plain row-major float32, BN folded (no padding or transposition). */
 typedef struct az_net_head_params {
@@ -336,17 +339,18 @@ typedef struct az_net_head_params {
  * [128][16 K], planes in K 0-3) followed by the az_net_tower image (az_b200/net.py pack_stem_weights /
  * pack_tower_weights); stem_bias: dev float [128]; tower_bias: dev float [depth][2][128];
  * priors: dev float [n][A]; values: dev float [n] - the buffers az_step consumes.
+ * layout: as az_net_tower (0 = one CTA per tile, 1 = CTA pairs; the stem stages are split the same way).
  * H * W <= 48, (128 / (H*W)) * A <= 32, channels 128, depth 1..4; states 8-byte, w_img 16-byte aligned. */
 int az_net_forward(const void *dev_states, const void *dev_w_img, const float *dev_stem_bias, const float *dev_tower_bias,
                    const az_net_head_params *heads, int32_t n, int32_t H, int32_t W, int32_t channels, int32_t depth,
-                   int32_t n_actions, float *dev_priors, float *dev_values, void *stream);
+                   int32_t n_actions, int32_t layout, float *dev_priors, float *dev_values, void *stream);
 /* az_net_forward on a gathered batch (az_step_gather): position i of the batch is tree dev_index[i], i < *dev_count
  * (read on the device: no host round trip); states / priors / values stay indexed by tree, n_max = their first
  * dimension.  Trees that are not listed keep their old priors / values. */
 int az_net_forward_gathered(const void *dev_states, const void *dev_w_img, const float *dev_stem_bias,
                             const float *dev_tower_bias, const az_net_head_params *heads, const int32_t *dev_index,
                             const int32_t *dev_count, int32_t n_max, int32_t H, int32_t W, int32_t channels, int32_t depth,
-                            int32_t n_actions, float *dev_priors, float *dev_values, void *stream);
+                            int32_t n_actions, int32_t layout, float *dev_priors, float *dev_values, void *stream);
 
 /* The dense layers of az_net_heads alone, on the output of az_net_head_convs: hd dev float [n][cells][3] -> priors / values
  * as above (same weights struct; conv_w / conv_b unused).  az_net_head_convs + az_net_heads_dense = az_net_heads with the

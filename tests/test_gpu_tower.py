@@ -35,20 +35,32 @@ def _reference(x, blocks):
     return t.permute(0, 2, 3, 1)
 
 
+LAYOUT = {"layout": 1}  # 0 = one CTA per tile, 1 = CTA pairs (cta_group::2); switched by the `layout` fixture
+
+
+@pytest.fixture(params=[0, 1], ids=["single-cta", "cta-pair"])
+def layout(request, monkeypatch):
+    """Every test below runs for both kernel variants: az_net_tower / az_net_forward layout 0 and 1."""
+    LAYOUT["layout"] = request.param
+    monkeypatch.setenv("AZ_TOWER_PAIR", str(request.param))
+    yield request.param
+    LAYOUT["layout"] = 1
+
+
 def _run(x, blocks, H, W):
     engine, native, net = _mods()
-    img, bias = net.pack_tower_weights(blocks)
+    img, bias = net.pack_tower_weights(blocks, pair=bool(LAYOUT["layout"]))
     img, bias = img.cuda(), bias.cuda()
     xd = x.to("cuda", torch.bfloat16).contiguous()
     out = torch.full_like(xd, float("nan"))
     native.check(native.lib().az_net_tower(engine._ptr(xd), engine._ptr(img), engine._ptr(bias), xd.shape[0], H, W, 128,
-                                           len(blocks), engine._ptr(out), engine._stream()))
+                                           len(blocks), LAYOUT["layout"], engine._ptr(out), engine._stream()))
     torch.cuda.synchronize()
     return out.float().cpu()
 
 
 @pytest.mark.parametrize("H,W,n,depth", [(6, 7, 3, 1), (6, 7, 1, 1), (6, 7, 500, 4), (8, 8, 131, 4), (7, 7, 9, 2), (9, 9, 5, 1)])
-def test_fused_tower_equals_the_float32_convolutions(H, W, n, depth):
+def test_fused_tower_equals_the_float32_convolutions(H, W, n, depth, layout):
     blocks = _blocks(depth, seed=H * 10 + depth)
     g = torch.Generator().manual_seed(n)
     x = torch.rand(n, H, W, 128, generator=g).to(torch.bfloat16)
@@ -62,7 +74,7 @@ def test_fused_tower_equals_the_float32_convolutions(H, W, n, depth):
     assert float((err > 2 ** -7 * want.abs().clamp(min=1.0)).float().mean()) < 0.01
 
 
-def test_every_tap_lands_on_the_right_cell_and_edges_are_zero_padded():
+def test_every_tap_lands_on_the_right_cell_and_edges_are_zero_padded(layout):
     """One-hot probes: input 1 at one cell / channel, conv1 = a single tap copying channel 0 -> 0, conv2 = centre-tap
     identity, no shortcut: the output must be the input shifted by the tap, and nothing may wrap around a board edge or
     leak into a neighbouring position of the same tile."""
@@ -87,7 +99,7 @@ def test_every_tap_lands_on_the_right_cell_and_edges_are_zero_padded():
             assert torch.equal(got, want), (ky, kx, (got - want).abs().nonzero()[:8].tolist())
 
 
-def test_shortcut_and_biases_reach_the_output():
+def test_shortcut_and_biases_reach_the_output(layout):
     H, W, n = 6, 7, 5
     g = torch.Generator().manual_seed(3)
     x = torch.rand(n, H, W, 128, generator=g).to(torch.bfloat16)
@@ -99,12 +111,12 @@ def test_shortcut_and_biases_reach_the_output():
     assert torch.allclose(got, want.to(torch.bfloat16).float(), rtol=2 ** -7, atol=1e-6)
 
 
-def test_inference_net_routes_through_the_fused_tower_and_matches_the_library_route():
+def test_inference_net_routes_through_the_fused_tower_and_matches_the_library_route(layout):
     engine, native, net = _mods()
     torch.manual_seed(5)
     fp32 = net.randomise_bn(net.PolicyValueNet(6, 7, 7))
     inf = net.InferenceNet(fp32)
-    assert inf.fused_tower
+    assert inf.fused_tower and inf.tower_layout == layout
     h0 = torch.rand(1000, 6, 7, 128, device="cuda").to(torch.bfloat16)
     a = inf.tower(h0).float()
     b = inf.tower_library(h0).float()
@@ -113,7 +125,7 @@ def test_inference_net_routes_through_the_fused_tower_and_matches_the_library_ro
     assert float(((a - b).abs() > 2 ** -6 * b.abs().clamp(min=1.0)).float().mean()) < 0.01
 
 
-def test_fused_tower_is_deterministic_and_independent_of_the_batch_split():
+def test_fused_tower_is_deterministic_and_independent_of_the_batch_split(layout):
     """A position's output may not depend on which tile / CTA it lands in."""
     blocks = _blocks(2, seed=11)
     g = torch.Generator().manual_seed(12)
@@ -135,7 +147,7 @@ def _states(n, H, W, seed):
 
 
 @pytest.mark.parametrize("n", [1, 3, 500, 4097])
-def test_whole_net_kernel_equals_the_float32_module(n):
+def test_whole_net_kernel_equals_the_float32_module(n, layout):
     """az_net_forward (stem + tower + heads in one kernel) against the fp32 PolicyValueNet and against the
     multi-kernel bf16 route it replaces."""
     import os
@@ -159,13 +171,14 @@ def test_whole_net_kernel_equals_the_float32_module(n):
         old = net.InferenceNet(fp32)
     finally:
         del os.environ["AZ_FUSED_NET"]
+    assert inf.tower_layout == layout
     assert not old.fused_net and old.fused_tower
     p2, v2 = old(x.cuda())
     # identical bf16 pipeline up to summation order inside the heads
     assert float((p - p2.cpu()).abs().max()) <= 1e-3 and float((v - v2.cpu()).abs().max()) <= 2e-3
 
 
-def test_whole_net_kernel_is_batch_independent():
+def test_whole_net_kernel_is_batch_independent(layout):
     engine, native, net = _mods()
     torch.manual_seed(8)
     inf = net.InferenceNet(net.randomise_bn(net.PolicyValueNet(6, 7, 7)))
@@ -176,7 +189,7 @@ def test_whole_net_kernel_is_batch_independent():
     assert torch.equal(p[100:461], p2) and torch.equal(v[100:461], v2)
 
 
-def test_gathered_batch_evaluates_exactly_the_listed_trees():
+def test_gathered_batch_evaluates_exactly_the_listed_trees(layout):
     """az_net_forward_gathered: rows index[:count] get the same priors / values as a plain forward, every other row keeps
     what it held; count = 0 is a no-op."""
     engine, native, net = _mods()
@@ -202,7 +215,7 @@ def test_gathered_batch_evaluates_exactly_the_listed_trees():
         assert (p[~listed.cuda()] == -5.0).all() and (v[~listed.cuda()] == -5.0).all()
 
 
-def test_whole_net_route_plays_the_same_games_as_the_per_tree_fused_route():
+def test_whole_net_route_plays_the_same_games_as_the_per_tree_fused_route(layout):
     """SelfPlayRunner routes: az_step_gather + az_net_forward_gathered against az_advance_fused + az_net_tower - same
     weights, same seeds: identical games (the evaluator is a pure function of the position; heads differ by summation
     order only, far below what could flip a visit count here)."""

@@ -137,3 +137,24 @@ def test_stem_stage_layout():
             p, xc = divmod(rem, W)
             if tile * ppt + p < n:
                 assert np.allclose(out[r], want[tile * ppt + p, y, xc], atol=1e-5)
+
+
+def test_pair_layout_is_the_single_layout_split_by_output_channel():
+    """pack_*_weights(pair=True): stage s, half h, chunk c, row n, element e == the single-CTA image at stage s, chunk c,
+    output channel 64 h + n, element e - CTA h of a pair streams bytes [s * 16 KB + h * 8 KB, + 8 KB)."""
+    from az_b200.net import pack_stem_weights
+
+    g = torch.Generator().manual_seed(5)
+    blocks = [((torch.randn(128, 128, 3, 3, generator=g)), torch.zeros(128), torch.randn(128, 128, 3, 3, generator=g),
+               torch.randn(128, 128, 1, 1, generator=g), torch.zeros(128))]
+    one, _ = pack_tower_weights(blocks)
+    two, _ = pack_tower_weights(blocks, pair=True)
+    a = one.float().reshape(38, 8, 128, 8)
+    b = two.float().reshape(38, 2, 8, 64, 8)
+    for h in range(2):
+        assert torch.equal(b[:, h], a[:, :, 64 * h: 64 * h + 64])
+    w = torch.randn(128, 4, 3, 3, generator=g)
+    s1 = pack_stem_weights(w).float().reshape(3, 8, 128, 8)
+    s2 = pack_stem_weights(w, pair=True).float().reshape(3, 2, 8, 64, 8)
+    for h in range(2):
+        assert torch.equal(s2[:, h], s1[:, :, 64 * h: 64 * h + 64])

@@ -27,7 +27,7 @@ def reference(x, blocks):
 def run(xd, img, bias, H, W, depth, out=None):
     out = torch.empty_like(xd) if out is None else out
     native.check(native.lib().az_net_tower(engine._ptr(xd), engine._ptr(img), engine._ptr(bias), xd.shape[0], H, W, 128,
-                                           depth, engine._ptr(out), engine._stream()))
+                                           depth, 0, engine._ptr(out), engine._stream()))
     return out
 
 

@@ -110,24 +110,16 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
-// arrive (release at cluster scope) on the barrier at offset `bar` in the shared memory of CTA `cta` of the cluster
+// arrive on the barrier at offset `bar` in the shared memory of CTA `cta` of the cluster.  Default semantics, as in
+// CUTLASS's ClusterBarrier::arrive(cta_id): the .release.cluster / .acquire.cluster forms compile to MEMBAR.ALL.GPU and
+// CCTL.IVALL around every stage (the first pair kernel ran 2.4x slower than the single-CTA one because of them); the data
+// these barriers guard lives in shared memory, which no cache shadows.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar),
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar),
         "r"(cta)
         : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (unsigned spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (spin > (1u << 24)) __trap();
-    }
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t is_leader;
@@ -295,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
         }
     }
-    asm volatile("fence.proxy.async;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (PAIR) cluster_sync();  // the peer's barriers exist and its buffers are zeroed before anything reaches across
@@ -350,13 +342,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
         };
         auto wait_stage = [&](uint32_t slot, uint32_t k) {
             mbar_wait(smem_u32(&s_full[slot]), k & 1);
-            if (PAIR) mbar_wait_cluster(smem_u32(&s_pfull[slot]), k & 1);  // ... and the peer's half
+            if (PAIR) mbar_wait(smem_u32(&s_pfull[slot]), k & 1);  // ... and the peer's half
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         };
-        auto wait_act = [&](uint32_t bar, uint32_t parity) {
-            if (PAIR) mbar_wait_cluster(bar, parity);
-            else mbar_wait(bar, parity);
-        };
+        auto wait_act = [&](uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
         // descriptor of the window a tap reads: left / right masked copy for dx = -1 / +1, shifted by the tap
         auto tap_window = [&](int tap, uint32_t centre) {
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -452,8 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
         // this half of the three copies is complete: every thread orders its stores for the tensor core's proxy, one
         // lane per warp arrives
         auto publish = [&](uint32_t bar) {
-            if (PAIR) asm volatile("fence.proxy.async;\n" ::: "memory");  // the MMA that reads these rows is issued by rank 0
-            else asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             __syncwarp();
             if (lane == 0) {

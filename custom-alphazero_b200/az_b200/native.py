@@ -131,6 +131,7 @@ SYMBOLS = {
     "az_net_heads": (ctypes.c_int, [_P, ctypes.POINTER(AzHeadWeights), _I, _I, _I, _I, _P, _P, _P]),
     "az_net_heads_dense": (ctypes.c_int, [_P, ctypes.POINTER(AzHeadWeights), _I, _I, _I, _P, _P, _P]),
     "az_net_conv1x1": (ctypes.c_int, [_P, _P, ctypes.c_int64, _I, _P, _P]),
+    "az_net_tower_timing": (ctypes.c_int, [_P]),
     "az_net_tower": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "az_net_forward": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(AzNetHeadParams), _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "az_net_forward_gathered": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(AzNetHeadParams), _P, _P, _I, _I, _I, _I, _I,

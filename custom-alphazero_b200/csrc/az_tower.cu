@@ -210,6 +210,8 @@ struct TowerParams {
     const int32_t* index;      // net mode, optional: position i of the batch is tree index[i] (az_step_gather) ...
     const int32_t* count;      // ... and the batch holds *count positions (read on the device)
     int n, W, cells, ppt, depth, n_tiles;
+    long long* timing;         // AZ_TOWER_DEBUG bit 3: per CTA {cycles total, MMA warp waiting for activations, for weights, epilogue warp 2
+                               // waiting for the accumulator, its body} (az_net_tower_timing)
     int debug;                 // timing experiments only (AZ_TOWER_DEBUG): bit 0 = do not refill weight stages after the first ring pass,
                                // bit 1 = epilogue skips its shared-memory stores, bit 2 = every tap reads the unshifted centre buffer
 };
@@ -340,12 +342,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
             if (PAIR) commit_pair(bar);
             else commit_to(bar);
         };
+        const bool timed = P.timing != nullptr;
+        long long t_act = 0, t_full = 0;
+        const long long t_begin = clock64();
         auto wait_stage = [&](uint32_t slot, uint32_t k) {
+            const long long t0 = timed ? clock64() : 0;
             mbar_wait(smem_u32(&s_full[slot]), k & 1);
             if (PAIR) mbar_wait(smem_u32(&s_pfull[slot]), k & 1);  // ... and the peer's half
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (timed) t_full += clock64() - t0;
         };
-        auto wait_act = [&](uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
+        auto wait_act = [&](uint32_t bar, uint32_t parity) {
+            const long long t0 = timed ? clock64() : 0;
+            mbar_wait(bar, parity);
+            if (timed) t_act += clock64() - t0;
+        };
         // descriptor of the window a tap reads: left / right masked copy for dx = -1 / +1, shifted by the tap
         auto tap_window = [&](int tap, uint32_t centre) {
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -418,6 +429,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                 }
             }
         }
+        if (timed && lane == 0) {
+            P.timing[blockIdx.x * 8 + 0] = clock64() - t_begin;
+            P.timing[blockIdx.x * 8 + 1] = t_act;
+            P.timing[blockIdx.x * 8 + 2] = t_full;
+        }
     } else {
         // ---------------------------------------------------------------- epilogue / tile load / tile store / heads
         const int e = tid - 64;                       // 0..255
@@ -482,8 +498,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
         // accumulator `acc` (0 / 1) + bias, ReLU, bf16 -> the three copies (centre buffer `centre`), channel half by
         // channel half; or (last layer) -> global memory / the heads.  next_pos0 >= 0 (net mode, last layer): the next
         // tile's planes are loaded as soon as the accumulator has been read, so that its stem runs under the heads.
+        long long t_acc = 0, t_body = 0;
+        const bool etimed = P.timing != nullptr && warp == 2;
         auto epilogue = [&](int acc, const float* bias, int centre, bool last, long long pos0, long long next_pos0) {
+            const long long te0 = etimed ? clock64() : 0;
             mbar_wait(bar_acc, acc_phase);
+            const long long te1 = etimed ? clock64() : 0;
+            t_acc += te1 - te0;
             acc_phase ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             __nv_bfloat16* grow = NET ? nullptr : P.y + (pos0 * P.cells + row_in_tile) * kC + sub * 32;
@@ -531,6 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                 if (!last) publish(ch == 0 ? bar_act0 : bar_act1);
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            if (etimed) t_body += clock64() - te1;
             if (NET && last) {
                 // buffers 0-2 are dead now: hand the next tile to the tensor core before the heads arithmetic
                 if (next_pos0 >= 0) load_planes(next_pos0);
@@ -632,6 +654,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                 epilogue(1, s_bias + kC + (b * 2 + 1) * kC, 0, b == P.depth - 1, pos0, next_pos0);  // accumulator 1 -> block output
             }
         }
+        if (etimed && lane == 0) {
+            P.timing[blockIdx.x * 8 + 3] = t_acc;
+            P.timing[blockIdx.x * 8 + 4] = t_body;
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -675,6 +701,8 @@ static int launch_tower(const TowerParams& P, int sms, cudaStream_t stream) {
     return AZ_OK;
 }
 
+static long long* g_timing = nullptr;  // az_net_tower_timing: device buffer [grid][8] for the next launches, or null
+
 static int tower_launch_checks(const char* who, int n, int H, int W, int channels, int depth, int* ppt_out) {
     if (n < 0 || H < 1 || W < 1) return az::fail_net(AZ_ERR_ARG, who);
     if (channels != kC) return az::fail_net(AZ_ERR_ARG, "az_net_tower / az_net_forward: built for 128 filters (config.py:71)");
@@ -689,6 +717,11 @@ static int tower_launch_checks(const char* who, int n, int H, int W, int channel
 
 }  // namespace tower
 }  // namespace az
+
+extern "C" __attribute__((visibility("default"))) int az_net_tower_timing(void* dev_buffer) {
+    az::tower::g_timing = static_cast<long long*>(dev_buffer);
+    return AZ_OK;
+}
 
 extern "C" __attribute__((visibility("default"))) int az_net_tower(const void* x, const void* w_img, const float* bias, int32_t n,
                                                                     int32_t H, int32_t W, int32_t channels, int32_t depth,
@@ -710,6 +743,7 @@ extern "C" __attribute__((visibility("default"))) int az_net_tower(const void* x
     P.y = static_cast<__nv_bfloat16*>(y);
     P.n = n, P.W = W, P.cells = H * W, P.ppt = ppt, P.depth = depth, P.n_tiles = (n + ppt - 1) / ppt;
     if (const char* dbg = getenv("AZ_TOWER_DEBUG")) P.debug = atoi(dbg);
+    P.timing = g_timing;
     return layout ? launch_tower<false, true>(P, sms, static_cast<cudaStream_t>(stream))
                   : launch_tower<false, false>(P, sms, static_cast<cudaStream_t>(stream));
 }
@@ -747,6 +781,7 @@ static int net_forward_impl(const void* states, const void* w_img, const float* 
     P.count = count;
     P.n = n, P.W = W, P.cells = cells, P.ppt = ppt, P.depth = depth, P.n_tiles = (n + ppt - 1) / ppt;
     if (const char* dbg = getenv("AZ_TOWER_DEBUG")) P.debug = atoi(dbg);
+    P.timing = g_timing;
     return layout ? launch_tower<true, true>(P, sms, static_cast<cudaStream_t>(stream))
                   : launch_tower<true, false>(P, sms, static_cast<cudaStream_t>(stream));
 }

@@ -320,6 +320,11 @@ int az_net_conv1x1(const void *dev_x, const void *dev_w, int64_t rows, int32_t c
 int az_net_tower(const void *dev_x, const void *dev_w_img, const float *dev_bias, int32_t n, int32_t H, int32_t W,
                  int32_t channels, int32_t depth, int32_t layout, void *dev_y, void *stream);
 
+/* Measurement aid: while dev_buffer (dev int64 [148][8], or NULL to switch off) is set, every az_net_tower / az_net_forward
+ * launch writes per CTA {cycles of the MMA warp's tile loop, of which waiting for activations, waiting for weight stages,
+ * cycles epilogue warp 2 waited for an accumulator, cycles of its epilogue bodies} (tools/time_tower.py). */
+int az_net_tower_timing(void *dev_buffer);
+
 /* Head weights of az_net_forward: plain row-major float32, BN folded (no padding or transposition). */
 typedef struct az_net_head_params {
     const float *conv_w;   /* dev [3][128]: rows 0-1 policy 1x1 conv (model.py:68-85), row 2 value 1x1 conv (:106-123) */

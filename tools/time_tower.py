@@ -68,3 +68,21 @@ print("cudnn", json.dumps(out["cudnn"]), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", "time_tower.json"), "w") as fp:
     json.dump(out, fp, indent=1)
+
+# ---- where do the cycles go?  per-CTA counters written by the kernel itself (az_net_tower_timing)
+from az_b200 import native  # noqa: E402
+from az_b200.engine import _ptr  # noqa: E402
+
+buf = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
+native.check(native.lib().az_net_tower_timing(_ptr(buf)))
+for f in flags[:1]:
+    os.environ["AZ_TOWER_DEBUG"] = str(f)
+    inf.tower(xs[0])
+    torch.cuda.synchronize()
+    b = buf.cpu().numpy().astype(float)
+    lead = b[b[:, 0] > 0]
+    epi = b[b[:, 3] > 0]
+    rep = {"mma_warp_cycles": lead[:, 0].mean(), "mma_wait_act": lead[:, 1].mean(), "mma_wait_weights": lead[:, 2].mean(),
+           "epi_wait_acc": epi[:, 3].mean(), "epi_body": epi[:, 4].mean(), "ctas_with_mma": int(len(lead))}
+    print("timing", json.dumps(rep), flush=True)
+native.check(native.lib().az_net_tower_timing(None))

@@ -505,8 +505,11 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
     return pend;
 }
 
+// 7 blocks of 4 warps per SM (<= 72 registers) for the one-word boards: 148 x 28 = 4 144 warp slots hold all 4 096 trees of the
+// headline configuration in ONE wave.  At 96 registers (5 blocks, 2 960 slots) the kernel ran 1.38 waves and the SMs were
+// busy 45-55 % of its duration (ncu, profiles/ncu_kstep_r2.csv): the second, partial wave doubled the tail.
 template <int NW, int KC, class R, bool NOISE = false>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (NW == 1 && KC == 1 && !NOISE) ? 7 : 1)
     k_step(Eng e, Aux aux, const void* __restrict__ priors, const void* __restrict__ values, int eval_dtype, void* states,
            int state_dtype, int32_t* leaf_valid, int32_t* leaf_list = nullptr, int32_t* leaf_count = nullptr) {
     __shared__ WarpScratch s_ws[kWarpsPerBlock];

@@ -53,7 +53,10 @@ constexpr int kLboA = kRows * 16;                 // byte distance between adjac
 constexpr int kActBytes = 16 * kLboA;             // 159 232
 constexpr int kStageBytes = 16384;                // [8 chunks][128 output channels][8 input channels] bf16
 constexpr int kLboB = 2048;                       // 128 rows x 16 bytes
-constexpr int kStages = 4;
+constexpr int kStages = 4;                        // 64 KB of weight ring: 4 x 16 KB, or 8 x 8 KB per CTA of a pair.  (Tried 3 / 6
+                                                  // slots so that a block of the per-tree kernel of ANOTHER tree group fits beside
+                                                  // this CTA: 3 % slower alone, and --groups 2..4 gained nothing - one 4-warp block
+                                                  // per SM cannot carry a group's trees within a net launch.  DESIGN.md section 8.)
 constexpr int kMaxDepth = 4;                      // config.py:63
 constexpr int kBiasBytes = ((1 + 2 * kMaxDepth) * kC + 3 * kC) * 4;  // stem + tower biases, the 1x1 head convolutions
 constexpr int kSmemBytes = kActBytes + kStages * kStageBytes + kBiasBytes;

@@ -432,6 +432,7 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
     int pend = (was_pending == 2 || (was_pending == 1 && !have_eval)) ? 1 : 0;
     if (pend) leaf = load_pos<NW>(e.leaf_board + (size_t)t * 2 * NW);  // not answered yet: hand the same leaf out (again)
     int freed = 0;
+    int staged_root = -1;  // node whose child block select_leaf has staged in ws.root_* during this launch (none yet)
     for (;;) {
         if (!pend && sims >= e.sims_target && e.inline_play) {
             // budget spent: play the move right here (K6) and carry on with the first simulation of the
@@ -452,15 +453,17 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
             }
             root = e.root_node[t];
             sims = 0;
+            staged_root = -1;  // new root (and possibly the other pool half): the staged block is stale
             if (++freed >= e.max_free) break;
         }
         if (pend || sims >= e.sims_target) break;
         Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
         int depth, term;
-        select_leaf<NW, KC, NOISE>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags, e.game_id[t], e.ply[t], sims);
+        select_leaf<NW, KC, NOISE>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags, e.game_id[t], e.ply[t], sims,
+                                   &staged_root);
         ndepth += depth;
         if (term) {  // mcts.py:179: terminal leaf, result 1 (win of the mover) or 0 (draw)
-            backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
+            backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane, staged_root);
             ++sims;
             ++nsim;
             if (++freed >= e.max_free) break;
@@ -472,7 +475,8 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
                 const float* cp = ws.cpri;
                 const uint32_t link = expand_leaf<NW>(e, r, A, Pr, pos, t, ws, lane, flags, AZ_PRIOR_F32,
                                                       [cp](int a) { return (double)cp[a]; });
-                backup_path(A, root, ws, depth, -(double)cv, link, lane);
+                backup_path(A, root, ws, depth, -(double)cv, link, lane, staged_root);
+                if (depth == 0) staged_root = -1;  // the root itself was expanded: its link changed
                 ++sims;
                 ++nsim;
                 ++nhit;
@@ -1126,6 +1130,10 @@ AZ_API int az_engine_create(const az_config* c, void* slab, size_t bytes, const 
     g.c_puct = c->c_puct;
     g.seed = c->seed;
     g.game_base = c->game_id_base;
+    {   // NS1 (north_star): root child block staged in shared memory across the simulations of a launch; AZ_ROOT_SMEM=0 off
+        const char* rs = getenv("AZ_ROOT_SMEM");
+        g.root_smem = rs ? (atoi(rs) != 0) : 1;
+    }
     g.games_target = c->games_target;
     g.status = reinterpret_cast<int32_t*>(b + L.status);
     g.ply = reinterpret_cast<int32_t*>(b + L.ply);

@@ -115,6 +115,7 @@ struct Eng {
     Rules r;
     int T, C, P, F;  // trees, node capacity per half, max plies, finished-ring entries
     int sims_target, greedy_idx, eval_mode, prior_mode, move_mode, max_free, lut_len, auto_restart, inline_play;
+    int root_smem;  // 1: select_leaf reads the root's child block from WarpScratch after the first simulation of a launch
     int dirichlet;
     double dir_alpha, dir_ratio;
     double c_puct;
@@ -162,6 +163,11 @@ struct WarpScratch {
     int32_t off[32];
     int32_t ob[32];
     float cpri[kMaxActions];  // priors of an evaluation-memo hit
+    // north_star "hot root nodes staged in shared memory": the root's child block (records + priors, <= 32 children) kept
+    // here across the simulations one launch runs on a tree, written through by the backup (Eng::root_smem)
+    NodeA root_rec[32];
+    double root_pr[32];
+    uint32_t root_link;
 };
 
 template <int NW>
@@ -187,9 +193,13 @@ __device__ __forceinline__ void store_pos(uint64_t* p, const Pos<NW>& v, int lan
 template <int NW, int KC, bool NOISE = false, class R>
 __device__ __forceinline__ int select_leaf(const Eng& e, const R& r, const NodeA* A, const double* Pr, int root, Pos<NW>& pos,
                                            WarpScratch& ws, int lane, int& depth, int& term, uint32_t& flags,
-                                           long long noise_game = 0, int noise_ply = 0, int noise_sim = 0) {
+                                           long long noise_game = 0, int noise_ply = 0, int noise_sim = 0,
+                                           int* staged_root = nullptr) {
     int node = root;
-    uint32_t link = load_node(A + root).link;
+    // staged_root (warp-uniform, owned by the caller's simulation loop): the node whose child block sits in ws.root_*
+    const bool use_stage = KC == 1 && staged_root != nullptr && e.root_smem;
+    const bool hit = use_stage && *staged_root == root;
+    uint32_t link = hit ? ws.root_link : load_node(A + root).link;
     depth = 0;
     term = 0;
     while (link) {
@@ -201,8 +211,13 @@ __device__ __forceinline__ int select_leaf(const Eng& e, const R& r, const NodeA
         for (int c = 0; c < KC; ++c) {
             int j = lane + 32 * c;
             if (j < k) {
-                rec[c] = load_node(A + base + j);
-                pr[c] = Pr[base + j];
+                if (KC == 1 && hit && depth == 0) {  // the root block: shared memory instead of an L2 / HBM round trip
+                    rec[c] = ws.root_rec[j];
+                    pr[c] = ws.root_pr[j];
+                } else {
+                    rec[c] = load_node(A + base + j);
+                    pr[c] = Pr[base + j];
+                }
                 ln += rec[c].n;
             } else {
                 rec[c].n = 0;
@@ -210,6 +225,14 @@ __device__ __forceinline__ int select_leaf(const Eng& e, const R& r, const NodeA
                 rec[c].link = 0;
                 pr[c] = 0.0;
             }
+        }
+        if (KC == 1 && use_stage && !hit && depth == 0) {  // first descent of this launch from this root: stage its block
+            if (lane < k) {
+                ws.root_rec[lane] = rec[0];
+                ws.root_pr[lane] = pr[0];
+            }
+            if (lane == 0) ws.root_link = link;
+            *staged_root = root;
         }
         // one level ahead: ask L2 for the child blocks of every child while this level is being scored,
         // so the next level's dependent loads find their lines on chip instead of paying an HBM round trip
@@ -469,8 +492,8 @@ __device__ __forceinline__ bool cache_lookup(const Eng& e, const R& r, const Pos
 // no atomics.  v0 is the value for the player who moved into the leaf; sign alternates upward.
 // new_link != 0 also publishes the leaf's fresh children in the same 16-byte store.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void backup_path(NodeA* A, int root, const WarpScratch& ws, int depth, double v0,
-                                            uint32_t new_link, int lane) {
+__device__ __forceinline__ void backup_path(NodeA* A, int root, WarpScratch& ws, int depth, double v0,
+                                            uint32_t new_link, int lane, int staged_root = -1) {
     for (int i = lane; i < depth; i += 32) {
         NodeA* p = A + ws.path[depth - 1 - i];
         NodeA rec = load_node(p);
@@ -478,6 +501,8 @@ __device__ __forceinline__ void backup_path(NodeA* A, int root, const WarpScratc
         rec.w = __dadd_rn(rec.w, (i & 1) ? -v0 : v0);
         if (i == 0 && new_link) rec.link = new_link;
         store_node(p, rec);
+        // write through: path[0] is a child of the root, i.e. an entry of the staged block
+        if (i == depth - 1 && staged_root == root) ws.root_rec[ws.path[0] - (int)(ws.root_link & 0xffffffu)] = rec;
     }
     if (depth == 0 && new_link && lane == 0) {  // first simulation on an edgeless root: nothing to back up
         NodeA rec = load_node(A + root);

@@ -14,6 +14,7 @@ eps 1e-3, momentum 0.99.  F = 128, depth = 4 (config.py:63,71): 1 267 037 traina
 """
 import math
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -146,6 +147,56 @@ class PolicyValueNet(nn.Module):
 
     def n_parameters(self):
         return sum(p.numel() for p in self.parameters())
+
+    # ---- the reference's own weight format: the list PolicyValueModel.get_weights() returns (model.py:168-176 hashes it,
+    # save_weights / load_weights at :190-212 store it).  Order as Keras 2.7 builds it (poetry.lock): per top-level layer
+    # (residual_tower, policy_head, value_head) all trainable variables in layer order, then the BatchNormalization
+    # moving statistics; kernels HWIO / [in, out].  A maintainer of the reference exports a checkpoint with
+    # `np.savez(path, *model.get_weights())` and loads it here with `net.load_keras_weights(list(np.load(path).values()))`.
+    def _keras_groups(self):
+        tower = [self.stem] + [cb for blk in self.blocks for cb in (blk.c1, blk.c2, blk.proj)]
+        return ((tower, []), ([self.policy_conv], [self.policy_fc]), ([self.value_conv], [self.value_fc1, self.value_fc2]))
+
+    def to_keras_weights(self):
+        """-> list of numpy arrays in PolicyValueModel.get_weights() order."""
+        out = []
+        for convs, denses in self._keras_groups():
+            for cb in convs:
+                out += [cb.conv.weight.detach().permute(2, 3, 1, 0), cb.conv.bias.detach(), cb.bn.weight.detach(), cb.bn.bias.detach()]
+            for fc in denses:
+                out += [fc.weight.detach().t(), fc.bias.detach()]
+            for cb in convs:
+                out += [cb.bn.running_mean, cb.bn.running_var]
+        return [t.cpu().contiguous().numpy().copy() for t in out]
+
+    def load_keras_weights(self, weights):
+        """Inverse of to_keras_weights: fills this module from a PolicyValueModel.get_weights() list (shapes checked)."""
+        weights = list(weights)
+        it = iter(weights)
+
+        def put(dst, arr, what):
+            src = torch.as_tensor(np.asarray(arr), dtype=dst.dtype)
+            if tuple(src.shape) != tuple(dst.shape):
+                raise ValueError(f"load_keras_weights: {what} has shape {tuple(src.shape)}, expected {tuple(dst.shape)}")
+            with torch.no_grad():
+                dst.copy_(src)
+
+        n_expected = sum(6 * len(c) + 2 * len(d) for c, d in self._keras_groups())
+        if len(weights) != n_expected:
+            raise ValueError(f"load_keras_weights: {len(weights)} arrays, this architecture has {n_expected}")
+        for convs, denses in self._keras_groups():
+            for cb in convs:
+                put(cb.conv.weight, np.transpose(np.asarray(next(it)), (3, 2, 0, 1)), "a convolution kernel")
+                put(cb.conv.bias, next(it), "a convolution bias")
+                put(cb.bn.weight, next(it), "a BatchNormalization gamma")
+                put(cb.bn.bias, next(it), "a BatchNormalization beta")
+            for fc in denses:
+                put(fc.weight, np.asarray(next(it)).T, "a dense kernel")
+                put(fc.bias, next(it), "a dense bias")
+            for cb in convs:
+                put(cb.bn.running_mean, next(it), "a BatchNormalization moving mean")
+                put(cb.bn.running_var, next(it), "a BatchNormalization moving variance")
+        return self
 
 
 class InferenceNet(nn.Module):

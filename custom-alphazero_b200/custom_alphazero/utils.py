@@ -1,17 +1,24 @@
 """File-system glue the self-play entry point needs (reference utils.py:24-133): which weights to play
 with.  Checkpoints of the B200 build are torch state dicts (`model.pt`) next to the reference's
-meta.json / MODEL_SAVED_SUCCESSFULLY sentinel; TensorFlow checkpoints cannot be read here."""
+meta.json / MODEL_SAVED_SUCCESSFULLY sentinel.  TensorFlow's checkpoint files cannot be parsed here (no TensorFlow), but the
+reference's weights can: `np.savez(os.path.join(path, "model_keras.npz"), *model.get_weights())` on the reference side
+gives a file load_with_meta() reads through PolicyValueNet.load_keras_weights (the get_weights() order and the
+HWIO / [in, out] layouts are restated in az_b200/net.py and checked against oracle/net_ref.py)."""
 import hashlib
 import json
 import os
 from typing import Optional
 
+import numpy as np
 import torch
 
 from az_b200.net import PolicyValueNet
 from custom_alphazero import paths
 from custom_alphazero.config import ConfigConnectN, ConfigModel, ConfigPath
 from custom_alphazero.connect_n.board import Board
+
+
+KERAS_WEIGHTS = "model_keras.npz"  # np.savez(path, *PolicyValueModel.get_weights()): arrays arr_0, arr_1, ...
 
 
 def model_hash(net: PolicyValueNet) -> str:
@@ -39,9 +46,15 @@ def save_with_meta(net: PolicyValueNet, path: str, steps: int = 0, learning_rate
 def load_with_meta(net: PolicyValueNet, path: str) -> dict:
     """model.py:190-201: refuses a checkpoint without the sentinel or whose weights do not match the stored hash."""
     assert os.path.exists(os.path.join(path, ConfigPath.model_success)), f"No verification file of the model found at {path}!"
-    net.load_state_dict(torch.load(os.path.join(path, ConfigPath.model_prefix + ".pt"), map_location="cpu"))
     with open(os.path.join(path, ConfigPath.model_meta)) as fp:
         meta = json.load(fp)
+    pt = os.path.join(path, ConfigPath.model_prefix + ".pt")
+    if not os.path.exists(pt) and os.path.exists(os.path.join(path, KERAS_WEIGHTS)):
+        # a checkpoint exported by the reference: its hash is Keras' (md5 of the printed arrays), not comparable with ours
+        with np.load(os.path.join(path, KERAS_WEIGHTS)) as z:
+            net.load_keras_weights([z[k] for k in sorted(z.files, key=lambda k: int(k.split("_")[1]))])
+        return meta
+    net.load_state_dict(torch.load(pt, map_location="cpu"))
     assert model_hash(net) == meta.get("hash"), f"Unexpected weights hash recovered during model loading at {path}!"
     return meta
 

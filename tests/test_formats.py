@@ -68,3 +68,30 @@ def test_append_queue_payload_shape(monkeypatch):
     assert ok and sent["url"].endswith("/api/queue/append")
     assert set(sent["data"]) == {"states", "policies", "values"} and sent["data"]["values"] == [1, -1]
     assert np.asarray(sent["data"]["states"]).shape == (2, 6, 7, 4)
+
+
+def test_checkpoint_exported_by_the_reference_loads(tmp_path):
+    """A reference-side export (np.savez of PolicyValueModel.get_weights() next to meta.json and the sentinel) is
+    readable: the path from a reference checkpoint to PolicyValueNet (model.py:190-212)."""
+    import numpy as np
+
+    from az_b200.net import PolicyValueNet, randomise_bn
+    from custom_alphazero.config import ConfigPath
+    from custom_alphazero.utils import KERAS_WEIGHTS, load_with_meta
+
+    torch.manual_seed(5)
+    src = randomise_bn(PolicyValueNet()).eval()
+    d = tmp_path / "iteration_3"
+    d.mkdir()
+    np.savez(d / KERAS_WEIGHTS, *src.to_keras_weights())  # what the maintainer runs on the reference side
+    json.dump({"steps": 12, "learning_rate": 0.01, "hash": 1234567890123456789012345678901234567890}, open(d / ConfigPath.model_meta, "w"))
+    with pytest.raises(AssertionError):  # no sentinel yet
+        load_with_meta(PolicyValueNet(), str(d))
+    open(d / ConfigPath.model_success, "wb").close()
+    dst = PolicyValueNet().eval()
+    meta = load_with_meta(dst, str(d))
+    assert meta["steps"] == 12
+    x = torch.zeros(2, 6, 7, 4)
+    x[..., 0] = 1
+    with torch.no_grad():
+        assert torch.equal(src(x)[0], dst(x)[0]) and torch.equal(src(x)[1], dst(x)[1])

@@ -87,9 +87,10 @@ def test_bf16_inference_net_close_to_fp32_module(H, W, A):
     p, v = inf(x.cuda().to(torch.bfloat16))
     dp = (p.cpu() - want_p).abs().max().item()
     dv = (v.cpu() - want_v.reshape(-1)).abs().max().item()
-    # bf16 weights and activations through 9 sequential 3x3 convolutions vs fp32: tolerance 2e-2 on the
-    # softmax outputs and 5e-2 on tanh values (measured ~5e-3 / ~1e-2; see DESIGN.md "Numerics")
-    assert dp < 2e-2 and dv < 5e-2, (dp, dv)
+    # bf16 weights and activations through 9 sequential 3x3 convolutions vs fp32: tolerance 8e-3 on the softmax outputs
+    # and on the tanh values (measured 2.4e-3 / 1.6e-3 on 4096 reachable positions: tests/test_gpu_a22.py asserts 4e-3 there)
+    print("bf16 vs fp32", H, W, dp, dv)
+    assert dp < 8e-3 and dv < 8e-3, (dp, dv)
     # the slow (library-only) GPU path computes the same function
     inf.fast = False
     p2, v2 = inf(x.cuda().to(torch.bfloat16))

@@ -165,7 +165,8 @@ def test_whole_net_kernel_equals_the_float32_module(n, layout):
     p, v = p.cpu(), v.cpu()
     assert torch.isfinite(p).all() and torch.allclose(p.sum(-1), torch.ones(n), atol=1e-5)
     # bf16 activations through 13 layers against float32: same bounds as the multi-kernel route (tests/test_gpu_net.py)
-    assert float((p - p32).abs().max()) <= 2e-2 and float((v - v32.reshape(-1)).abs().max()) <= 5e-2
+    print("whole net vs fp32", n, float((p - p32).abs().max()), float((v - v32.reshape(-1)).abs().max()))
+    assert float((p - p32).abs().max()) <= 8e-3 and float((v - v32.reshape(-1)).abs().max()) <= 8e-3
     os.environ["AZ_FUSED_NET"] = "0"
     try:
         old = net.InferenceNet(fp32)

@@ -210,3 +210,33 @@ def test_device_header_reproduces_the_playout_fixture():
             pos = cr.host_play(pos, m[0] | m[1] << 6 | cr.PROMO_LETTERS.index(m[2]) << 12, True)
         lines.append("{}|{}|{}\n".format(",".join(map(str, picked)), cr.host_status(pos), pos.tolist()))
     assert hashlib.sha256("".join(lines).encode()).hexdigest()[:16] == want["sha"]
+
+
+def _divide_cases():
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "chess_perft_divide.json")) as fp:
+        return json.load(fp)["cases"]
+
+
+@pytest.mark.parametrize("case", _divide_cases(), ids=lambda c: f"{c['fen'].split()[0][:12]}-d{c['depth']}")
+def test_published_perft_divide_per_root_move(case):
+    """the published per-root-move counts (typed in from the published tables, see the fixture), for
+    the mailbox oracle and for the DEVICE rules header compiled for the host.  A wrong count under one root move names
+    the piece of the generator that is wrong, which a total cannot."""
+    acts = cr.all_possible_moves()
+    index = {m: i for i, m in enumerate(acts)}
+    s = cr.from_fen(case["fen"])
+    pos = cr.to_pos(s)
+    d = case["depth"]
+    assert sum(case["divide"].values()) == case["total"]
+    got_oracle, got_header = {}, {}
+    for m in cr.legal(s):
+        got_oracle[cr.uci(m)] = cr.perft(cr.push(s, m, keep_same_player=False), d - 1)
+        code = m[0] | m[1] << 6 | cr.PROMO_LETTERS.index(m[2]) << 12
+        got_header[cr.uci(m)] = cr.host_perft_mirrored(cr.host_play(pos, code, True), d - 1)
+    assert got_oracle == case["divide"]
+    assert got_header == case["divide"]
+    listed, _, unlisted = cr.host_legal(pos)
+    assert unlisted == 0 and sorted(index[m] for m in cr.legal(s)) == listed

@@ -230,3 +230,23 @@ def test_integration_md_chess_stub_runs():
     assert count.tolist() == [20, 48, 0] and [s & 3 for s in status.tolist()] == [0, 0, 1]
     planes = ns["full_state"](boards)
     assert np.array_equal(planes.cpu().numpy(), chess.chess_encode(np.stack([chess.position_from_fen(f) for f in fens])))
+
+
+def test_published_perft_divide_on_the_device():
+    """The published per-root-move perft counts (tests/golden/chess_perft_divide.json, typed in from the published tables)
+    through az_chess_legal / az_chess_play / az_chess_perft."""
+    import json
+    import os
+
+    chess = _chess()
+    with open(os.path.join(os.path.dirname(__file__), "golden", "chess_perft_divide.json")) as fp:
+        cases = json.load(fp)["cases"]
+    for case in cases:
+        root = chess.position_from_fen(case["fen"])[None]
+        mask, count, status = chess.chess_legal(root)
+        _, act = np.nonzero(mask)
+        children, st = chess.chess_play(np.repeat(root, len(act), axis=0), act.astype(np.int32), keep_same_player=True)
+        assert (st >= 0).all()
+        counts = chess.chess_perft(children, case["depth"] - 1)
+        got = {chess.action_uci(int(a)): int(c) for a, c in zip(act, counts)}
+        assert got == case["divide"], case["fen"]

@@ -141,6 +141,7 @@ SYMBOLS = {
     "az_advance_fused": (ctypes.c_int, [_P, _P, ctypes.POINTER(AzHeadWeights), _P, _P, _P, _P, _P]),
     "az_debug_dirichlet": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_double, _I, _I, _P, _P]),
     "az_debug_timeline": (ctypes.c_int, [_P, _P, _I]),
+    "az_net_debug_timeline": (ctypes.c_int, [_P, _I]),
     "az_decode_samples": (ctypes.c_int, [ctypes.POINTER(AzConfig), _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
     # chess (az_chess_pos = 8 x uint64, passed as plain device pointers)
     "az_chess_action_table": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint16)]),

@@ -127,7 +127,7 @@ class SelfPlayRunner:
         # evaluator-free simulations (terminal leaves, in-line moves) continued on a forked stream while the
         # tower runs: keeps max_free_sims - the tail of the per-tree kernel, which the tower waits for - small
         self.extra_sims = int(extra_sims)
-        self._extra_streams = [torch.cuda.Stream(device=self.device) for _ in self.groups] if self.extra_sims else []
+        self._extra_streams = [torch.cuda.Stream(device=self.device, priority=0) for _ in self.groups] if self.extra_sims else []
         self.unroll = int(unroll)
         self.use_graph = use_graph
         self.graph = None
@@ -136,7 +136,7 @@ class SelfPlayRunner:
         # kernels of libaz_b200 launched per advance and group: az_advance_fused, or az_step + az_net_stem +
         # az_net_heads (+ az_play sweeps); + az_net_tower when the tower is the hand-written kernel
         if self.whole_net:
-            self.launches_per_advance = 2 * groups
+            self.launches_per_advance = (3 if extra_sims else 2) * groups
         else:
             self.launches_per_advance = ((1 if self.fused else 3) + (1 if extra_sims and self.fused else 0)
                                          + (1 if getattr(self.net, "fused_tower", False) else 0)) * groups
@@ -187,7 +187,19 @@ class SelfPlayRunner:
         elif self.whole_net:
             # the tree step alone, then the whole net in one kernel on exactly the trees that have a leaf pending
             g.engine.step(g.priors, g.values, g.states, g.valid, g.leaf_list, g.leaf_count)
-            self.net(g.states, g.priors, g.values, index=g.leaf_list, count=g.leaf_count)
+            if self.extra_sims:
+                # trees that spent their max_free_sims evaluator-free simulations without meeting a leaf that needs the net
+                # have nothing to wait for: they go on simulating on a low-priority side stream, whose blocks the scheduler
+                # places on the SMs the net kernel's last, partial round of tiles leaves idle
+                cur = torch.cuda.current_stream()
+                side = self._extra_streams[self.groups.index(g)]
+                side.wait_stream(cur)
+                self.net(g.states, g.priors, g.values, index=g.leaf_list, count=g.leaf_count)
+                with torch.cuda.stream(side):
+                    g.engine.extra_sims(self.extra_sims)
+                cur.wait_stream(side)
+            else:
+                self.net(g.states, g.priors, g.values, index=g.leaf_list, count=g.leaf_count)
         else:
             g.engine.step(g.priors, g.values, g.states, g.valid)
             self.net(g.states, g.priors, g.values)
@@ -230,7 +242,9 @@ class SelfPlayRunner:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # captured on a high-priority stream: kernel nodes keep the priority of the stream they were captured on, so the
+        # net and the tree step win the SMs over the low-priority az_extra_sims branch whenever both have blocks waiting
+        with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=self.device, priority=-1)):
             self._advance_all(self.unroll)
         self.graph = graph
 

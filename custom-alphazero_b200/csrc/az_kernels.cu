@@ -515,11 +515,19 @@ __device__ __forceinline__ int step_tree(const Eng& e, const Aux& aux, const R& 
 template <int NW, int KC, class R, bool NOISE = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, (NW == 1 && KC == 1 && !NOISE) ? 7 : 1)
     k_step(Eng e, Aux aux, const void* __restrict__ priors, const void* __restrict__ values, int eval_dtype, void* states,
-           int state_dtype, int32_t* leaf_valid, int32_t* leaf_list = nullptr, int32_t* leaf_count = nullptr) {
+           int state_dtype, int32_t* leaf_valid, int32_t* leaf_list = nullptr, int32_t* leaf_count = nullptr,
+           unsigned long long* timeline = nullptr) {
     __shared__ WarpScratch s_ws[kWarpsPerBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * kWarpsPerBlock + warp;
     if (t >= e.T) return;
+    // optional timeline slot {first start, last end} in globaltimer ns (az_debug_timeline): measurement aid
+    auto stamp = [] {
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        return t_;
+    };
+    if (timeline && lane == 0) atomicMin(timeline, stamp());
     WarpScratch& ws = s_ws[warp];
     const auto r = RulesView<R>::get(e);
     Pos<NW> leaf;
@@ -549,6 +557,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (NW == 1 && KC == 1 && !N
         // the leaf batch as a dense list of tree indices (az_step_gather): the net then runs on the trees that really
         // have a leaf pending - 3 900 of 4 096 in steady state, which is 9 instead of 10 rounds of the net kernel's tiles
         if (pend && leaf_list) leaf_list[atomicAdd(leaf_count, 1)] = t;
+        if (timeline) atomicMax(timeline + 1, stamp());
     }
 }
 
@@ -1248,13 +1257,21 @@ AZ_API int az_begin_search(az_engine* e, int32_t sims, void* stream) {
         AZ_CUDA(cudaGetLastError());                                                                      \
     } while (0)
 
+static unsigned long long* next_timeline_slot(az_engine* e) {
+    if (!e->timeline || e->timeline_slots <= 0) return nullptr;
+    unsigned long long* tl = e->timeline + 2 * (e->timeline_next % e->timeline_slots);
+    e->timeline_next += 1;
+    return tl;
+}
+
 AZ_API int az_step(az_engine* e, const void* priors, const void* values, int32_t eval_dtype, void* states,
                        int32_t state_dtype, int32_t* leaf_valid, void* stream) {
     if (!e || !states || !leaf_valid) return fail(AZ_ERR_ARG, "az_step: null pointer%s");
     if ((priors == nullptr) != (values == nullptr)) return fail(AZ_ERR_ARG, "az_step: priors and values go together%s");
     if ((eval_dtype != AZ_F32 && eval_dtype != AZ_F64) || (state_dtype != AZ_BF16 && state_dtype != AZ_F32))
         return fail(AZ_ERR_ARG, "az_step: unsupported dtype%s");
-    AZ_DISPATCH(k_step, e->eng, e->aux, priors, values, eval_dtype, states, state_dtype, leaf_valid);
+    AZ_DISPATCH(k_step, e->eng, e->aux, priors, values, eval_dtype, states, state_dtype, leaf_valid, nullptr, nullptr,
+                next_timeline_slot(e));
     return AZ_OK;
 }
 
@@ -1265,7 +1282,8 @@ AZ_API int az_step_gather(az_engine* e, const void* priors, const void* values, 
     if ((eval_dtype != AZ_F32 && eval_dtype != AZ_F64) || (state_dtype != AZ_BF16 && state_dtype != AZ_F32))
         return fail(AZ_ERR_ARG, "az_step_gather: unsupported dtype%s");
     AZ_CUDA(cudaMemsetAsync(leaf_count, 0, sizeof(int32_t), static_cast<cudaStream_t>(stream)));
-    AZ_DISPATCH(k_step, e->eng, e->aux, priors, values, eval_dtype, states, state_dtype, leaf_valid, leaf_list, leaf_count);
+    AZ_DISPATCH(k_step, e->eng, e->aux, priors, values, eval_dtype, states, state_dtype, leaf_valid, leaf_list, leaf_count,
+                next_timeline_slot(e));
     return AZ_OK;
 }
 

@@ -26,8 +26,9 @@
 //            cp.async.bulk into a 4-deep ring, full / empty mbarriers;
 //   warp 1   MMA issuer: one lane issues 4 tcgen05.mma (128 x 128 x 16) per stage; conv1 -> TMEM columns 0-127, the
 //            1x1 shortcut (needs only x) and then conv2 -> columns 128-255, so the shortcut runs under epilogue 1;
-//   warps 2-9  epilogue: tcgen05.ld (32 lanes x 32 columns), + bias, ReLU, bf16, three masked 16-byte stores per chunk
-//            (conflict free: a warp writes 512 contiguous bytes), fence.proxy.async, arrive on the "activations ready"
+//   warps 2-9  epilogue: tcgen05.ld (32 lanes x 32 columns), + bias, ReLU + bf16 pair in one cvt.rn.relu.bf16x2, up to three
+//            16-byte stores per chunk (the masked copies never write their zero rows, which stay zero from the start;
+//            conflict free: a warp writes 512 contiguous bytes), fence.proxy.async, arrive on the "activations ready"
 //            barrier.  The same warps load a tile from global memory at its start and store it after the last block.
 // SASS: UTCHMMA (tcgen05.mma), UBLKCP (cp.async.bulk), LDTM (tcgen05.ld).
 #include <cuda_bf16.h>
@@ -183,9 +184,11 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
         : "r"(taddr)
         : "memory");
 }
+// relu(hi) : relu(lo) as one bf16x2 word, round to nearest even (one instruction instead of two FMNMX + F2FP)
 __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(fmaxf(lo, 0.0f), fmaxf(hi, 0.0f));
-    return *reinterpret_cast<uint32_t*>(&v);
+    uint32_t v;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(v) : "f"(hi), "f"(lo));
+    return v;
 }
 
 struct HeadParams {
@@ -215,6 +218,7 @@ struct TowerParams {
     int n, W, cells, ppt, depth, n_tiles;
     long long* timing;         // AZ_TOWER_DEBUG bit 3: per CTA {cycles total, MMA warp waiting for activations, for weights, epilogue warp 2
                                // waiting for the accumulator, its body} (az_net_tower_timing)
+    unsigned long long* timeline;  // az_net_debug_timeline: {first CTA start, last CTA end} of this launch, globaltimer ns
     int debug;                 // timing experiments only (AZ_TOWER_DEBUG): bit 0 = do not refill weight stages after the first ring pass,
                                // bit 1 = epilogue skips its shared-memory stores, bit 2 = every tap reads the unshifted centre buffer
 };
@@ -246,6 +250,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
     __shared__ __align__(8) uint64_t s_full[2 * kStages], s_empty[2 * kStages], s_pfull[2 * kStages], s_acc, s_act[2];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (P.timeline && tid == 0) {
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        atomicMin(P.timeline, t_);
+    }
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     // work units: a tile per CTA, or a pair of tiles per CTA pair (rank r takes the r-th tile of the unit)
     const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -491,8 +500,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                 }
                 const uint32_t off = (uint32_t)lsub * kLboA + (uint32_t)lr * 16u;
                 *reinterpret_cast<uint4*>(smem + buf_row0(0) + off) = v4;
-                *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = lx == P.W - 1 ? zero4 : v4;
-                *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = lx == 0 ? zero4 : v4;
+                if (lx != P.W - 1) *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = v4;
+                if (lx != 0) *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = v4;
             }
             publish(bar_act0);
             publish(bar_act1);
@@ -548,8 +557,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                     } else if (row_live && !(P.debug & 2)) {
                         const uint32_t off = (uint32_t)kc * kLboA + (uint32_t)r * 16u;
                         *reinterpret_cast<uint4*>(smem + buf_row0(centre) + off) = o;
-                        *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = zero_l ? zero4 : o;
-                        *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = zero_r ? zero4 : o;
+                        if (!zero_l) *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = o;
+                        if (!zero_r) *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = o;
                     }
                 }
                 if (!last) publish(ch == 0 ? bar_act0 : bar_act1);
@@ -645,8 +654,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
                         for (int c = 0; c < 4; ++c) {
                             const uint32_t off = (uint32_t)(ch * 8 + lsub * 4 + c) * kLboA + (uint32_t)lr * 16u;
                             *reinterpret_cast<uint4*>(smem + buf_row0(0) + off) = v[ch * 4 + c];
-                            *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = zl ? zero4 : v[ch * 4 + c];
-                            *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = zr ? zero4 : v[ch * 4 + c];
+                            if (!zl) *reinterpret_cast<uint4*>(smem + buf_row0(1) + off) = v[ch * 4 + c];
+                            if (!zr) *reinterpret_cast<uint4*>(smem + buf_row0(2) + off) = v[ch * 4 + c];
                         }
                     }
                     publish(ch == 0 ? bar_act0 : bar_act1);
@@ -665,6 +674,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (PAIR) cluster_sync();  // nobody frees TMEM or exits while the pair's MMAs / remote arrivals may still be in flight
+    if (P.timeline && tid == 0) {
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        atomicMax(P.timeline + 1, t_);
+    }
     if (warp == 0) {
         if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kTmemCols) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(kTmemCols) : "memory");
@@ -705,6 +719,14 @@ static int launch_tower(const TowerParams& P, int sms, cudaStream_t stream) {
 }
 
 static long long* g_timing = nullptr;  // az_net_tower_timing: device buffer [grid][8] for the next launches, or null
+static unsigned long long* g_timeline = nullptr;  // az_net_debug_timeline: slots {start, end}, one per launch, round robin
+static int g_timeline_slots = 0, g_timeline_next = 0;
+static unsigned long long* next_timeline_slot() {
+    if (!g_timeline || g_timeline_slots <= 0) return nullptr;
+    unsigned long long* tl = g_timeline + 2 * (g_timeline_next % g_timeline_slots);
+    g_timeline_next += 1;
+    return tl;
+}
 
 static int tower_launch_checks(const char* who, int n, int H, int W, int channels, int depth, int* ppt_out) {
     if (n < 0 || H < 1 || W < 1) return az::fail_net(AZ_ERR_ARG, who);
@@ -723,6 +745,14 @@ static int tower_launch_checks(const char* who, int n, int H, int W, int channel
 
 extern "C" __attribute__((visibility("default"))) int az_net_tower_timing(void* dev_buffer) {
     az::tower::g_timing = static_cast<long long*>(dev_buffer);
+    return AZ_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int az_net_debug_timeline(void* dev_slots, int32_t n_slots) {
+    if (n_slots < 0) return az::fail_net(AZ_ERR_ARG, "az_net_debug_timeline: bad argument");
+    az::tower::g_timeline = static_cast<unsigned long long*>(dev_slots);
+    az::tower::g_timeline_slots = dev_slots ? n_slots : 0;
+    az::tower::g_timeline_next = 0;
     return AZ_OK;
 }
 
@@ -747,6 +777,7 @@ extern "C" __attribute__((visibility("default"))) int az_net_tower(const void* x
     P.n = n, P.W = W, P.cells = H * W, P.ppt = ppt, P.depth = depth, P.n_tiles = (n + ppt - 1) / ppt;
     if (const char* dbg = getenv("AZ_TOWER_DEBUG")) P.debug = atoi(dbg);
     P.timing = g_timing;
+    P.timeline = next_timeline_slot();
     return layout ? launch_tower<false, true>(P, sms, static_cast<cudaStream_t>(stream))
                   : launch_tower<false, false>(P, sms, static_cast<cudaStream_t>(stream));
 }
@@ -785,6 +816,7 @@ static int net_forward_impl(const void* states, const void* w_img, const float* 
     P.n = n, P.W = W, P.cells = cells, P.ppt = ppt, P.depth = depth, P.n_tiles = (n + ppt - 1) / ppt;
     if (const char* dbg = getenv("AZ_TOWER_DEBUG")) P.debug = atoi(dbg);
     P.timing = g_timing;
+    P.timeline = next_timeline_slot();
     return layout ? launch_tower<true, true>(P, sms, static_cast<cudaStream_t>(stream))
                   : launch_tower<true, false>(P, sms, static_cast<cudaStream_t>(stream));
 }

@@ -325,6 +325,12 @@ int az_net_tower(const void *dev_x, const void *dev_w_img, const float *dev_bias
  * cycles epilogue warp 2 waited for an accumulator, cycles of its epilogue bodies} (tools/time_tower.py). */
 int az_net_tower_timing(void *dev_buffer);
 
+/* Measurement aid, the net-side twin of az_debug_timeline: successive az_net_tower / az_net_forward[_gathered] launches
+ * record {first CTA start, last CTA end} (globaltimer, ns) into dev_slots[2 * (launch % n_slots)], initialised by the
+ * caller to {UINT64_MAX, 0}; NULL switches it off.  The slot is chosen at launch (or graph-capture) time
+ * (tools/explore_timeline2.py: where the time of one advance goes inside graph replays). */
+int az_net_debug_timeline(void *dev_slots, int32_t n_slots);
+
 /* Head weights of az_net_forward: plain row-major float32, BN folded (no padding or transposition). */
 typedef struct az_net_head_params {
     const float *conv_w;   /* dev [3][128]: rows 0-1 policy 1x1 conv (model.py:68-85), row 2 value 1x1 conv (:106-123) */
@@ -396,7 +402,7 @@ int az_advance_fused(az_engine *e, const void *dev_tower_out, const az_head_weig
  * (out: dev double [n][k]); sample i uses the Philox counter (game = i, ply = 0, simulation = 0). */
 int az_debug_dirichlet(uint64_t seed, double alpha, int32_t k, int32_t n, double *dev_out, void *stream);
 
-/* Measurement aid: successive az_advance_fused launches record {first block start, last warp end} (globaltimer,
+/* Measurement aid: successive az_advance_fused / az_step / az_step_gather launches record {first block start, last warp end} (globaltimer,
  * ns) into dev_slots[2 * (launch % n_slots)], which the caller initialises to {UINT64_MAX, 0}.  NULL switches it
  * off.  The slot is chosen at launch (or graph-capture) time. */
 int az_debug_timeline(az_engine *e, void *dev_slots, int32_t n_slots);

@@ -60,6 +60,64 @@ class UCTEdge:
         return self.exploitation_term() + self.exploration_term(override_prior)
 
 
+class _TreeSnapshot:
+    """Read access to the device tree of one search object, fetched on demand: the root's child block alone (what
+    play_game, the arena and the tests read after a search: k records) costs four small copies; anything deeper pulls
+    the live part of the pool once.  Nothing is copied for a tree nobody looks at (the reference's callers usually read
+    only `current_root.edges`).  A snapshot that was read is frozen in full before the tree changes; one that was never
+    read dies with the tree state it described."""
+
+    def __init__(self, engine):
+        self.e = engine
+        self.half = int(engine.view("half")[0])
+        self.root = int(engine.view("root_node")[0])
+        self.full = None       # {"W", "N", "link", "P"} numpy arrays of the used part of the live half
+        self.root_block = None
+        self.stale = False
+        self.touched = False
+
+    def _check(self):
+        if self.stale:
+            raise RuntimeError("this UCTNode describes a tree state that was searched or played past before anybody read it; "
+                               "read mcts.current_root after the search / play you are interested in")
+
+    def freeze(self):
+        """Called by the search object right before it changes the tree."""
+        if self.touched and self.full is None:
+            self._pull()
+        elif not self.touched:
+            self.stale = True
+
+    def _pull(self):
+        self._check()
+        e = self.e
+        w, n, link = e.node_view()
+        used = int(e.view("n_nodes")[0])
+        h = self.half
+        self.full = {"W": w[0, h, :used].cpu().numpy(), "N": n[0, h, :used].cpu().numpy(),
+                     "link": link[0, h, :used].cpu().numpy(), "P": e.view("node_p")[0, h, :used].cpu().numpy()}
+
+    def block(self, index):
+        """Child block of node `index`: (k, N[k], W[k], P[k], first child index)."""
+        self.touched = True
+        if self.full is None and index == self.root:
+            if self.root_block is None:
+                self._check()
+                w, n, link = self.e.node_view()
+                lk = int(link[0, self.half, index]) & 0xFFFFFFFF
+                base, k = lk & 0xFFFFFF, lk >> 24
+                sl = slice(base, base + k)
+                self.root_block = (k, n[0, self.half, sl].cpu().numpy(), w[0, self.half, sl].cpu().numpy(),
+                                   self.e.view("node_p")[0, self.half, sl].cpu().numpy(), base)
+            return self.root_block
+        if self.full is None:
+            self._pull()
+        lk = int(self.full["link"][index]) & 0xFFFFFFFF
+        base, k = lk & 0xFFFFFF, lk >> 24
+        sl = slice(base, base + k)
+        return k, self.full["N"][sl], self.full["W"][sl], self.full["P"][sl], base
+
+
 class UCTNode:
     """Snapshot of one device node.  `edges` are materialised on first access from the tree export;
     `board` by replaying the path's moves on a copy of the root board (K2 kernel)."""
@@ -84,14 +142,12 @@ class UCTNode:
             self._edges = []
             ex = self._export
             if ex is not None:
-                link = int(ex["link"][self._index]) & 0xFFFFFFFF
-                base, k = link & 0xFFFFFF, link >> 24
+                k, n, w, p, base = ex.block(self._index)
                 if k:
                     moves = self.board.moves
                     for j in range(k):
-                        c = base + j
-                        child = UCTNode(None, None, ex, c, _parent_board=lambda s=self: s.board, _move=moves[j])
-                        self._edges.append(UCTEdge(self, child, moves[j], float(ex["P"][c]), int(ex["N"][c]), float(ex["W"][c])))
+                        child = UCTNode(None, None, ex, base + j, _parent_board=lambda s=self: s.board, _move=moves[j])
+                        self._edges.append(UCTEdge(self, child, moves[j], float(p[j]), int(n[j]), float(w[j])))
         return self._edges
 
     def get_best_edge(self) -> UCTEdge:
@@ -129,25 +185,25 @@ class MCTS:
         self._states = torch.zeros((1, H, W, 4), dtype=torch.float32, device=dev)
         self._valid = torch.zeros(1, dtype=torch.int32, device=dev)
         self._staged = None  # (priors tensor [1, A], values tensor [1]) waiting for the next az_step
+        self._snapshots = []
         self.root = self.initialize_root()
         self.current_root = self.root
 
     # ------------------------------------------------------------------ tree views
-    def _export(self):
-        e = self._engine
-        w, n, link = e.node_view()
-        half = int(e.view("half")[0])
-        used = int(e.view("n_nodes")[0])
-        return {"W": w[0, half, :used].cpu().numpy(), "N": n[0, half, :used].cpu().numpy(),
-                "link": link[0, half, :used].cpu().numpy(), "P": e.view("node_p")[0, half, :used].cpu().numpy(),
-                "root": int(e.view("root_node")[0])}
-
     def _root_view(self) -> UCTNode:
-        ex = self._export()
-        return UCTNode(deepcopy(self.board), None, ex, ex["root"])
+        snap = _TreeSnapshot(self._engine)
+        self._snapshots.append(snap)
+        return UCTNode(deepcopy(self.board), None, snap, snap.root)
+
+    def _tree_changes(self):
+        """Before the device tree is modified: snapshots somebody has read are completed, the others are dropped."""
+        for snap in self._snapshots:
+            snap.freeze()
+        self._snapshots = []
 
     def initialize_root(self) -> UCTNode:
         """mcts.py:108-109: an edgeless root at the caller's position (az_set_roots)."""
+        self._tree_changes()
         cells = (self.board.array * np.int8(self.board.turn)).astype(np.int8)[None]
         self._engine.set_roots([0], cells, [self.board.fullmove_number])
         self._staged = None
@@ -177,6 +233,8 @@ class MCTS:
     def select(self) -> Optional[np.ndarray]:
         """Runs az_step: applies the staged evaluation (expand + backup of the previous leaf), selects
         the next leaf and returns its NN input, or None when no evaluation is needed right now."""
+        if self._snapshots:
+            self._tree_changes()
         pr, va = self._staged if self._staged is not None else (None, None)
         self._engine.step(pr, va, self._states, self._valid)
         self._staged = None
@@ -196,6 +254,7 @@ class MCTS:
         self.path_cache = []
 
     def search(self, iterations_number: int):
+        self._tree_changes()
         self._engine.begin_search(int(iterations_number))
         while True:
             state = self.select()
@@ -211,6 +270,7 @@ class MCTS:
     def play(self, greedy: bool = False, return_details: bool = False, deterministic: bool = False
              ) -> Union[Tuple[np.ndarray, np.ndarray, np.ndarray, Move], Board]:
         e = self._engine
+        self._tree_changes()
         rec = int(e.view("rec_len")[0])
         if not deterministic:
             # np.random.choice(edges, 1, p=pi) consumes exactly one random_sample() of the global stream

@@ -143,6 +143,39 @@ def test_compat_mcts_model_hook_and_cache(c4):
     assert all(set(k) <= set("XO.\n") for k in cache)
 
 
+def test_tree_views_are_fetched_on_demand(c4):
+    """UCTNode / UCTEdge views (mcts.py:22-105 of the reference are live Python objects): reading the root's edges copies
+    the root's child block only, deeper nodes pull the live pool once, a view that was read keeps its values when the
+    tree moves on, and a view nobody read refuses to describe a tree that no longer exists."""
+    import custom_alphazero.mcts.mcts as m
+    from custom_alphazero.connect_n.board import Board
+    from oracle import evaluators
+
+    f = evaluators.hash_evaluator(7)
+    saved = m.infer_sample
+    m.infer_sample = lambda state, concurrency=False: f(state)
+    try:
+        t = m.MCTS(Board(), Board.get_all_possible_moves(), False, {})
+        unread = t.current_root
+        t.search(60)
+        with pytest.raises(RuntimeError):
+            unread.edges
+        root = t.current_root
+        snap = root._export
+        n60 = [e.visit_count for e in root.edges]
+        assert sum(n60) == 59 and snap.full is None and snap.root_block is not None  # four small copies, no pool copy
+        t.search(60)  # the view that was read is completed before the tree changes ...
+        assert snap.full is not None and [e.visit_count for e in root.edges] == n60
+        deep = root.edges[int(np.argmax(n60))].child
+        assert sum(e.visit_count for e in deep.edges) == max(n60) - 1  # ... and still describes the 60-simulation tree
+        n120 = [e.visit_count for e in t.current_root.edges]
+        assert sum(n120) == 119 and all(b >= a for a, b in zip(n60, n120))
+        grand = t.current_root.edges[int(np.argmax(n120))].child
+        assert sum(e.visit_count for e in grand.edges) == max(n120) - 1 and t.current_root._export.full is not None
+    finally:
+        m.infer_sample = saved
+
+
 def test_self_play_play_returns_reference_shaped_arrays(c4):
     from custom_alphazero import self_play
     from custom_alphazero.config import ConfigB200, ConfigSelfPlay

@@ -193,9 +193,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bounded CPU baseline sample (0 = skip)")
     ap.add_argument("--unroll", type=int, default=8)
     ap.add_argument("--groups", type=int, default=1, help="tree slices advanced on parallel graph branches")
-    ap.add_argument("--max-free", type=int, default=8)
+    ap.add_argument("--max-free", type=int, default=None, help="evaluator-free simulations per tree inside one az_step (default: the runner's choice)")
     ap.add_argument("--extra-sims", type=int, default=0,
                     help="evaluator-free simulations continued beside the net (az_extra_sims on a side stream) for trees without a pending leaf")
+    ap.add_argument("--net-tree-sims", type=int, default=None,
+                    help="evaluator-free simulations continued INSIDE the net kernel (az_net_forward_trees) for trees without a pending leaf")
     ap.add_argument("--node-capacity", type=int, default=0, help="nodes per tree per pool half (0 = the engine's default sizing)")
     ap.add_argument("--no-fused", action="store_true", help="three-kernel route instead of az_advance_fused")
     ap.add_argument("--no-whole-net", action="store_true",
@@ -273,7 +275,7 @@ def main():
 
     runner = selfplay.SelfPlayRunner(rules, n_trees=T, sims_per_move=S, net=fp32, games_target=1 << 40,
                                      game_id_base=rank << 40, seed=1234, move_mode="philox", auto_restart=True,
-                                     unroll=args.unroll, fin_capacity=4 * T, groups=args.groups, max_free_sims=args.max_free, fused=not args.no_fused, extra_sims=args.extra_sims,
+                                     unroll=args.unroll, fin_capacity=4 * T, groups=args.groups, max_free_sims=args.max_free, fused=not args.no_fused, extra_sims=args.extra_sims, net_tree_sims=args.net_tree_sims,
                                      node_capacity=args.node_capacity or None,
                                      eval_cache_log2=args.memo_log2, whole_net=False if args.no_whole_net else None)
     params = list(runner.net.parameters())
@@ -488,7 +490,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{cfg_name}: {games_job} concurrent {rules.height}x{rules.width} Connect-{rules.n} self-play games ({T} per GPU) x {S} simulations/move, bf16 net leaf evaluation",
-                       "games_per_gpu": T, "games_total": games_job, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": args.max_free, "extra_sims_beside_net": args.extra_sims, "node_capacity": int(runner.engine.cfg.node_capacity), "fused_advance": bool(runner.fused), "whole_net_kernel": bool(runner.whole_net),
+                       "games_per_gpu": T, "games_total": games_job, "sims_per_move": S, "advances_per_step": ADV, "groups": args.groups, "max_free_sims": int(runner.max_free_sims), "extra_sims_beside_net": args.extra_sims, "tree_sims_inside_net": int(runner.net_tree_sims), "node_capacity": int(runner.engine.cfg.node_capacity), "fused_advance": bool(runner.fused), "whole_net_kernel": bool(runner.whole_net),
                        "fused_tower": bool(getattr(runner.net, "fused_tower", False)), "evaluation_memo_log2": args.memo_log2, "board": f"{rules.height}x{rules.width}", "n_connect": rules.n, "gravity": rules.gravity,
                        "net": f"4-block 128-filter projection-residual tower, {fp32.n_parameters()} params, random init",
                        "preroll_steps": args.preroll,

@@ -136,6 +136,8 @@ SYMBOLS = {
     "az_net_forward": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(AzNetHeadParams), _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "az_net_forward_gathered": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(AzNetHeadParams), _P, _P, _I, _I, _I, _I, _I,
                                                _I, _I, _P, _P, _P]),
+    "az_net_forward_trees": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(AzNetHeadParams), _P, _P, _I, _I, _I, _I, _I,
+                                            _I, _I, _P, _P, _P, _I, _P]),
     "az_net_dense_heads": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "az_net_head_convs": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "az_advance_fused": (ctypes.c_int, [_P, _P, ctypes.POINTER(AzHeadWeights), _P, _P, _P, _P, _P]),

@@ -352,14 +352,16 @@ class InferenceNet(nn.Module):
         return self._head_struct
 
     @torch.no_grad()
-    def forward(self, x_nhwc, priors_out=None, values_out=None, index=None, count=None):
+    def forward(self, x_nhwc, priors_out=None, values_out=None, index=None, count=None, trees=None):
         """x [B, H, W, 4] -> (policy [B, A] float32 softmax, value [B] float32 tanh).  On the GPU fast path
         the results are written into priors_out / values_out when given (no extra copy kernels).
         index (int32 [B]) / count (int32 [1]), whole-net kernel only: evaluate just the rows index[:count] (the leaf list
-        of az_step_gather); the other rows of priors_out / values_out keep their contents."""
+        of az_step_gather); the other rows of priors_out / values_out keep their contents.
+        trees = (engine handle, max_sims), gathered batch only: az_net_forward_trees - the engine's trees without a leaf in
+        flight go on with evaluator-free simulations inside the net kernel."""
         if index is not None:
             assert self.fused_net and x_nhwc.is_cuda and priors_out is not None, "a gathered batch needs az_net_forward"
-            return self._forward_fast(x_nhwc, priors_out, values_out, index, count)
+            return self._forward_fast(x_nhwc, priors_out, values_out, index, count, trees)
         if self.fast and x_nhwc.is_cuda:
             return self._forward_fast(x_nhwc, priors_out, values_out)
         B = x_nhwc.shape[0]
@@ -443,7 +445,7 @@ class InferenceNet(nn.Module):
                 value2_w=self.v2_w.data_ptr(), value2_b=self.v2_b.data_ptr())
         return self._net_heads
 
-    def _forward_fast(self, x_nhwc, priors_out, values_out, index=None, count=None):
+    def _forward_fast(self, x_nhwc, priors_out, values_out, index=None, count=None, trees=None):
         import ctypes
 
         from .engine import _ptr, _stream
@@ -456,6 +458,12 @@ class InferenceNet(nn.Module):
             if priors_out is None:
                 priors_out = torch.empty((B, self.n_actions), dtype=torch.float32, device=x_nhwc.device)
                 values_out = torch.empty(B, dtype=torch.float32, device=x_nhwc.device)
+            if index is not None and trees is not None:
+                check(lib().az_net_forward_trees(_ptr(x_nhwc), _ptr(self.net_img), _ptr(self.stem_b32), _ptr(self.tower_bias),
+                                                 ctypes.byref(self._net_heads_arg()), _ptr(index), _ptr(count), B, H, W,
+                                                 self.filters, self.depth, self.n_actions, self.tower_layout,
+                                                 _ptr(priors_out), _ptr(values_out), trees[0], int(trees[1]), _stream()))
+                return priors_out, values_out
             if index is not None:
                 check(lib().az_net_forward_gathered(_ptr(x_nhwc), _ptr(self.net_img), _ptr(self.stem_b32), _ptr(self.tower_bias),
                                                     ctypes.byref(self._net_heads_arg()), _ptr(index), _ptr(count), B, H, W,

@@ -83,9 +83,9 @@ class SelfPlayRunner:
 
     def __init__(self, rules=Rules(), n_trees=4096, sims_per_move=800, net=None, *, games_target=None,
                  game_id_base=0, seed=0, move_mode="philox", auto_restart=True, dtype=torch.bfloat16, unroll=8,
-                 use_graph=True, max_free_sims=8, node_capacity=None, fin_capacity=None, device=None,
+                 use_graph=True, max_free_sims=None, node_capacity=None, fin_capacity=None, device=None,
                  index_move_greedy=8, groups=1, fused=True, extra_sims=0, dirichlet_noise=False, dirichlet_alpha=0.03,
-                 dirichlet_ratio=0.25, eval_cache_log2=0, whole_net=None):
+                 dirichlet_ratio=0.25, eval_cache_log2=0, whole_net=None, net_tree_sims=None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.rules = rules
         T, A = int(n_trees), rules.n_actions
@@ -96,6 +96,17 @@ class SelfPlayRunner:
         groups = max(1, min(int(groups), T))
         if games_target is None:
             games_target = T
+        # whole-net route on the 6x7 fast path: trees without a pending leaf go on with up to net_tree_sims evaluator-free
+        # simulations INSIDE the net kernel (az_net_forward_trees), so az_step only needs a short max_free_sims: the serial
+        # tail of the tree step (a few trees running up to 8 terminal-leaf simulations one after the other while 4 000
+        # others wait) moves under the net.  Measured (bench.py, profiles/experiments_r2_session2.json): 2 + 16 gives
+        # 14.6 M simulations/s against 12.7 M for 8 + 0.
+        can_inside = (self.whole_net and not dirichlet_noise
+                      and (rules.width, rules.height, rules.n, bool(rules.gravity)) == (7, 6, 4, True))
+        self.net_tree_sims = (16 if net_tree_sims is None else int(net_tree_sims)) if can_inside else 0
+        if max_free_sims is None:
+            max_free_sims = 2 if self.net_tree_sims else 8
+        self.max_free_sims = int(max_free_sims)
         self.groups = []
         t0 = g0 = 0
         for i in range(groups):
@@ -112,12 +123,6 @@ class SelfPlayRunner:
             t0 += ti
             g0 += gi
         self.n_trees = T
-        # Routes of one advance.  whole_net (default where the net has it): az_step (the tree step alone) + az_net_forward
-        # (stem, tower and heads in ONE tcgen05 kernel: planes in, priors / values out, no activation in HBM).  Else
-        # fused: heads + tree step + stem in one per-tree launch (az_advance_fused) around the tower kernel; else the
-        # three-kernel route az_step + stem + tower + heads.
-        has_net = bool(getattr(self.net, "fused_net", False))
-        self.whole_net = has_net if whole_net is None else (bool(whole_net) and has_net)
         self.fused = bool(fused) and getattr(self.net, "fast", False) and not self.whole_net
         if self.fused:
             for g in self.groups:
@@ -187,7 +192,9 @@ class SelfPlayRunner:
         elif self.whole_net:
             # the tree step alone, then the whole net in one kernel on exactly the trees that have a leaf pending
             g.engine.step(g.priors, g.values, g.states, g.valid, g.leaf_list, g.leaf_count)
-            if self.extra_sims:
+            if self.net_tree_sims:
+                self.net(g.states, g.priors, g.values, index=g.leaf_list, count=g.leaf_count, trees=(g.engine._h, self.net_tree_sims))
+            elif self.extra_sims:
                 # trees that spent their max_free_sims evaluator-free simulations without meeting a leaf that needs the net
                 # have nothing to wait for: they go on simulating on a low-priority side stream, whose blocks the scheduler
                 # places on the SMs the net kernel's last, partial round of tiles leaves idle

@@ -131,16 +131,7 @@ __device__ __forceinline__ void bump(long long* p, long long v) {
     if (v) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
 }
 
-// Rules as seen by a kernel instance: the runtime struct, or the compile-time headline configuration.
-using C4Rules = FixedRules<7, 6, 4, 1>;
-template <class R>
-struct RulesView {
-    __device__ static __forceinline__ const Rules& get(const Eng& e) { return e.r; }
-};
-template <int W_, int H_, int N_, int G_>
-struct RulesView<FixedRules<W_, H_, N_, G_>> {
-    __device__ static __forceinline__ FixedRules<W_, H_, N_, G_> get(const Eng&) { return {}; }
-};
+// (RulesView / C4Rules: az_tree.cuh)
 
 // ------------------------------------------------------------------------------------------ k_play
 // rank (edge index) of a legal action among the moves in board order
@@ -1017,6 +1008,13 @@ struct az_engine {
     unsigned long long* timeline = nullptr;  // az_debug_timeline
     int timeline_slots = 0, timeline_next = 0;
 };
+
+// the engine's device view for az_net_forward_trees (az_tower.cu); 1 = plain 6x7 connect-4 fast path (compile-time rules,
+// one child chunk, no root noise), 0 = anything else
+int az::engine_view(const az_engine* e, az::Eng* out) {
+    *out = e->eng;
+    return (e->c4 && e->eng.dirichlet == 0) ? 1 : 0;
+}
 
 static int check_cfg(const az_config* c) {
     if (!c) return fail(AZ_ERR_ARG, "null config%s");

@@ -38,6 +38,7 @@
 #include <cstdlib>
 
 #include "../../include/az_b200.h"
+#include "az_tree.cuh"
 
 namespace az {
 int fail_net(int code, const char* msg);
@@ -63,6 +64,7 @@ constexpr int kBiasBytes = ((1 + 2 * kMaxDepth) * kC + 3 * kC) * 4;  // stem + t
 constexpr int kSmemBytes = kActBytes + kStages * kStageBytes + kBiasBytes;
 constexpr int kStagesPerBlock = 38;               // conv1: 9 taps x 2, shortcut: 2, conv2: 9 taps x 2
 constexpr int kThreads = 320;
+constexpr int kTreeWarps = 2;                     // az_net_forward_trees: warps 10-13 run evaluator-free simulations beside the net
 constexpr uint32_t kTmemCols = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -218,6 +220,8 @@ struct TowerParams {
     int n, W, cells, ppt, depth, n_tiles;
     long long* timing;         // AZ_TOWER_DEBUG bit 3: per CTA {cycles total, MMA warp waiting for activations, for weights, epilogue warp 2
                                // waiting for the accumulator, its body} (az_net_tower_timing)
+    Eng eng;                   // TREES: the engine whose trees without a pending leaf go on simulating beside the net ...
+    int tree_cap;              // ... up to this many evaluator-free simulations per tree and launch
     unsigned long long* timeline;  // az_net_debug_timeline: {first CTA start, last CTA end} of this launch, globaltimer ns
     int debug;                 // timing experiments only (AZ_TOWER_DEBUG): bit 0 = do not refill weight stages after the first ring pass,
                                // bit 1 = epilogue skips its shared-memory stores, bit 2 = every tap reads the unshifted centre buffer
@@ -241,8 +245,16 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;\n
 // PAIR = true : two CTAs of a cluster (one SM pair) run as one: cta_group::2 MMAs issued by rank 0 over both CTAs' tiles,
 //              each CTA streams half of every weight stage (8 KB, 8-deep ring), the peer's warp 1 forwards "my half has
 //              landed" to rank 0, epilogue warps of both CTAs arrive on rank 0's barriers, commits are multicast.
-template <bool NET, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
+// TREES = true (net mode, 6x7 engines): kTreeWarps more warps per CTA (az_net_forward_trees).  The net kernel leaves 85 % of its
+//              issue slots idle and owns its SM (227 KB of shared memory), so nothing can run BESIDE it; these warps run
+//              INSIDE it: every tree of P.eng that has no leaf in flight - its last simulations ended in terminal leaves
+//              and used up az_step's max_free_sims - goes on simulating (free_sims_tree, az_tree.cuh) instead of waiting
+//              for the next az_step.  The serial tail of the tree step moves under the net.
+template <bool NET, bool PAIR, bool TREES = false>
+__global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k_tower(TowerParams P) {
+    constexpr int kBlockThreads = kThreads + (TREES ? kTreeWarps * 32 : 0);
+    __shared__ PathScratch s_path[TREES ? kTreeWarps : 1];
+    __shared__ int s_stop;  // TREES: raised by warp 1 when this CTA starts its last tile - the tree warps start nothing new
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int kRing = PAIR ? 2 * kStages : kStages;             // ring slots
     constexpr uint32_t kSlotBytes = PAIR ? kStageBytes / 2 : kStageBytes;  // bytes of a weight stage this CTA holds
@@ -272,14 +284,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
     }
 
     // one-time: zero the activation area (pads and dead rows stay zero for ever), biases, barriers, TMEM
-    for (int i = tid; i < kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < P.depth * 2 * kC; i += kThreads) s_bias[kC + i] = P.bias[i];
+    for (int i = tid; i < kActBytes / 16; i += kBlockThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < P.depth * 2 * kC; i += kBlockThreads) s_bias[kC + i] = P.bias[i];
     if (NET) {
-        for (int i = tid; i < kC; i += kThreads) s_bias[i] = P.stem_bias[i];
+        for (int i = tid; i < kC; i += kBlockThreads) s_bias[i] = P.stem_bias[i];
         // the existing heads kernel feeds the 1x1 convolutions to the tensor cores as bf16: same rounding here
-        for (int i = tid; i < 3 * kC; i += kThreads) s_headw[i] = __bfloat162float(__float2bfloat16(P.heads.conv_w[i]));
+        for (int i = tid; i < 3 * kC; i += kBlockThreads) s_headw[i] = __bfloat162float(__float2bfloat16(P.heads.conv_w[i]));
     }
     if (tid == 0) {
+        s_stop = 0;
         for (int s = 0; s < kRing; ++s) {
             mbar_init(smem_u32(&s_full[s]), 1);
             mbar_init(smem_u32(&s_empty[s]), 1);
@@ -330,13 +343,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
     } else if (warp == 1 && PAIR && rank != 0) {
         // ---------------------------------------------------------------- peer CTA: tell rank 0 that my half of a stage is here
         uint32_t cnt = 0;
-        for (int unit = unit0; unit * kTpu < P.n_tiles; unit += n_units)
+        for (int unit = unit0; unit * kTpu < P.n_tiles; unit += n_units) {
+            if (TREES && lane == 0 && (unit + n_units) * kTpu >= P.n_tiles) *(volatile int*)&s_stop = 1;
             for (int s = 0; s < stages_per_tile; ++s, ++cnt) {
                 const uint32_t slot = cnt % kRing, k = cnt / kRing;
                 mbar_wait(smem_u32(&s_full[slot]), k & 1);
                 if (lane == 0) mbar_arrive_remote(smem_u32(&s_pfull[slot]), 0u);
                 __syncwarp();
             }
+        }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
         // The whole warp runs the control flow (waits included) so that everything stays warp-uniform; one elected
@@ -391,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
             ++cnt;
         };
         for (int unit = unit0; unit * kTpu < P.n_tiles; unit += n_units) {
+            if (TREES && lane == 0 && (unit + n_units) * kTpu >= P.n_tiles) *(volatile int*)&s_stop = 1;
             if (NET) {
                 // stem: the four planes of a cell sit in chunk column 0 (column 1 is zero), one K = 16 MMA per tap; a
                 // stage carries the [128][16] weights of four taps
@@ -446,6 +462,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
             P.timing[blockIdx.x * 8 + 1] = t_act;
             P.timing[blockIdx.x * 8 + 2] = t_full;
         }
+    } else if (TREES && warp >= kThreads / 32) {
+        // ---------------------------------------------------------------- tree warps: evaluator-free simulations beside the net
+        const int tw = warp - kThreads / 32;
+        const auto rules = RulesView<C4Rules>::get(P.eng);
+        for (int t = (int)blockIdx.x * kTreeWarps + tw; t < P.eng.T && !*(volatile int*)&s_stop; t += (int)gridDim.x * kTreeWarps)
+            free_sims_tree<1, 1>(P.eng, rules, t, s_path[tw], lane, P.tree_cap, &s_stop);
     } else {
         // ---------------------------------------------------------------- epilogue / tile load / tile store / heads
         const int e = tid - 64;                       // 0..255
@@ -685,12 +707,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tower(TowerParams P) {
     }
 }
 
-// launches k_tower<NET, PAIR>: a plain grid of one CTA per SM, or clusters of two CTAs
-template <bool NET, bool PAIR>
+// launches k_tower<NET, PAIR, TREES>: a plain grid of one CTA per SM, or clusters of two CTAs
+template <bool NET, bool PAIR, bool TREES = false>
 static int launch_tower(const TowerParams& P, int sms, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_tower<NET, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_tower<NET, PAIR, TREES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
             return az::fail_net(AZ_ERR_CUDA, "az_net_tower / az_net_forward: shared memory request refused");
         configured = true;
     }
@@ -698,7 +720,7 @@ static int launch_tower(const TowerParams& P, int sms, cudaStream_t stream) {
     cudaLaunchAttribute attr[1];
     if (PAIR) {
         const int units = (P.n_tiles + 1) / 2, max_units = sms / 2;
-        cfg.gridDim = dim3(2u * (unsigned)(units < max_units ? units : max_units));
+        cfg.gridDim = dim3(2u * (unsigned)((units < max_units && !TREES) ? units : max_units));
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
         attr[0].val.clusterDim.y = 1;
@@ -706,12 +728,12 @@ static int launch_tower(const TowerParams& P, int sms, cudaStream_t stream) {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     } else {
-        cfg.gridDim = dim3((unsigned)(P.n_tiles < sms ? P.n_tiles : sms));
+        cfg.gridDim = dim3((unsigned)((P.n_tiles < sms && !TREES) ? P.n_tiles : sms));
     }
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kThreads + (TREES ? kTreeWarps * 32 : 0));
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = stream;
-    if (cudaLaunchKernelEx(&cfg, k_tower<NET, PAIR>, P) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, k_tower<NET, PAIR, TREES>, P) != cudaSuccess) {
         cudaGetLastError();
         return az::fail_net(AZ_ERR_CUDA, "az_net_tower / az_net_forward: launch failed");
     }
@@ -785,7 +807,7 @@ extern "C" __attribute__((visibility("default"))) int az_net_tower(const void* x
 static int net_forward_impl(const void* states, const void* w_img, const float* stem_bias, const float* tower_bias,
                             const az_net_head_params* heads, const int32_t* index, const int32_t* count, int32_t n, int32_t H,
                             int32_t W, int32_t channels, int32_t depth, int32_t n_actions, int32_t layout, float* priors,
-                            float* values, void* stream) {
+                            float* values, void* stream, const az_engine* trees = nullptr, int32_t tree_sims = 0) {
     using namespace az::tower;
     if (n == 0) return AZ_OK;
     if (!states || !w_img || !stem_bias || !tower_bias || !heads || !priors || !values || (layout != 0 && layout != 1))
@@ -817,6 +839,13 @@ static int net_forward_impl(const void* states, const void* w_img, const float* 
     if (const char* dbg = getenv("AZ_TOWER_DEBUG")) P.debug = atoi(dbg);
     P.timing = g_timing;
     P.timeline = next_timeline_slot();
+    if (trees && tree_sims > 0) {
+        if (az::engine_view(trees, &P.eng) != 1 || H != 6 || W != 7)
+            return az::fail_net(AZ_ERR_ARG, "az_net_forward_trees: the engine must be the plain 6x7 connect-4 configuration (no root noise)");
+        P.tree_cap = tree_sims;
+        return layout ? launch_tower<true, true, true>(P, sms, static_cast<cudaStream_t>(stream))
+                      : launch_tower<true, false, true>(P, sms, static_cast<cudaStream_t>(stream));
+    }
     return layout ? launch_tower<true, true>(P, sms, static_cast<cudaStream_t>(stream))
                   : launch_tower<true, false>(P, sms, static_cast<cudaStream_t>(stream));
 }
@@ -837,4 +866,13 @@ extern "C" __attribute__((visibility("default"))) int az_net_forward_gathered(
     if (!index || !count) return az::fail_net(AZ_ERR_ARG, "az_net_forward_gathered: null index / count");
     return net_forward_impl(states, w_img, stem_bias, tower_bias, heads, index, count, n_max, H, W, channels, depth, n_actions,
                             layout, priors, values, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int az_net_forward_trees(
+    const void* states, const void* w_img, const float* stem_bias, const float* tower_bias, const az_net_head_params* heads,
+    const int32_t* index, const int32_t* count, int32_t n_max, int32_t H, int32_t W, int32_t channels, int32_t depth,
+    int32_t n_actions, int32_t layout, float* priors, float* values, az_engine* engine, int32_t max_sims, void* stream) {
+    if (!index || !count || !engine || max_sims < 1) return az::fail_net(AZ_ERR_ARG, "az_net_forward_trees: bad argument");
+    return net_forward_impl(states, w_img, stem_bias, tower_bias, heads, index, count, n_max, H, W, channels, depth, n_actions,
+                            layout, priors, values, stream, engine, max_sims);
 }

@@ -190,9 +190,9 @@ __device__ __forceinline__ void store_pos(uint64_t* p, const Pos<NW>& v, int lan
 // K1 select (mcts.py:111-120).  pos: root position in, leaf position out.
 // Returns the leaf node; depth/ws.path receive the path; term = 0 none, 1 mover won, 2 draw.
 // ------------------------------------------------------------------------------------------
-template <int NW, int KC, bool NOISE = false, class R>
+template <int NW, int KC, bool NOISE = false, class R, class WS = WarpScratch>
 __device__ __forceinline__ int select_leaf(const Eng& e, const R& r, const NodeA* A, const double* Pr, int root, Pos<NW>& pos,
-                                           WarpScratch& ws, int lane, int& depth, int& term, uint32_t& flags,
+                                           WS& ws, int lane, int& depth, int& term, uint32_t& flags,
                                            long long noise_game = 0, int noise_ply = 0, int noise_sim = 0,
                                            int* staged_root = nullptr) {
     int node = root;
@@ -492,7 +492,8 @@ __device__ __forceinline__ bool cache_lookup(const Eng& e, const R& r, const Pos
 // no atomics.  v0 is the value for the player who moved into the leaf; sign alternates upward.
 // new_link != 0 also publishes the leaf's fresh children in the same 16-byte store.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void backup_path(NodeA* A, int root, WarpScratch& ws, int depth, double v0,
+template <class WS>
+__device__ __forceinline__ void backup_path(NodeA* A, int root, WS& ws, int depth, double v0,
                                             uint32_t new_link, int lane, int staged_root = -1) {
     for (int i = lane; i < depth; i += 32) {
         NodeA* p = A + ws.path[depth - 1 - i];
@@ -511,6 +512,76 @@ __device__ __forceinline__ void backup_path(NodeA* A, int root, WarpScratch& ws,
     }
     __syncwarp();
 }
+
+// Scratch of a warp that runs evaluator-free simulations only (select + backup): the stored path.  (The staging
+// members exist for select_leaf / backup_path to compile; such a warp never stages a root block.)
+struct PathScratch {
+    int32_t path[64];
+    NodeA root_rec[1];
+    double root_pr[1];
+    uint32_t root_link;
+};
+
+// Evaluator-free simulations of ONE tree without a leaf in flight, for warps that have nothing else to do while the net
+// runs (az_net_forward_trees): up to `cap` simulations that end in a terminal leaf (mcts.py:179) are finished on the
+// spot; the first leaf that needs the evaluator is parked exactly as az_extra_sims parks it (pending = 2: the next
+// az_step hands it out).  Moves are never played here: a tree whose budget is spent stays in SEARCH with pending = 0 and
+// the next az_step plays its move in line.  Same simulations in the same order as step_tree would run them - only
+// earlier - so per-tree results cannot change.  Boards of up to 63 cells (PathScratch::path).  `stop`: a shared-memory
+// word the caller raises when no further simulation should be started.
+template <int NW, int KC, class R>
+__device__ __forceinline__ void free_sims_tree(const Eng& e, const R& r, int t, PathScratch& ws, int lane, int cap,
+                                               const volatile int* stop = nullptr) {
+    const int st = e.status[t];
+    if ((st & AZ_PHASE_MASK) != AZ_PHASE_SEARCH || e.pending[t] != 0) return;
+    int sims = e.sims_done[t];
+    if (sims >= e.sims_target) return;
+    uint32_t flags = 0;
+    const size_t pool = ((size_t)t * 2 + e.half[t]) * e.C;
+    NodeA* A = e.node_a + pool;
+    const double* Pr = e.node_p + pool;
+    const int root = e.root_node[t];
+    long long nsim = 0, ndepth = 0;
+    int pend = 0;
+    for (int done = 0; done < cap && sims < e.sims_target; ++done) {
+        if (stop && *stop) break;  // the host kernel is about to finish: never keep it waiting (warp-uniform: one shared word)
+        Pos<NW> pos = load_pos<NW>(e.root_board + (size_t)t * 2 * NW);
+        int depth, term;
+        select_leaf<NW, KC, false>(e, r, A, Pr, root, pos, ws, lane, depth, term, flags);
+        ndepth += depth;
+        if (!term) {  // needs the evaluator: park the leaf
+            for (int i = lane; i < depth; i += 32) e.path[(size_t)t * kMaxDepth + i] = ws.path[i];
+            store_pos<NW>(e.leaf_board + (size_t)t * 2 * NW, pos, lane);
+            if (lane == 0) e.path_len[t] = depth;
+            pend = 2;
+            break;
+        }
+        backup_path(A, root, ws, depth, term == 1 ? 1.0 : 0.0, 0u, lane);
+        ++sims;
+        ++nsim;
+    }
+    if (lane == 0) {
+        if (nsim) atomicAdd(reinterpret_cast<unsigned long long*>(e.counters + (size_t)t * 8 + 0), (unsigned long long)nsim);
+        if (ndepth) atomicAdd(reinterpret_cast<unsigned long long*>(e.counters + (size_t)t * 8 + 4), (unsigned long long)ndepth);
+        e.sims_done[t] = sims;
+        e.pending[t] = pend;
+        if (flags) e.status[t] = st | (int)flags;
+    }
+    __syncwarp();
+}
+
+int engine_view(const ::az_engine* e, Eng* out);  // az_kernels.cu (host): device view of an engine, 1 = plain 6x7 fast path
+
+// Rules as seen by a kernel instance: the runtime struct, or the compile-time headline configuration.
+using C4Rules = FixedRules<7, 6, 4, 1>;
+template <class R>
+struct RulesView {
+    __device__ static __forceinline__ const Rules& get(const Eng& e) { return e.r; }
+};
+template <int W_, int H_, int N_, int G_>
+struct RulesView<FixedRules<W_, H_, N_, G_>> {
+    __device__ static __forceinline__ FixedRules<W_, H_, N_, G_> get(const Eng&) { return {}; }
+};
 
 // ------------------------------------------------------------------------------------------
 // in-kernel evaluators (oracle/evaluators.py)

@@ -80,7 +80,8 @@ class ConfigB200:
     concurrent_games = 4096  # trees resident on one GPU (one warp each)
     games_per_iteration = 4096  # games one call of self_play.play() finishes (reference: cpu_count - 1)
     graph_unroll = 8  # lock-step advances captured per CUDA graph
-    max_free_sims = 8  # terminal-leaf simulations one advance may finish per tree
+    max_free_sims = None  # terminal-leaf simulations one az_step may finish per tree; None = the runner's choice (2 where idle
+    # trees go on simulating inside the net kernel, az_net_forward_trees; else 8)
     seed = 0  # Philox key of the move sampler
     eval_cache_log2 = 20  # device memo of leaf evaluations with 2^n entries (the reference's plays_inferences); 0 = off
     chess_max_plies = 512  # chess: a game still running after this many plies is recorded as a draw

@@ -153,7 +153,7 @@ def _play_chess(run_id: str, games: int, iteration: int):
     r = ChessSelfPlayRunner(n_trees=min(ConfigB200.concurrent_games, games), sims_per_move=ConfigSelfPlay.mcts_iterations,
                             net=best_saved_model(run_id), games_target=games, game_id_base=iteration * games,
                             seed=ConfigB200.seed, move_mode="philox", auto_restart=True, unroll=ConfigB200.graph_unroll,
-                            max_free_sims=ConfigB200.max_free_sims, index_move_greedy=ConfigMCTS.index_move_greedy,
+                            max_free_sims=ConfigB200.max_free_sims or 8, index_move_greedy=ConfigMCTS.index_move_greedy,
                             max_plies=ConfigB200.chess_max_plies)
     _live["runner"] = r
     states, policies, rewards, known = r.run_until_done()

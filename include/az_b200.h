@@ -363,6 +363,20 @@ int az_net_forward_gathered(const void *dev_states, const void *dev_w_img, const
                             const int32_t *dev_count, int32_t n_max, int32_t H, int32_t W, int32_t channels, int32_t depth,
                             int32_t n_actions, int32_t layout, float *dev_priors, float *dev_values, void *stream);
 
+/* az_net_forward_gathered with the idle trees of `engine` simulating INSIDE the same kernel (two more warps per CTA):
+ * every tree without a leaf in flight - its last simulations ended in terminal leaves (mcts/mcts.py:179) and used up
+ * az_step's max_free_sims - runs up to max_sims more evaluator-free simulations while the tensor cores evaluate the
+ * others' leaves; the first leaf that does need the evaluator is parked and handed out by the next az_step (as
+ * az_extra_sims parks it); moves are left to the next az_step.  The same simulations in the same order, only earlier:
+ * per-tree results do not change.  The net kernel owns its SMs (227 KB of shared memory per CTA), so no other kernel can
+ * run beside it; it issues an instruction in only 15 % of its cycles, which is what these warps use.  The engine must be
+ * the plain 6x7 connect-4 configuration (compile-time rules, no root noise), else AZ_ERR_ARG. */
+int az_net_forward_trees(const void *dev_states, const void *dev_w_img, const float *dev_stem_bias,
+                         const float *dev_tower_bias, const az_net_head_params *heads, const int32_t *dev_index,
+                         const int32_t *dev_count, int32_t n_max, int32_t H, int32_t W, int32_t channels, int32_t depth,
+                         int32_t n_actions, int32_t layout, float *dev_priors, float *dev_values, az_engine *engine,
+                         int32_t max_sims, void *stream);
+
 /* The dense layers of az_net_heads alone, on the output of az_net_head_convs: hd dev float [n][cells][3] -> priors / values
  * as above (same weights struct; conv_w / conv_b unused).  az_net_head_convs + az_net_heads_dense = az_net_heads with the
  * convolutions read in 128-bit loads and accumulated in float32. */

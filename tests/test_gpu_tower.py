@@ -238,3 +238,49 @@ def test_whole_net_route_plays_the_same_games_as_the_per_tree_fused_route(layout
     assert ta["games"] == tb["games"] == 160
     same = sum(int(np.array_equal(a["action"][g][: a["len"][g]], b["action"][g][: b["len"][g]])) for g in range(160))
     assert same >= 150, same  # a rare near-tie may resolve differently between the two head implementations
+
+
+def test_tree_warps_inside_the_net_kernel_change_no_game(layout):
+    """az_net_forward_trees: trees without a pending leaf go on with evaluator-free simulations inside the net kernel
+    (short max_free_sims in az_step, the rest under the net).  The simulations of a tree are the same in the same order,
+    only earlier, and the net kernel is batch independent: every game, move for move and visit for visit, and the totals
+    must equal the default route's."""
+    from az_b200 import selfplay
+
+    engine, native, net = _mods()
+    rules = engine.Rules(7, 6, 4, True)
+    out = []
+    for mf, inside in ((8, 0), (2, 8), (1, 3)):
+        torch.manual_seed(0)
+        fp32 = net.randomise_bn(net.PolicyValueNet())
+        r = selfplay.SelfPlayRunner(rules, n_trees=96, sims_per_move=48, net=fp32, games_target=160, unroll=4, seed=3,
+                                    max_free_sims=mf, net_tree_sims=inside)
+        assert r.whole_net and r.net_tree_sims == inside
+        r.run_until_done(poll_every=64, max_advances=400000)
+        fin = {k: v.cpu().numpy() for k, v in r.finished_device().items()}
+        order = np.argsort(fin["game_id"])
+        out.append(({k: v[order] for k, v in fin.items()}, r.totals()))
+    (a, ta) = out[0]
+    assert ta["games"] == 160
+    for b, tb in out[1:]:
+        assert tb["games"] == 160 and tb["sims"] == ta["sims"] and tb["evals"] == ta["evals"] and tb["moves"] == ta["moves"]
+        for k in ("game_id", "len", "result"):
+            assert np.array_equal(a[k], b[k]), k
+        for g in range(160):
+            n = int(a["len"][g])
+            assert np.array_equal(a["action"][g][:n], b["action"][g][:n]) and np.array_equal(a["visits"][g][:n], b["visits"][g][:n]), g
+
+
+def test_tree_warps_need_the_plain_connect4_engine():
+    engine, native, net = _mods()
+    from az_b200.engine import _ptr, _stream
+
+    inf = net.InferenceNet(net.PolicyValueNet(6, 7, 7))
+    eng = engine.TreeEngine(engine.Rules(7, 6, 4, True), n_trees=8, sims_per_move=10, dirichlet_noise=True)
+    x = torch.zeros((8, 6, 7, 4), dtype=torch.bfloat16, device="cuda")
+    p = torch.zeros((8, 7), dtype=torch.float32, device="cuda")
+    v = torch.zeros(8, dtype=torch.float32, device="cuda")
+    idx = torch.zeros(8, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    with pytest.raises(native.NativeError):
+        inf(x, p, v, index=idx, count=cnt, trees=(eng._h, 4))

@@ -96,6 +96,12 @@ class SelfPlayRunner:
         groups = max(1, min(int(groups), T))
         if games_target is None:
             games_target = T
+        # Routes of one advance.  whole_net (default where the net has it): az_step (the tree step alone) + az_net_forward
+        # (stem, tower and heads in ONE tcgen05 kernel: planes in, priors / values out, no activation in HBM).  Else
+        # fused: heads + tree step + stem in one per-tree launch (az_advance_fused) around the tower kernel; else the
+        # three-kernel route az_step + stem + tower + heads.
+        has_net = bool(getattr(self.net, "fused_net", False))
+        self.whole_net = has_net if whole_net is None else (bool(whole_net) and has_net)
         # whole-net route on the 6x7 fast path: trees without a pending leaf go on with up to net_tree_sims evaluator-free
         # simulations INSIDE the net kernel (az_net_forward_trees), so az_step only needs a short max_free_sims: the serial
         # tail of the tree step (a few trees running up to 8 terminal-leaf simulations one after the other while 4 000

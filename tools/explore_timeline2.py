@@ -11,7 +11,8 @@ rules = engine.Rules(7, 6, 4, True)
 torch.manual_seed(0)
 U = 8
 r = selfplay.SelfPlayRunner(rules, n_trees=4096, sims_per_move=800, net=N.PolicyValueNet(), games_target=1 << 40, unroll=U,
-                            max_free_sims=int(os.environ.get("MF", "8")), fin_capacity=16384)
+                            max_free_sims=int(os.environ["MF"]) if "MF" in os.environ else None,
+                            net_tree_sims=int(os.environ["INSIDE"]) if "INSIDE" in os.environ else None, fin_capacity=16384)
 r.run(int(os.environ.get("PREROLL", "40000"))); torch.cuda.synchronize()
 for g in r.groups: g.engine.fin_clear()
 ts = torch.zeros(2 * U, dtype=torch.int64, device="cuda")
@@ -39,6 +40,7 @@ def med(k):
     return float(np.median(v)), float(np.mean(v)), float(np.min(v)), float(np.max(v))
 out = {k: dict(zip(("median", "mean", "min", "max"), med(k))) for k in ("step_us", "step_to_net_us", "net_us", "net_to_step_us", "period_us")}
 out["leaves_last"] = rows[-1]["leaves_last"]
+out["max_free_sims"], out["tree_sims_inside_net"] = r.max_free_sims, r.net_tree_sims
 print(json.dumps(out, indent=1))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump({"summary": out, "rows": rows}, open(os.path.join(ROOT, "gpurun_out", "timeline2.json"), "w"), indent=1)
+json.dump({"summary": out, "rows": rows}, open(os.path.join(ROOT, "gpurun_out", os.environ.get("OUT", "timeline2.json")), "w"), indent=1)

@@ -250,12 +250,12 @@ def test_tree_warps_inside_the_net_kernel_change_no_game(layout):
     engine, native, net = _mods()
     rules = engine.Rules(7, 6, 4, True)
     out = []
-    for mf, inside in ((8, 0), (2, 8), (1, 3)):
+    for mf, inside, beside in ((8, 0, 0), (2, 8, 0), (1, 3, 0), (2, 0, 6)):  # beside: az_extra_sims on a side stream
         torch.manual_seed(0)
         fp32 = net.randomise_bn(net.PolicyValueNet())
         r = selfplay.SelfPlayRunner(rules, n_trees=96, sims_per_move=48, net=fp32, games_target=160, unroll=4, seed=3,
-                                    max_free_sims=mf, net_tree_sims=inside)
-        assert r.whole_net and r.net_tree_sims == inside
+                                    max_free_sims=mf, net_tree_sims=inside, extra_sims=beside)
+        assert r.whole_net and r.net_tree_sims == inside and r.extra_sims == beside
         r.run_until_done(poll_every=64, max_advances=400000)
         fin = {k: v.cpu().numpy() for k, v in r.finished_device().items()}
         order = np.argsort(fin["game_id"])

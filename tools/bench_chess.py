@@ -84,7 +84,7 @@ def main(args, ClockSampler, load_peaks):
     fp32 = chess_net()
     runner = ChessSelfPlayRunner(n_trees=T, sims_per_move=S, net=fp32, games_target=1 << 40, game_id_base=rank << 40,
                                  seed=1234, move_mode="philox", auto_restart=True, unroll=args.unroll,
-                                 max_free_sims=args.max_free, max_plies=args.max_plies,
+                                 max_free_sims=args.max_free or 8, max_plies=args.max_plies,
                                  sample_capacity=max(1024, T * (2 + 2 * ADV // S)))
     flat_dev = runner.net.flat_weights()
     n_w = flat_dev.numel()
@@ -243,7 +243,7 @@ def main(args, ClockSampler, load_peaks):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"C5: {T} concurrent chess self-play games per GPU x {S} simulations/move, bf16 net leaf evaluation",
-                       "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "max_free_sims": args.max_free,
+                       "games_per_gpu": T, "sims_per_move": S, "advances_per_step": ADV, "max_free_sims": args.max_free or 8,
                        "max_plies": args.max_plies, "leaf_planes": int(runner.states.shape[-1]),
                        "net": f"4-block 128-filter projection-residual tower, 8x8x118 in, 1880 actions, {fp32.n_parameters()} params, random init",
                        "l2": "working set per advance (node pools ~GBs + 134 MB activations per conv at 8192 trees) exceeds the 126 MB L2"},

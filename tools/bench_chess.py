@@ -184,9 +184,11 @@ def main(args, ClockSampler, load_peaks):
         ach = T * runner.flops_per_eval_executed / (net_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_sustained"], "traffic": None,
-                "kernel": "policy/value net forward timed alone: az_chess_stem (from the 64-byte boards), 12 cuDNN tcgen05 implicit-GEMM "
-                          "convolutions with fused epilogues, az_net_head_convs, az_net_dense_heads (tcgen05: policy over 1 880 "
-                          "actions + softmax, value MLP)",
+                "kernel": "policy/value net forward timed alone: az_chess_stem_tc (from the 64-byte boards), "
+                          + ("az_net_tower (the 4-block residual tower as one persistent tcgen05 kernel, two 8x8 positions per tile)"
+                             if getattr(runner.net, "fused_tower", False) else
+                             "12 cuDNN tcgen05 implicit-GEMM convolutions with fused epilogues")
+                          + ", az_net_head_convs, az_net_dense_heads (tcgen05: policy over 1 880 actions + softmax, value MLP)",
                 "flops_per_launch": T * runner.flops_per_eval_executed, "flops_per_launch_reference_net": T * runner.flops_per_eval,
                 "flops_note": "executed FLOPs: with tail_planes the stem multiplies the 34 planes that can be non-zero on the self-play path instead of 118",
                 "positions_per_launch": T, "ms_per_launch": net_ms,

@@ -7,7 +7,9 @@
 Workload (config C2 of BASELINE.json, per GPU): 4096 concurrent 6x7 Connect-4 games, 800 simulations
 per move, every leaf evaluated by the bf16 policy/value net (random-init weights of the reference
 architecture: synthetic), finished games refilled so the batch stays full.  One "step" = 800 lock-step
-advances of all trees = one move's worth of simulations for every game (~3.3 M simulations per GPU).
+advances of all trees = one move's worth of simulations for every game (~4.5 M simulations per GPU).  An advance is two
+launches of our own kernels: az_step_gather (the tree step) and az_net_forward_trees (the whole net in one tcgen05
+kernel, with the idle trees' evaluator-free simulations on two extra warps per CTA).
 N > 1: weak scaling by default - every rank owns 4096 games and a net replica (32768 games at N = 8); --scaling strong
 --total-games 32768 is config C3 as BASELINE.json words it (32768 games sharded across the GPUs).  The only collectives
 are the weight broadcast (side stream, never on the simulation path) and, in the e2e leg, the game-record gather to the

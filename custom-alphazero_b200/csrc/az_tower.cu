@@ -30,6 +30,8 @@
 //            16-byte stores per chunk (the masked copies never write their zero rows, which stay zero from the start;
 //            conflict free: a warp writes 512 contiguous bytes), fence.proxy.async, arrive on the "activations ready"
 //            barrier.  The same warps load a tile from global memory at its start and store it after the last block.
+//   warps 10-11 (az_net_forward_trees only): evaluator-free simulations of the engine's trees that have no leaf in flight
+//            (free_sims_tree, az_tree.cuh) - the kernel owns its SM but issues in ~15 % of its cycles.
 // SASS: UTCHMMA (tcgen05.mma), UBLKCP (cp.async.bulk), LDTM (tcgen05.ld).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>

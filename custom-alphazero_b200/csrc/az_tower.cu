@@ -188,6 +188,13 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
         : "r"(taddr)
         : "memory");
 }
+// Pins 32 registers behind the preceding volatile asm (tcgen05.wait::ld): no use of them may be scheduled above it.
+__device__ __forceinline__ void pin32(uint32_t (&v)[32]) {
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                      "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+    asm volatile("" : "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                      "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
+}
 // relu(hi) : relu(lo) as one bf16x2 word, round to nearest even (one instruction instead of two FMNMX + F2FP)
 __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
     uint32_t v;
@@ -256,6 +263,7 @@ template <bool NET, bool PAIR, bool TREES = false>
 __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k_tower(TowerParams P) {
     constexpr int kBlockThreads = kThreads + (TREES ? kTreeWarps * 32 : 0);
     __shared__ PathScratch s_path[TREES ? kTreeWarps : 1];
+    __shared__ long long s_pub0;  // az_net_tower_timing: clock at which epilogue warp 2 last announced a first channel half
     __shared__ int s_stop;  // TREES: raised by warp 1 when this CTA starts its last tile - the tree warps start nothing new
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int kRing = PAIR ? 2 * kStages : kStages;             // ring slots
@@ -372,7 +380,7 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
             else commit_to(bar);
         };
         const bool timed = P.timing != nullptr;
-        long long t_act = 0, t_full = 0;
+        long long t_act = 0, t_full = 0, t_wake = 0;
         const long long t_begin = clock64();
         auto wait_stage = [&](uint32_t slot, uint32_t k) {
             const long long t0 = timed ? clock64() : 0;
@@ -443,6 +451,7 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
                         wait_act(kb == 0 ? bar_act0 : bar_act1, act_phase);
+                        if (timed && kb == 0) t_wake += clock64() - *(volatile long long*)&s_pub0;
                         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap)  // conv2 accumulates on top of the shortcut
@@ -463,6 +472,7 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
             P.timing[blockIdx.x * 8 + 0] = clock64() - t_begin;
             P.timing[blockIdx.x * 8 + 1] = t_act;
             P.timing[blockIdx.x * 8 + 2] = t_full;
+            P.timing[blockIdx.x * 8 + 7] = t_wake;
         }
     } else if (TREES && warp >= kThreads / 32) {
         // ---------------------------------------------------------------- tree warps: evaluator-free simulations beside the net
@@ -534,7 +544,7 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
         // accumulator `acc` (0 / 1) + bias, ReLU, bf16 -> the three copies (centre buffer `centre`), channel half by
         // channel half; or (last layer) -> global memory / the heads.  next_pos0 >= 0 (net mode, last layer): the next
         // tile's planes are loaded as soon as the accumulator has been read, so that its stem runs under the heads.
-        long long t_acc = 0, t_body = 0;
+        long long t_acc = 0, t_body = 0, t_ld = 0, t_half0 = 0;
         const bool etimed = P.timing != nullptr && warp == 2;
         auto epilogue = [&](int acc, const float* bias, int centre, bool last, long long pos0, long long next_pos0) {
             const long long te0 = etimed ? clock64() : 0;
@@ -545,13 +555,20 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             __nv_bfloat16* grow = NET ? nullptr : P.y + (pos0 * P.cells + row_in_tile) * kC + sub * 32;
             const bool store_global = !NET && last && row_live && pos0 + rp < P.n;
-            uint32_t v[2][32];  // both channel halves in flight before the first is used
+            uint32_t v[2][32];  // the first channel half alone is waited for; the second arrives while the first is processed
             tmem_ld32_nowait(taddr + (uint32_t)(acc * 128), v[0]);
-            tmem_ld32_nowait(taddr + (uint32_t)(acc * 128 + 64), v[1]);
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            pin32(v[0]);
+            const long long te2 = etimed ? clock64() : 0;
+            t_ld += te2 - te1;
+            tmem_ld32_nowait(taddr + (uint32_t)(acc * 128 + 64), v[1]);
             float hsum0 = 0.f, hsum1 = 0.f, hsum2 = 0.f;  // net mode, last layer: this thread's share of the 1x1 head convolutions
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
+                if (ch == 1) {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                    pin32(v[1]);
+                }
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const float* bb = bias + ch * 64 + sub * 32 + c4 * 8;
@@ -586,6 +603,11 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
                     }
                 }
                 if (!last) publish(ch == 0 ? bar_act0 : bar_act1);
+                if (etimed && ch == 0) {
+                    const long long te3 = clock64();
+                    t_half0 += te3 - te2;
+                    if (lane == 0) s_pub0 = te3;  // when this warp announced channels 0-63 (read by the MMA warp when it wakes up)
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             if (etimed) t_body += clock64() - te1;
@@ -693,6 +715,8 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
         if (etimed && lane == 0) {
             P.timing[blockIdx.x * 8 + 3] = t_acc;
             P.timing[blockIdx.x * 8 + 4] = t_body;
+            P.timing[blockIdx.x * 8 + 5] = t_ld;
+            P.timing[blockIdx.x * 8 + 6] = t_half0;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");

@@ -83,6 +83,8 @@ for f in flags[:1]:
     lead = b[b[:, 0] > 0]
     epi = b[b[:, 3] > 0]
     rep = {"mma_warp_cycles": lead[:, 0].mean(), "mma_wait_act": lead[:, 1].mean(), "mma_wait_weights": lead[:, 2].mean(),
-           "epi_wait_acc": epi[:, 3].mean(), "epi_body": epi[:, 4].mean(), "ctas_with_mma": int(len(lead))}
+           "epi_wait_acc": epi[:, 3].mean(), "epi_body": epi[:, 4].mean(), "epi_tmem_load_first_half": epi[:, 5].mean(),
+           "epi_first_half_until_published": epi[:, 6].mean(), "mma_wake_after_first_publish_of_warp2": lead[:, 7].mean(),
+           "ctas_with_mma": int(len(lead)), "layers_per_cta": 9.23 * 8}
     print("timing", json.dumps(rep), flush=True)
 native.check(native.lib().az_net_tower_timing(None))

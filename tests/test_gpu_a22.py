@@ -236,3 +236,63 @@ def test_engine_with_the_float32_module_equals_the_oracle_with_the_float32_modul
         np.testing.assert_array_equal(fin["action"][g][:L] & 0xFFFF, want["moves"])
         np.testing.assert_array_equal(fin["visits"][g][:L], want["visits"])
     assert L >= 7 and want["evals"] > 0
+
+
+# ------------------------------------------------------------------ the headline route end to end
+def _philox_uniform(seed, game, ply):
+    """Philox4x32-10 exactly as csrc/az_tree.cuh:philox_uniform (counter = game id lo/hi, ply, 0)."""
+    M0, M1, W0, W1, mask = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    c = [game & mask, (game >> 32) & mask, ply & mask, 0]
+    k0, k1 = seed & mask, (seed >> 32) & mask
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & mask, p1 & mask, ((p0 >> 32) ^ c[3] ^ k1) & mask, p0 & mask]
+        k0, k1 = (k0 + W0) & mask, (k1 + W1) & mask
+    return ((c[0] >> 5) * 67108864.0 + (c[1] >> 6)) / 9007199254740992.0
+
+
+@pytest.mark.parametrize("memo", [0, 12])
+def test_headline_route_equals_the_oracle_search_fed_by_the_same_net_kernel(memo):
+    """The route bench.py times - az_step_gather + az_net_forward_trees under CUDA graphs: gathered leaf batch, tree warps
+    inside the net kernel, moves played in line, Philox sampling, refill, finished-game ring (and, second case, the device
+    evaluation memo of the product entry point) - against the C oracle's MCTS (float32 mode) whose evaluator is the SAME net
+    kernel called on one position at a time (the kernel is batch independent, tests/test_gpu_tower.py).  Every game, whichever
+    tree slot played it: moves, per-ply visit counts and result identical.  The evaluator is a real, position-dependent
+    bf16 net, so a wrong prior / move pairing, value sign, leaf list entry or parked leaf would show."""
+    from az_b200 import selfplay
+    from oracle import c_oracle
+
+    engine, env, net = _mods()
+    rules = engine.Rules(7, 6, 4, True)
+    torch.manual_seed(4)
+    fp32 = _sharpen(net.randomise_bn(net.PolicyValueNet(6, 7, 7)), 3.0).eval()
+    T, G, sims, seed, base = 24, 36, 64, 77, 5000
+    r = selfplay.SelfPlayRunner(rules, n_trees=T, sims_per_move=sims, net=fp32, games_target=G, game_id_base=base, seed=seed,
+                                move_mode="philox", auto_restart=True, unroll=4, fin_capacity=G, eval_cache_log2=memo)
+    assert r.whole_net and r.net_tree_sims > 0 and r.max_free_sims == 2
+    r.run_until_done(poll_every=64, max_advances=400000)
+    fin = {k: v.cpu().numpy() for k, v in r.finished_device().items()}
+    assert sorted(fin["game_id"].tolist()) == list(range(base, base + G))
+    inf = r.net
+    x1 = torch.zeros((1, 6, 7, 4), dtype=torch.bfloat16, device="cuda")
+
+    def cb(state):
+        x1.copy_(torch.from_numpy(np.ascontiguousarray(state, dtype=np.float32))[None])
+        p, v = inf(x1)
+        return p[0].cpu().numpy().astype(np.float64), float(v[0])
+
+    crules = c_oracle.make_rules(7, 6, 4, True)
+    lengths = set()
+    for i, g in enumerate(fin["game_id"]):
+        u = [_philox_uniform(seed, int(g), ply) for ply in range(rules.max_plies)]
+        want = c_oracle.play_game(crules, sims, "callback", uniforms=u, prior_mode=c_oracle.PRIOR_F32, callback=cb)
+        n = len(want["moves"])
+        lengths.add(n)
+        assert fin["len"][i] == n and fin["result"][i] == want["result"], int(g)
+        np.testing.assert_array_equal(fin["action"][i][:n] & 0xFFFF, want["moves"])
+        np.testing.assert_array_equal(fin["visits"][i][:n], want["visits"])
+    assert len(lengths) > 3  # the games really differ
+    tot = r.totals()
+    assert tot["games"] == G and tot["sims"] == sims * tot["moves"]
+    if memo:
+        assert tot["memo_hits"] > 0

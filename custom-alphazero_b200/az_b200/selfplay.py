@@ -49,12 +49,7 @@ def decode_samples(rules: Rules, fin_dev, exclude_null_games=False, with_distanc
     check(lib().az_decode_samples(ctypes.byref(cfg), _ptr(boards), _ptr(visits), _ptr(actions), _ptr(lens),
                                   _ptr(results), _ptr(offsets), n, _ptr(states), _ptr(policies), _ptr(values),
                                   _stream()))
-    # device -> host through pinned buffers (torch's host allocator caches them across calls), one synchronisation
-    host = [torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True) for t in (states, policies, values)]
-    for h, t in zip(host, (states, policies, values)):
-        h.copy_(t, non_blocking=True)
-    torch.cuda.current_stream(dev).synchronize()
-    out = (host[0].numpy(), host[1].numpy(), host[2].numpy().astype(np.int64))
+    out = (states.cpu().numpy(), policies.cpu().numpy(), values.cpu().numpy().astype(np.int64))
     if with_distance:
         host_lens = lens.cpu().numpy()
         dist_to_end = np.concatenate([np.arange(int(ln))[::-1] for ln in host_lens]) if S else np.zeros(0, np.int64)

@@ -1,5 +1,9 @@
 """Policy/value network of the reference, restated for PyTorch (the only dense contraction on the
-self-play path; it runs bf16 on the tensor cores through cuDNN/cuBLAS under the step's CUDA graph).
+self-play path).  PolicyValueNet is the trainable fp32 module; InferenceNet folds it for inference and routes the
+forward pass: on the 6x7 headline shapes the WHOLE net is one hand-written tcgen05 kernel (az_net_forward, csrc/az_tower.cu),
+for 8x8 / chess the residual tower is that kernel without its two ends (az_net_tower) between hand-written stem / head
+kernels, and cuDNN's fused-epilogue convolutions remain as the comparison arm and for boards the kernel's tiling does not
+cover (9x9).
 
 Architecture follows /root/reference/custom_alphazero/model/tensorflow/model.py:21-188 and
 base_layers.py:20-125 (the TensorFlow/Keras model; the PyTorch copy in the reference is dead code):

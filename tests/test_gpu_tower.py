@@ -240,7 +240,8 @@ def test_whole_net_route_plays_the_same_games_as_the_per_tree_fused_route(layout
     assert same >= 150, same  # a rare near-tie may resolve differently between the two head implementations
 
 
-def test_tree_warps_inside_the_net_kernel_change_no_game(layout):
+@pytest.mark.parametrize("T,G", [(96, 160), (5, 9)])
+def test_tree_warps_inside_the_net_kernel_change_no_game(layout, T, G):
     """az_net_forward_trees: trees without a pending leaf go on with evaluator-free simulations inside the net kernel
     (short max_free_sims in az_step, the rest under the net).  The simulations of a tree are the same in the same order,
     only earlier, and the net kernel is batch independent: every game, move for move and visit for visit, and the totals
@@ -253,7 +254,7 @@ def test_tree_warps_inside_the_net_kernel_change_no_game(layout):
     for mf, inside, beside in ((8, 0, 0), (2, 8, 0), (1, 3, 0), (2, 0, 6)):  # beside: az_extra_sims on a side stream
         torch.manual_seed(0)
         fp32 = net.randomise_bn(net.PolicyValueNet())
-        r = selfplay.SelfPlayRunner(rules, n_trees=96, sims_per_move=48, net=fp32, games_target=160, unroll=4, seed=3,
+        r = selfplay.SelfPlayRunner(rules, n_trees=T, sims_per_move=48, net=fp32, games_target=G, unroll=4, seed=3,
                                     max_free_sims=mf, net_tree_sims=inside, extra_sims=beside)
         assert r.whole_net and r.net_tree_sims == inside and r.extra_sims == beside
         r.run_until_done(poll_every=64, max_advances=400000)
@@ -261,12 +262,12 @@ def test_tree_warps_inside_the_net_kernel_change_no_game(layout):
         order = np.argsort(fin["game_id"])
         out.append(({k: v[order] for k, v in fin.items()}, r.totals()))
     (a, ta) = out[0]
-    assert ta["games"] == 160
+    assert ta["games"] == G
     for b, tb in out[1:]:
-        assert tb["games"] == 160 and tb["sims"] == ta["sims"] and tb["evals"] == ta["evals"] and tb["moves"] == ta["moves"]
+        assert tb["games"] == G and tb["sims"] == ta["sims"] and tb["evals"] == ta["evals"] and tb["moves"] == ta["moves"]
         for k in ("game_id", "len", "result"):
             assert np.array_equal(a[k], b[k]), k
-        for g in range(160):
+        for g in range(G):
             n = int(a["len"][g])
             assert np.array_equal(a["action"][g][:n], b["action"][g][:n]) and np.array_equal(a["visits"][g][:n], b["visits"][g][:n]), g
 

@@ -19,6 +19,9 @@ ts = torch.zeros(2 * U, dtype=torch.int64, device="cuda")
 tn = torch.zeros(2 * U, dtype=torch.int64, device="cuda")
 check(lib().az_debug_timeline(r.engine._h, _ptr(ts), U))
 check(lib().az_net_debug_timeline(_ptr(tn), U))
+cyc = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
+if os.environ.get("CYCLES"):
+    check(lib().az_net_tower_timing(_ptr(cyc)))  # in-kernel cycle counters of the last launch: true SM clock = cycles / time
 r.graph = None
 r.capture()
 def clear():
@@ -40,6 +43,15 @@ def med(k):
     return float(np.median(v)), float(np.mean(v)), float(np.min(v)), float(np.max(v))
 out = {k: dict(zip(("median", "mean", "min", "max"), med(k))) for k in ("step_us", "step_to_net_us", "net_us", "net_to_step_us", "period_us")}
 out["leaves_last"] = rows[-1]["leaves_last"]
+if os.environ.get("CYCLES"):
+    c = cyc.cpu().numpy().astype(float)
+    lead = c[c[:, 0] > 0]
+    out["mma_warp_cycles_last_launch_max"] = float(lead[:, 0].max())
+    out["mma_warp_cycles_last_launch_mean"] = float(lead[:, 0].mean())
+    out["net_us_last_launch"] = rows[-1]["net_us"]
+    out["implied_sm_mhz"] = float(lead[:, 0].max()) / rows[-1]["net_us"]
+    out["wait_act_mean"] = float(lead[:, 1].mean()); out["wait_weights_mean"] = float(lead[:, 2].mean())
+    check(lib().az_net_tower_timing(None))
 out["max_free_sims"], out["tree_sims_inside_net"] = r.max_free_sims, r.net_tree_sims
 print(json.dumps(out, indent=1))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -20,7 +20,7 @@
 // Four activation buffers (x, x-left, x-right, h) of 128 + 22 rows share one row space: 159 KB.
 //
 // Roles (320 threads, 1 CTA per SM, persistent over tiles):
-//   warp 0   producer: one lane streams the weight stages (16 KB = one tap x 64 input channels x 128 output channels,
+//   warp 0   producer: one elected lane streams the weight stages (16 KB = one tap x 64 input channels x 128 output channels,
 //            pre-packed by the host in the UMMA layout, in the order they are consumed: per convolution the
 //            input-channel half is the outer loop, the tap the inner one) from global memory with
 //            cp.async.bulk into a 4-deep ring, full / empty mbarriers;
@@ -129,6 +129,10 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
         "r"(cta)
         : "memory");
 }
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {  // a value the compiler must keep in a register, not rematerialise
+    asm volatile("mov.u32 %0, %0;\n" : "+r"(v));
+    return v;
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t is_leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(is_leader));
@@ -202,6 +206,58 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
     return v;
 }
 
+// One weight stage of the tower as ONE block of PTX: the poll of the NEXT stage's "full" barrier is issued first, the four
+// K = 16 MMAs and the commit that frees this stage's slot follow, and only then is the poll's answer read - so the ~70 cycles
+// a poll takes (tools/mma_rate.cu) overlap the issue of the MMAs instead of preceding them.  Before this the issuing warp
+// spent 222 of its 392 cycles per stage in two serial polls (counters of az_net_tower_timing: never once was a stage
+// missing), and the tensor pipe, which needs a stage every 256 cycles, starved.  All lanes execute it (the poll is
+// warp-uniform); only the elected lane issues.  Returns the poll's answer.
+template <bool PAIR>
+__device__ __forceinline__ uint32_t issue_stage(uint32_t d_tmem, uint32_t a_lo, uint32_t a_step, uint32_t b_lo, uint32_t b_step,
+                                                uint32_t first_accumulate, uint32_t empty_bar, uint32_t next_full_bar,
+                                                uint32_t next_parity, uint32_t leader) {
+    uint32_t ready;
+    if (PAIR)
+        asm volatile(
+            "{\n\t.reg .pred pn, pl, pa, pt;\n\t.reg .b64 da, db;\n\t.reg .b32 ra, rb;\n\t"
+            "setp.ne.b32 pl, %10, 0;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 pn, [%8], %9;\n\t"
+            "mov.b64 da, {%2, %12};\n\tmov.b64 db, {%4, %12};\n\t"
+            "@pl tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %11, pa;\n\t"
+            "add.u32 ra, %2, %3;\n\tadd.u32 rb, %4, %5;\n\tmov.b64 da, {ra, %12};\n\tmov.b64 db, {rb, %12};\n\t"
+            "@pl tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %11, pt;\n\t"
+            "add.u32 ra, ra, %3;\n\tadd.u32 rb, rb, %5;\n\tmov.b64 da, {ra, %12};\n\tmov.b64 db, {rb, %12};\n\t"
+            "@pl tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %11, pt;\n\t"
+            "add.u32 ra, ra, %3;\n\tadd.u32 rb, rb, %5;\n\tmov.b64 da, {ra, %12};\n\tmov.b64 db, {rb, %12};\n\t"
+            "@pl tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %11, pt;\n\t"
+            "@pl tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %13;\n\t"
+            "selp.u32 %0, 1, 0, pn;\n\t}\n"
+            : "=r"(ready)
+            : "r"(d_tmem), "r"(a_lo), "r"(a_step), "r"(b_lo), "r"(b_step), "r"(first_accumulate), "r"(empty_bar), "r"(next_full_bar),
+              "r"(next_parity), "r"(leader), "r"(kIdesc2), "r"(kDescHi), "h"((uint16_t)3)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred pn, pl, pa, pt;\n\t.reg .b64 da, db;\n\t.reg .b32 ra, rb;\n\t"
+            "setp.ne.b32 pl, %10, 0;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 pn, [%8], %9;\n\t"
+            "mov.b64 da, {%2, %12};\n\tmov.b64 db, {%4, %12};\n\t"
+            "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %11, pa;\n\t"
+            "add.u32 ra, %2, %3;\n\tadd.u32 rb, %4, %5;\n\tmov.b64 da, {ra, %12};\n\tmov.b64 db, {rb, %12};\n\t"
+            "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %11, pt;\n\t"
+            "add.u32 ra, ra, %3;\n\tadd.u32 rb, rb, %5;\n\tmov.b64 da, {ra, %12};\n\tmov.b64 db, {rb, %12};\n\t"
+            "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %11, pt;\n\t"
+            "add.u32 ra, ra, %3;\n\tadd.u32 rb, rb, %5;\n\tmov.b64 da, {ra, %12};\n\tmov.b64 db, {rb, %12};\n\t"
+            "@pl tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %11, pt;\n\t"
+            "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+            "selp.u32 %0, 1, 0, pn;\n\t}\n"
+            : "=r"(ready)
+            : "r"(d_tmem), "r"(a_lo), "r"(a_step), "r"(b_lo), "r"(b_step), "r"(first_accumulate), "r"(empty_bar), "r"(next_full_bar),
+              "r"(next_parity), "r"(leader), "r"(kIdesc), "r"(kDescHi)
+            : "memory");
+    return ready;
+}
+
 struct HeadParams {
     const float* conv_w;    // [3][128] 1x1 head convolutions (rows 0-1 policy, row 2 value), BN folded
     const float* conv_b;    // [3]
@@ -233,7 +289,10 @@ struct TowerParams {
     int tree_cap;              // ... up to this many evaluator-free simulations per tree and launch
     unsigned long long* timeline;  // az_net_debug_timeline: {first CTA start, last CTA end} of this launch, globaltimer ns
     int debug;                 // timing experiments only (AZ_TOWER_DEBUG): bit 0 = do not refill weight stages after the first ring pass,
-                               // bit 1 = epilogue skips its shared-memory stores, bit 2 = every tap reads the unshifted centre buffer
+                               // bit 1 = epilogue skips its shared-memory stores, bit 2 = every tap reads the unshifted centre buffer,
+                               // bit 4 = no epilogue at all and the MMA warp never waits for activations: the tensor pipe and the
+                               // weight ring alone (results are garbage); with bit 4: bit 5 = no weight ring either (producer and
+                               // peer forwarder idle, the MMA warp never waits for a stage)
 };
 
 constexpr int kStemStages = 3;     // 9 taps x [128 output channels][16 K: 4 planes + zeros] = 4 taps per 16 KB stage
@@ -269,7 +328,7 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
     constexpr int kRing = PAIR ? 2 * kStages : kStages;             // ring slots
     constexpr uint32_t kSlotBytes = PAIR ? kStageBytes / 2 : kStageBytes;  // bytes of a weight stage this CTA holds
     constexpr uint32_t kLboW = PAIR ? kLboB / 2 : kLboB;            // 64 or 128 rows x 16 bytes per chunk column
-    __shared__ __align__(8) uint64_t s_full[2 * kStages], s_empty[2 * kStages], s_pfull[2 * kStages], s_acc, s_act[2];
+    __shared__ __align__(8) uint64_t s_full[2 * kStages], s_empty[2 * kStages], s_acc, s_act[2];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (P.timeline && tid == 0) {
@@ -304,9 +363,10 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
     if (tid == 0) {
         s_stop = 0;
         for (int s = 0; s < kRing; ++s) {
-            mbar_init(smem_u32(&s_full[s]), 1);
+            // a stage is there when this CTA's bulk copy has landed; for rank 0 of a pair: ... and the peer's warp 1 has
+            // announced its half (one barrier, so the issuing warp polls ONCE per stage)
+            mbar_init(smem_u32(&s_full[s]), (PAIR && rank == 0) ? 2 : 1);
             mbar_init(smem_u32(&s_empty[s]), 1);
-            mbar_init(smem_u32(&s_pfull[s]), 1);
         }
         mbar_init(bar_acc, 1);
         mbar_init(bar_act0, kTpu * (kThreads - 64) / 32);  // one arrival per epilogue warp (of both CTAs of a pair)
@@ -333,41 +393,62 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
 
     if (warp == 0) {
         // ---------------------------------------------------------------- producer
-        if (lane == 0) {
-            uint32_t cnt = 0;
-            for (int unit = unit0; unit * kTpu < P.n_tiles; unit += n_units) {
-                const uint8_t* src = P.w_img + rank * kSlotBytes;  // pair: rank r streams output channels 64 r .. 64 r + 63
-                for (int s = 0; s < stages_per_tile; ++s, ++cnt, src += kStageBytes) {
-                    const uint32_t slot = cnt % kRing, k = cnt / kRing;
-                    mbar_wait(smem_u32(&s_empty[slot]), (k & 1) ^ 1);
-                    const uint32_t full = smem_u32(&s_full[slot]);
-                    if ((P.debug & 1) && cnt >= (uint32_t)kRing) {
-                        mbar_arrive(full);
-                        continue;
-                    }
-                    mbar_expect_tx(full, kSlotBytes);
-                    bulk_g2s(stages + slot * kSlotBytes, src, kSlotBytes, full);
+        // The whole warp runs the loop (the poll is warp-uniform) and one elected lane issues from a predicated block of
+        // PTX, so that the loop stays on the uniform datapath.  The first version ran inside `if (lane == 0)`: the compiler
+        // then wraps the bulk copy in a broadcast loop (ELECT / R2UR.BROADCAST / BRA.U.ANY) and re-derives the barrier
+        // addresses from SR_CgaCtaId every stage - 378 cycles per stage (clock stamps, tools/time_tower.py flag 64), which
+        // was what bounded the whole kernel: the tensor pipe needs a stage every 256 cycles.
+        const uint32_t lead = elect_one() ? 1u : 0u;
+        // (opaque copies: otherwise the compiler re-derives these addresses from SR_CgaCtaId in every iteration)
+        const uint32_t full0 = opaque(smem_u32(&s_full[0])), empty0 = opaque(smem_u32(&s_empty[0])), ring0 = opaque(stages);
+        uint32_t cnt = 0;
+        for (int unit = unit0; unit * kTpu < P.n_tiles && !(P.debug & 32); unit += n_units) {
+            const uint8_t* src = P.w_img + rank * kSlotBytes;  // pair: rank r streams output channels 64 r .. 64 r + 63
+            for (int s = 0; s < stages_per_tile; ++s, ++cnt, src += kStageBytes) {
+                const uint32_t slot = cnt % kRing, k = cnt / kRing;
+                mbar_wait(empty0 + slot * 8u, (k & 1) ^ 1);
+                if ((P.debug & 64) && P.timing && blockIdx.x == 0 && cnt < 2048 && lane == 0) P.timing[148 * 8 + cnt] = clock64();
+                if ((P.debug & 1) && cnt >= (uint32_t)kRing) {
+                    if (lead) mbar_arrive(full0 + slot * 8u);
+                    __syncwarp();
+                    continue;
                 }
+                asm volatile(
+                    "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %4, 0;\n\t"
+                    "@pl mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %3;\n\t"
+                    "@pl cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2], %3, [%0];\n\t}\n" ::"r"(
+                        full0 + slot * 8u),
+                    "r"(ring0 + slot * kSlotBytes), "l"(src), "r"(kSlotBytes), "r"(lead)
+                    : "memory");
             }
         }
     } else if (warp == 1 && PAIR && rank != 0) {
         // ---------------------------------------------------------------- peer CTA: tell rank 0 that my half of a stage is here
         uint32_t cnt = 0;
-        for (int unit = unit0; unit * kTpu < P.n_tiles; unit += n_units) {
+        const uint32_t lead = elect_one() ? 1u : 0u;
+        const uint32_t full0 = opaque(smem_u32(&s_full[0]));
+        uint32_t remote_full0;  // the same barriers in rank 0's shared memory
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote_full0) : "r"(full0), "r"(0u));
+        for (int unit = unit0; unit * kTpu < P.n_tiles && !(P.debug & 32); unit += n_units) {
             if (TREES && lane == 0 && (unit + n_units) * kTpu >= P.n_tiles) *(volatile int*)&s_stop = 1;
             for (int s = 0; s < stages_per_tile; ++s, ++cnt) {
                 const uint32_t slot = cnt % kRing, k = cnt / kRing;
-                mbar_wait(smem_u32(&s_full[slot]), k & 1);
-                if (lane == 0) mbar_arrive_remote(smem_u32(&s_pfull[slot]), 0u);
-                __syncwarp();
+                mbar_wait(full0 + slot * 8u, k & 1);
+                asm volatile(
+                    "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %1, 0;\n\t"
+                    "@pl mbarrier.arrive.shared::cluster.b64 _, [%0];\n\t}\n" ::"r"(remote_full0 + slot * 8u),
+                    "r"(lead)
+                    : "memory");
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer
-        // The whole warp runs the control flow (waits included) so that everything stays warp-uniform; one elected
-        // lane issues.  Taps, channel halves and K steps are fully unrolled: every descriptor is base + constant.
+      // ---------------------------------------------------------------- MMA issuer
+      // ONE elected lane runs the whole role (waits included); the other 31 wait at the end of the kernel.  Inside an
+      // elect.sync region every value is trivially warp-uniform, so the compiler keeps descriptors, counters and barrier
+      // addresses on the uniform datapath (UIADD3 / UMOV feeding UTCHMMA directly, no R2UR).
+      if (elect_one()) {
         uint32_t cnt = 0, act_phase = 0;
-        const bool leader = elect_one();
+        const bool leader = true;
         const uint32_t a_step = 2u * (kLboA >> 4), a_half = 8u * (kLboA >> 4), b_step = 2u * (kLboW >> 4);
         const uint32_t a_buf = (uint32_t)kBufRows;  // descriptor units (16 B) between buffers = rows
         const uint32_t a0 = desc_lo(act + buf_row0(0), kLboA), b0 = desc_lo(stages, kLboW);
@@ -383,13 +464,14 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
         long long t_act = 0, t_full = 0, t_wake = 0;
         const long long t_begin = clock64();
         auto wait_stage = [&](uint32_t slot, uint32_t k) {
+            if (P.debug & 32) return;
             const long long t0 = timed ? clock64() : 0;
-            mbar_wait(smem_u32(&s_full[slot]), k & 1);
-            if (PAIR) mbar_wait(smem_u32(&s_pfull[slot]), k & 1);  // ... and the peer's half
+            mbar_wait(smem_u32(&s_full[slot]), k & 1);  // pair: completes when BOTH halves of the stage have landed
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (timed) t_full += clock64() - t0;
         };
         auto wait_act = [&](uint32_t bar, uint32_t parity) {
+            if (P.debug & 16) return;  // timing experiment: the tensor pipe alone (no epilogue, garbage results)
             const long long t0 = timed ? clock64() : 0;
             mbar_wait(bar, parity);
             if (timed) t_act += clock64() - t0;
@@ -400,23 +482,27 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
             return (P.debug & 4) ? centre
                                  : (dx < 0 ? a0 + a_buf : (dx > 0 ? a0 + 2u * a_buf : centre)) + (uint32_t)(dy * rowstride + dx);
         };
-        // one weight stage = 64 input channels of one tap: four K = 16 steps
+        // one weight stage = 64 input channels of one tap: four K = 16 steps.  `ready`: the poll issued inside the previous
+        // stage already found this stage's weights (issue_stage); otherwise wait for them the slow way.
+        uint32_t ready = 0;
+        const uint32_t lead = leader ? 1u : 0u;
         auto stage_mmas = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t first_accumulate) {
             const uint32_t slot = cnt % kRing, k = cnt / kRing;
-            wait_stage(slot, k);
-            if (leader) {
-                const uint32_t b_lo = b0 + slot * (kSlotBytes >> 4);
-                mma(d_tmem, a_lo, b_lo, first_accumulate);
-                mma(d_tmem, a_lo + a_step, b_lo + b_step, 1u);
-                mma(d_tmem, a_lo + 2 * a_step, b_lo + 2 * b_step, 1u);
-                mma(d_tmem, a_lo + 3 * a_step, b_lo + 3 * b_step, 1u);
-                commit(smem_u32(&s_empty[slot]));  // frees the slot (in both CTAs of a pair) when these MMAs have read it
+            if (!ready) wait_stage(slot, k);
+            else if (!(P.debug & 32)) asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if ((P.debug & 64) && P.timing && blockIdx.x == 0 && cnt < 2048) {
+                P.timing[148 * 8 + 2048 + cnt] = clock64();
+                P.timing[148 * 8 + 4096 + cnt] = ready;
             }
-            __syncwarp();
+            const uint32_t nslot = (cnt + 1) % kRing, nk = (cnt + 1) / kRing;
+            ready = issue_stage<PAIR>(d_tmem, a_lo, a_step, b0 + slot * (kSlotBytes >> 4), b_step, first_accumulate,
+                                      smem_u32(&s_empty[slot]), smem_u32(&s_full[nslot]), nk & 1, lead);
             ++cnt;
         };
+        const bool dbg_centre = (P.debug & 4) != 0;
+        const uint32_t row_step = dbg_centre ? 0u : (uint32_t)rowstride;
         for (int unit = unit0; unit * kTpu < P.n_tiles; unit += n_units) {
-            if (TREES && lane == 0 && (unit + n_units) * kTpu >= P.n_tiles) *(volatile int*)&s_stop = 1;
+            if (TREES && (unit + n_units) * kTpu >= P.n_tiles) *(volatile int*)&s_stop = 1;
             if (NET) {
                 // stem: the four planes of a cell sit in chunk column 0 (column 1 is zero), one K = 16 MMA per tap; a
                 // stage carries the [128][16] weights of four taps
@@ -424,6 +510,7 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
                 wait_act(bar_act1, act_phase);
                 act_phase ^= 1;
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                ready = 0;  // the stem's stages wait the plain way
 #pragma unroll
                 for (int s = 0; s < kStemStages; ++s) {
                     const uint32_t slot = cnt % kRing, k = cnt / kRing;
@@ -435,11 +522,9 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
                             if (4 * s + tt < 9) mma(tmem, tap_window(4 * s + tt, a0), b_lo + (uint32_t)tt * b_step, (s | tt) ? 1u : 0u);
                         commit(smem_u32(&s_empty[slot]));
                     }
-                    __syncwarp();
                     ++cnt;
                 }
                 if (leader) commit(bar_acc);
-                __syncwarp();
             }
             for (int b = 0; b < P.depth; ++b) {
 #pragma unroll 1
@@ -451,15 +536,21 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
                         wait_act(kb == 0 ? bar_act0 : bar_act1, act_phase);
-                        if (timed && kb == 0) t_wake += clock64() - *(volatile long long*)&s_pub0;
+                        
                         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-#pragma unroll
-                        for (int tap = 0; tap < 9; ++tap)  // conv2 accumulates on top of the shortcut
-                            stage_mmas(d_tmem, tap_window(tap, centre) + (uint32_t)kb * a_half, (tap == 0 && kb == 0) ? half : 1u);
+                        // the three taps of a filter row per iteration, rows rolled: the fully unrolled version (38 stages of
+                        // straight-line code per block) ran at the tensor pipe's rate only on some GPCs - instruction fetch
+                        const uint32_t kbo = (uint32_t)kb * a_half;
+                        uint32_t row = 0u - row_step;  // dy = -1
+#pragma unroll 1
+                        for (int dy = 0; dy < 3; ++dy, row += row_step) {  // conv2 accumulates on top of the shortcut
+                            stage_mmas(d_tmem, (dbg_centre ? centre : a0 + a_buf - 1u) + row + kbo, (dy == 0 && kb == 0) ? half : 1u);
+                            stage_mmas(d_tmem, centre + row + kbo, 1u);
+                            stage_mmas(d_tmem, (dbg_centre ? centre : a0 + 2u * a_buf + 1u) + row + kbo, 1u);
+                        }
                     }
                     act_phase ^= 1;
                     if (leader) commit(bar_acc);
-                    __syncwarp();
                     if (half == 0) {
                         // the shortcut needs only x: it runs while the epilogue turns accumulator 0 into h
                         stage_mmas(tmem + 128u, a0, 0u);
@@ -468,12 +559,17 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
                 }
             }
         }
-        if (timed && lane == 0) {
+        if ((P.debug & 16) && cnt > 0) {  // nobody else waits for the last MMAs in this mode: do it here, before TMEM is freed
+            const uint32_t last = cnt - 1;
+            mbar_wait(smem_u32(&s_empty[last % kRing]), (last / kRing) & 1);
+        }
+        if (timed) {
             P.timing[blockIdx.x * 8 + 0] = clock64() - t_begin;
             P.timing[blockIdx.x * 8 + 1] = t_act;
             P.timing[blockIdx.x * 8 + 2] = t_full;
             P.timing[blockIdx.x * 8 + 7] = t_wake;
         }
+      }
     } else if (TREES && warp >= kThreads / 32) {
         // ---------------------------------------------------------------- tree warps: evaluator-free simulations beside the net
         const int tw = warp - kThreads / 32;
@@ -679,8 +775,8 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
 
         // a CTA of a pair whose tile lies beyond the batch still takes part in every barrier: it computes on zeros and
         // stores nothing (pos0 >= n)
-        if (NET && unit0 * kTpu < P.n_tiles) load_planes((long long)(unit0 * kTpu + (int)rank) * P.ppt);  // later tiles: inside the last epilogue
-        for (int unit = unit0; unit * kTpu < P.n_tiles; unit += n_units) {
+        if (NET && unit0 * kTpu < P.n_tiles && !(P.debug & 16)) load_planes((long long)(unit0 * kTpu + (int)rank) * P.ppt);  // later tiles: inside the last epilogue
+        for (int unit = unit0; unit * kTpu < P.n_tiles && !(P.debug & 16); unit += n_units) {
             const long long pos0 = (long long)(unit * kTpu + (int)rank) * P.ppt;
             const long long next_pos0 = (unit + n_units) * kTpu < P.n_tiles ? (long long)((unit + n_units) * kTpu + (int)rank) * P.ppt : -1;
             if (NET) {

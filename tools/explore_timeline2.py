@@ -51,6 +51,7 @@ if os.environ.get("CYCLES"):
     out["net_us_last_launch"] = rows[-1]["net_us"]
     out["implied_sm_mhz"] = float(lead[:, 0].max()) / rows[-1]["net_us"]
     out["wait_act_mean"] = float(lead[:, 1].mean()); out["wait_weights_mean"] = float(lead[:, 2].mean())
+    out["per_cta_total_wait_act_wait_weights"] = [[int(c[i, 0]), int(c[i, 1]), int(c[i, 2])] for i in range(148) if c[i, 0] > 0]
     check(lib().az_net_tower_timing(None))
 out["max_free_sims"], out["tree_sims_inside_net"] = r.max_free_sims, r.net_tree_sims
 print(json.dumps(out, indent=1))

@@ -73,13 +73,26 @@ with open(os.path.join(ROOT, "gpurun_out", "time_tower.json"), "w") as fp:
 from az_b200 import native  # noqa: E402
 from az_b200.engine import _ptr  # noqa: E402
 
-buf = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
+buf = torch.zeros(148 * 8 + 3 * 2048, dtype=torch.int64, device="cuda")
 native.check(native.lib().az_net_tower_timing(_ptr(buf)))
-for f in flags[:1]:
+for f in flags:
     os.environ["AZ_TOWER_DEBUG"] = str(f)
     inf.tower(xs[0])
     torch.cuda.synchronize()
-    b = buf.cpu().numpy().astype(float)
+    stamps = buf[148 * 8:].cpu().numpy().reshape(3, 2048)
+    b = buf[:148 * 8].reshape(148, 8).cpu().numpy().astype(float)
+    if f & 64:
+        import numpy as np
+        emp, iss, rdy = stamps
+        nst = int((iss > 0).sum())
+        d_iss = np.diff(iss[:nst])
+        print("stamps", json.dumps({"stages": nst, "issue_period_median": float(np.median(d_iss)), "issue_period_mean": float(d_iss.mean()),
+              "ready_frac": float(rdy[:nst].mean()),
+              "issue_s_to_empty_s+8_median": float(np.median(emp[8:nst] - iss[:nst - 8])),
+              "empty_s_to_issue_s_median": float(np.median(iss[8:nst] - emp[8:nst])),
+              "issue_deltas_300": d_iss[300:340].tolist(), "ready_300": rdy[300:340].tolist(),
+              "empty_deltas_first24": np.diff(emp[:25]).tolist(), "empty_deltas_300": np.diff(emp[300:341]).tolist(),
+              "issue_minus_empty_300": (iss[300:340] - emp[300:340]).tolist()}), flush=True)
     lead = b[b[:, 0] > 0]
     epi = b[b[:, 3] > 0]
     rep = {"mma_warp_cycles": lead[:, 0].mean(), "mma_wait_act": lead[:, 1].mean(), "mma_wait_weights": lead[:, 2].mean(),
@@ -87,4 +100,5 @@ for f in flags[:1]:
            "epi_first_half_until_published": epi[:, 6].mean(), "mma_wake_after_first_publish_of_warp2": lead[:, 7].mean(),
            "ctas_with_mma": int(len(lead)), "layers_per_cta": 9.23 * 8}
     print("timing", json.dumps(rep), flush=True)
+    print("per_cta_issue_cycles(total-wait_act-wait_weights)", f, [int(x[0] - x[1] - x[2]) for x in lead], flush=True)
 native.check(native.lib().az_net_tower_timing(None))

@@ -20,12 +20,14 @@
 // Four activation buffers (x, x-left, x-right, h) of 128 + 22 rows share one row space: 159 KB.
 //
 // Roles (320 threads, 1 CTA per SM, persistent over tiles):
-//   warp 0   producer: one elected lane streams the weight stages (16 KB = one tap x 64 input channels x 128 output channels,
-//            pre-packed by the host in the UMMA layout, in the order they are consumed: per convolution the
-//            input-channel half is the outer loop, the tap the inner one) from global memory with
-//            cp.async.bulk into a 4-deep ring, full / empty mbarriers;
-//   warp 1   MMA issuer: one lane issues 4 tcgen05.mma (128 x 128 x 16) per stage; conv1 -> TMEM columns 0-127, the
-//            1x1 shortcut (needs only x) and then conv2 -> columns 128-255, so the shortcut runs under epilogue 1;
+//   warp 0   producer: the whole warp runs the loop, one elected lane streams the weight stages (16 KB = one tap x 64 input
+//            channels x 128 output channels, pre-packed by the host in the UMMA layout, in the order they are consumed: per
+//            convolution the input-channel half is the outer loop, the tap the inner one) from global memory with
+//            cp.async.bulk into a 4-deep ring (pairs: 8 x 8 KB), full / empty mbarriers.  It must hand over a stage every
+//            256 cycles: everything in its loop stays on the uniform datapath (see the comment there);
+//   warp 1   MMA issuer: ONE elected lane runs the role and issues 4 tcgen05.mma (128 x 128 x 16) per stage from one block of
+//            PTX that also polls the next stage's barrier (issue_stage); conv1 -> TMEM columns 0-127, the 1x1 shortcut
+//            (needs only x) and then conv2 -> columns 128-255, so the shortcut runs under epilogue 1;
 //   warps 2-9  epilogue: tcgen05.ld (32 lanes x 32 columns), + bias, ReLU + bf16 pair in one cvt.rn.relu.bf16x2, up to three
 //            16-byte stores per chunk (the masked copies never write their zero rows, which stay zero from the start;
 //            conflict free: a warp writes 512 contiguous bytes), fence.proxy.async, arrive on the "activations ready"

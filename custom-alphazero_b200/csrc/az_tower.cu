@@ -644,7 +644,8 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
         // tile's planes are loaded as soon as the accumulator has been read, so that its stem runs under the heads.
         long long t_acc = 0, t_body = 0, t_ld = 0, t_half0 = 0;
         const bool etimed = P.timing != nullptr && warp == 2;
-        auto epilogue = [&](int acc, const float* bias, int centre, bool last, long long pos0, long long next_pos0) {
+        float hsum0 = 0.f, hsum1 = 0.f, hsum2 = 0.f;  // net mode, last layer: this thread's share of the 1x1 head convolutions
+        auto epilogue = [&](int acc, const float* bias, int centre, bool last, long long pos0) {
             const long long te0 = etimed ? clock64() : 0;
             mbar_wait(bar_acc, acc_phase);
             const long long te1 = etimed ? clock64() : 0;
@@ -660,7 +661,7 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
             const long long te2 = etimed ? clock64() : 0;
             t_ld += te2 - te1;
             tmem_ld32_nowait(taddr + (uint32_t)(acc * 128 + 64), v[1]);
-            float hsum0 = 0.f, hsum1 = 0.f, hsum2 = 0.f;  // net mode, last layer: this thread's share of the 1x1 head convolutions
+            if (NET && last) hsum0 = hsum1 = hsum2 = 0.f;
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 if (ch == 1) {
@@ -709,17 +710,21 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             if (etimed) t_body += clock64() - te1;
-            if (NET && last) {
-                // buffers 0-2 are dead now: hand the next tile to the tensor core before the heads arithmetic
-                if (next_pos0 >= 0) load_planes(next_pos0);
-                // ---- heads (model.py:68-149) for the tile's positions.  (1) the two column groups of a row meet in scratch
+        };
+        // ---- heads (model.py:68-149) for the tile's positions, from the 1x1 head convolution shares the last epilogue left in
+        // hsum0-2.  Two parts, so that the NEXT tile's stem epilogue can run between them: the tensor core then works on that
+        // tile's first convolution while these warps do the dense layers of this one.
+        auto heads_partials = [&]() {  // (1) the two column groups of a row meet in scratch
+            if (row_live) {
+                float* part = scratch(sub) + r * 3;
+                part[0] = hsum0;
+                part[1] = hsum1;
+                part[2] = hsum2;
+            }
+        };
+        auto heads_dense = [&](long long pos0) {
+            {
                 const int cells = P.cells, A = P.heads.A;
-                if (row_live) {
-                    float* part = scratch(sub) + r * 3;
-                    part[0] = hsum0;
-                    part[1] = hsum1;
-                    part[2] = hsum2;
-                }
                 epi_barrier();
                 // (2) + bias, ReLU: policy planes NHWC-flattened [position][cell][2], value plane [position][cell]
                 float* hp_s = scratch(2);
@@ -778,11 +783,13 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
         // a CTA of a pair whose tile lies beyond the batch still takes part in every barrier: it computes on zeros and
         // stores nothing (pos0 >= n)
         if (NET && unit0 * kTpu < P.n_tiles && !(P.debug & 16)) load_planes((long long)(unit0 * kTpu + (int)rank) * P.ppt);  // later tiles: inside the last epilogue
+        bool stem_done = false;
         for (int unit = unit0; unit * kTpu < P.n_tiles && !(P.debug & 16); unit += n_units) {
             const long long pos0 = (long long)(unit * kTpu + (int)rank) * P.ppt;
             const long long next_pos0 = (unit + n_units) * kTpu < P.n_tiles ? (long long)((unit + n_units) * kTpu + (int)rank) * P.ppt : -1;
             if (NET) {
-                epilogue(0, s_bias, 0, false, pos0, -1);  // stem: accumulator 0 + bias, ReLU -> x and its masked copies
+                // stem: accumulator 0 + bias, ReLU -> x and its masked copies (later tiles: done inside the previous tile's tail)
+                if (!stem_done) epilogue(0, s_bias, 0, false, pos0);
             } else {
                 // ---- tile in: x, x-left-masked, x-right-masked; channels 0-63 first
                 uint4 v[8];
@@ -806,8 +813,17 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
                 }
             }
             for (int b = 0; b < P.depth; ++b) {
-                epilogue(0, s_bias + kC + (b * 2) * kC, 3, false, pos0, -1);                      // accumulator 0 -> h
-                epilogue(1, s_bias + kC + (b * 2 + 1) * kC, 0, b == P.depth - 1, pos0, next_pos0);  // accumulator 1 -> block output
+                epilogue(0, s_bias + kC + (b * 2) * kC, 3, false, pos0);                // accumulator 0 -> h
+                epilogue(1, s_bias + kC + (b * 2 + 1) * kC, 0, b == P.depth - 1, pos0);  // accumulator 1 -> block output
+            }
+            if (NET) {
+                // buffers 0-2 are dead now: hand the next tile to the tensor core, turn its stem into x as soon as that is
+                // there, and only then do this tile's dense heads - under the next tile's first convolution
+                if (next_pos0 >= 0) load_planes(next_pos0);
+                heads_partials();
+                stem_done = next_pos0 >= 0;
+                if (stem_done) epilogue(0, s_bias, 0, false, next_pos0);
+                heads_dense(pos0);
             }
         }
         if (etimed && lane == 0) {

@@ -212,8 +212,8 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
 // K = 16 MMAs and the commit that frees this stage's slot follow, and only then is the poll's answer read - so the ~70 cycles
 // a poll takes (tools/mma_rate.cu) overlap the issue of the MMAs instead of preceding them.  Before this the issuing warp
 // spent 222 of its 392 cycles per stage in two serial polls (counters of az_net_tower_timing: never once was a stage
-// missing), and the tensor pipe, which needs a stage every 256 cycles, starved.  All lanes execute it (the poll is
-// warp-uniform); only the elected lane issues.  Returns the poll's answer.
+// missing).  `leader` = 1 in the one elected lane that runs the MMA role (the predicate is kept so that the block can also be
+// executed by a whole warp with one issuing lane).  Returns the poll's answer.
 template <bool PAIR>
 __device__ __forceinline__ uint32_t issue_stage(uint32_t d_tmem, uint32_t a_lo, uint32_t a_step, uint32_t b_lo, uint32_t b_step,
                                                 uint32_t first_accumulate, uint32_t empty_bar, uint32_t next_full_bar,

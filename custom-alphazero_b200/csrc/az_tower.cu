@@ -537,6 +537,12 @@ __global__ void __launch_bounds__(kThreads + (TREES ? kTreeWarps * 32 : 0), 1) k
                     // load) has written that half of the three copies; it writes channels 64-127 underneath them
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
+                        // weights first: the poll issued a boundary ago usually came too early to see the next stage; asking
+                        // again costs nothing here, the warp is about to wait for the epilogue anyway
+                        if (!ready) {
+                            wait_stage(cnt % kRing, cnt / kRing);
+                            ready = 1;
+                        }
                         wait_act(kb == 0 ? bar_act0 : bar_act1, act_phase);
                         
                         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
